@@ -1,0 +1,754 @@
+"""Log-likelihoods and log-posteriors evaluated on the GPU.
+
+Host-side mirror of the hot-path classes of ``chi/_log_pdfs.py`` (seam B3,
+SURVEY.md section 8b): ``LogLikelihood``, ``HierarchicalLogLikelihood``,
+``LogPosterior`` and ``HierarchicalLogPosterior`` with the pints ``LogPDF``
+protocol (``__call__``, ``evaluateS1``, ``n_parameters``) plus the batched
+entry points ``evaluate_batch`` / ``evaluateS1_batch`` that evaluate many
+parameter vectors (MCMC chains, optimiser populations) in one launch.
+
+Where the reference loops over individuals in Python and crosses into a
+compiled CVODES module once per individual (chi/_log_pdfs.py:289-292), a
+hierarchical log-likelihood here owns ONE device-resident problem holding
+every individual's observations and dosing regimen, and one evaluation is
+K3a -> K1+K2 -> K3b -> K3c on the GPU (csrc/core.cu: run_hier).
+"""
+import copy
+import warnings
+
+import numpy as np
+
+from chi_b200 import _lib
+from chi_b200._error_models import ErrorModel
+from chi_b200._mechanistic_models import (
+    MechanisticModel, SBMLModel, ReducedMechanisticModel, _events_of)
+from chi_b200._population_models import (
+    PopulationModel, ComposedPopulationModel, set_population)
+
+try:
+    import pints as _pints
+    _LogPDFBase = _pints.LogPDF
+    _LogPriorBase = _pints.LogPrior
+except Exception:  # pragma: no cover
+    _pints = None
+    _LogPDFBase = object
+    _LogPriorBase = None
+
+try:
+    import chi as _chi
+except Exception:  # pragma: no cover
+    _chi = None
+
+
+def _vector(x):
+    """pints.vector: read-only 1-d float copy."""
+    x = np.array(x, dtype=float, copy=True).reshape(-1)
+    x.setflags(write=False)
+    return x
+
+
+def _failure_warning(status):
+    warnings.warn(
+        'An error occured while solving the mechanistic model: \n'
+        'integrator status %s.\n A score of -infinity is returned.'
+        % str(status), RuntimeWarning)
+
+
+class _DeviceLikelihoods(object):
+    """Device-resident data of one or many structurally identical
+    individual log-likelihoods (one ``chi_b200_problem``)."""
+
+    def __init__(self, mechanistic_model, error_kinds, times, observations,
+                 regimens, device=0):
+        """times / observations: per individual, per output arrays."""
+        if isinstance(mechanistic_model, ReducedMechanisticModel):
+            raise NotImplementedError(
+                'ReducedMechanisticModel is not supported inside device '
+                'log-likelihoods yet; fix parameters on the log-likelihood.')
+        if not isinstance(mechanistic_model, SBMLModel):
+            raise TypeError(
+                'Device log-likelihoods need a chi_b200.SBMLModel / '
+                'PKPDModel mechanistic model.')
+        self.model = mechanistic_model
+        code = mechanistic_model.model_code()
+        self.n_mech = mechanistic_model.n_parameters()
+        self.error_kinds = list(error_kinds)
+        self.n_ids = len(times)
+        self.device = device
+        out_ids = [code.output_names.index(o)
+                   for o in mechanistic_model._output_names]
+        kinds = [_lib.ERR_KINDS[k] for k in self.error_kinds]
+        self.n_sigma = sum(2 if k == 'cam' else 1 for k in self.error_kinds)
+        self.n_dim = self.n_mech + self.n_sigma
+
+        lib = _lib.lib()
+        self.problem = _lib.Problem(_lib.find_model(code), device)
+        h = self.problem.handle
+        _, p_out = _lib.i32(out_ids)
+        _, p_kind = _lib.i32(kinds)
+        _lib.check(lib.chi_b200_problem_set_outputs(
+            h, len(out_ids), p_out, p_kind))
+        atol, rtol, max_steps = mechanistic_model.tolerance()
+        _lib.check(lib.chi_b200_problem_set_tolerances(
+            h, rtol, atol, max_steps))
+
+        # records: per individual the (time, output, value) triples sorted by
+        # time -- the union grid + masks of chi/_log_pdfs.py:845-883 in
+        # ragged form
+        rec_off = [0]
+        rec_t, rec_obs, rec_out = [], [], []
+        dose_off = [0]
+        events = []
+        self.n_obs = []
+        for i in range(self.n_ids):
+            ts = np.concatenate(
+                [np.asarray(t, dtype=float) for t in times[i]])
+            ys = np.concatenate(
+                [np.asarray(y, dtype=float) for y in observations[i]])
+            os_ = np.concatenate(
+                [np.full(len(t), o, dtype=np.int32)
+                 for o, t in enumerate(times[i])])
+            order = np.lexsort((os_, ts))
+            rec_t.append(ts[order])
+            rec_obs.append(ys[order])
+            rec_out.append(os_[order])
+            rec_off.append(rec_off[-1] + len(ts))
+            self.n_obs.append(len(ts))
+            ev = _events_of(regimens[i] if regimens is not None else None)
+            events.append(ev)
+            dose_off.append(dose_off[-1] + len(ev))
+        cat = np.concatenate
+        self._rec_off = np.array(rec_off, dtype=np.int64)
+        a1, p1 = _lib.i64(self._rec_off)
+        a2, p2 = _lib.f64(cat(rec_t) if rec_off[-1] else np.zeros(0))
+        with np.errstate(all='ignore'):
+            a3, p3 = _lib.f64(cat(rec_obs) if rec_off[-1] else np.zeros(0))
+        a4, p4 = _lib.i32(cat(rec_out) if rec_off[-1] else np.zeros(0))
+        a5, p5 = _lib.i64(dose_off)
+        a6, p6 = _lib.f64(cat(events).reshape(-1) if dose_off[-1]
+                          else np.zeros(0))
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            _lib.check(lib.chi_b200_problem_upload(
+                h, self.n_ids, p1, p2, p3, p4, p5, p6))
+
+    def set_sensitivity_columns(self, columns):
+        _, p = _lib.i32(columns)
+        _lib.check(_lib.lib().chi_b200_problem_set_sensitivity_columns(
+            self.problem.handle, len(columns), p))
+
+    def simulate(self, psi, ids=None, with_sens=False):
+        """Batched ``simulate``: psi (B, n_mech) -> model output at every
+        record of every system (concatenated) [and sensitivities]."""
+        psi = np.ascontiguousarray(psi, dtype=float).reshape(-1, self.n_mech)
+        B = psi.shape[0]
+        idv = np.arange(B) % self.n_ids if ids is None else np.asarray(ids)
+        rows = int(np.sum(self._rec_off[idv + 1] - self._rec_off[idv]))
+        lib = _lib.lib()
+        a_x, p_x = _lib.f64(psi)
+        p_ids = None
+        if ids is not None:
+            a_i, p_ids = _lib.i32(ids)
+        y, p_y = _lib.out_f64(max(rows, 1))
+        s, p_s = _lib.out_f64((max(rows, 1), self.n_mech))
+        status, p_st = _lib.out_i32(B)
+        _lib.check(lib.chi_b200_simulate(
+            self.problem.handle, B, p_ids, p_x, 1 if with_sens else 0, p_y,
+            p_s if with_sens else None, p_st))
+        return y[:rows], s[:rows], status
+
+    def loglik(self, x, ids=None, with_grad=False):
+        """x: (B, n_dim) -> ll (B,), grad (B, n_dim), status (B,)."""
+        x = np.ascontiguousarray(x, dtype=float).reshape(-1, self.n_dim)
+        B = x.shape[0]
+        lib = _lib.lib()
+        a_x, p_x = _lib.f64(x)
+        p_ids = None
+        if ids is not None:
+            a_i, p_ids = _lib.i32(ids)
+        ll, p_ll = _lib.out_f64(B)
+        grad, p_g = _lib.out_f64((B, self.n_dim))
+        status, p_st = _lib.out_i32(B)
+        _lib.check(lib.chi_b200_loglik(
+            self.problem.handle, B, p_ids, p_x, 1 if with_grad else 0, p_ll,
+            p_g if with_grad else None, p_st, None, None))
+        return ll, grad, status
+
+
+class LogLikelihood(_LogPDFBase):
+    """Log-likelihood of one individual, see chi/_log_pdfs.py:637-1149."""
+
+    def __init__(
+            self, mechanistic_model, error_model, observations, times,
+            outputs=None):
+        if not isinstance(mechanistic_model, MechanisticModel):
+            raise TypeError(
+                'The mechanistic model as to be an instance of a '
+                'chi.MechanisticModel.')
+        if not isinstance(error_model, list):
+            error_model = [error_model]
+        mechanistic_model = mechanistic_model.copy()
+        if outputs is not None:
+            mechanistic_model.set_outputs(outputs)
+        n_outputs = mechanistic_model.n_outputs()
+        if len(error_model) != n_outputs:
+            raise ValueError(
+                'One error model has to be provided for each mechanistic '
+                'model output.')
+        for em in error_model:
+            if not isinstance(em, ErrorModel):
+                raise TypeError(
+                    'The error models have to instances of a '
+                    'chi.ErrorModel.')
+        if n_outputs == 1:
+            if len(observations) != n_outputs:
+                observations = [observations]
+            if len(times) != n_outputs:
+                times = [times]
+        if len(observations) != n_outputs:
+            raise ValueError(
+                'The observations have the wrong length. For a '
+                'multi-output problem the observations are expected to be '
+                'a list of array-like objects with measurements for each '
+                'of the mechanistic model outputs.')
+        if len(times) != n_outputs:
+            raise ValueError(
+                'The times have the wrong length. For a multi-output problem '
+                'the times are expected to be a list of array-like objects '
+                'with the measurement time points for each of the mechanistic '
+                'model outputs.')
+        observations = [_vector(obs) for obs in observations]
+        times = [_vector(ts) for ts in times]
+        for ts in times:
+            if np.any(ts < 0):
+                raise ValueError('Times cannot be negative.')
+            if np.any(ts[:-1] > ts[1:]):
+                raise ValueError('Times must be increasing.')
+        for output_id, output_times in enumerate(times):
+            if observations[output_id].shape != output_times.shape:
+                raise ValueError(
+                    'The observations and times have to be of the same '
+                    'dimension.')
+            order = np.argsort(output_times, kind='stable')
+            times[output_id] = output_times[order]
+            observations[output_id] = observations[output_id][order]
+        error_model = [copy.deepcopy(em) for em in error_model]
+
+        self._mechanistic_model = mechanistic_model
+        self._error_models = error_model
+        self._observations = observations
+        self._output_times = times
+        self._n_obs = [len(obs) for obs in observations]
+        self._set_error_model_parameter_names()
+        self._set_number_and_parameter_names()
+        self._id = None
+        self._device = None
+
+    # -- device ----------------------------------------------------------------
+    def _regimen(self):
+        try:
+            return self._mechanistic_model.dosing_regimen()
+        except AttributeError:
+            return None
+
+    def _get_device(self):
+        if self._device is None:
+            self._device = _DeviceLikelihoods(
+                self._mechanistic_model,
+                [em._kind for em in self._error_models],
+                [self._output_times], [self._observations],
+                [self._regimen()])
+        return self._device
+
+    def __call__(self, parameters):
+        """chi/_log_pdfs.py:802-843."""
+        parameters = np.asarray(parameters, dtype=float)
+        ll, _, status = self._get_device().loglik(parameters[None, :])
+        if status[0] != 0:
+            _failure_warning(status[0])
+            return -np.inf
+        return float(ll[0])
+
+    def evaluateS1(self, parameters):
+        """chi/_log_pdfs.py:973-1027."""
+        parameters = np.asarray(parameters, dtype=float)
+        ll, grad, status = self._get_device().loglik(
+            parameters[None, :], with_grad=True)
+        if status[0] != 0:
+            _failure_warning(status[0])
+            return -np.inf, np.full(shape=len(parameters), fill_value=np.inf)
+        return float(ll[0]), grad[0].copy()
+
+    def _set_error_model_parameter_names(self):
+        """chi/_log_pdfs.py:885-909."""
+        for error_model in self._error_models:
+            error_model.set_parameter_names(None)
+        n_outputs = self._mechanistic_model.n_outputs()
+        if n_outputs > 1:
+            outputs = self._mechanistic_model.outputs()
+            for output_id, error_model in enumerate(self._error_models):
+                names = error_model.get_parameter_names()
+                output = outputs[output_id]
+                names = [output + ' ' + name for name in names]
+                error_model.set_parameter_names(names)
+
+    def _set_number_and_parameter_names(self):
+        """chi/_log_pdfs.py:911-930."""
+        parameter_names = self._mechanistic_model.parameters()
+        n_error_params = []
+        for error_model in self._error_models:
+            parameter_names += error_model.get_parameter_names()
+            n_error_params.append(error_model.n_parameters())
+        self._parameter_names = parameter_names
+        self._n_parameters = len(self._parameter_names)
+        self._n_mechanistic_params = self._mechanistic_model.n_parameters()
+        self._n_error_params = n_error_params
+
+    def get_id(self, *args, **kwargs):
+        return self._id
+
+    def get_parameter_names(self, *args, **kwargs):
+        return copy.copy(self._parameter_names)
+
+    def get_submodels(self):
+        return dict({
+            'Mechanistic model': self._mechanistic_model.copy(),
+            'Error models': copy.copy(self._error_models)})
+
+    def n_parameters(self, *args, **kwargs):
+        return self._n_parameters
+
+    def n_observations(self):
+        return self._n_obs
+
+    def set_id(self, label):
+        if isinstance(label, float):
+            label = int(label)
+        self._id = str(label)
+
+
+def _check_structure(log_likelihoods):
+    first = log_likelihoods[0]
+    key = first._mechanistic_model.model_key()
+    outs = first._mechanistic_model._output_names
+    kinds = [em._kind for em in first._error_models]
+    for ll in log_likelihoods[1:]:
+        if ll._mechanistic_model.model_key() != key or \
+                ll._mechanistic_model._output_names != outs or \
+                [em._kind for em in ll._error_models] != kinds:
+            raise ValueError(
+                'The log-likelihoods of a hierarchical model have to be '
+                'structurally identical (same mechanistic model, outputs and '
+                'error models).')
+
+
+class HierarchicalLogLikelihood(object):
+    """chi/_log_pdfs.py:18-403."""
+
+    def __init__(
+            self, log_likelihoods, population_model, covariates=None):
+        for log_likelihood in log_likelihoods:
+            if not isinstance(log_likelihood, LogLikelihood):
+                raise ValueError(
+                    'The log-likelihoods have to be instances of a '
+                    'chi.LogLikelihood.')
+        if not isinstance(population_model, PopulationModel):
+            raise ValueError(
+                'The population model has to be an instances of '
+                'chi.PopulationModel.')
+        n_parameters = population_model.n_dim()
+        for log_likelihood in log_likelihoods:
+            if log_likelihood.n_parameters() != n_parameters:
+                raise ValueError(
+                    'The dimension of the population model does not match the '
+                    'the dimensions of the log-likelihood parameter space.')
+        n_ids = len(log_likelihoods)
+        if population_model.n_covariates() > 0:
+            if covariates is None:
+                raise ValueError(
+                    'The population model needs covariates, but no covariates '
+                    'have been provided.')
+            n_cov = population_model.n_covariates()
+            try:
+                covariates = np.asarray(covariates).reshape(n_ids, n_cov)
+            except ValueError:
+                raise ValueError(
+                    'The covariates do not have the correct format. '
+                    'Covariates need to be of shape (n_ids, n_cov).')
+        _check_structure(log_likelihoods)
+        self._log_likelihoods = log_likelihoods
+        self._label_log_likelihoods()
+        first = log_likelihoods[0]
+        device = _DeviceLikelihoods(
+            first._mechanistic_model,
+            [em._kind for em in first._error_models],
+            [ll._output_times for ll in log_likelihoods],
+            [ll._observations for ll in log_likelihoods],
+            [ll._regimen() for ll in log_likelihoods])
+        self._setup(device, population_model, covariates,
+                    first.get_parameter_names(),
+                    [ll.get_id() for ll in log_likelihoods])
+
+    @classmethod
+    def from_arrays(cls, mechanistic_model, error_models, times,
+                    observations, population_model, regimens=None,
+                    covariates=None, ids=None):
+        """Builds the hierarchical log-likelihood straight from ragged
+        arrays (one entry per individual; single output: arrays, multiple
+        outputs: lists of arrays) without creating one Python object per
+        individual -- the ingestion path for 10^4-10^5 individuals."""
+        if not isinstance(error_models, list):
+            error_models = [error_models]
+        n_out = mechanistic_model.n_outputs()
+        if len(error_models) != n_out:
+            raise ValueError(
+                'One error model has to be provided for each mechanistic '
+                'model output.')
+        n_ids = len(times)
+        if n_out == 1:
+            times = [[t] if np.ndim(t[0]) == 0 else t for t in times]
+            observations = [[y] if np.ndim(y[0]) == 0 else y
+                            for y in observations]
+        self = cls.__new__(cls)
+        self._log_likelihoods = None
+        template = LogLikelihood(
+            mechanistic_model, error_models, observations[0], times[0])
+        device = _DeviceLikelihoods(
+            template._mechanistic_model,
+            [em._kind for em in template._error_models], times, observations,
+            regimens)
+        if population_model.n_covariates() > 0:
+            if covariates is None:
+                raise ValueError(
+                    'The population model needs covariates, but no covariates '
+                    'have been provided.')
+            covariates = np.asarray(covariates).reshape(
+                n_ids, population_model.n_covariates())
+        if ids is None:
+            ids = ['Log-likelihood %d' % (k + 1) for k in range(n_ids)]
+        self._setup(device, population_model, covariates,
+                    template.get_parameter_names(), [str(i) for i in ids])
+        return self
+
+    def _setup(self, device, population_model, covariates, ll_names, ids):
+        self._device = device
+        self._population_model = population_model
+        self._covariates = covariates
+        self._n_ids = device.n_ids
+        self._n_dim = population_model.n_dim()
+        self._ll_parameter_names = list(ll_names)
+        self._ids = list(ids)
+        if self._n_dim != device.n_dim:
+            raise ValueError(
+                'The dimension of the population model does not match the '
+                'the dimensions of the log-likelihood parameter space.')
+        population_model.set_n_ids(self._n_ids)
+        self._n_parameters = int(np.sum(
+            population_model.n_hierarchical_parameters(self._n_ids)))
+        self._n_bottom = self._n_parameters - \
+            population_model.n_hierarchical_parameters(self._n_ids)[1]
+        self._n_obs = list(device.n_obs)
+        set_population(device.problem, population_model._blocks(), covariates)
+        sizes = np.zeros(4, dtype=np.int64)
+        _lib.check(_lib.lib().chi_b200_population_sizes(
+            device.problem.handle, sizes.ctypes.data_as(_lib.c_i64p)))
+        assert sizes[0] == self._n_bottom, (sizes, self._n_bottom)
+        assert sizes[0] + sizes[1] == self._n_parameters
+
+    def _label_log_likelihoods(self):
+        """chi/_log_pdfs.py:147-161."""
+        ids = []
+        for idl, log_likelihood in enumerate(self._log_likelihoods):
+            _id = log_likelihood.get_id()
+            if not _id:
+                _id = 'Log-likelihood %d' % (idl + 1)
+            if _id in ids:
+                raise ValueError('Log-likelihood IDs need to be unique.')
+            log_likelihood.set_id(_id)
+            ids.append(_id)
+
+    # -- evaluation ------------------------------------------------------------
+    def _evaluate(self, X, with_grad):
+        X = np.ascontiguousarray(X, dtype=float).reshape(
+            -1, self._n_parameters)
+        C = X.shape[0]
+        lib = _lib.lib()
+        a_x, p_x = _lib.f64(X)
+        score, p_s = _lib.out_f64(C)
+        grad, p_g = _lib.out_f64((C, self._n_parameters))
+        status, p_st = _lib.out_i32(C)
+        _lib.check(lib.chi_b200_hier_logpdf(
+            self._device.problem.handle, C, p_x, 1 if with_grad else 0, p_s,
+            p_g if with_grad else None, p_st))
+        if np.any(status != 0):
+            _failure_warning(status[status != 0][0])
+            score[status != 0] = -np.inf
+        return score, grad, status
+
+    def evaluate_batch(self, X):
+        """Scores of many parameter vectors, shape ``(n_vectors,)``."""
+        return self._evaluate(X, False)[0]
+
+    def evaluateS1_batch(self, X):
+        """Scores and gradients of many parameter vectors."""
+        score, grad, _ = self._evaluate(X, True)
+        return score, grad
+
+    def __call__(self, parameters):
+        """chi/_log_pdfs.py:104-145."""
+        return float(self._evaluate(np.asarray(parameters), False)[0][0])
+
+    def evaluateS1(self, parameters):
+        """chi/_log_pdfs.py:255-300."""
+        score, grad, _ = self._evaluate(np.asarray(parameters), True)
+        return float(score[0]), grad[0].copy()
+
+    def counters(self):
+        """systems, accepted steps, rejected steps, kernel launches of the
+        last evaluation."""
+        out = np.zeros(4, dtype=np.int64)
+        _lib.check(_lib.lib().chi_b200_problem_counters(
+            self._device.problem.handle, out.ctypes.data_as(_lib.c_i64p)))
+        return out
+
+    # -- bookkeeping -------------------------------------------------------------
+    def get_id(self, unique=False):
+        """chi/_log_pdfs.py:302-325."""
+        ids = list(self._ids)
+        if unique:
+            return ids
+        n_copies = self._n_bottom // self._n_ids
+        _ids = []
+        for _id in ids:
+            _ids += [_id] * n_copies
+        ids = _ids
+        ids += [None] * self._population_model.n_parameters()
+        return ids
+
+    def get_parameter_names(
+            self, exclude_bottom_level=False, include_ids=False):
+        """chi/_log_pdfs.py:327-367."""
+        current_dim = 0
+        names = list(self._ll_parameter_names)
+        n = []
+        special_dims, _, _ = self._population_model.get_special_dims()
+        for info in special_dims:
+            start_dim, end_dim, _, _, _ = info
+            n += names[current_dim:start_dim]
+            current_dim = end_dim
+        n += names[current_dim:]
+        names = n
+        names = names * self._n_ids
+        names += self._population_model.get_parameter_names()
+        if include_ids:
+            ids = self.get_id()
+            n = []
+            for idn, name in enumerate(names):
+                if ids[idn]:
+                    name = ids[idn] + ' ' + name
+                n.append(name)
+            names = n
+        if exclude_bottom_level:
+            names = names[self._n_bottom:]
+        return names
+
+    def get_population_model(self):
+        return self._population_model
+
+    def n_log_likelihoods(self):
+        return self._n_ids
+
+    def n_parameters(self, exclude_bottom_level=False):
+        if exclude_bottom_level:
+            return self._population_model.n_parameters()
+        return self._n_parameters
+
+    def n_observations(self):
+        return self._n_obs
+
+
+class HierarchicalLogPosterior(_LogPDFBase):
+    """chi/_log_pdfs.py:406-634."""
+
+    def __init__(self, log_likelihood, log_prior):
+        if not isinstance(log_likelihood, HierarchicalLogLikelihood):
+            raise TypeError(
+                'The log-likelihood has to be an instance of a '
+                'chi.HierarchicalLogLikelihood.')
+        _check_prior(log_prior)
+        n_top = log_likelihood.n_parameters(exclude_bottom_level=True)
+        if log_prior.n_parameters() != n_top:
+            raise ValueError(
+                'The log-prior has to have as many parameters as population '
+                'parameters in the log-likelihood. There are '
+                '<' + str(n_top) + '> population parameters.')
+        self._log_prior = log_prior
+        self._log_likelihood = log_likelihood
+        self._n_parameters = log_likelihood.n_parameters()
+        self._n_bottom = self._n_parameters - n_top
+
+    def __call__(self, parameters):
+        """chi/_log_pdfs.py:463-472."""
+        parameters = np.asarray(parameters)
+        score = self._log_prior(parameters[self._n_bottom:])
+        if np.isinf(score):
+            return score
+        return score + self._log_likelihood(parameters)
+
+    def evaluateS1(self, parameters):
+        """chi/_log_pdfs.py:474-498."""
+        parameters = np.asarray(parameters)
+        score, sens = self._log_prior.evaluateS1(parameters[self._n_bottom:])
+        if np.isinf(score):
+            return score, np.full(shape=len(parameters), fill_value=np.inf)
+        ll_score, sensitivities = self._log_likelihood.evaluateS1(parameters)
+        score += ll_score
+        sensitivities[self._n_bottom:] += sens
+        return score, sensitivities
+
+    def evaluate_batch(self, X):
+        """Batched ``__call__``: the prior is evaluated per vector on the
+        host (top-level slice only), all likelihoods in one GPU pass."""
+        X = np.asarray(X, dtype=float).reshape(-1, self._n_parameters)
+        prior = np.array([self._log_prior(x[self._n_bottom:]) for x in X])
+        score = self._log_likelihood.evaluate_batch(X)
+        score = prior + score
+        score[np.isinf(prior)] = prior[np.isinf(prior)]
+        return score
+
+    def evaluateS1_batch(self, X):
+        X = np.asarray(X, dtype=float).reshape(-1, self._n_parameters)
+        score, grad = self._log_likelihood.evaluateS1_batch(X)
+        for c, x in enumerate(X):
+            p, s = self._log_prior.evaluateS1(x[self._n_bottom:])
+            if np.isinf(p):
+                score[c] = p
+                grad[c] = np.inf
+                continue
+            score[c] += p
+            grad[c, self._n_bottom:] += s
+        return score, grad
+
+    def get_log_likelihood(self):
+        return self._log_likelihood
+
+    def get_log_prior(self):
+        return self._log_prior
+
+    def get_id(self, unique=False):
+        return self._log_likelihood.get_id(unique)
+
+    def get_parameter_names(
+            self, exclude_bottom_level=False, include_ids=False):
+        return self._log_likelihood.get_parameter_names(
+            exclude_bottom_level, include_ids)
+
+    def get_population_model(self):
+        return self._log_likelihood.get_population_model()
+
+    def n_ids(self):
+        return self._log_likelihood.n_log_likelihoods()
+
+    def n_parameters(self, exclude_bottom_level=False):
+        return self._log_likelihood.n_parameters(exclude_bottom_level)
+
+    def sample_initial_parameters(self, n_samples=1, seed=None):
+        """chi/_log_pdfs.py:552-634."""
+        n_samples = int(n_samples)
+        if n_samples <= 0:
+            raise ValueError(
+                'The number of samples has to be greater or equal to 1.')
+        initial_params = np.empty(shape=(n_samples, self._n_parameters))
+        np.random.seed(seed)
+        n_top = self._log_prior.n_parameters()
+        n_bottom = self._n_parameters - n_top
+        initial_params[:, n_bottom:] = self._log_prior.sample(n_samples)
+        if n_bottom == 0:
+            return initial_params
+        if seed is not None:
+            seed += 1
+        rng = np.random.default_rng(seed=seed)
+        n_ids = self._log_likelihood.n_log_likelihoods()
+        covariates = self._log_likelihood._covariates
+        population_model = self._log_likelihood.get_population_model()
+        bottom_parameters = []
+        for sample_id in range(n_samples):
+            kwargs = {}
+            if population_model.n_covariates() > 0:
+                kwargs['covariates'] = covariates
+            bottom_parameters.append(population_model.sample(
+                parameters=initial_params[sample_id, n_bottom:],
+                n_samples=n_ids, seed=rng, **kwargs))
+        dims = population_model._hier_columns()
+        for idx, bottom_params in enumerate(bottom_parameters):
+            bottom_parameters[idx] = bottom_params[:, dims].flatten()
+        initial_params[:, :n_bottom] = np.vstack(bottom_parameters)
+        return initial_params
+
+
+def _check_prior(log_prior):
+    ok = all(hasattr(log_prior, name) for name in (
+        '__call__', 'evaluateS1', 'n_parameters', 'sample'))
+    if _LogPriorBase is not None and isinstance(log_prior, _LogPriorBase):
+        ok = True
+    if not ok:
+        raise TypeError(
+            'The log-prior has to be an instance of a pints.LogPrior.')
+
+
+class LogPosterior(_LogPDFBase):
+    """chi/_log_pdfs.py:1152-1322."""
+
+    def __init__(self, log_likelihood, log_prior):
+        if not isinstance(log_likelihood, LogLikelihood):
+            raise TypeError(
+                'The log-likelihood has to extend chi.LogLikelihood.')
+        _check_prior(log_prior)
+        if log_prior.n_parameters() != log_likelihood.n_parameters():
+            raise ValueError(
+                'The log-prior and the log-likelihood must have the same '
+                'dimension.')
+        self._log_prior = log_prior
+        self._log_likelihood = log_likelihood
+        self._n_parameters = log_likelihood.n_parameters()
+
+    def __call__(self, parameters):
+        """chi/_log_pdfs.py:1245-1251."""
+        score = self._log_prior(parameters)
+        if np.isinf(score):
+            return score
+        return score + self._log_likelihood(parameters)
+
+    def evaluateS1(self, parameters):
+        """chi/_log_pdfs.py:1253-1273."""
+        score, sens = self._log_prior.evaluateS1(parameters)
+        if np.isinf(score):
+            return score, np.full(shape=len(parameters), fill_value=np.inf)
+        ll_score, sensitivities = self._log_likelihood.evaluateS1(parameters)
+        score += ll_score
+        sensitivities += sens
+        return score, sensitivities
+
+    def get_log_likelihood(self):
+        return self._log_likelihood
+
+    def get_log_prior(self):
+        return self._log_prior
+
+    def get_id(self, *args, **kwargs):
+        return self._log_likelihood.get_id()
+
+    def get_parameter_names(self, *args, **kwargs):
+        return self._log_likelihood.get_parameter_names()
+
+    def n_parameters(self, *args, **kwargs):
+        return self._n_parameters
+
+    def sample_initial_parameters(self, n_samples=1, seed=None):
+        """chi/_log_pdfs.py:1302-1322."""
+        n_samples = int(n_samples)
+        if n_samples <= 0:
+            raise ValueError(
+                'The number of samples has to be greater or equal to 1.')
+        np.random.seed(seed)
+        return self._log_prior.sample(n_samples)

@@ -1,0 +1,135 @@
+"""Minimal host-side log-priors with the ``pints.LogPrior`` protocol.
+
+chi takes its priors from pints (``pints.LogPrior``; call sites
+chi/_log_pdfs.py:444, 468, 486, 1229, 1247, 1262).  pints is a caller of the
+hot path, not part of it, and is not installed in this image; these classes
+are duck-typed stand-ins so that posteriors can be assembled in tests and
+benchmarks.  A real ``pints.LogPrior`` works in their place.  Priors act on
+the handful of top-level parameters only and stay on the host, as in chi.
+"""
+import numpy as np
+
+try:
+    import pints as _pints
+    _Base = _pints.LogPrior
+except Exception:  # pragma: no cover
+    _Base = object
+
+
+class GaussianLogPrior(_Base):
+    """``pints.GaussianLogPrior(mean, sd)``."""
+
+    def __init__(self, mean, sd):
+        self._mean = float(mean)
+        self._sd = float(sd)
+        if self._sd <= 0:
+            raise ValueError('sd must be positive.')
+
+    def __call__(self, x):
+        z = (float(np.asarray(x).reshape(-1)[0]) - self._mean) / self._sd
+        return -0.5 * np.log(2 * np.pi) - np.log(self._sd) - 0.5 * z * z
+
+    def evaluateS1(self, x):
+        z = (float(np.asarray(x).reshape(-1)[0]) - self._mean) / self._sd
+        return self(x), np.array([-z / self._sd])
+
+    def n_parameters(self):
+        return 1
+
+    def sample(self, n=1):
+        return np.random.normal(self._mean, self._sd, size=(n, 1))
+
+
+class LogNormalLogPrior(_Base):
+    """``pints.LogNormalLogPrior(log_mean, scale)``."""
+
+    def __init__(self, log_mean, scale):
+        self._mu = float(log_mean)
+        self._s = float(scale)
+        if self._s <= 0:
+            raise ValueError('scale must be positive.')
+
+    def __call__(self, x):
+        x = float(np.asarray(x).reshape(-1)[0])
+        if x <= 0:
+            return -np.inf
+        z = (np.log(x) - self._mu) / self._s
+        return -0.5 * np.log(2 * np.pi) - np.log(self._s) - np.log(x) \
+            - 0.5 * z * z
+
+    def evaluateS1(self, x):
+        xv = float(np.asarray(x).reshape(-1)[0])
+        if xv <= 0:
+            return -np.inf, np.array([np.inf])
+        z = (np.log(xv) - self._mu) / self._s
+        return self(x), np.array([-(1 + z / self._s) / xv])
+
+    def n_parameters(self):
+        return 1
+
+    def sample(self, n=1):
+        return np.random.lognormal(self._mu, self._s, size=(n, 1))
+
+
+class UniformLogPrior(_Base):
+    """``pints.UniformLogPrior(lower, upper)`` (one dimension)."""
+
+    def __init__(self, lower, upper):
+        self._a = float(lower)
+        self._b = float(upper)
+        if not self._b > self._a:
+            raise ValueError('upper must exceed lower.')
+
+    def __call__(self, x):
+        x = float(np.asarray(x).reshape(-1)[0])
+        if x < self._a or x >= self._b:
+            return -np.inf
+        return -np.log(self._b - self._a)
+
+    def evaluateS1(self, x):
+        return self(x), np.zeros(1)
+
+    def n_parameters(self):
+        return 1
+
+    def sample(self, n=1):
+        return np.random.uniform(self._a, self._b, size=(n, 1))
+
+
+class ComposedLogPrior(_Base):
+    """``pints.ComposedLogPrior(*priors)``: independent product."""
+
+    def __init__(self, *priors):
+        if not priors:
+            raise ValueError('Must have at least one sub-prior.')
+        self._priors = list(priors)
+        self._n = sum(p.n_parameters() for p in self._priors)
+
+    def __call__(self, x):
+        x = np.asarray(x, dtype=float).reshape(-1)
+        out = 0.0
+        lo = 0
+        for p in self._priors:
+            hi = lo + p.n_parameters()
+            out += p(x[lo:hi])
+            lo = hi
+        return out
+
+    def evaluateS1(self, x):
+        x = np.asarray(x, dtype=float).reshape(-1)
+        out = 0.0
+        grads = []
+        lo = 0
+        for p in self._priors:
+            hi = lo + p.n_parameters()
+            v, g = p.evaluateS1(x[lo:hi])
+            out += v
+            grads.append(np.asarray(g, dtype=float).reshape(-1))
+            lo = hi
+        return out, np.concatenate(grads)
+
+    def n_parameters(self):
+        return self._n
+
+    def sample(self, n=1):
+        return np.hstack([p.sample(n) for p in self._priors])

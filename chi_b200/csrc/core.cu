@@ -1,0 +1,1500 @@
+// chi_b200 -- core library: C ABI, model registry, problem handles, static
+// population data, population-model kernels (K3) and the hierarchical
+// log-pdf pipeline.  See include/chi_b200.h for the contract of every entry
+// point and the reference interface it replaces.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/chi_b200.h"
+#include "model_api.cuh"
+
+using namespace chi_b200;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) {
+  g_error = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                       \
+  do {                                                                        \
+    cudaError_t err__ = (expr);                                               \
+    if (err__ != cudaSuccess)                                                 \
+      return fail(-2, std::string(#expr) + ": " +                             \
+                          cudaGetErrorString(err__));                         \
+  } while (0)
+
+std::vector<const ModelVTable*>& registry() {
+  static std::vector<const ModelVTable*> r;
+  return r;
+}
+
+// growable device buffer
+struct DevBuf {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    size_t want = std::max(bytes, size_t(256));
+    cudaError_t err = cudaMalloc(&ptr, want);
+    if (err == cudaSuccess) cap = want;
+    return err;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return static_cast<T*>(ptr);
+  }
+};
+
+constexpr int MAX_POP_DIM = 32;
+constexpr int MAX_POP_COV = 8;
+constexpr int POP_BLOCK = 256;
+
+// One dimension of the composed population model, flattened for the device.
+struct PopDim {
+  int32_t kind;
+  int32_t centered;
+  int32_t hcol;        // column among the hierarchical dims, -1 for special
+  int32_t top0;        // pooled: theta idx; hetero: base; else mu idx
+  int32_t top1;        // sigma idx
+  int32_t het_stride;  // hetero: n_dim of the block
+  int32_t het_off;     // hetero: dim inside the block
+  int32_t n_cov;
+  int32_t cov0;
+  int32_t beta_mu;     // theta idx of the beta row of (mu, d), -1 none
+  int32_t beta_sigma;
+  int32_t red_mu;      // slot of mu / pooled theta in the reduced vector
+  int32_t red_sigma;
+  int32_t red_beta_mu;
+  int32_t red_beta_sigma;
+};
+
+struct PopDesc {
+  int32_t n_dim;
+  int32_t n_hdim;
+  int32_t n_cov_total;
+  int32_t n_red;       // reduced top-level slots (all but heterogeneous)
+  PopDim dim[MAX_POP_DIM];
+};
+
+}  // namespace
+
+struct chi_b200_problem {
+  const ModelVTable* vt = nullptr;
+  int model = -1;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+
+  // configuration
+  int32_t n_out = 0;
+  int32_t out_id[MAX_OUT];
+  int32_t err_kind[MAX_OUT];
+  int32_t err_off[MAX_OUT];
+  int32_t n_sigma = 0;
+  int32_t n_cols = 0;
+  int32_t col_param[MAX_COLS];
+  double rtol = 1e-8, atol = 1e-10;
+  int32_t max_steps = 100000;
+  int32_t variant = -1;
+
+  // static data
+  int64_t n_ids = 0;
+  int64_t n_rec = 0;
+  std::vector<int64_t> h_rec_off;
+  DevBuf rec_off, rec_t, rec_obs, rec_logobs, rec_out;
+  DevBuf seg_off, seg_t, seg_rate;
+
+  // population model
+  bool has_pop = false;
+  PopDesc pop;
+  int64_t n_top = 0;
+  std::vector<int32_t> red_to_top;  // reduced slot -> theta index
+  DevBuf covariates;
+  int64_t id_begin = 0, id_end = 0;
+
+  // scratch
+  DevBuf x, ll, grad, status, nst, nrj, ids, traj_off, traj_y, traj_s;
+  DevBuf hx, hscore, hgrad, hstatus, partial, popflag;
+  int64_t counters[4] = {0, 0, 0, 0};
+
+  // optional device timing of the solve kernel (bench / roofline)
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double solve_ms_sum = 0.0;
+  int64_t solve_launches = 0;
+};
+
+// ============================================================================
+// Population kernels (K3)
+// ============================================================================
+namespace {
+
+constexpr double LOG_2PI = 1.8378770664093454836;
+constexpr double LOG_2PI_HALF_C = 0.91893853320467274178;
+
+// theta_i(mu, sigma) of individual i for dimension d (covariate shift,
+// chi/_covariate_models.py:257-284)
+__device__ __forceinline__ void pop_mu_sigma(const PopDim& D,
+                                             const double* top,
+                                             const double* cov, int n_cov_tot,
+                                             int64_t i, double& mu,
+                                             double& sigma) {
+  mu = top[D.top0];
+  sigma = top[D.top1];
+  if (D.n_cov > 0) {
+    const double* xi = cov + i * n_cov_tot + D.cov0;
+    if (D.beta_mu >= 0)
+      for (int k = 0; k < D.n_cov; ++k) mu = fma(xi[k], top[D.beta_mu + k], mu);
+    if (D.beta_sigma >= 0)
+      for (int k = 0; k < D.n_cov; ++k)
+        sigma = fma(xi[k], top[D.beta_sigma + k], sigma);
+  }
+}
+
+// K3a: x[c] = [bottom | top] -> psi of every (chain, individual) system.
+// Also writes the system -> individual map and flags chains whose population
+// parameters are invalid (sigma < 0; chi/_population_models.py:1594-1595,
+// 1639-1641, 2438-2439, 2480-2482).
+__global__ void pop_forward_kernel(PopDesc P, int32_t C, int64_t n_ids,
+                                   int64_t id_begin, int64_t id_end,
+                                   int64_t n_params, int64_t n_bottom,
+                                   const double* __restrict__ x,
+                                   const double* __restrict__ cov,
+                                   double* __restrict__ xsys,
+                                   double* __restrict__ eta_out,
+                                   int32_t* __restrict__ ids,
+                                   int32_t* __restrict__ popflag) {
+  const int64_t n_sh = id_end - id_begin;
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (tid >= n_sh * C) return;
+  const int64_t c = tid / n_sh;
+  const int64_t i = id_begin + (tid - c * n_sh);
+  const double* xc = x + c * n_params;
+  const double* top = xc + n_bottom;
+  const double* bot = xc + i * P.n_hdim;
+  double* out = xsys + tid * P.n_dim;
+  if (ids) ids[tid] = static_cast<int32_t>(i);
+  bool bad = false;
+  for (int d = 0; d < P.n_dim; ++d) {
+    const PopDim& D = P.dim[d];
+    double eta, psi;
+    if (D.kind == CHI_B200_POP_POOLED) {
+      eta = psi = top[D.top0];
+    } else if (D.kind == CHI_B200_POP_HETEROGENEOUS) {
+      eta = psi = top[D.top0 + i * D.het_stride + D.het_off];
+    } else {
+      eta = bot[D.hcol];
+      double mu, sigma;
+      pop_mu_sigma(D, top, cov, P.n_cov_total, i, mu, sigma);
+      if (sigma < 0.0) bad = true;
+      if (D.centered) {
+        psi = eta;
+      } else if (sigma < 0.0) {
+        psi = NAN;
+      } else if (D.kind == CHI_B200_POP_GAUSSIAN) {
+        psi = fma(sigma, eta, mu);
+      } else {
+        psi = exp(fma(sigma, eta, mu));
+      }
+    }
+    out[d] = psi;
+    if (eta_out) eta_out[tid * P.n_dim + d] = eta;
+  }
+  if (bad && popflag) popflag[c] = 1;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// K3b: population densities and back-propagation of d ll / d psi to
+// (eta, theta).  One thread per (chain, individual); top-level sums are
+// reduced per warp, then per block in a fixed order, and written as partials
+// [c][block][1 + n_red] (slot 0 = score) for the deterministic final sum.
+__global__ void __launch_bounds__(POP_BLOCK)
+pop_backward_kernel(PopDesc P, int64_t n_ids, int64_t id_begin,
+                    int64_t id_end, int64_t n_params, int64_t n_bottom,
+                    int32_t with_grad, const double* __restrict__ x,
+                    const double* __restrict__ cov,
+                    const double* __restrict__ ll,     // [C][n_sh] or null
+                    const double* __restrict__ dlp,    // [C][n_sh][n_dim] or null
+                    double* __restrict__ grad,         // [C][n_params]
+                    double* __restrict__ partial) {
+  extern __shared__ double sacc[];  // [warps][1 + n_red]
+  const int n_slots = 1 + P.n_red;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_warps = blockDim.x >> 5;
+  const int64_t n_sh = id_end - id_begin;
+  const int64_t c = blockIdx.y;
+  const int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const bool live = k < n_sh;
+  const int64_t i = id_begin + (live ? k : 0);
+  const double* xc = x + c * n_params;
+  const double* top = xc + n_bottom;
+  const double* bot = xc + i * P.n_hdim;
+  const double* g_in = dlp ? dlp + (c * n_sh + (live ? k : 0)) * P.n_dim : nullptr;
+  double* gc = grad ? grad + c * n_params : nullptr;
+
+  for (int s = lane; s < n_slots; s += 32) sacc[warp * n_slots + s] = 0.0;
+  __syncwarp();
+
+  double score = (live && ll) ? ll[c * n_sh + k] : 0.0;
+  for (int d = 0; d < P.n_dim; ++d) {
+    const PopDim& D = P.dim[d];
+    const double dl = (live && g_in) ? g_in[d] : 0.0;
+    if (D.kind == CHI_B200_POP_POOLED) {
+      // PooledModel._shape(reduce=True): d theta = sum_i d ll/d psi_i
+      // (chi/_population_models.py:2792-2810)
+      if (with_grad) {
+        const double s = warp_sum(dl);
+        if (lane == 0) sacc[warp * n_slots + 1 + D.red_mu] += s;
+      }
+    } else if (D.kind == CHI_B200_POP_HETEROGENEOUS) {
+      // HeterogeneousModel._shape(reduce=True): d theta = d ll/d psi flat
+      // (chi/_population_models.py:1907-1926)
+      if (with_grad && live)
+        gc[n_bottom + D.top0 + i * D.het_stride + D.het_off] = dl;
+    } else {
+      double mu = 0.0, sigma = 1.0, eta = 0.0;
+      if (live) {
+        pop_mu_sigma(D, top, cov, P.n_cov_total, i, mu, sigma);
+        eta = bot[D.hcol];
+      }
+      double s_i, deta, dmu, dsg;
+      if (!D.centered) {
+        // chi/_population_models.py:1474-1493 (Gaussian),
+        // 2306-2339 (LogNormal)
+        s_i = -(0.5 * LOG_2PI + 0.5 * eta * eta);
+        if (D.kind == CHI_B200_POP_GAUSSIAN) {
+          deta = dl * sigma - eta;
+          dmu = dl;
+          dsg = dl * eta;
+        } else {
+          const double psi = exp(fma(sigma, eta, mu));
+          deta = dl * sigma * psi - eta;
+          dmu = dl * psi;
+          dsg = dl * eta * psi;
+        }
+      } else {
+        const double var = sigma * sigma;
+        if (D.kind == CHI_B200_POP_GAUSSIAN) {
+          // chi/_population_models.py:1454-1472, 1513-1549
+          const double r = eta - mu;
+          s_i = -(0.5 * log(2.0 * M_PI * var) + r * r / (2.0 * var));
+          deta = -r / var + dl;
+          dmu = r / var;
+          dsg = (-1.0 + r * r / var) / sigma;
+        } else {
+          // chi/_population_models.py:2285-2303, 2362-2392
+          const double lo = log(eta);
+          const double r = lo - mu;
+          s_i = -(0.5 * log(2.0 * M_PI * var) + lo + r * r / 2.0 / var);
+          deta = -(r / var + 1.0) / eta + dl;
+          dmu = r / var;
+          dsg = (-1.0 + r * r / var) / sigma;
+        }
+      }
+      if (live) {
+        score += s_i;
+        if (with_grad) gc[i * P.n_hdim + D.hcol] = deta;
+      } else {
+        dmu = dsg = 0.0;
+      }
+      if (with_grad) {
+        double s = warp_sum(dmu);
+        if (lane == 0) sacc[warp * n_slots + 1 + D.red_mu] += s;
+        s = warp_sum(dsg);
+        if (lane == 0) sacc[warp * n_slots + 1 + D.red_sigma] += s;
+        if (D.n_cov > 0) {
+          // covariate adjoint, chi/_covariate_models.py:315-318
+          const double* xi = cov + i * P.n_cov_total + D.cov0;
+          for (int q = 0; q < D.n_cov; ++q) {
+            const double xq = live ? xi[q] : 0.0;
+            if (D.beta_mu >= 0) {
+              s = warp_sum(dmu * xq);
+              if (lane == 0) sacc[warp * n_slots + 1 + D.red_beta_mu + q] += s;
+            }
+            if (D.beta_sigma >= 0) {
+              s = warp_sum(dsg * xq);
+              if (lane == 0)
+                sacc[warp * n_slots + 1 + D.red_beta_sigma + q] += s;
+            }
+          }
+        }
+      }
+    }
+  }
+  {
+    const double s = warp_sum(live ? score : 0.0);
+    if (lane == 0) sacc[warp * n_slots] += s;
+  }
+  __syncthreads();
+  double* pout = partial + (c * gridDim.x + blockIdx.x) * n_slots;
+  for (int s = threadIdx.x; s < n_slots; s += blockDim.x) {
+    double v = 0.0;
+    for (int w = 0; w < n_warps; ++w) v += sacc[w * n_slots + s];
+    pout[s] = v;
+  }
+}
+
+// K3c: fixed-order sum of the block partials; scatters the reduced slots into
+// the top-level gradient; applies the NaN -> -inf rule of the population
+// likelihoods (chi/_population_models.py:1469-1470, 2300-2301) and the
+// invalid-population flag.
+__global__ void pop_final_kernel(int32_t n_red, int64_t n_blocks,
+                                 int64_t n_params, int64_t n_bottom,
+                                 int32_t with_grad,
+                                 const int32_t* __restrict__ red_to_top,
+                                 const double* __restrict__ partial,
+                                 const int32_t* __restrict__ popflag,
+                                 double* __restrict__ score,
+                                 double* __restrict__ grad) {
+  const int64_t c = blockIdx.x;
+  const int n_slots = 1 + n_red;
+  const bool bad = popflag && popflag[c];
+  for (int s = threadIdx.x; s < n_slots; s += blockDim.x) {
+    double v = 0.0;
+    for (int64_t b = 0; b < n_blocks; ++b)
+      v += partial[(c * n_blocks + b) * n_slots + s];
+    if (s == 0) {
+      if (bad || v != v) v = -INFINITY;
+      score[c] = v;
+    } else if (with_grad) {
+      grad[c * n_params + n_bottom + red_to_top[s - 1]] = v;
+    }
+  }
+}
+
+__global__ void fill_kernel(double* p, int64_t n, double v) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// chain status = max over the chain's systems
+__global__ void chain_status_kernel(int64_t n_sh, const int32_t* st,
+                                    int32_t* out) {
+  const int64_t c = blockIdx.x;
+  int m = 0;
+  for (int64_t k = threadIdx.x; k < n_sh; k += blockDim.x)
+    m = max(m, st[c * n_sh + k]);
+  m = __reduce_max_sync(0xffffffffu, m);
+  __shared__ int sm[32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int r = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) r = max(r, sm[w]);
+    out[c] = r;
+  }
+}
+
+// sum of step counters
+__global__ void count_kernel(int64_t n, const int32_t* a, const int32_t* b,
+                             unsigned long long* out) {
+  unsigned long long sa = 0, sb = 0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+       i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    sa += a[i];
+    sb += b[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out, sa);
+    atomicAdd(out + 1, sb);
+  }
+}
+
+// Stand-alone error model (one individual): one warp.
+__global__ void error_model_kernel(int32_t kind, double s0, double s1,
+                                   int64_t n_obs, int32_t n_par,
+                                   const double* __restrict__ ybar,
+                                   const double* __restrict__ sens,
+                                   const double* __restrict__ obs,
+                                   int32_t with_grad, double* out,
+                                   double* pointwise) {
+  // out: [ll | grad (n_par + n_sigma)]
+  const int lane = threadIdx.x;
+  const int n_sig = kind == ERR_CAM ? 2 : 1;
+  const bool invalid = (s0 <= 0.0) || (kind == ERR_CAM && s1 <= 0.0);
+  bool bad_y = false;
+  if (kind == ERR_LOGNORMAL)
+    for (int64_t j = lane; j < n_obs; j += 32) bad_y |= ybar[j] <= 0.0;
+  bad_y = __any_sync(0xffffffffu, bad_y);
+  if (invalid || bad_y) {
+    if (lane == 0) out[0] = -INFINITY;
+    if (with_grad)
+      for (int k = lane; k < n_par + n_sig; k += 32) out[1 + k] = INFINITY;
+    if (pointwise)
+      for (int64_t j = lane; j < n_obs; j += 32) pointwise[j] = -INFINITY;
+    return;
+  }
+  double ll = 0.0, d0 = 0.0, d1 = 0.0;
+  // gradient w.r.t. psi: lane-strided over observations, then reduced
+  for (int k = 0; k < (with_grad ? n_par : 0); k += 1) {
+    (void)k;
+  }
+  extern __shared__ double wbuf[];  // weights per observation
+  for (int64_t j = lane; j < n_obs; j += 32) {
+    const double yb = ybar[j], yo = obs[j];
+    double w, l;
+    if (kind == ERR_GAUSSIAN) {
+      const double is = 1.0 / s0, q = (yo - yb) * is;
+      l = -(LOG_2PI_HALF_C + log(s0) + 0.5 * q * q);
+      w = q * is;
+      d0 += (q * q - 1.0) * is;
+    } else if (kind == ERR_LOGNORMAL) {
+      const double is = 1.0 / s0, lo = log(yo);
+      const double q = (lo - log(yb) + 0.5 * s0 * s0) * is;
+      l = -(LOG_2PI_HALF_C + log(s0) + lo + 0.5 * q * q);
+      w = q * is / yb;
+      d0 += -q + (q * q - 1.0) * is;
+    } else {
+      const bool cam = kind == ERR_CAM;
+      const double sb = cam ? s0 : 0.0, sr = cam ? s1 : s0;
+      const double st = fma(sr, yb, sb), ist = 1.0 / st;
+      const double q = (yo - yb) * ist, q2i = q * q * ist;
+      l = -(LOG_2PI_HALF_C + log(st) + 0.5 * q * q);
+      w = q * ist - sr * ist + sr * q2i;
+      if (cam) {
+        d0 += q2i - ist;
+        d1 += (q2i - ist) * yb;
+      } else {
+        d0 += (q2i - ist) * yb;
+      }
+    }
+    ll += l;
+    if (pointwise) pointwise[j] = l;
+    wbuf[j] = w;
+  }
+  __syncwarp();
+  ll = warp_sum(ll);
+  d0 = warp_sum(d0);
+  d1 = warp_sum(d1);
+  if (lane == 0) out[0] = ll;
+  if (with_grad) {
+    for (int k = 0; k < n_par; ++k) {
+      double g = 0.0;
+      for (int64_t j = lane; j < n_obs; j += 32)
+        g = fma(wbuf[j], sens[j * n_par + k], g);
+      g = warp_sum(g);
+      if (lane == 0) out[1 + k] = g;
+    }
+    if (lane == 0) {
+      out[1 + n_par] = d0;
+      if (n_sig == 2) out[2 + n_par] = d1;
+    }
+  }
+}
+
+}  // namespace
+
+// ============================================================================
+// C ABI
+// ============================================================================
+
+extern "C" {
+
+int chi_b200_register_model(const ModelVTable* vt) {
+  for (auto* m : registry())
+    if (std::strcmp(m->key, vt->key) == 0) return 0;
+  registry().push_back(vt);
+  return 0;
+}
+
+int chi_b200_abi_version(void) { return CHI_B200_ABI_VERSION; }
+
+const char* chi_b200_last_error(void) { return g_error.c_str(); }
+
+int chi_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int chi_b200_host_alloc(void** ptr, int64_t bytes) {
+  CUDA_TRY(cudaHostAlloc(ptr, static_cast<size_t>(bytes), cudaHostAllocDefault));
+  return 0;
+}
+
+int chi_b200_host_free(void* ptr) {
+  CUDA_TRY(cudaFreeHost(ptr));
+  return 0;
+}
+
+int chi_b200_n_models(void) { return static_cast<int>(registry().size()); }
+
+int chi_b200_model_find(const char* key) {
+  auto& r = registry();
+  for (size_t i = 0; i < r.size(); ++i)
+    if (std::strcmp(r[i]->key, key) == 0) return static_cast<int>(i);
+  return -1;
+}
+
+const char* chi_b200_model_key(int model) {
+  if (model < 0 || model >= chi_b200_n_models()) return "";
+  return registry()[model]->key;
+}
+
+int chi_b200_model_info(int model, int32_t info[8]) {
+  if (model < 0 || model >= chi_b200_n_models())
+    return fail(-1, "model id out of range");
+  const ModelVTable* vt = registry()[model];
+  info[0] = vt->n_states;
+  info[1] = vt->n_consts;
+  info[2] = vt->n_outputs;
+  info[3] = vt->linear;
+  info[4] = vt->flops_rhs;
+  info[5] = vt->flops_jac;
+  info[6] = vt->flops_dfdc;
+  info[7] = vt->flops_hess;
+  return 0;
+}
+
+int chi_b200_model_variants(int model, int32_t* n, int32_t* lanes,
+                            int32_t* cols, int32_t capacity) {
+  if (model < 0 || model >= chi_b200_n_models())
+    return fail(-1, "model id out of range");
+  const ModelVTable* vt = registry()[model];
+  *n = vt->n_variants;
+  for (int i = 0; i < vt->n_variants && i < capacity; ++i) {
+    lanes[i] = vt->variant_lanes[i];
+    cols[i] = vt->variant_cols[i];
+  }
+  return 0;
+}
+
+int chi_b200_model_describe(int model, int device, int variant,
+                            int32_t out[4]) {
+  if (model < 0 || model >= chi_b200_n_models())
+    return fail(-1, "model id out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  int regs = 0, block = 0, bpsm = 0, local = 0;
+  CUDA_TRY(registry()[model]->describe(variant, &regs, &block, &bpsm, &local));
+  out[0] = regs;
+  out[1] = block;
+  out[2] = bpsm;
+  out[3] = local;
+  return 0;
+}
+
+int chi_b200_problem_create(int model, int device, chi_b200_problem** out) {
+  // model == -1: population-only problem (stand-alone population models)
+  if (model < -1 || model >= chi_b200_n_models())
+    return fail(-1, "model id out of range");
+  int n_dev = chi_b200_device_count();
+  if (n_dev <= 0)
+    return fail(-3, "no CUDA device available: chi_b200 has no CPU fallback");
+  if (device < 0 || device >= n_dev) return fail(-1, "device out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  auto* p = new chi_b200_problem();
+  p->vt = model >= 0 ? registry()[model] : nullptr;
+  p->model = model;
+  p->device = device;
+  cudaError_t err = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+  if (err != cudaSuccess) {
+    delete p;
+    return fail(-2, cudaGetErrorString(err));
+  }
+  if (!p->vt) {
+    *out = p;
+    return 0;
+  }
+  // defaults: all states as outputs are not assumed; caller sets outputs.
+  p->n_cols = p->vt->n_states + p->vt->n_consts;
+  if (p->n_cols > MAX_COLS) {
+    delete p;
+    return fail(-1, "too many mechanistic parameters");
+  }
+  for (int i = 0; i < p->n_cols; ++i) p->col_param[i] = i;
+  *out = p;
+  return 0;
+}
+
+void chi_b200_problem_destroy(chi_b200_problem* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  for (DevBuf* b :
+       {&p->rec_off, &p->rec_t, &p->rec_obs, &p->rec_logobs, &p->rec_out,
+        &p->seg_off, &p->seg_t, &p->seg_rate, &p->covariates, &p->x, &p->ll,
+        &p->grad, &p->status, &p->nst, &p->nrj, &p->ids, &p->traj_off,
+        &p->traj_y, &p->traj_s, &p->hx, &p->hscore, &p->hgrad, &p->hstatus,
+        &p->partial, &p->popflag})
+    b->release();
+  if (p->ev0) cudaEventDestroy(p->ev0);
+  if (p->ev1) cudaEventDestroy(p->ev1);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+int chi_b200_problem_set_outputs(chi_b200_problem* p, int32_t n_out,
+                                 const int32_t* output_ids,
+                                 const int32_t* err_kinds) {
+  if (!p->vt) return fail(-1, "problem has no mechanistic model");
+  if (n_out < 0 || n_out > MAX_OUT) return fail(-1, "too many outputs");
+  int off = 0;
+  for (int o = 0; o < n_out; ++o) {
+    if (output_ids[o] < 0 || output_ids[o] >= p->vt->n_outputs)
+      return fail(-1, "output id out of range");
+    const int kind = err_kinds ? err_kinds[o] : ERR_GAUSSIAN;
+    if (kind < 0 || kind > ERR_MULTIPLICATIVE)
+      return fail(-1, "unknown error model kind");
+    p->out_id[o] = output_ids[o];
+    p->err_kind[o] = kind;
+    p->err_off[o] = off;
+    off += (kind == ERR_CAM) ? 2 : 1;
+  }
+  p->n_out = n_out;
+  p->n_sigma = err_kinds ? off : 0;
+  return 0;
+}
+
+int chi_b200_problem_set_sensitivity_columns(chi_b200_problem* p,
+                                             int32_t n_cols,
+                                             const int32_t* param_idx) {
+  if (!p->vt) return fail(-1, "problem has no mechanistic model");
+  const int P = p->vt->n_states + p->vt->n_consts;
+  if (n_cols < 0 || n_cols > P || n_cols > MAX_COLS)
+    return fail(-1, "invalid number of sensitivity columns");
+  for (int i = 0; i < n_cols; ++i) {
+    if (param_idx[i] < 0 || param_idx[i] >= P)
+      return fail(-1, "sensitivity parameter index out of range");
+    p->col_param[i] = param_idx[i];
+  }
+  p->n_cols = n_cols;
+  return 0;
+}
+
+int chi_b200_problem_set_tolerances(chi_b200_problem* p, double rtol,
+                                    double atol, int32_t max_steps) {
+  if (!(rtol > 0.0) || !(atol > 0.0) || max_steps <= 0)
+    return fail(-1, "tolerances must be positive");
+  p->rtol = rtol;
+  p->atol = atol;
+  p->max_steps = max_steps;
+  return 0;
+}
+
+int chi_b200_problem_set_n_ids(chi_b200_problem* p, int64_t n_ids) {
+  if (p->vt) return fail(-1, "n_ids follows from the uploaded data");
+  if (n_ids <= 0) return fail(-1, "n_ids must be positive");
+  p->n_ids = n_ids;
+  p->id_begin = 0;
+  p->id_end = n_ids;
+  return 0;
+}
+
+int chi_b200_problem_set_variant(chi_b200_problem* p, int32_t variant) {
+  if (!p->vt) return fail(-1, "problem has no mechanistic model");
+  if (variant >= p->vt->n_variants) return fail(-1, "variant out of range");
+  p->variant = variant;
+  return 0;
+}
+
+int chi_b200_problem_set_shard(chi_b200_problem* p, int64_t id_begin,
+                               int64_t id_end) {
+  if (id_begin < 0 || id_end > p->n_ids || id_begin > id_end)
+    return fail(-1, "invalid shard");
+  p->id_begin = id_begin;
+  p->id_end = id_end;
+  return 0;
+}
+
+int chi_b200_problem_set_timing(chi_b200_problem* p, int32_t enabled) {
+  CUDA_TRY(cudaSetDevice(p->device));
+  if (enabled && !p->ev0) {
+    CUDA_TRY(cudaEventCreate(&p->ev0));
+    CUDA_TRY(cudaEventCreate(&p->ev1));
+  }
+  p->timing = enabled != 0;
+  p->solve_ms_sum = 0.0;
+  p->solve_launches = 0;
+  return 0;
+}
+
+int chi_b200_problem_timings(chi_b200_problem* p, double out[2]) {
+  out[0] = p->solve_ms_sum;
+  out[1] = static_cast<double>(p->solve_launches);
+  return 0;
+}
+
+int chi_b200_problem_counters(chi_b200_problem* p, int64_t out[4]) {
+  for (int i = 0; i < 4; ++i) out[i] = p->counters[i];
+  return 0;
+}
+
+}  // extern "C"
+
+// Expands (level, start, duration, period, multiplier) events into the
+// piecewise-constant dose rate of one individual on [0, t_end]
+// (semantics of myokit.pacing.blocktrain as used at
+// chi/_mechanistic_models.py:853-855).
+static void expand_events(const double* ev, int64_t n_ev, double t_end,
+                          std::vector<double>& seg_t,
+                          std::vector<double>& seg_rate) {
+  struct Pulse {
+    double on, off, level;
+  };
+  std::vector<Pulse> pulses;
+  for (int64_t k = 0; k < n_ev; ++k) {
+    const double level = ev[5 * k], start = ev[5 * k + 1],
+                 dur = ev[5 * k + 2], period = ev[5 * k + 3],
+                 mult = ev[5 * k + 4];
+    if (period == 0.0) {
+      pulses.push_back({start, start + dur, level});
+      continue;
+    }
+    for (int64_t j = 0;; ++j) {
+      const double on = start + static_cast<double>(j) * period;
+      if (on >= t_end || (mult > 0 && j >= static_cast<int64_t>(mult))) break;
+      pulses.push_back({on, on + dur, level});
+    }
+  }
+  std::vector<double> edges;
+  edges.push_back(0.0);
+  for (auto& q : pulses) {
+    if (q.on < t_end) edges.push_back(std::max(q.on, 0.0));
+    if (q.off < t_end) edges.push_back(std::max(q.off, 0.0));
+  }
+  std::sort(edges.begin(), edges.end());
+  edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+  for (size_t k = 0; k < edges.size(); ++k) {
+    const double a = edges[k];
+    const double b = (k + 1 < edges.size()) ? edges[k + 1] : t_end;
+    const double mid = 0.5 * (a + std::max(b, a));
+    double rate = 0.0;
+    for (auto& q : pulses)
+      if (q.on <= mid && mid < q.off) rate += q.level;
+    seg_t.push_back(a);
+    seg_rate.push_back(rate);
+  }
+}
+
+template <class T>
+static cudaError_t upload(DevBuf& buf, const std::vector<T>& v) {
+  cudaError_t err = buf.reserve(std::max<size_t>(v.size(), 1) * sizeof(T));
+  if (err != cudaSuccess) return err;
+  if (v.empty()) return cudaSuccess;
+  return cudaMemcpy(buf.ptr, v.data(), v.size() * sizeof(T),
+                    cudaMemcpyHostToDevice);
+}
+
+extern "C" {
+
+int chi_b200_problem_upload(chi_b200_problem* p, int64_t n_ids,
+                            const int64_t* rec_off, const double* rec_t,
+                            const double* rec_obs, const int32_t* rec_out,
+                            const int64_t* dose_off,
+                            const double* dose_events) {
+  if (!p->vt) return fail(-1, "problem has no mechanistic model");
+  if (n_ids <= 0) return fail(-1, "n_ids must be positive");
+  if (p->n_out <= 0) return fail(-1, "set outputs before uploading data");
+  CUDA_TRY(cudaSetDevice(p->device));
+  const int64_t n_rec = rec_off[n_ids];
+  std::vector<int64_t> off(rec_off, rec_off + n_ids + 1);
+  std::vector<double> t(rec_t, rec_t + n_rec);
+  std::vector<double> obs(n_rec, 0.0), logobs(n_rec, 0.0);
+  std::vector<int32_t> out(n_rec, 0);
+  for (int64_t i = 0; i < n_ids; ++i) {
+    if (off[i + 1] < off[i]) return fail(-1, "rec_off must be non-decreasing");
+    for (int64_t r = off[i]; r < off[i + 1]; ++r) {
+      if (t[r] < 0.0) return fail(-1, "Times cannot be negative.");
+      if (r > off[i] && t[r] < t[r - 1])
+        return fail(-1, "Times must be increasing.");
+      const int32_t o = rec_out ? rec_out[r] : 0;
+      if (o < 0 || o >= p->n_out) return fail(-1, "rec_out out of range");
+      out[r] = o;
+      if (rec_obs) {
+        obs[r] = rec_obs[r];
+        logobs[r] = std::log(rec_obs[r]);
+      }
+    }
+  }
+  std::vector<int64_t> seg_off(n_ids + 1, 0);
+  std::vector<double> seg_t, seg_rate;
+  for (int64_t i = 0; i < n_ids; ++i) {
+    const double t_end = off[i + 1] > off[i] ? t[off[i + 1] - 1] : 0.0;
+    const int64_t e0 = dose_off ? dose_off[i] : 0;
+    const int64_t e1 = dose_off ? dose_off[i + 1] : 0;
+    expand_events(dose_events ? dose_events + 5 * e0 : nullptr, e1 - e0,
+                  t_end, seg_t, seg_rate);
+    seg_off[i + 1] = static_cast<int64_t>(seg_t.size());
+  }
+  CUDA_TRY(upload(p->rec_off, off));
+  CUDA_TRY(upload(p->rec_t, t));
+  CUDA_TRY(upload(p->rec_obs, obs));
+  CUDA_TRY(upload(p->rec_logobs, logobs));
+  CUDA_TRY(upload(p->rec_out, out));
+  CUDA_TRY(upload(p->seg_off, seg_off));
+  CUDA_TRY(upload(p->seg_t, seg_t));
+  CUDA_TRY(upload(p->seg_rate, seg_rate));
+  p->n_ids = n_ids;
+  p->n_rec = n_rec;
+  p->h_rec_off = off;
+  p->id_begin = 0;
+  p->id_end = n_ids;
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- launch helpers ---------------------------------------------------------
+namespace {
+
+void fill_args(const chi_b200_problem* p, SolveArgs& a) {
+  std::memset(&a, 0, sizeof(a));
+  a.n_ids = static_cast<int32_t>(p->n_ids);
+  a.rec_off = p->rec_off.as<int64_t>();
+  a.rec_t = p->rec_t.as<double>();
+  a.rec_obs = p->rec_obs.as<double>();
+  a.rec_logobs = p->rec_logobs.as<double>();
+  a.rec_out = p->rec_out.as<int32_t>();
+  a.seg_off = p->seg_off.as<int64_t>();
+  a.seg_t = p->seg_t.as<double>();
+  a.seg_rate = p->seg_rate.as<double>();
+  a.n_out = p->n_out;
+  for (int o = 0; o < p->n_out; ++o) {
+    a.out_id[o] = p->out_id[o];
+    a.err_kind[o] = p->err_kind[o];
+    a.err_off[o] = p->err_off[o];
+  }
+  a.n_sigma = p->n_sigma;
+  a.n_cols = p->n_cols;
+  for (int i = 0; i < p->n_cols; ++i) a.col_param[i] = p->col_param[i];
+  a.rtol = p->rtol;
+  a.atol = p->atol;
+  a.max_steps = p->max_steps;
+}
+
+int launch_loglik(chi_b200_problem* p, int64_t B, const int32_t* d_ids,
+                  const double* d_x, int with_grad, double* d_ll,
+                  double* d_grad, int32_t* d_status, int32_t* d_nst,
+                  int32_t* d_nrj, cudaStream_t stream) {
+  if (!p->vt) return fail(-1, "problem has no mechanistic model");
+  if (p->n_ids <= 0) return fail(-1, "no population data uploaded");
+  const int P = p->vt->n_states + p->vt->n_consts;
+  SolveArgs a;
+  fill_args(p, a);
+  a.B = B;
+  a.ids = d_ids;
+  a.x = d_x;
+  a.x_stride = P + p->n_sigma;
+  a.mode = 1;
+  a.with_sens = with_grad ? 1 : 0;
+  a.ll = d_ll;
+  a.grad = d_grad;
+  a.grad_stride = P + p->n_sigma;
+  a.status = d_status;
+  a.n_steps = d_nst;
+  a.n_rej = d_nrj;
+  if (with_grad && p->n_cols < P) {
+    // columns without sensitivities read as zero gradient
+    const int64_t n = B * a.grad_stride;
+    fill_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+        d_grad, n, 0.0);
+  }
+  if (p->timing) CUDA_TRY(cudaEventRecord(p->ev0, stream));
+  CUDA_TRY(p->vt->launch(a, p->variant, stream));
+  if (p->timing) {
+    CUDA_TRY(cudaEventRecord(p->ev1, stream));
+    CUDA_TRY(cudaEventSynchronize(p->ev1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+    p->solve_ms_sum += ms;
+    p->solve_launches += 1;
+  }
+  p->counters[3] += 1;
+  return 0;
+}
+
+// DFMA micro-benchmark: 8 independent FMA chains per thread.
+__global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3,
+         x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b);
+    x3 = fma(x3, a, b); x4 = fma(x4, a, b); x5 = fma(x5, a, b);
+    x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 123.456) out[0] = s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int chi_b200_loglik_dev(chi_b200_problem* p, int64_t B, const int32_t* d_ids,
+                        const double* d_x, int32_t with_grad, double* d_ll,
+                        double* d_grad, int32_t* d_status, int32_t* d_n_steps,
+                        int32_t* d_n_rej, void* stream) {
+  CUDA_TRY(cudaSetDevice(p->device));
+  p->counters[3] = 0;
+  return launch_loglik(p, B, d_ids, d_x, with_grad, d_ll, d_grad, d_status,
+                       d_n_steps, d_n_rej, static_cast<cudaStream_t>(stream));
+}
+
+int chi_b200_loglik(chi_b200_problem* p, int64_t B, const int32_t* ids,
+                    const double* x, int32_t with_grad, double* ll,
+                    double* grad, int32_t* status, int32_t* n_steps,
+                    int32_t* n_rej) {
+  if (B <= 0) return 0;
+  if (!p->vt) return fail(-1, "problem has no mechanistic model");
+  CUDA_TRY(cudaSetDevice(p->device));
+  const int nd = p->vt->n_states + p->vt->n_consts + p->n_sigma;
+  cudaStream_t s = p->stream;
+  CUDA_TRY(p->x.reserve(B * nd * sizeof(double)));
+  CUDA_TRY(p->ll.reserve(B * sizeof(double)));
+  CUDA_TRY(p->status.reserve(B * sizeof(int32_t)));
+  CUDA_TRY(p->nst.reserve(B * sizeof(int32_t)));
+  CUDA_TRY(p->nrj.reserve(B * sizeof(int32_t)));
+  if (with_grad) CUDA_TRY(p->grad.reserve(B * nd * sizeof(double)));
+  if (ids) {
+    CUDA_TRY(p->ids.reserve(B * sizeof(int32_t)));
+    CUDA_TRY(cudaMemcpyAsync(p->ids.ptr, ids, B * sizeof(int32_t),
+                             cudaMemcpyHostToDevice, s));
+  }
+  CUDA_TRY(cudaMemcpyAsync(p->x.ptr, x, B * nd * sizeof(double),
+                           cudaMemcpyHostToDevice, s));
+  p->counters[3] = 0;
+  int rc = launch_loglik(p, B, ids ? p->ids.as<int32_t>() : nullptr,
+                         p->x.as<double>(), with_grad, p->ll.as<double>(),
+                         with_grad ? p->grad.as<double>() : nullptr,
+                         p->status.as<int32_t>(), p->nst.as<int32_t>(),
+                         p->nrj.as<int32_t>(), s);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(ll, p->ll.ptr, B * sizeof(double),
+                           cudaMemcpyDeviceToHost, s));
+  if (with_grad && grad)
+    CUDA_TRY(cudaMemcpyAsync(grad, p->grad.ptr, B * nd * sizeof(double),
+                             cudaMemcpyDeviceToHost, s));
+  if (status)
+    CUDA_TRY(cudaMemcpyAsync(status, p->status.ptr, B * sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, s));
+  if (n_steps)
+    CUDA_TRY(cudaMemcpyAsync(n_steps, p->nst.ptr, B * sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, s));
+  if (n_rej)
+    CUDA_TRY(cudaMemcpyAsync(n_rej, p->nrj.ptr, B * sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  p->counters[0] = B;
+  return 0;
+}
+
+int chi_b200_simulate(chi_b200_problem* p, int64_t B, const int32_t* ids,
+                      const double* psi, int32_t with_sens, double* y_out,
+                      double* s_out, int32_t* status) {
+  if (B <= 0) return 0;
+  if (!p->vt) return fail(-1, "problem has no mechanistic model");
+  if (p->n_ids <= 0) return fail(-1, "no population data uploaded");
+  CUDA_TRY(cudaSetDevice(p->device));
+  const int P = p->vt->n_states + p->vt->n_consts;
+  cudaStream_t s = p->stream;
+  std::vector<int64_t> toff(B + 1, 0);
+  for (int64_t b = 0; b < B; ++b) {
+    const int64_t id = ids ? ids[b] : b % p->n_ids;
+    if (id < 0 || id >= p->n_ids) return fail(-1, "individual id out of range");
+    toff[b + 1] = toff[b] + (p->h_rec_off[id + 1] - p->h_rec_off[id]);
+  }
+  const int64_t rows = toff[B];
+  CUDA_TRY(p->x.reserve(B * P * sizeof(double)));
+  CUDA_TRY(p->status.reserve(B * sizeof(int32_t)));
+  CUDA_TRY(p->traj_off.reserve((B + 1) * sizeof(int64_t)));
+  CUDA_TRY(p->traj_y.reserve(std::max<int64_t>(rows, 1) * sizeof(double)));
+  if (with_sens)
+    CUDA_TRY(p->traj_s.reserve(std::max<int64_t>(rows * p->n_cols, 1) *
+                               sizeof(double)));
+  if (ids) {
+    CUDA_TRY(p->ids.reserve(B * sizeof(int32_t)));
+    CUDA_TRY(cudaMemcpyAsync(p->ids.ptr, ids, B * sizeof(int32_t),
+                             cudaMemcpyHostToDevice, s));
+  }
+  CUDA_TRY(cudaMemcpyAsync(p->x.ptr, psi, B * P * sizeof(double),
+                           cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(p->traj_off.ptr, toff.data(),
+                           (B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
+                           s));
+  SolveArgs a;
+  fill_args(p, a);
+  a.B = B;
+  a.ids = ids ? p->ids.as<int32_t>() : nullptr;
+  a.x = p->x.as<double>();
+  a.x_stride = P;
+  a.mode = 0;
+  a.with_sens = with_sens ? 1 : 0;
+  a.traj_off = p->traj_off.as<int64_t>();
+  a.traj_y = p->traj_y.as<double>();
+  a.traj_s = p->traj_s.as<double>();
+  a.status = p->status.as<int32_t>();
+  CUDA_TRY(p->vt->launch(a, p->variant, s));
+  if (rows > 0) {
+    CUDA_TRY(cudaMemcpyAsync(y_out, p->traj_y.ptr, rows * sizeof(double),
+                             cudaMemcpyDeviceToHost, s));
+    if (with_sens && s_out)
+      CUDA_TRY(cudaMemcpyAsync(s_out, p->traj_s.ptr,
+                               rows * p->n_cols * sizeof(double),
+                               cudaMemcpyDeviceToHost, s));
+  }
+  if (status)
+    CUDA_TRY(cudaMemcpyAsync(status, p->status.ptr, B * sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  p->counters[0] = B;
+  p->counters[3] = 1;
+  return 0;
+}
+
+int chi_b200_error_model(int32_t device, int32_t kind, const double* sigma,
+                         int64_t n_obs, int32_t n_par, const double* ybar,
+                         const double* sens, const double* obs,
+                         int32_t with_grad, double* out, double* pointwise) {
+  if (chi_b200_device_count() <= 0)
+    return fail(-3, "no CUDA device available: chi_b200 has no CPU fallback");
+  if (kind < 0 || kind > ERR_MULTIPLICATIVE)
+    return fail(-1, "unknown error model kind");
+  if (n_obs * sizeof(double) > 200 * 1024)
+    return fail(-1, "too many observations for the stand-alone error model");
+  CUDA_TRY(cudaSetDevice(device));
+  const int n_sig = kind == ERR_CAM ? 2 : 1;
+  const int n_out = 1 + (with_grad ? n_par + n_sig : 0);
+  DevBuf d_y, d_s, d_o, d_out, d_pw;
+  auto cleanup = [&]() {
+    d_y.release(); d_s.release(); d_o.release(); d_out.release();
+    d_pw.release();
+  };
+  const size_t nb = std::max<int64_t>(n_obs, 1) * sizeof(double);
+  cudaError_t err = d_y.reserve(nb);
+  if (err == cudaSuccess) err = d_o.reserve(nb);
+  if (err == cudaSuccess) err = d_out.reserve(n_out * sizeof(double));
+  if (err == cudaSuccess && with_grad)
+    err = d_s.reserve(std::max<size_t>(nb * n_par, 8));
+  if (err == cudaSuccess && pointwise) err = d_pw.reserve(nb);
+  if (err == cudaSuccess && n_obs > 0) {
+    err = cudaMemcpy(d_y.ptr, ybar, n_obs * sizeof(double),
+                     cudaMemcpyHostToDevice);
+    if (err == cudaSuccess)
+      err = cudaMemcpy(d_o.ptr, obs, n_obs * sizeof(double),
+                       cudaMemcpyHostToDevice);
+    if (err == cudaSuccess && with_grad && n_par > 0)
+      err = cudaMemcpy(d_s.ptr, sens, n_obs * n_par * sizeof(double),
+                       cudaMemcpyHostToDevice);
+  }
+  if (err == cudaSuccess) {
+    const size_t smem = std::max<int64_t>(n_obs, 1) * sizeof(double);
+    if (smem > 48 * 1024)
+      err = cudaFuncSetAttribute(error_model_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem));
+    if (err == cudaSuccess) {
+      error_model_kernel<<<1, 32, smem>>>(
+          kind, sigma[0], n_sig == 2 ? sigma[1] : 0.0, n_obs, n_par,
+          d_y.as<double>(), d_s.as<double>(), d_o.as<double>(), with_grad,
+          d_out.as<double>(), pointwise ? d_pw.as<double>() : nullptr);
+      err = cudaGetLastError();
+    }
+  }
+  if (err == cudaSuccess)
+    err = cudaMemcpy(out, d_out.ptr, n_out * sizeof(double),
+                     cudaMemcpyDeviceToHost);
+  if (err == cudaSuccess && pointwise && n_obs > 0)
+    err = cudaMemcpy(pointwise, d_pw.ptr, n_obs * sizeof(double),
+                     cudaMemcpyDeviceToHost);
+  cleanup();
+  if (err != cudaSuccess) return fail(-2, cudaGetErrorString(err));
+  return 0;
+}
+
+// ---- population ---------------------------------------------------------------
+
+int chi_b200_population_set(chi_b200_problem* p, int32_t n_blocks,
+                            const int32_t* kind, const int32_t* n_dim,
+                            const int32_t* centered, const int32_t* n_cov,
+                            const int32_t* n_sel, const int32_t* sel_pidx,
+                            const int32_t* sel_didx,
+                            const double* covariates) {
+  if (p->n_ids <= 0) return fail(-1, "upload population data first");
+  CUDA_TRY(cudaSetDevice(p->device));
+  PopDesc& D = p->pop;
+  std::memset(&D, 0, sizeof(D));
+  p->red_to_top.clear();
+  int d0 = 0, h0 = 0, c0 = 0, sel0 = 0;
+  int64_t top = 0;
+  for (int b = 0; b < n_blocks; ++b) {
+    const int nd = n_dim[b];
+    if (d0 + nd > MAX_POP_DIM) return fail(-1, "too many population dims");
+    const int nc = n_cov ? n_cov[b] : 0;
+    const int ns = (n_sel && nc > 0) ? n_sel[b] : 0;
+    if (nc > MAX_POP_COV) return fail(-1, "too many covariates in a block");
+    if (nc > 0 && kind[b] != CHI_B200_POP_GAUSSIAN &&
+        kind[b] != CHI_B200_POP_LOGNORMAL)
+      return fail(-1, "covariate blocks must be Gaussian or LogNormal");
+    for (int j = 0; j < nd; ++j) {
+      PopDim& q = D.dim[d0 + j];
+      q.kind = kind[b];
+      q.centered = centered ? centered[b] : 1;
+      q.hcol = -1;
+      q.n_cov = nc;
+      q.cov0 = c0;
+      q.beta_mu = q.beta_sigma = -1;
+      q.red_mu = q.red_sigma = q.red_beta_mu = q.red_beta_sigma = -1;
+      if (kind[b] == CHI_B200_POP_POOLED) {
+        q.top0 = static_cast<int32_t>(top + j);
+        q.red_mu = static_cast<int32_t>(p->red_to_top.size());
+        p->red_to_top.push_back(q.top0);
+      } else if (kind[b] == CHI_B200_POP_HETEROGENEOUS) {
+        q.top0 = static_cast<int32_t>(top);
+        q.het_stride = nd;
+        q.het_off = j;
+      } else if (kind[b] == CHI_B200_POP_GAUSSIAN ||
+                 kind[b] == CHI_B200_POP_LOGNORMAL) {
+        q.hcol = h0 + j;
+        q.top0 = static_cast<int32_t>(top + j);
+        q.top1 = static_cast<int32_t>(top + nd + j);
+      } else {
+        return fail(-1, "unknown population block kind");
+      }
+    }
+    if (kind[b] == CHI_B200_POP_GAUSSIAN || kind[b] == CHI_B200_POP_LOGNORMAL) {
+      // reduced slots in theta order: mu_1..mu_d, sigma_1..sigma_d, betas
+      for (int j = 0; j < nd; ++j) {
+        D.dim[d0 + j].red_mu = static_cast<int32_t>(p->red_to_top.size());
+        p->red_to_top.push_back(D.dim[d0 + j].top0);
+      }
+      for (int j = 0; j < nd; ++j) {
+        D.dim[d0 + j].red_sigma = static_cast<int32_t>(p->red_to_top.size());
+        p->red_to_top.push_back(D.dim[d0 + j].top1);
+      }
+      for (int s = 0; s < ns; ++s) {
+        const int pi = sel_pidx[sel0 + s], di = sel_didx[sel0 + s];
+        if (pi < 0 || pi > 1 || di < 0 || di >= nd)
+          return fail(-1, "covariate selection out of range");
+        PopDim& q = D.dim[d0 + di];
+        const int32_t t = static_cast<int32_t>(top + 2 * nd + s * nc);
+        const int32_t rslot = static_cast<int32_t>(p->red_to_top.size());
+        for (int k = 0; k < nc; ++k) p->red_to_top.push_back(t + k);
+        if (pi == 0) {
+          q.beta_mu = t;
+          q.red_beta_mu = rslot;
+        } else {
+          q.beta_sigma = t;
+          q.red_beta_sigma = rslot;
+        }
+      }
+      h0 += nd;
+      top += 2 * nd + static_cast<int64_t>(ns) * nc;
+    } else if (kind[b] == CHI_B200_POP_POOLED) {
+      top += nd;
+    } else {
+      top += p->n_ids * nd;
+    }
+    sel0 += ns;
+    c0 += nc;
+    d0 += nd;
+  }
+  D.n_dim = d0;
+  D.n_hdim = h0;
+  D.n_cov_total = c0;
+  D.n_red = static_cast<int32_t>(p->red_to_top.size());
+  p->n_top = top;
+  const int nd_ll =
+      p->vt ? p->vt->n_states + p->vt->n_consts + p->n_sigma : D.n_dim;
+  if (D.n_dim != nd_ll)
+    return fail(-1,
+                "The dimension of the population model does not match the "
+                "dimensions of the log-likelihood parameter space.");
+  if (c0 > 0) {
+    if (!covariates)
+      return fail(-1,
+                  "The population model needs covariates, but no covariates "
+                  "have been provided.");
+    std::vector<double> cv(covariates, covariates + p->n_ids * c0);
+    CUDA_TRY(upload(p->covariates, cv));
+  }
+  // red_to_top lives at the tail of the partial buffer's sibling: keep a
+  // dedicated device copy in popflag's neighbour (small)
+  p->has_pop = true;
+  return 0;
+}
+
+int chi_b200_population_sizes(chi_b200_problem* p, int64_t out[4]) {
+  if (!p->has_pop) return fail(-1, "no population model set");
+  out[0] = p->n_ids * p->pop.n_hdim;
+  out[1] = p->n_top;
+  out[2] = p->pop.n_dim;
+  out[3] = p->pop.n_hdim;
+  return 0;
+}
+
+}  // extern "C"
+
+namespace {
+
+// Runs K3a -> (K1+K2) -> K3b -> K3c for C parameter vectors resident on the
+// device.  `d_dlp_in` / `skip_solve` serve the stand-alone population entry.
+int run_hier(chi_b200_problem* p, int32_t C, const double* d_x,
+             int32_t with_grad, double* d_score, double* d_grad,
+             int32_t* d_status, bool skip_solve, const double* d_dlp_in,
+             double* d_eta_out, double* d_psi_out, cudaStream_t s) {
+  if (!p->has_pop) return fail(-1, "no population model set");
+  const PopDesc& D = p->pop;
+  const int64_t n_sh = p->id_end - p->id_begin;
+  const int64_t n_bottom = p->n_ids * D.n_hdim;
+  const int64_t n_params = n_bottom + p->n_top;
+  const int64_t B = n_sh * C;
+  const int nd = D.n_dim;
+  if (B <= 0) return 0;
+  CUDA_TRY(p->x.reserve(B * nd * sizeof(double)));
+  CUDA_TRY(p->ids.reserve(B * sizeof(int32_t)));
+  CUDA_TRY(p->ll.reserve(B * sizeof(double)));
+  CUDA_TRY(p->status.reserve(B * sizeof(int32_t)));
+  CUDA_TRY(p->nst.reserve(B * sizeof(int32_t)));
+  CUDA_TRY(p->nrj.reserve(B * sizeof(int32_t)));
+  if (with_grad) CUDA_TRY(p->grad.reserve(B * nd * sizeof(double)));
+  const int64_t n_blk = (n_sh + POP_BLOCK - 1) / POP_BLOCK;
+  const int n_slots = 1 + D.n_red;
+  // partial buffer: [C][n_blk][n_slots] doubles, then red_to_top (int32)
+  const size_t partial_bytes = static_cast<size_t>(C) * n_blk * n_slots * sizeof(double);
+  const size_t r2t_bytes = std::max<size_t>(D.n_red, 1) * sizeof(int32_t);
+  CUDA_TRY(p->partial.reserve(partial_bytes + r2t_bytes));
+  int32_t* d_r2t = reinterpret_cast<int32_t*>(
+      static_cast<char*>(p->partial.ptr) + partial_bytes);
+  if (D.n_red > 0)
+    CUDA_TRY(cudaMemcpyAsync(d_r2t, p->red_to_top.data(),
+                             D.n_red * sizeof(int32_t),
+                             cudaMemcpyHostToDevice, s));
+  CUDA_TRY(p->popflag.reserve(C * sizeof(int32_t)));
+  CUDA_TRY(cudaMemsetAsync(p->popflag.ptr, 0, C * sizeof(int32_t), s));
+
+  double* xs = d_psi_out ? d_psi_out : p->x.as<double>();
+  pop_forward_kernel<<<static_cast<unsigned>((B + 255) / 256), 256, 0, s>>>(
+      D, C, p->n_ids, p->id_begin, p->id_end, n_params, n_bottom, d_x,
+      p->covariates.as<double>(), xs, d_eta_out, p->ids.as<int32_t>(),
+      p->popflag.as<int32_t>());
+  CUDA_TRY(cudaGetLastError());
+  p->counters[3] += 1;
+
+  const double* d_ll = nullptr;
+  const double* d_dlp = d_dlp_in;
+  if (!skip_solve) {
+    int rc = launch_loglik(p, B, p->ids.as<int32_t>(), xs, with_grad,
+                           p->ll.as<double>(),
+                           with_grad ? p->grad.as<double>() : nullptr,
+                           p->status.as<int32_t>(), p->nst.as<int32_t>(),
+                           p->nrj.as<int32_t>(), s);
+    if (rc) return rc;
+    d_ll = p->ll.as<double>();
+    d_dlp = with_grad ? p->grad.as<double>() : nullptr;
+    if (d_status) {
+      chain_status_kernel<<<C, 128, 0, s>>>(n_sh, p->status.as<int32_t>(),
+                                            d_status);
+      CUDA_TRY(cudaGetLastError());
+      p->counters[3] += 1;
+    }
+  }
+  dim3 grid(static_cast<unsigned>(n_blk), static_cast<unsigned>(C));
+  const size_t smem = (POP_BLOCK / 32) * n_slots * sizeof(double);
+  pop_backward_kernel<<<grid, POP_BLOCK, smem, s>>>(
+      D, p->n_ids, p->id_begin, p->id_end, n_params, n_bottom, with_grad,
+      d_x, p->covariates.as<double>(), d_ll, d_dlp, d_grad,
+      p->partial.as<double>());
+  CUDA_TRY(cudaGetLastError());
+  pop_final_kernel<<<C, 64, 0, s>>>(D.n_red, n_blk, n_params, n_bottom,
+                                    with_grad, d_r2t, p->partial.as<double>(),
+                                    p->popflag.as<int32_t>(), d_score, d_grad);
+  CUDA_TRY(cudaGetLastError());
+  p->counters[3] += 2;
+  p->counters[0] = B;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int chi_b200_hier_logpdf_dev(chi_b200_problem* p, int32_t C,
+                             const double* d_x, int32_t with_grad,
+                             double* d_score, double* d_grad,
+                             int32_t* d_status, void* stream) {
+  CUDA_TRY(cudaSetDevice(p->device));
+  p->counters[3] = 0;
+  return run_hier(p, C, d_x, with_grad, d_score, d_grad, d_status, false,
+                  nullptr, nullptr, nullptr,
+                  static_cast<cudaStream_t>(stream));
+}
+
+int chi_b200_hier_logpdf(chi_b200_problem* p, int32_t C, const double* x,
+                         int32_t with_grad, double* score, double* grad,
+                         int32_t* status) {
+  if (!p->has_pop) return fail(-1, "no population model set");
+  if (!p->vt) return fail(-1, "problem has no mechanistic model");
+  if (C <= 0) return 0;
+  CUDA_TRY(cudaSetDevice(p->device));
+  cudaStream_t s = p->stream;
+  const int64_t n_params = p->n_ids * p->pop.n_hdim + p->n_top;
+  CUDA_TRY(p->hx.reserve(C * n_params * sizeof(double)));
+  CUDA_TRY(p->hscore.reserve(C * sizeof(double)));
+  CUDA_TRY(p->hstatus.reserve(C * sizeof(int32_t)));
+  if (with_grad) {
+    CUDA_TRY(p->hgrad.reserve(C * n_params * sizeof(double)));
+    // entries of individuals outside this shard stay zero
+    if (p->id_end - p->id_begin != p->n_ids)
+      CUDA_TRY(cudaMemsetAsync(p->hgrad.ptr, 0,
+                               C * n_params * sizeof(double), s));
+  }
+  CUDA_TRY(cudaMemcpyAsync(p->hx.ptr, x, C * n_params * sizeof(double),
+                           cudaMemcpyHostToDevice, s));
+  p->counters[3] = 0;
+  int rc = run_hier(p, C, p->hx.as<double>(), with_grad,
+                    p->hscore.as<double>(),
+                    with_grad ? p->hgrad.as<double>() : nullptr,
+                    p->hstatus.as<int32_t>(), false, nullptr, nullptr,
+                    nullptr, s);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(score, p->hscore.ptr, C * sizeof(double),
+                           cudaMemcpyDeviceToHost, s));
+  if (with_grad && grad)
+    CUDA_TRY(cudaMemcpyAsync(grad, p->hgrad.ptr,
+                             C * n_params * sizeof(double),
+                             cudaMemcpyDeviceToHost, s));
+  if (status)
+    CUDA_TRY(cudaMemcpyAsync(status, p->hstatus.ptr, C * sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (p->nst.ptr) {
+    // aggregate step counters for the roofline model
+    unsigned long long* d_cnt = nullptr;
+    CUDA_TRY(cudaMalloc(&d_cnt, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), s));
+    const int64_t B = (p->id_end - p->id_begin) * C;
+    count_kernel<<<148, 256, 0, s>>>(B, p->nst.as<int32_t>(),
+                                     p->nrj.as<int32_t>(), d_cnt);
+    unsigned long long h_cnt[2] = {0, 0};
+    cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    cudaFree(d_cnt);
+    p->counters[1] = static_cast<int64_t>(h_cnt[0]);
+    p->counters[2] = static_cast<int64_t>(h_cnt[1]);
+  }
+  return 0;
+}
+
+int chi_b200_population_eval(chi_b200_problem* p, const double* top,
+                             const double* bottom, const double* dlogp_dpsi,
+                             int32_t with_grad, double* eta, double* psi,
+                             double* score, double* grad) {
+  if (!p->has_pop) return fail(-1, "no population model set");
+  CUDA_TRY(cudaSetDevice(p->device));
+  cudaStream_t s = p->stream;
+  const PopDesc& D = p->pop;
+  const int64_t n_bottom = p->n_ids * D.n_hdim;
+  const int64_t n_params = n_bottom + p->n_top;
+  const int64_t nd = D.n_dim;
+  const int64_t id0 = p->id_begin, id1 = p->id_end;
+  p->id_begin = 0;
+  p->id_end = p->n_ids;
+  DevBuf d_eta, d_psi, d_dlp;
+  auto done = [&](int rc) {
+    d_eta.release(); d_psi.release(); d_dlp.release();
+    p->id_begin = id0;
+    p->id_end = id1;
+    return rc;
+  };
+  std::vector<double> hx(n_params);
+  std::copy(bottom, bottom + n_bottom, hx.begin());
+  std::copy(top, top + p->n_top, hx.begin() + n_bottom);
+  cudaError_t err = p->hx.reserve(n_params * sizeof(double));
+  if (err == cudaSuccess) err = p->hscore.reserve(sizeof(double));
+  if (err == cudaSuccess) err = p->hgrad.reserve(n_params * sizeof(double));
+  if (err == cudaSuccess) err = d_eta.reserve(p->n_ids * nd * sizeof(double));
+  if (err == cudaSuccess) err = d_psi.reserve(p->n_ids * nd * sizeof(double));
+  if (err == cudaSuccess && dlogp_dpsi) {
+    err = d_dlp.reserve(p->n_ids * nd * sizeof(double));
+    if (err == cudaSuccess)
+      err = cudaMemcpyAsync(d_dlp.ptr, dlogp_dpsi,
+                            p->n_ids * nd * sizeof(double),
+                            cudaMemcpyHostToDevice, s);
+  }
+  if (err == cudaSuccess)
+    err = cudaMemcpyAsync(p->hx.ptr, hx.data(), n_params * sizeof(double),
+                          cudaMemcpyHostToDevice, s);
+  if (err != cudaSuccess) return done(fail(-2, cudaGetErrorString(err)));
+  int rc = run_hier(p, 1, p->hx.as<double>(), with_grad,
+                    p->hscore.as<double>(), p->hgrad.as<double>(), nullptr,
+                    true, dlogp_dpsi ? d_dlp.as<double>() : nullptr,
+                    d_eta.as<double>(), d_psi.as<double>(), s);
+  if (rc) return done(rc);
+  if (eta)
+    cudaMemcpyAsync(eta, d_eta.ptr, p->n_ids * nd * sizeof(double),
+                    cudaMemcpyDeviceToHost, s);
+  if (psi)
+    cudaMemcpyAsync(psi, d_psi.ptr, p->n_ids * nd * sizeof(double),
+                    cudaMemcpyDeviceToHost, s);
+  if (score)
+    cudaMemcpyAsync(score, p->hscore.ptr, sizeof(double),
+                    cudaMemcpyDeviceToHost, s);
+  if (with_grad && grad)
+    cudaMemcpyAsync(grad, p->hgrad.ptr, n_params * sizeof(double),
+                    cudaMemcpyDeviceToHost, s);
+  err = cudaStreamSynchronize(s);
+  if (err != cudaSuccess) return done(fail(-2, cudaGetErrorString(err)));
+  return done(0);
+}
+
+int chi_b200_fp64_peak(int32_t device, double* tflops, double* sm_clock_mhz) {
+  if (chi_b200_device_count() <= 0)
+    return fail(-3, "no CUDA device available: chi_b200 has no CPU fallback");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  double* d_out = nullptr;
+  CUDA_TRY(cudaMalloc(&d_out, sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256;
+  const int iters = 1 << 15;
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0));
+    fp64_peak_kernel<<<blocks, threads>>>(d_out, iters, 0.999999, 1e-7);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8.0 * iters * static_cast<double>(blocks) * threads;
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  *tflops = best;
+  if (sm_clock_mhz) *sm_clock_mhz = prop.clockRate * 1e-3;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// chi_b200 -- interface between generated model code, the integrator template
+// and the core library.  sm_100a only; host code is C++17.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#ifdef __CUDACC__
+#define CHI_HD __host__ __device__ __forceinline__
+#else
+#define CHI_HD inline
+#endif
+
+namespace chi_b200 {
+
+constexpr int MAX_OUT = 8;    // outputs selected per problem
+constexpr int MAX_COLS = 32;  // sensitivity columns (mechanistic parameters)
+constexpr int MAX_SIGMA = 2 * MAX_OUT;
+
+// Error-model kinds (chi/_error_models.py): parameters per kind 1,1,2,1.
+enum ErrKind : int32_t {
+  ERR_GAUSSIAN = 0,        // GaussianErrorModel                :539-869
+  ERR_LOGNORMAL = 1,       // LogNormalErrorModel               :872-1228
+  ERR_CAM = 2,             // ConstantAndMultiplicativeGaussian :182-536
+  ERR_MULTIPLICATIVE = 3,  // MultiplicativeGaussianErrorModel  :1231-1580
+};
+
+// Per-system status words (0 = ok).  The host maps any non-zero status to the
+// reference's failure convention: score -inf, gradient +inf, RuntimeWarning
+// (chi/_log_pdfs.py:812-821, 990-996).
+enum Status : int32_t {
+  ST_OK = 0,
+  ST_MAX_STEPS = 1,
+  ST_STEP_UNDERFLOW = 2,
+  ST_NON_FINITE = 3,
+};
+
+// Everything one launch of the solve kernel needs.  All pointers are device
+// pointers.  Passed by value (fits the 4 KB kernel parameter space).
+struct SolveArgs {
+  int64_t B;                 // number of (individual x chain) systems
+  int32_t n_ids;             // individuals in the uploaded population
+  const int32_t* ids;        // [B] individual of each system, or null: b % n_ids
+  const double* x;           // [B][x_stride]: psi (P) then sigma parameters
+  int32_t x_stride;
+
+  // static per-individual data (uploaded once, L2 resident)
+  const int64_t* rec_off;    // [n_ids+1] observation records, sorted by time
+  const double* rec_t;
+  const double* rec_obs;
+  const double* rec_logobs;
+  const int32_t* rec_out;    // index into out_id[] below
+  const int64_t* seg_off;    // [n_ids+1] piecewise-constant dose-rate segments
+  const double* seg_t;       // segment start times (first is 0)
+  const double* seg_rate;
+
+  int32_t n_out;
+  int32_t out_id[MAX_OUT];   // model output ids
+  int32_t err_kind[MAX_OUT];
+  int32_t err_off[MAX_OUT];  // offset of the output's sigmas inside the sigma block
+  int32_t n_sigma;
+
+  int32_t n_cols;            // sensitivity columns
+  int32_t col_param[MAX_COLS];  // mechanistic parameter index of each column
+
+  int32_t mode;              // 0: simulate (write trajectories); 1: log-likelihood
+  int32_t with_sens;
+  double rtol, atol;
+  int32_t max_steps;
+
+  // outputs
+  const int64_t* traj_off;   // [B] first trajectory row of each system (mode 0)
+  double* traj_y;            // [rows]
+  double* traj_s;            // [rows][n_cols]
+  double* ll;                // [B]
+  double* grad;              // [B][grad_stride] (psi columns then sigmas)
+  int32_t grad_stride;
+  int32_t* status;           // [B]
+  int32_t* n_steps;          // [B] accepted steps (may be null)
+  int32_t* n_rej;            // [B] rejected steps (may be null)
+};
+
+// What a compiled model contributes to the registry of the core library.
+struct ModelVTable {
+  const char* key;
+  int32_t n_states, n_consts, n_outputs, linear;
+  int32_t flops_rhs, flops_jac, flops_dfdc, flops_hess;
+  // group geometry of the sensitivity kernel: lanes per system and
+  // sensitivity columns per lane (see integrator.cuh)
+  int32_t n_variants;
+  const int32_t* variant_lanes;
+  const int32_t* variant_cols;
+  // launches the solve on `stream`; variant < 0 picks the default.
+  cudaError_t (*launch)(const SolveArgs& args, int variant,
+                        cudaStream_t stream);
+  // occupancy / register report for a variant (-1: forward kernel)
+  cudaError_t (*describe)(int variant, int* regs, int* block,
+                          int* blocks_per_sm, int* local_bytes);
+};
+
+}  // namespace chi_b200
+
+extern "C" int chi_b200_register_model(const chi_b200::ModelVTable* vt);

@@ -1,0 +1,50 @@
+"""Builds oracle/csolver/libchi_port.so (g++ -O3 -fopenmp).
+
+TEST INFRASTRUCTURE ONLY.  Compiles the host port of the per-system solve for
+every built-in model listed in chi_b200/csrc/gen/index.json.
+"""
+import json
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+GEN = os.path.join(ROOT, 'chi_b200', 'csrc', 'gen')
+LIB = os.path.join(HERE, 'libchi_port.so')
+
+
+def build(force=False):
+    with open(os.path.join(GEN, 'index.json')) as f:
+        index = json.load(f)
+    lines = []
+    for key in sorted(index):
+        lines.append('#include "../../chi_b200/csrc/gen/model_%s.cuh"' % key)
+    lines.append('#define CHI_PORT_MODELS \\')
+    for key in sorted(index):
+        lines.append('  CHI_PORT_MODEL("%s", Model_%s) \\' % (key, key))
+    lines.append('')
+    text = '\n'.join(lines) + '\n'
+    inc = os.path.join(HERE, 'port_models.inc')
+    if not os.path.exists(inc) or open(inc).read() != text:
+        with open(inc, 'w') as f:
+            f.write(text)
+    srcs = [os.path.join(HERE, 'port.cpp'), inc,
+            os.path.join(ROOT, 'chi_b200', 'csrc', 'integrator.cuh'),
+            os.path.join(ROOT, 'chi_b200', 'csrc', 'model_api.cuh')]
+    srcs += [os.path.join(GEN, 'model_%s.cuh' % k) for k in index]
+    if not force and os.path.exists(LIB) and all(
+            os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
+        return LIB
+    cmd = ['g++', '-O3', '-std=c++17', '-fPIC', '-shared', '-fopenmp',
+           '-ffp-contract=fast', '-march=x86-64-v3',
+           '-I/usr/local/cuda/include', os.path.join(HERE, 'port.cpp'),
+           '-o', LIB]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE,
+                          stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError('g++ failed:\n' + proc.stdout)
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force=True))

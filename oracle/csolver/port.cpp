@@ -1,0 +1,61 @@
+// CPU port of the chi_b200 solve for baseline timing and debugging.
+//
+// TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  This translation unit
+// compiles the *same* per-system routine the CUDA kernel runs
+// (chi_b200/csrc/integrator.cuh: solve_system<M, 1, P>) for the host with
+// g++ -O3, one system per call, so that
+//   * bench.py can time "the reference's cost structure" on the host cores:
+//     one native adaptive stiff solve with forward sensitivities per
+//     individual (what chi gets from myokit/CVODES,
+//     chi/_mechanistic_models.py:490-533), driven either by a Python loop
+//     over individuals (chi/_log_pdfs.py:289-292) or by an OpenMP loop;
+//   * the integrator's step control can be debugged without a GPU.
+// It is a port of the product algorithm, not an independent check: parity is
+// established against oracle/ode_exact.py, never against this file.
+#include <cstdint>
+#include <cstring>
+#include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../../chi_b200/csrc/integrator.cuh"
+#include "port_models.inc"   // generated: includes + dispatch table
+
+using namespace chi_b200;
+
+template <class M>
+static void run_all(const SolveArgs& a, int n_threads) {
+  (void)n_threads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads)
+#endif
+  for (int64_t b = 0; b < a.B; ++b) {
+    if (a.with_sens)
+      solve_system<M, 1, M::P>(a, b, 0, 0, 0, 1u);
+    else
+      solve_system<M, 1, 0>(a, b, 0, 0, 0, 1u);
+  }
+}
+
+extern "C" int chi_port_solve(const char* key, const SolveArgs* a,
+                              int n_threads) {
+#define CHI_PORT_MODEL(KEY, TYPE)                                            \
+  if (std::strcmp(key, KEY) == 0) {                                          \
+    run_all<TYPE>(*a, n_threads);                                            \
+    return 0;                                                                \
+  }
+  CHI_PORT_MODELS
+#undef CHI_PORT_MODEL
+  return -1;
+}
+
+extern "C" int chi_port_sizeof_args(void) { return (int)sizeof(SolveArgs); }
+
+extern "C" int chi_port_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}

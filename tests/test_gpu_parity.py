@@ -1,0 +1,459 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star):
+  * trajectories and sensitivities: rtol 1e-6 (scaled by the column maximum)
+    at the default integrator tolerances, and ~1e-9 at rtol 1e-11;
+  * summed log-pdf: 1e-8 relative, gradient 1e-6 relative, both with the
+    integrator at rtol 1e-11 / atol 1e-13;
+  * statistical stages fed identical inputs: 1e-12.
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+import chi_b200
+from oracle import ode_exact, stats
+
+pytestmark = pytest.mark.gpu
+
+TIGHT = dict(abs_tol=1e-13, rel_tol=1e-11)
+
+
+def _events(model):
+    reg = model.dosing_regimen()
+    if reg is None:
+        return []
+    return [tuple(row) for row in reg.as_array()]
+
+
+def _scaled_err(a, b, axis=0):
+    scale = np.max(np.abs(b), axis=axis, keepdims=True)
+    scale[scale == 0] = 1.0
+    return np.max(np.abs(a - b) / scale)
+
+
+CASES = {
+    # name: (library ctor, oracle ctor, direct, output, psi, regimen kwargs)
+    'one_cmt_direct_bolus': (
+        'one_compartment_pk_model', ode_exact.one_compartment, True,
+        'central.drug_concentration', [0.0, 2.0, 1.0],
+        dict(dose=10, start=0, duration=0.01)),
+    'one_cmt_indirect': (
+        'one_compartment_pk_model', ode_exact.one_compartment, False,
+        'central.drug_concentration', [0.3, 0.1, 2.0, 3.0, 1.0],
+        dict(dose=4, start=0.5, duration=0.01, period=1.5, num=3)),
+    'two_cmt_direct_infusion': (
+        'two_compartment_pk_model', ode_exact.two_compartment, True,
+        'central.drug_concentration', [0.0, 0.0, 2.0, 1.0, 5.0, 1.0, 10.0],
+        dict(dose=10, start=0, duration=1.0, period=8, num=3)),
+    'two_cmt_indirect_indefinite': (
+        'two_compartment_pk_model', ode_exact.two_compartment, False,
+        'central.drug_concentration',
+        [0.1, 0.2, 0.3, 2.0, 10.0, 1.0, 5.0, 1.0, 10.0],
+        dict(dose=2, period=1)),
+    'tgi_direct_daily': (
+        'erlotinib_tumour_growth_inhibition_model',
+        ode_exact.tumour_growth_inhibition_pkpd, True,
+        'global.tumour_volume', [0.0, 0.2, 2.0, 1.0, 0.5, 0.3, 0.1],
+        dict(dose=5, start=0, duration=0.01, period=1, num=30)),
+    'tgi_indirect_daily': (
+        'erlotinib_tumour_growth_inhibition_model',
+        ode_exact.tumour_growth_inhibition_pkpd, False,
+        'global.tumour_volume',
+        [0.0, 0.0, 0.2, 2.0, 3.0, 1.0, 0.5, 0.05, 0.1],
+        dict(dose=5, start=0, duration=0.01, period=1, num=30)),
+}
+
+TIMES = {
+    'one_cmt_direct_bolus': np.linspace(0.1, 10, 100),
+    'one_cmt_indirect': np.array([0.0, 0.25, 0.5, 0.505, 1.0, 2.0, 2.7, 6.0]),
+    'two_cmt_direct_infusion': np.sort(
+        np.random.default_rng(1).uniform(0.25, 24, 10)),
+    'two_cmt_indirect_indefinite': np.array([0.5, 1, 1.5, 2, 2.5, 3]),
+    'tgi_direct_daily': np.arange(0.0, 31.0),
+    'tgi_indirect_daily': np.arange(0.0, 31.0),
+}
+
+
+def _build(name):
+    lib_name, oracle_ctor, direct, output, psi, reg = CASES[name]
+    model = getattr(chi_b200.library.ModelLibrary(), lib_name)()
+    model.set_administration('central', direct=direct)
+    model.set_outputs([output])
+    model.set_dosing_regimen(**reg)
+    omodel = oracle_ctor(direct)
+    omodel.set_outputs([output])
+    assert model.parameters() == omodel.parameter_names
+    return model, omodel, np.array(psi, float), TIMES[name]
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_simulate_matches_exact_solution(name):
+    model, omodel, psi, times = _build(name)
+    y_ref, s_ref = ode_exact.simulate(omodel, psi, times, _events(model))
+
+    # forward only, default tolerances: 1e-6 contract
+    y = model.simulate(parameters=psi, times=times)
+    assert y.shape == (1, len(times))
+    assert _scaled_err(y, y_ref, axis=1) < 1e-6
+
+    # with sensitivities, default tolerances: 1e-6 contract
+    model.enable_sensitivities(True)
+    y, s = model.simulate(parameters=psi, times=times)
+    assert s.shape == (len(times), 1, len(psi))
+    assert _scaled_err(y, y_ref, axis=1) < 1e-6
+    assert _scaled_err(s[:, 0, :], s_ref[:, 0, :]) < 1e-6
+
+    # tight tolerances: converges to the exact solution
+    model.set_tolerance(**TIGHT)
+    y, s = model.simulate(parameters=psi, times=times)
+    assert _scaled_err(y, y_ref, axis=1) < 2e-10
+    assert _scaled_err(s[:, 0, :], s_ref[:, 0, :]) < 2e-9
+
+
+def test_simulate_multiple_outputs_and_subset_sensitivities():
+    model, omodel, psi, times = _build('two_cmt_direct_infusion')
+    outs = ['central.drug_amount', 'peripheral.drug_concentration',
+            'central.drug_concentration']
+    model.set_outputs(outs)
+    omodel.set_outputs(outs)
+    model.set_tolerance(**TIGHT)
+    names = ['global.elimination_rate', 'peripheral.size',
+             'central.drug_amount']
+    model.enable_sensitivities(True, names)
+    y, s = model.simulate(parameters=psi, times=times)
+    y_ref, s_ref = ode_exact.simulate(omodel, psi, times, _events(model))
+    cols = [model.parameters().index(n) for n in sorted(
+        names, key=model.parameters().index)]
+    assert y.shape == (3, len(times)) and s.shape == (len(times), 3, 3)
+    assert _scaled_err(y, y_ref, axis=1) < 2e-10
+    for o in range(3):
+        assert _scaled_err(s[:, o, :], s_ref[:, o, cols]) < 2e-9
+
+
+def test_simulate_no_dose_and_koch_models():
+    lib = chi_b200.library.ModelLibrary()
+    model = lib.tumour_growth_inhibition_model_koch()
+    assert model.parameters() == [
+        'global.tumour_volume', 'global.drug_concentration', 'global.kappa',
+        'global.lambda_0', 'global.lambda_1']
+    omodel = ode_exact.tumour_growth_koch()
+    psi = np.array([0.3, 1.2, 0.2, 0.4, 0.7])
+    times = np.linspace(0, 20, 15)
+    model.set_tolerance(**TIGHT)
+    model.enable_sensitivities(True)
+    y, s = model.simulate(psi, times)
+    y_ref, s_ref = ode_exact.simulate(omodel, psi, times, [])
+    assert _scaled_err(y, y_ref, axis=1) < 2e-10
+    assert _scaled_err(s[:, 0, :], s_ref[:, 0, :]) < 2e-9
+
+
+ERR = [
+    ('gaussian', chi_b200.GaussianErrorModel, [0.3]),
+    ('lognormal', chi_b200.LogNormalErrorModel, [0.2]),
+    ('cam', chi_b200.ConstantAndMultiplicativeGaussianErrorModel, [0.1, 0.2]),
+    ('multiplicative', chi_b200.MultiplicativeGaussianErrorModel, [0.25]),
+]
+
+
+@pytest.mark.parametrize('kind,cls,sigma', ERR)
+def test_error_models_match_oracle(kind, cls, sigma):
+    rng = np.random.default_rng(3)
+    em = cls()
+    n_sig, f_ll, f_s1 = stats.ERROR_MODELS[kind]
+    for n_obs, n_par in [(1, 1), (7, 3), (100, 9), (1000, 4)]:
+        ybar = rng.uniform(0.5, 3.0, n_obs)
+        obs = rng.uniform(0.5, 3.0, n_obs)
+        sens = rng.normal(size=(n_obs, n_par))
+        ll, grad = em.compute_sensitivities(sigma, ybar, sens, obs)
+        ll_ref, grad_ref = f_s1(sigma, ybar, sens, obs)
+        assert ll == pytest.approx(ll_ref, rel=1e-12)
+        np.testing.assert_allclose(grad, grad_ref, rtol=1e-11, atol=1e-12)
+        assert em.compute_log_likelihood(sigma, ybar, obs) == pytest.approx(
+            f_ll(sigma, ybar, obs), rel=1e-12)
+        np.testing.assert_allclose(
+            em.compute_pointwise_ll(sigma, ybar, obs),
+            stats.error_pointwise_ll(kind, sigma, ybar, obs), rtol=1e-12)
+    # sigma <= 0 -> -inf / inf (chi/_error_models.py:238-240, 297-300, ...)
+    bad = [-s for s in sigma]
+    ll, grad = em.compute_sensitivities(bad, [1.0, 2.0], np.ones((2, 2)),
+                                        [1.0, 2.0])
+    assert ll == -np.inf and np.all(np.isinf(grad)) and np.all(grad > 0)
+    assert em.compute_log_likelihood(bad, [1.0], [1.0]) == -np.inf
+
+
+def test_lognormal_error_model_nonpositive_output():
+    em = chi_b200.LogNormalErrorModel()
+    ll, grad = em.compute_sensitivities(
+        [0.2], [1.0, -0.5], np.ones((2, 2)), [1.0, 2.0])
+    assert ll == -np.inf and np.all(grad == np.inf)
+
+
+def _oracle_individual(omodel, kind, times, obs, events, n_mech):
+    def simulate(psi, with_sens):
+        return ode_exact.simulate(
+            omodel, psi, times, events, sensitivities=with_sens)
+
+    masks = np.ones((1, len(times)), bool)
+
+    def s1(x):
+        return stats.loglikelihood_s1(
+            simulate, n_mech, [kind], [obs], masks, x, True)
+
+    def ll(x):
+        return stats.loglikelihood_s1(
+            simulate, n_mech, [kind], [obs], masks, x, False)
+    return ll, s1
+
+
+@pytest.mark.parametrize('kind,cls,sigma', ERR)
+def test_log_likelihood_matches_oracle(kind, cls, sigma):
+    """config C1-like: LogLikelihood.__call__ / evaluateS1."""
+    model, omodel, psi, times = _build('one_cmt_direct_bolus')
+    model.set_tolerance(**TIGHT)
+    rng = np.random.default_rng(1)
+    y_ref, _ = ode_exact.simulate(omodel, psi, times, _events(model))
+    obs = np.abs(y_ref[0] * (1 + 0.1 * rng.normal(size=len(times)))) + 1e-3
+    ll = chi_b200.LogLikelihood(model, cls(), obs, times)
+    assert ll.get_parameter_names()[:3] == model.parameters()
+    x = np.array(list(psi) + list(sigma))
+    x[0] = 0.5
+    f_ll, f_s1 = _oracle_individual(
+        omodel, kind, times, obs, _events(model), len(psi))
+    score, grad = ll.evaluateS1(x)
+    score_ref, grad_ref = f_s1(x)
+    assert score == pytest.approx(score_ref, rel=1e-8)
+    np.testing.assert_allclose(
+        grad, grad_ref, rtol=1e-6, atol=1e-6 * np.max(np.abs(grad_ref)))
+    assert ll(x) == pytest.approx(f_ll(x), rel=1e-8)
+
+
+def test_log_likelihood_two_outputs_ragged_times():
+    """Two outputs on different grids (chi/tests/test_log_pdfs.py:1674-1697
+    style fixture): union grid + masks."""
+    model, omodel, psi, _ = _build('one_cmt_indirect')
+    outs = ['central.drug_amount', 'dose.drug_amount']
+    model.set_outputs(outs)
+    omodel.set_outputs(outs)
+    model.set_tolerance(**TIGHT)
+    t0 = np.array([0.5, 1.0, 2.0, 4.0])
+    t1 = np.array([1.0, 3.0, 4.0])
+    obs0 = np.array([0.4, 0.9, 1.1, 0.6])
+    obs1 = np.array([2.0, 1.0, 0.7])
+    ll = chi_b200.LogLikelihood(
+        model, [chi_b200.GaussianErrorModel(),
+                chi_b200.LogNormalErrorModel()], [obs0, obs1], [t0, t1])
+    names = ll.get_parameter_names()
+    assert names[-2:] == ['central.drug_amount Sigma',
+                          'dose.drug_amount Sigma log']
+    x = np.array(list(psi) + [0.3, 0.4])
+    union, masks = stats.union_times([t0, t1])
+
+    def simulate(p, with_sens):
+        return ode_exact.simulate(
+            omodel, p, union, _events(model), sensitivities=with_sens)
+    ref, gref = stats.loglikelihood_s1(
+        simulate, len(psi), ['gaussian', 'lognormal'], [obs0, obs1], masks,
+        x, True)
+    score, grad = ll.evaluateS1(x)
+    assert score == pytest.approx(ref, rel=1e-8)
+    np.testing.assert_allclose(
+        grad, gref, rtol=1e-6, atol=1e-6 * np.max(np.abs(gref)))
+
+
+def test_log_likelihood_invalid_sigma_and_failure_convention():
+    model, omodel, psi, times = _build('one_cmt_direct_bolus')
+    obs = np.ones(len(times))
+    ll = chi_b200.LogLikelihood(
+        model, chi_b200.GaussianErrorModel(), obs, times)
+    score, grad = ll.evaluateS1(list(psi) + [-1.0])
+    assert score == -np.inf and np.all(grad == np.inf)
+    # integrator failure -> RuntimeWarning, -inf, +inf gradient
+    model.set_tolerance(abs_tol=1e-13, rel_tol=1e-11, max_steps=5)
+    ll = chi_b200.LogLikelihood(
+        model, chi_b200.GaussianErrorModel(), obs, times)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        score, grad = ll.evaluateS1(list(psi) + [0.1])
+    assert score == -np.inf and np.all(grad == np.inf)
+    assert any(issubclass(x.category, RuntimeWarning) for x in w)
+
+
+def _pop_cases(n_ids):
+    G, L, P, H = (chi_b200.GaussianModel, chi_b200.LogNormalModel,
+                  chi_b200.PooledModel, chi_b200.HeterogeneousModel)
+    C = chi_b200.CovariatePopulationModel
+    Lin = chi_b200.LinearCovariateModel
+    return [
+        ([P(2), L(5, centered=False), P(1)],
+         [('pooled', 2), ('lognormal', 5, False), ('pooled', 1)]),
+        ([L(3, centered=True)], [('lognormal', 3, True)]),
+        ([G(2, centered=True), P(1), G(2, centered=False)],
+         [('gaussian', 2, True), ('pooled', 1), ('gaussian', 2, False)]),
+        ([H(1, n_ids=n_ids), L(2, centered=False), P(2)],
+         [('hetero', 1), ('lognormal', 2, False), ('pooled', 2)]),
+        ([P(2), C(L(5, centered=False), Lin(n_cov=2)), P(2)],
+         [('pooled', 2), ('covariate', ('lognormal', 5, False), 2),
+          ('pooled', 2)]),
+        ([C(G(2, centered=True), Lin(n_cov=1)), L(1, centered=True)],
+         [('covariate', ('gaussian', 2, True), 1), ('lognormal', 1, True)]),
+        ([C(L(2, centered=True), Lin(n_cov=3)), H(2, n_ids=n_ids)],
+         [('covariate', ('lognormal', 2, True), 3), ('hetero', 2)]),
+    ]
+
+
+def _oracle_layout(models, spec, n_ids):
+    blocks = []
+    for m, b in zip(models, spec):
+        if b[0] == 'covariate':
+            pidx, didx = m._covariate_model.get_set_population_parameters()
+            blocks.append(('covariate', b[1], b[2], pidx, didx))
+        else:
+            blocks.append(b)
+    return stats.PopLayout(blocks, n_ids)
+
+
+@pytest.mark.parametrize('n_ids', [1, 7, 300])
+def test_population_models_match_oracle(n_ids):
+    rng = np.random.default_rng(n_ids)
+    for models, spec in _pop_cases(n_ids):
+        pm = chi_b200.ComposedPopulationModel(models)
+        pm.set_n_ids(n_ids)
+        lay = _oracle_layout(models, spec, n_ids)
+        n_b, n_t = pm.n_hierarchical_parameters(n_ids)
+        assert (n_b, n_t) == (lay.n_bottom, lay.n_top)
+        n_cov = pm.n_covariates()
+        cov = rng.normal(size=(n_ids, n_cov)) if n_cov else None
+        top = rng.uniform(0.2, 1.5, n_t)
+        for i, name in enumerate(pm.get_parameter_names()):
+            if 'Cov.' in name:
+                top[i] *= 0.05
+        bottom = rng.uniform(0.3, 2.0, n_b)
+        eta = pm.compute_individual_parameters(
+            top, bottom, cov, return_eta=True)
+        eta_ref = stats.pop_individual_parameters(
+            lay, top, bottom, cov, return_eta=True)
+        np.testing.assert_allclose(eta, eta_ref, rtol=1e-14)
+        psi = pm.compute_individual_parameters(top, eta, cov)
+        psi_ref = stats.pop_individual_parameters(lay, top, eta_ref, cov)
+        np.testing.assert_allclose(psi, psi_ref, rtol=1e-13)
+        score = pm.compute_log_likelihood(top, eta, covariates=cov)
+        assert score == pytest.approx(
+            stats.pop_log_likelihood(lay, top, eta_ref, cov), rel=1e-12)
+        dlp = rng.normal(size=(n_ids, lay.n_dim))
+        score, grad = pm.compute_sensitivities(
+            top, eta, dlogp_dpsi=dlp, reduce=True, covariates=cov)
+        s_ref, g_ref = stats.pop_sensitivities_reduced(
+            lay, top, eta_ref, dlp, cov)
+        assert score == pytest.approx(s_ref, rel=1e-12)
+        np.testing.assert_allclose(
+            grad, g_ref, rtol=1e-11, atol=1e-12 * np.max(np.abs(g_ref)))
+
+
+def test_population_negative_sigma_is_minus_inf():
+    pm = chi_b200.ComposedPopulationModel(
+        [chi_b200.LogNormalModel(2, centered=False), chi_b200.PooledModel(1)])
+    pm.set_n_ids(3)
+    top = np.array([0.1, 0.2, 0.3, -0.4, 1.0])
+    bottom = np.linspace(0.1, 0.6, 6)
+    eta = pm.compute_individual_parameters(top, bottom, return_eta=True)
+    score, _ = pm.compute_sensitivities(
+        top, eta, dlogp_dpsi=np.ones((3, 3)), reduce=True)
+    assert score == -np.inf
+
+
+def _hier_oracle(prob, n_ids, kind):
+    ll = prob['log_likelihood']
+    pm = prob['population_model']
+    models = pm.get_population_models()
+    spec = []
+    for m in models:
+        if isinstance(m, chi_b200.PooledModel):
+            spec.append(('pooled', m.n_dim()))
+        elif isinstance(m, chi_b200.CovariatePopulationModel):
+            spec.append(('covariate', ('lognormal', 5, False), 2))
+        else:
+            spec.append(('lognormal', m.n_dim(), False))
+    lay = _oracle_layout(models, spec, n_ids)
+    omodel = ode_exact.two_compartment(True)
+    omodel.set_outputs(['central.drug_concentration'])
+    fns = []
+    for i in range(n_ids):
+        ev = [tuple(r) for r in prob['regimens'][i].as_array()]
+        fns.append(_oracle_individual(
+            omodel, kind, prob['times'][i], prob['observations'][i], ev, 7))
+    return lay, fns
+
+
+@pytest.mark.parametrize('error,covariates', [
+    ('lognormal', False), ('cam', True), ('gaussian', False)])
+def test_hierarchical_log_posterior_matches_oracle(error, covariates):
+    """configs C2 / C5 at a size the oracle finishes in seconds."""
+    from chi_b200 import _synthetic
+    n_ids = 12
+    prob = _synthetic.two_compartment_problem(
+        n_ids, seed=5, n_doses=3, error=error, covariates=covariates,
+        rtol=1e-11, atol=1e-13)
+    post = prob['log_posterior']
+    lay, fns = _hier_oracle(prob, n_ids, error)
+    rng = np.random.default_rng(0)
+    x = prob['x0'] * (1 + 0.02 * rng.normal(size=len(prob['x0'])))
+    assert len(x) == post.n_parameters() == lay.n_parameters
+    ref, gref = stats.posterior_s1(
+        lay, lambda i, p: fns[i][1](p), prob['log_prior'], x,
+        prob['covariates'])
+    score, grad = post.evaluateS1(x)
+    assert score == pytest.approx(ref, rel=1e-8)
+    np.testing.assert_allclose(
+        grad, gref, rtol=1e-6, atol=1e-6 * np.max(np.abs(gref)))
+    ref0 = stats.posterior_call(
+        lay, lambda i, p: fns[i][0](p), prob['log_prior'], x,
+        prob['covariates'])
+    assert post(x) == pytest.approx(ref0, rel=1e-8)
+    # batched entry points agree with the per-vector calls
+    X = np.vstack([x, prob['x0'], x * 1.01])
+    scores = post.evaluate_batch(X)
+    assert scores[0] == pytest.approx(score, rel=1e-13)
+    s1, g1 = post.evaluateS1_batch(X)
+    np.testing.assert_allclose(g1[0], grad, rtol=1e-13)
+    np.testing.assert_allclose(s1, scores, rtol=1e-12)
+
+
+def test_hierarchical_parameter_layout():
+    """chi/tests/test_log_pdfs.py:740-767 and SURVEY.md section 8a."""
+    from chi_b200 import _synthetic
+    prob = _synthetic.two_compartment_problem(3, seed=1)
+    ll = prob['log_likelihood']
+    names = ll.get_parameter_names()
+    assert len(names) == 28 and ll.n_parameters() == 28
+    assert names[0:5] == [
+        'central.size', 'global.elimination_rate',
+        'global.transition_rate_c2p', 'global.transition_rate_p2c',
+        'peripheral.size']
+    assert names[15:17] == ['Pooled central.drug_amount',
+                            'Pooled peripheral.drug_amount']
+    assert names[27] == 'Pooled Sigma log'
+    sd, n_pooled, n_het = prob['population_model'].get_special_dims()
+    assert sd == [[0, 2, 0, 2, True], [7, 8, 12, 13, True]]
+    assert (n_pooled, n_het) == (3, 0)
+    ids = ll.get_id()
+    assert ids[0] == ids[4] and ids[5] != ids[4] and ids[-1] is None
+
+
+def test_gpu_kernel_matches_cpu_port():
+    """The host port (oracle/csolver) runs the same algorithm; the two
+    must agree to rounding."""
+    from oracle import cport
+    model, omodel, psi, times = _build('two_cmt_direct_infusion')
+    model.enable_sensitivities(True)
+    y, s = model.simulate(psi, times)
+    key = cport.find_key('two_compartment_pk_model', 'central', True)
+    assert key == model.model_key()
+    pop = cport.Population(
+        key, ['central.drug_concentration'], None, [times], None, None,
+        [_events(model)])
+    yc, sc, st, _, _ = pop.simulate(psi, rtol=1e-8, atol=1e-10)
+    assert st[0] == 0
+    np.testing.assert_allclose(y[0], yc, rtol=1e-9)
+    np.testing.assert_allclose(s[:, 0, :], sc, rtol=1e-7, atol=1e-12)
