@@ -1,0 +1,635 @@
+#!/usr/bin/env python
+"""Benchmark of the likelihood hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W          # product (CUDA)
+    python bench.py --impl reference --gpus N ...          # CPU reference arm
+
+Metric: log-posterior+gradient evaluations per second of the hierarchical
+two-compartment PK model (BASELINE.json configs[1]).  One *step* evaluates a
+batch of `--chains` parameter vectors (`HierarchicalLogPosterior.evaluateS1`
+for each) over all `--n-ids` individuals; one evaluation = one parameter
+vector over all individuals.
+
+Multi-GPU (`torchrun`, one rank per GPU):
+  --shard chains        every rank evaluates its own batch of chains on all
+                        individuals: no data-path collective (default)
+  --shard individuals   every rank holds `--n-ids` individuals of an
+                        N x n_ids population and evaluates all chains on its
+                        shard; one NCCL all-reduce of [score | d theta] per
+                        step (the large-population mode of the north star)
+
+The JSON line carries `value` (inputs resident in HBM, device-timed),
+`e2e` (public API with host buffers, host<->device copies and the host-side
+prior inside the timed region), `roofline` (FP64: algorithmic flops of the
+solve kernel / its CUDA-event time / measured DFMA peak) and `cpu_baseline`
+(the oracle's CPU restatement of the reference path on the host cores).
+"""
+import argparse
+import json
+import multiprocessing
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'log-posterior+gradient evals/sec (ODE+sens)'
+UNIT = 'evals/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='chi_b200',
+                    choices=['chi_b200', 'reference'])
+    ap.add_argument('--n-ids', type=int, default=1000)
+    ap.add_argument('--chains', type=int, default=128,
+                    help='parameter vectors per step and GPU')
+    ap.add_argument('--n-doses', type=int, default=3)
+    ap.add_argument('--n-obs', type=int, default=10)
+    ap.add_argument('--rtol', type=float, default=1e-6)
+    ap.add_argument('--atol', type=float, default=1e-8)
+    ap.add_argument('--shard', default='chains',
+                    choices=['chains', 'individuals'])
+    ap.add_argument('--variant', type=int, default=-1)
+    ap.add_argument('--cpu-seconds', type=float, default=10.0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--seed', type=int, default=0)
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {
+        'workload': (
+            'C2: two-compartment PK (direct infusion into central, %d doses '
+            'of U(5,15) over 1.0, period 8), %d individuals x %d obs at '
+            'sorted U(0.25,24), LogNormalErrorModel, population = '
+            'Composed[Pooled(2), LogNormal(5, non-centered), Pooled(1)], '
+            'HierarchicalLogPosterior.evaluateS1 batched over %d parameter '
+            'vectors per step and GPU' % (
+                args.n_doses, args.n_ids, args.n_obs, args.chains)),
+        'n_ids': args.n_ids, 'chains_per_step_per_gpu': args.chains,
+        'n_obs': args.n_obs, 'n_doses': args.n_doses,
+        'rtol': args.rtol, 'atol': args.atol,
+        'parallelism': '%s-sharded x%d' % (args.shard, n_gpus),
+        'l2': 'flushed between timed steps (256 MiB write)',
+    }
+
+
+# --------------------------------------------------------------------------
+# flop model ("Algorithmic flops")
+# --------------------------------------------------------------------------
+
+def flops_per_step(n, n_cols, info):
+    """Algorithmic flops of one RODAS4 step attempt of one system:
+    state column once + n_cols sensitivity columns (FMA = 2)."""
+    linear = bool(info[3])
+    f_rhs, f_jac, f_dfdc, f_hess = [int(v) for v in info[4:8]]
+    inv = {1: 2, 2: 12, 3: 51}.get(n, (2 * n ** 3) // 3 + 2 * n * n)
+    comb = 2 * n * 15                     # sum_i a_ij U_j, 15 (i, j) pairs
+    solve = 6 * n * (2 * n - 1)           # six W^-1 mat-vecs
+    state = comb + comb + 6 * 2 * n + 6 * f_rhs + solve
+    sens = comb + comb + 6 * 2 * n + 6 * (
+        n * (2 * n - 1) + f_dfdc + f_hess + 2 * n) + solve
+    jac = (0 if linear else 7 * f_jac) if n_cols else (
+        0 if linear else f_jac)
+    new = (n_cols + 1) * (2 * n * 5 + n + 8 * n)
+    return inv + state + n_cols * sens + jac + new + 10
+
+
+def flops_per_record(n, n_cols):
+    """Output map, its directional derivatives and the error model."""
+    return 3 + n_cols * (2 * n + 3) + 25 + 2 * n_cols
+
+
+# --------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------
+
+class ClockSampler(object):
+    FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,'
+              'clocks_event_reasons.active,'
+              'clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.device),
+                 '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits',
+                 '-lms', '100'], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                 'sw_power_cap']
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {
+            'sm_mhz': float(np.median(sm)) if sm else None,
+            'sm_max_mhz': float(np.max(smax)) if smax else None,
+            'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# --------------------------------------------------------------------------
+# CPU baseline (oracle): the reference's cost structure on the host cores
+# --------------------------------------------------------------------------
+
+class ReferencePathCPU(object):
+    """chi's evaluation architecture restated on the CPU
+    (oracle/stats.py + oracle/csolver): a Python loop over individuals, one
+    compiled adaptive stiff solve with forward sensitivities per individual
+    (-> ybar, S), numpy error model per individual, numpy population model
+    (chi/_log_pdfs.py:255-300, 973-1027)."""
+
+    def __init__(self, data, rtol, atol):
+        from oracle import cport, stats
+        self.stats = stats
+        self.cport = cport
+        self.rtol, self.atol = rtol, atol
+        self.n_ids = len(data['times'])
+        key = cport.find_key('two_compartment_pk_model', 'central', True)
+        self.pops = []
+        for i in range(self.n_ids):
+            self.pops.append(cport.Population(
+                key, ['central.drug_concentration'], None,
+                [data['times'][i]], None, None, [data['events'][i]]))
+        self.obs = data['observations']
+        self.layout = stats.PopLayout(
+            [('pooled', 2), ('lognormal', 5, False), ('pooled', 1)],
+            self.n_ids)
+        self.prior = data['prior']
+        self.whole = cport.Population(
+            key, ['central.drug_concentration'], ['lognormal'],
+            data['times'], data['observations'], None, data['events'])
+
+    def individual_s1(self, i, x):
+        pop = self.pops[i]
+        y, s, status, _, _ = pop.simulate(
+            x[:7], rtol=self.rtol, atol=self.atol)
+        return self.stats.lognormal_error_s1(x[7:], y, s, self.obs[i])
+
+    def evaluateS1(self, x):
+        return self.stats.posterior_s1(
+            self.layout, self.individual_s1, self.prior, x)
+
+    def openmp_systems_per_second(self, x, seconds, threads):
+        """Best-effort CPU: C++ loop over individuals with OpenMP, fused
+        error model, no Python in the loop."""
+        lay = self.layout
+        eta = self.stats.pop_individual_parameters(
+            lay, x[lay.n_bottom:], x[:lay.n_bottom], None, return_eta=True)
+        psi = self.stats.pop_individual_parameters(
+            lay, x[lay.n_bottom:], eta, None)
+        reps = 1
+        t_used, n_sys = 0.0, 0
+        while t_used < seconds:
+            X = np.tile(psi, (reps, 1))
+            ids = np.tile(np.arange(self.n_ids, dtype=np.int32), reps)
+            t0 = time.perf_counter()
+            self.whole.loglik(X, ids=ids, with_grad=True, rtol=self.rtol,
+                              atol=self.atol, n_threads=threads)
+            dt = time.perf_counter() - t0
+            t_used += dt
+            n_sys += len(X)
+            if dt < 1.0:
+                reps *= 2
+        return n_sys / t_used
+
+
+def _reference_worker(payload):
+    data, rtol, atol, x, seconds = payload
+    os.environ['OMP_NUM_THREADS'] = '1'
+    ref = ReferencePathCPU(data, rtol, atol)
+    for _ in range(max(1, data.get('warmup', 1))):
+        ref.evaluateS1(x)  # warm-up (library load, caches)
+    n = 0
+    t0 = time.perf_counter()
+    while True:
+        ref.evaluateS1(x)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt >= seconds:
+            return n, dt
+
+
+def reference_evals_per_second(data, rtol, atol, x, seconds, procs):
+    """One process per core, each evaluating the full log-posterior +
+    gradient (what pints.ParallelEvaluator gives chi over chains,
+    chi/_inference.py:740)."""
+    ctx = multiprocessing.get_context('spawn')
+    with ctx.Pool(procs) as pool:
+        res = pool.map(
+            _reference_worker, [(data, rtol, atol, x, seconds)] * procs)
+    return sum(n / dt for n, dt in res)
+
+
+TWO_CMT_TYPICAL = np.array([2.0, 1.0, 5.0, 1.0, 10.0])
+
+
+def host_design(n_ids, seed, n_obs, n_doses):
+    """Synthetic design in plain numpy -- the same draws as
+    chi_b200._synthetic.two_compartment_design (tests/test_host_bench.py
+    checks that), so the reference arm needs nothing from the product."""
+    rng = np.random.default_rng(seed)
+    times = [np.sort(rng.uniform(0.25, 24.0, n_obs)) for _ in range(n_ids)]
+    doses = rng.uniform(5.0, 15.0, n_ids)
+    events = []
+    for i in range(n_ids):
+        if n_doses > 1:
+            events.append([(doses[i] / 1.0, 0.0, 1.0, 8.0, float(n_doses))])
+        else:
+            events.append([(doses[i] / 1.0, 0.0, 1.0, 0.0, 0.0)])
+    return times, events
+
+
+class HostPrior(object):
+    """Independent Gaussian / log-normal priors on the top-level parameters
+    (numpy; the counterpart of a pints.ComposedLogPrior)."""
+
+    def __init__(self, kinds, locs, scales):
+        self.kinds = np.asarray(kinds)
+        self.locs = np.asarray(locs, float)
+        self.scales = np.asarray(scales, float)
+
+    def n_parameters(self):
+        return len(self.kinds)
+
+    def evaluateS1(self, x):
+        x = np.asarray(x, float)
+        score = 0.0
+        grad = np.zeros(len(x))
+        for k, (kind, m, s) in enumerate(
+                zip(self.kinds, self.locs, self.scales)):
+            if kind == 0:
+                z = (x[k] - m) / s
+                score += -0.5 * np.log(2 * np.pi) - np.log(s) - 0.5 * z * z
+                grad[k] = -z / s
+            else:
+                if x[k] <= 0:
+                    return -np.inf, np.full(len(x), np.inf)
+                z = (np.log(x[k]) - m) / s
+                score += -0.5 * np.log(2 * np.pi) - np.log(s) \
+                    - np.log(x[k]) - 0.5 * z * z
+                grad[k] = -(1 + z / s) / x[k]
+        return score, grad
+
+    def __call__(self, x):
+        return self.evaluateS1(x)[0]
+
+
+def c2_prior():
+    mu_log = np.log(TWO_CMT_TYPICAL)
+    kinds = [0, 0] + [0] * 5 + [1] * 5 + [1]
+    locs = [0.0, 0.0] + list(mu_log) + [np.log(0.3)] * 5 + [np.log(0.1)]
+    scales = [1.0, 1.0] + [1.0] * 5 + [0.5] * 5 + [0.5]
+    return HostPrior(kinds, locs, scales)
+
+
+# --------------------------------------------------------------------------
+# arms
+# --------------------------------------------------------------------------
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle's restatement of the reference path, all host
+    cores, bounded sample (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle import ode_exact
+    times, events = host_design(
+        args.n_ids, args.seed, args.n_obs, args.n_doses)
+    rng = np.random.default_rng(args.seed + 12345)
+    n_ids = args.n_ids
+    mu_log = np.log(TWO_CMT_TYPICAL)
+    sigma_log = np.full(5, 0.3)
+    eta = rng.normal(size=(n_ids, 5))
+    psi_mid = np.exp(mu_log[None, :] + sigma_log[None, :] * eta)
+    # observations from the exact solution (the GPU is not used in this arm)
+    omodel = ode_exact.two_compartment(True)
+    omodel.set_outputs(['central.drug_concentration'])
+    observations = []
+    n_gen = min(n_ids, 64)
+    for i in range(n_ids):
+        j = i % n_gen
+        if i < n_gen:
+            psi = np.concatenate([[0.0, 0.0], psi_mid[i]])
+            y = ode_exact.simulate(
+                omodel, psi, times[i], events[i], sensitivities=False)[0]
+            observations.append(
+                y * rng.lognormal(-0.005, 0.1, size=len(y)))
+        else:
+            # reuse designs beyond the first 64 individuals (data values do
+            # not change the cost of an evaluation)
+            times[i] = times[j]
+            events[i] = events[j]
+            psi_mid[i] = psi_mid[j]
+            eta[i] = eta[j]
+            observations.append(observations[j])
+    data = {'times': times, 'observations': observations, 'events': events,
+            'prior': c2_prior(), 'warmup': args.warmup}
+    x = np.concatenate(
+        [eta.reshape(-1), [0.0, 0.0], mu_log, sigma_log, [0.1]])
+    cores = os.cpu_count() or 1
+    # a "step" of this arm is one full evaluateS1 in one process; every
+    # process does `warmup` untimed evaluations and then evaluates for a
+    # bounded time (at least `steps` evaluations in total across processes)
+    per_step = max(args.cpu_seconds, 2.0)
+    value = reference_evals_per_second(
+        data, args.rtol, args.atol, x, per_step, cores)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 / value if value > 0 else None,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args, world),
+        'cpu_baseline': {
+            'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': (
+                'full evaluateS1 of the %d-individual model repeated for '
+                '%.1f s on %d processes (one per core): Python loop '
+                'over individuals, one compiled RODAS4+sensitivities solve '
+                'per individual, numpy error and population models '
+                '(oracle/stats.py, oracle/csolver)' % (
+                    n_ids, per_step, cores))},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+def run_product(args, rank, world, local_rank):
+    import torch
+    import chi_b200
+    from chi_b200 import _lib, _synthetic
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+
+    n_total = args.n_ids * (world if args.shard == 'individuals' else 1)
+    prob = _synthetic.two_compartment_problem(
+        n_total, seed=args.seed, n_obs=args.n_obs, n_doses=args.n_doses,
+        error='lognormal', rtol=args.rtol, atol=args.atol)
+    post = prob['log_posterior']
+    ll = prob['log_likelihood']
+    n_params = post.n_parameters()
+    n_bottom = n_params - ll.n_parameters(exclude_bottom_level=True)
+    n_top = n_params - n_bottom
+    handle = ll._device.problem.handle
+    lib = _lib.lib()
+    if args.variant >= 0:
+        _lib.check(lib.chi_b200_problem_set_variant(handle, args.variant))
+    if args.shard == 'individuals' and world > 1:
+        ll.set_shard(rank * args.n_ids, (rank + 1) * args.n_ids)
+
+    C = args.chains
+    rng = np.random.default_rng(args.seed + 100 + (
+        rank if args.shard == 'chains' else 0))
+    X_host = _lib.pinned_empty((C, n_params))
+    X_host[:] = prob['x0'][None, :] * (
+        1.0 + 0.01 * rng.normal(size=(C, n_params)))
+    d_x = torch.from_numpy(np.array(X_host)).to(dev)
+    d_score = torch.empty(C, dtype=torch.float64, device=dev)
+    d_grad = torch.zeros(C, n_params, dtype=torch.float64, device=dev)
+    d_status = torch.zeros(C, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32,
+                        device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device():
+        ll.evaluate_device(d_x.data_ptr(), C, True, d_score.data_ptr(),
+                           d_grad.data_ptr(), d_status.data_ptr(),
+                           stream.cuda_stream)
+        if dist is not None and args.shard == 'individuals':
+            packed = torch.cat([d_score[:, None], d_grad[:, n_bottom:]], 1)
+            dist.all_reduce(packed)
+            d_score.copy_(packed[:, 0])
+            d_grad[:, n_bottom:] = packed[:, 1:]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing ------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    ll.set_timing(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches = 0
+    steps_acc = steps_rej = 0
+    counters = np.zeros(4, dtype=np.int64)
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                      # L2 flush, outside the event pair
+        ev[k][0].record(stream)
+        step_device()
+        ev[k][1].record(stream)
+        _lib.check(lib.chi_b200_problem_counters(
+            handle, counters.ctypes.data_as(_lib.c_i64p)))
+        launches += int(counters[3])
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    solve_ms, solve_launches = ll.timings()
+    ll.set_timing(False)
+    if dist is not None:
+        t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    assert int(d_status.max().item()) == 0, 'integrator failures in bench'
+    assert bool(torch.isfinite(d_score).all().item())
+
+    evals = args.steps * C * (world if args.shard == 'chains' else 1)
+    value = evals / (dev_ms * 1e-3)
+
+    # step counters of the last step (host API call gives them)
+    score_h, _ = ll.evaluateS1_batch(np.array(X_host), copy=False)
+    score_h0 = float(score_h[0])
+    cnt = ll.counters()
+    n_sys = int(cnt[0])
+    steps_acc, steps_rej = int(cnt[1]), int(cnt[2])
+
+    # ---- end to end through the public API ---------------------------------
+    for _ in range(max(1, args.warmup)):
+        post.evaluateS1_batch(X_host, copy=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s, g = post.evaluateS1_batch(X_host, copy=False)
+        _ = float(s[0])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = evals / e2e_s
+
+    # ---- roofline of the dominant kernel (solve) -----------------------------
+    info = np.zeros(8, dtype=np.int32)
+    model_id = lib.chi_b200_model_find(prob['model'].model_key().encode())
+    _lib.check(lib.chi_b200_model_info(
+        model_id, info.ctypes.data_as(_lib.c_i32p)))
+    n_states = int(info[0])
+    n_cols = n_states + int(info[1])
+    f_step = flops_per_step(n_states, n_cols, info)
+    n_rec = args.n_obs
+    flops_launch = (steps_acc + steps_rej) * f_step + \
+        n_sys * n_rec * flops_per_record(n_states, n_cols)
+    peak = np.zeros(2)
+    _lib.check(lib.chi_b200_fp64_peak(
+        local_rank, peak[0:1].ctypes.data_as(_lib.c_f64p),
+        peak[1:2].ctypes.data_as(_lib.c_f64p)))
+    solve_avg_ms = solve_ms / max(solve_launches, 1)
+    achieved = flops_launch / (solve_avg_ms * 1e-3) * 1e-12
+    alg_bytes = n_sys * 8 * (2 * (n_cols + 1) + 2) + n_sys * n_rec * 28
+    variants = np.zeros((3, 8), dtype=np.int32)
+    nv = np.zeros(1, dtype=np.int32)
+    lib.chi_b200_model_variants(
+        model_id, nv.ctypes.data_as(_lib.c_i32p),
+        variants[0].ctypes.data_as(_lib.c_i32p),
+        variants[1].ctypes.data_as(_lib.c_i32p), 8)
+    vsel = args.variant if args.variant >= 0 else 0
+    desc = np.zeros(4, dtype=np.int32)
+    lib.chi_b200_model_describe(
+        model_id, local_rank, vsel, desc.ctypes.data_as(_lib.c_i32p))
+    roofline = {
+        'bound': 'fp64', 'achieved': achieved, 'peak': float(peak[0]),
+        'unit': 'TFLOP/s', 'frac': achieved / float(peak[0]),
+        'traffic': None,
+        'peak_source': ('measured in this run: DFMA micro-kernel '
+                        '(chi_b200_fp64_peak); MEASURED_PEAKS.json has no '
+                        'FP64 figure'),
+        'kernel': 'solve_kernel<two-compartment, G=%d, MC=%d>' % (
+            int(variants[0][vsel]), int(variants[1][vsel])),
+        'kernel_ms': solve_avg_ms, 'kernel_share_of_step':
+            solve_ms / dev_ms if dev_ms > 0 else None,
+        'flops_per_step_attempt': f_step,
+        'steps_per_system': (steps_acc + steps_rej) / max(n_sys, 1),
+        'rejected_fraction': steps_rej / max(steps_acc + steps_rej, 1),
+        'registers': int(desc[0]), 'blocks_per_sm': int(desc[2]),
+        'hbm_gbs_algorithmic': alg_bytes / (solve_avg_ms * 1e-3) * 1e-9,
+    }
+
+    # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        data = {
+            'times': prob['times'], 'observations': prob['observations'],
+            'events': [[tuple(r) for r in reg.as_array()]
+                       for reg in prob['regimens']],
+            'prior': prob['log_prior']}
+        cores = os.cpu_count() or 1
+        x = np.array(X_host[0])
+        v = reference_evals_per_second(
+            data, args.rtol, args.atol, x, args.cpu_seconds, cores)
+        ref = ReferencePathCPU(data, args.rtol, args.atol)
+        omp = ref.openmp_systems_per_second(
+            x, min(5.0, args.cpu_seconds), cores) / args.n_ids
+        sc, gc = ref.evaluateS1(x)
+        cpu = {
+            'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': (
+                'evaluateS1 of the same %d-individual model for %.0f s on '
+                '%d processes (one per core): Python loop over individuals, '
+                'one compiled solve with sensitivities per individual, numpy '
+                'error/population models (oracle/stats.py + oracle/csolver)'
+                % (args.n_ids, args.cpu_seconds, cores)),
+            'openmp_no_python_value': omp,
+            'gpu_vs_cpu_score_rel_diff': float(
+                abs(sc - (score_h0 + prob['log_prior'](
+                    x[n_bottom:]))) / abs(sc)),
+        }
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'config': workload_config(args, world),
+            'e2e': {
+                'value': e2e_value, 'unit': UNIT,
+                'h2d_bytes_per_step': int(C * n_params * 8),
+                'd2h_bytes_per_step': int(C * (n_params + 1) * 8 + C * 4),
+                'ms_per_step': e2e_s * 1e3 / args.steps},
+            'gpu_launches': launches,
+            'system_solves_per_s': value * n_total if args.shard == 'chains'
+            else value * n_total,
+            'wall_ms_per_step_incl_flush': t_wall * 1e3 / args.steps,
+            'clocks': clocks, 'roofline': roofline,
+        }
+        if cpu is not None:
+            line['cpu_baseline'] = cpu
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    run_product(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

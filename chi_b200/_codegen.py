@@ -184,8 +184,7 @@ class ModelCode(object):
         a('  static constexpr int FLOPS_RHS = %d;' % fl_rhs)
         a('  static constexpr int FLOPS_JAC = %d;' % fl_jac)
         a('  static constexpr int FLOPS_DFDC = %d;' % fl_dfdc)
-        a('  static constexpr int FLOPS_HESS = %d;' % (
-            0 if self.linear else fl_hess))
+        a('  static constexpr int FLOPS_HESS = %d;' % fl_hess)
         a('  static const char* key() { return "%s"; }' % self.key)
         a('  CHI_HD static void rhs(const double* y, const double* c, '
           'double u, double* f) {')

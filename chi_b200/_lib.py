@@ -179,6 +179,34 @@ def out_i32(shape):
     return a, a.ctypes.data_as(c_i32p)
 
 
+class _PinnedBlock(object):
+    def __init__(self, nbytes):
+        self.ptr = c_vp()
+        check(lib().chi_b200_host_alloc(ctypes.byref(self.ptr), int(nbytes)))
+
+    def __del__(self):
+        try:
+            if self.ptr.value:
+                lib().chi_b200_host_free(self.ptr)
+        except Exception:  # pragma: no cover
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array backed by page-locked host memory (cudaHostAlloc), so the
+    library's cudaMemcpyAsync calls are true asynchronous DMA transfers."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    block = _PinnedBlock(max(n * dtype.itemsize, 8))
+    buf = (ctypes.c_char * (n * dtype.itemsize)).from_address(block.ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+    _pinned_owner[id(arr)] = (arr, block)
+    return arr
+
+
+_pinned_owner = {}
+
+
 class Problem(object):
     """Owner of one ``chi_b200_problem`` handle."""
 

@@ -468,15 +468,30 @@ class HierarchicalLogLikelihood(object):
             ids.append(_id)
 
     # -- evaluation ------------------------------------------------------------
+    def _host_buffers(self, C, with_grad):
+        """Page-locked result buffers, reused across calls."""
+        cache = getattr(self, '_pinned', None)
+        if cache is None or cache[0] < C or (with_grad and cache[3] is None):
+            score = _lib.pinned_empty((C,))
+            status = _lib.pinned_empty((C,), np.int32)
+            grad = _lib.pinned_empty((C, self._n_parameters)) \
+                if with_grad else (cache[3] if cache and cache[0] >= C
+                                   else None)
+            cache = (C, score, status, grad)
+            self._pinned = cache
+        _, score, status, grad = cache
+        return score[:C], status[:C], (grad[:C] if grad is not None else None)
+
     def _evaluate(self, X, with_grad):
         X = np.ascontiguousarray(X, dtype=float).reshape(
             -1, self._n_parameters)
         C = X.shape[0]
         lib = _lib.lib()
         a_x, p_x = _lib.f64(X)
-        score, p_s = _lib.out_f64(C)
-        grad, p_g = _lib.out_f64((C, self._n_parameters))
-        status, p_st = _lib.out_i32(C)
+        score, status, grad = self._host_buffers(C, with_grad)
+        p_s = score.ctypes.data_as(_lib.c_f64p)
+        p_st = status.ctypes.data_as(_lib.c_i32p)
+        p_g = grad.ctypes.data_as(_lib.c_f64p) if with_grad else None
         _lib.check(lib.chi_b200_hier_logpdf(
             self._device.problem.handle, C, p_x, 1 if with_grad else 0, p_s,
             p_g if with_grad else None, p_st))
@@ -485,13 +500,18 @@ class HierarchicalLogLikelihood(object):
             score[status != 0] = -np.inf
         return score, grad, status
 
-    def evaluate_batch(self, X):
-        """Scores of many parameter vectors, shape ``(n_vectors,)``."""
-        return self._evaluate(X, False)[0]
+    def evaluate_batch(self, X, copy=True):
+        """Scores of many parameter vectors, shape ``(n_vectors,)``.  With
+        ``copy=False`` the returned array is the page-locked result buffer,
+        valid until the next evaluation."""
+        score = self._evaluate(X, False)[0]
+        return score.copy() if copy else score
 
-    def evaluateS1_batch(self, X):
+    def evaluateS1_batch(self, X, copy=True):
         """Scores and gradients of many parameter vectors."""
         score, grad, _ = self._evaluate(X, True)
+        if copy:
+            return score.copy(), grad.copy()
         return score, grad
 
     def __call__(self, parameters):
@@ -502,6 +522,37 @@ class HierarchicalLogLikelihood(object):
         """chi/_log_pdfs.py:255-300."""
         score, grad, _ = self._evaluate(np.asarray(parameters), True)
         return float(score[0]), grad[0].copy()
+
+    def evaluate_device(self, d_x, n_vectors, with_grad, d_score, d_grad,
+                        d_status, stream=0):
+        """Evaluates ``n_vectors`` parameter vectors that are already
+        resident on the device.  All arguments are raw device pointers
+        (ints), ``stream`` a ``cudaStream_t``; nothing is copied and the call
+        does not synchronise."""
+        _lib.check(_lib.lib().chi_b200_hier_logpdf_dev(
+            self._device.problem.handle, int(n_vectors), int(d_x),
+            1 if with_grad else 0, int(d_score),
+            int(d_grad) if with_grad else None, int(d_status),
+            int(stream) if stream else None))
+
+    def set_shard(self, id_begin, id_end):
+        """Restricts evaluation to individuals ``[id_begin, id_end)``; the
+        returned score and top-level gradient are then partial sums that the
+        caller all-reduces over the ranks (multi-GPU)."""
+        _lib.check(_lib.lib().chi_b200_problem_set_shard(
+            self._device.problem.handle, int(id_begin), int(id_end)))
+
+    def set_timing(self, enabled):
+        _lib.check(_lib.lib().chi_b200_problem_set_timing(
+            self._device.problem.handle, 1 if enabled else 0))
+
+    def timings(self):
+        """(sum of solve-kernel milliseconds, launches) since timing was
+        enabled."""
+        out = np.zeros(2)
+        _lib.check(_lib.lib().chi_b200_problem_timings(
+            self._device.problem.handle, out.ctypes.data_as(_lib.c_f64p)))
+        return float(out[0]), int(out[1])
 
     def counters(self):
         """systems, accepted steps, rejected steps, kernel launches of the
@@ -606,19 +657,21 @@ class HierarchicalLogPosterior(_LogPDFBase):
         sensitivities[self._n_bottom:] += sens
         return score, sensitivities
 
-    def evaluate_batch(self, X):
+    def evaluate_batch(self, X, copy=True):
         """Batched ``__call__``: the prior is evaluated per vector on the
         host (top-level slice only), all likelihoods in one GPU pass."""
         X = np.asarray(X, dtype=float).reshape(-1, self._n_parameters)
         prior = np.array([self._log_prior(x[self._n_bottom:]) for x in X])
-        score = self._log_likelihood.evaluate_batch(X)
+        score = self._log_likelihood.evaluate_batch(X, copy=False)
         score = prior + score
         score[np.isinf(prior)] = prior[np.isinf(prior)]
         return score
 
-    def evaluateS1_batch(self, X):
+    def evaluateS1_batch(self, X, copy=True):
+        """Batched ``evaluateS1``.  With ``copy=False`` the results are views
+        of the page-locked result buffers (valid until the next call)."""
         X = np.asarray(X, dtype=float).reshape(-1, self._n_parameters)
-        score, grad = self._log_likelihood.evaluateS1_batch(X)
+        score, grad = self._log_likelihood.evaluateS1_batch(X, copy=False)
         for c, x in enumerate(X):
             p, s = self._log_prior.evaluateS1(x[self._n_bottom:])
             if np.isinf(p):
@@ -627,6 +680,8 @@ class HierarchicalLogPosterior(_LogPDFBase):
                 continue
             score[c] += p
             grad[c, self._n_bottom:] += s
+        if copy:
+            return score.copy(), grad.copy()
         return score, grad
 
     def get_log_likelihood(self):

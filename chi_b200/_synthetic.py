@@ -96,6 +96,8 @@ def two_compartment_problem(n_ids, seed=0, n_obs=10, n_doses=1,
     population_model = chi_b200.ComposedPopulationModel([
         chi_b200.PooledModel(n_dim=2), middle,
         chi_b200.PooledModel(n_dim=len(sig))])
+    population_model.set_dim_names(
+        model.parameters() + error_model.get_parameter_names())
 
     # synthesise observations with the product's batched simulate
     psi = np.hstack([np.zeros((n_ids, 2)), psi_mid])

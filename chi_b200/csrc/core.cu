@@ -130,7 +130,7 @@ struct chi_b200_problem {
 
   // scratch
   DevBuf x, ll, grad, status, nst, nrj, ids, traj_off, traj_y, traj_s;
-  DevBuf hx, hscore, hgrad, hstatus, partial, popflag;
+  DevBuf hx, hscore, hgrad, hstatus, partial, popflag, r2t;
   int64_t counters[4] = {0, 0, 0, 0};
 
   // optional device timing of the solve kernel (bench / roofline)
@@ -643,7 +643,7 @@ void chi_b200_problem_destroy(chi_b200_problem* p) {
         &p->seg_off, &p->seg_t, &p->seg_rate, &p->covariates, &p->x, &p->ll,
         &p->grad, &p->status, &p->nst, &p->nrj, &p->ids, &p->traj_off,
         &p->traj_y, &p->traj_s, &p->hx, &p->hscore, &p->hgrad, &p->hstatus,
-        &p->partial, &p->popflag})
+        &p->partial, &p->popflag, &p->r2t})
     b->release();
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
@@ -1235,8 +1235,7 @@ int chi_b200_population_set(chi_b200_problem* p, int32_t n_blocks,
     std::vector<double> cv(covariates, covariates + p->n_ids * c0);
     CUDA_TRY(upload(p->covariates, cv));
   }
-  // red_to_top lives at the tail of the partial buffer's sibling: keep a
-  // dedicated device copy in popflag's neighbour (small)
+  CUDA_TRY(upload(p->r2t, p->red_to_top));
   p->has_pop = true;
   return 0;
 }
@@ -1277,16 +1276,11 @@ int run_hier(chi_b200_problem* p, int32_t C, const double* d_x,
   if (with_grad) CUDA_TRY(p->grad.reserve(B * nd * sizeof(double)));
   const int64_t n_blk = (n_sh + POP_BLOCK - 1) / POP_BLOCK;
   const int n_slots = 1 + D.n_red;
-  // partial buffer: [C][n_blk][n_slots] doubles, then red_to_top (int32)
-  const size_t partial_bytes = static_cast<size_t>(C) * n_blk * n_slots * sizeof(double);
-  const size_t r2t_bytes = std::max<size_t>(D.n_red, 1) * sizeof(int32_t);
-  CUDA_TRY(p->partial.reserve(partial_bytes + r2t_bytes));
-  int32_t* d_r2t = reinterpret_cast<int32_t*>(
-      static_cast<char*>(p->partial.ptr) + partial_bytes);
-  if (D.n_red > 0)
-    CUDA_TRY(cudaMemcpyAsync(d_r2t, p->red_to_top.data(),
-                             D.n_red * sizeof(int32_t),
-                             cudaMemcpyHostToDevice, s));
+  // partial buffer: [C][n_blk][n_slots] doubles
+  const size_t partial_bytes =
+      static_cast<size_t>(C) * n_blk * n_slots * sizeof(double);
+  CUDA_TRY(p->partial.reserve(partial_bytes));
+  const int32_t* d_r2t = p->r2t.as<int32_t>();
   CUDA_TRY(p->popflag.reserve(C * sizeof(int32_t)));
   CUDA_TRY(cudaMemsetAsync(p->popflag.ptr, 0, C * sizeof(int32_t), s));
 

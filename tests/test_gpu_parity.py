@@ -410,14 +410,18 @@ def test_hierarchical_log_posterior_matches_oracle(error, covariates):
     ref0 = stats.posterior_call(
         lay, lambda i, p: fns[i][0](p), prob['log_prior'], x,
         prob['covariates'])
-    assert post(x) == pytest.approx(ref0, rel=1e-8)
-    # batched entry points agree with the per-vector calls
+    score0 = post(x)
+    assert score0 == pytest.approx(ref0, rel=1e-8)
+    # batched entry points agree with the per-vector calls (the forward-only
+    # and the sensitivity kernels take different steps, so they agree with
+    # one another only to the integrator tolerance)
     X = np.vstack([x, prob['x0'], x * 1.01])
     scores = post.evaluate_batch(X)
-    assert scores[0] == pytest.approx(score, rel=1e-13)
+    assert scores[0] == pytest.approx(score0, rel=1e-13)
     s1, g1 = post.evaluateS1_batch(X)
+    assert s1[0] == pytest.approx(score, rel=1e-13)
     np.testing.assert_allclose(g1[0], grad, rtol=1e-13)
-    np.testing.assert_allclose(s1, scores, rtol=1e-12)
+    np.testing.assert_allclose(s1, scores, rtol=1e-9)
 
 
 def test_hierarchical_parameter_layout():
