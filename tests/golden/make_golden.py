@@ -1,0 +1,341 @@
+"""Generates tests/golden/*.json from the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference's statistical modules (``chi/_error_models.py``,
+``_population_models.py``, ``_covariate_models.py``, ``_log_pdfs.py``) are
+loaded by path through ``oracle/refload.py`` (stub ``myokit``/``pints``) and
+evaluated on seeded random inputs.  Everything above the ODE solve therefore
+comes from chi's own code.  The ODE solve itself (myokit/CVODES, not
+installed) is replaced by a ``chi.MechanisticModel`` subclass that returns the
+exact solution from ``oracle/ode_exact.py`` -- the same seam the reference's
+own tests use for their toy models (chi/tests/test_log_pdfs.py:18-113).
+
+Files written:
+  stats_golden.json  error models and population models
+  hier_golden.json   LogLikelihood / HierarchicalLogPosterior (configs C1,
+                     C2, C5 at small sizes), keyed by parameter name
+"""
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ode_exact, refload  # noqa: E402
+
+warnings.simplefilter('ignore')
+chi = refload.load()
+import pints  # noqa: E402  (the stub registered by refload)
+
+
+def tolist(a):
+    return np.asarray(a, dtype=float).tolist()
+
+
+# --------------------------------------------------------------------------
+# error models
+# --------------------------------------------------------------------------
+
+def error_model_cases(rng):
+    models = [
+        ('gaussian', chi.GaussianErrorModel(), 1),
+        ('lognormal', chi.LogNormalErrorModel(), 1),
+        ('cam', chi.ConstantAndMultiplicativeGaussianErrorModel(), 2),
+        ('multiplicative', chi.MultiplicativeGaussianErrorModel(), 1)]
+    out = []
+    for kind, em, n_sig in models:
+        for n_obs, n_par in [(1, 1), (6, 3), (25, 9)]:
+            ybar = rng.uniform(0.5, 3.0, n_obs)
+            obs = rng.uniform(0.5, 3.0, n_obs)
+            sens = rng.normal(size=(n_obs, n_par))
+            sigma = rng.uniform(0.1, 1.0, n_sig)
+            ll, grad = em.compute_sensitivities(sigma, ybar, sens, obs)
+            out.append({
+                'kind': kind, 'sigma': tolist(sigma), 'ybar': tolist(ybar),
+                'obs': tolist(obs), 'sens': tolist(sens), 'll': float(ll),
+                'grad': tolist(grad),
+                'll_call': float(em.compute_log_likelihood(sigma, ybar, obs)),
+                'pointwise': tolist(
+                    em.compute_pointwise_ll(sigma, ybar, obs))})
+    return out
+
+
+# --------------------------------------------------------------------------
+# population models
+# --------------------------------------------------------------------------
+
+POP_SPECS = [
+    [['pooled', 2], ['lognormal', 5, False], ['pooled', 1]],
+    [['lognormal', 3, True]],
+    [['gaussian', 2, True], ['pooled', 1], ['gaussian', 2, False]],
+    [['hetero', 1], ['lognormal', 2, False], ['pooled', 2]],
+    [['pooled', 2], ['covariate', ['lognormal', 5, False], 2], ['pooled', 2]],
+    [['covariate', ['gaussian', 2, True], 1], ['lognormal', 1, True]],
+    [['covariate', ['lognormal', 2, True], 3], ['hetero', 2]],
+    [['covariate', ['gaussian', 2, False], 2]],
+]
+
+
+def build_ref_population(spec):
+    models = []
+    for b in spec:
+        if b[0] == 'pooled':
+            models.append(chi.PooledModel(n_dim=b[1]))
+        elif b[0] == 'hetero':
+            models.append(chi.HeterogeneousModel(n_dim=b[1]))
+        elif b[0] == 'gaussian':
+            models.append(chi.GaussianModel(n_dim=b[1], centered=b[2]))
+        elif b[0] == 'lognormal':
+            models.append(chi.LogNormalModel(n_dim=b[1], centered=b[2]))
+        else:
+            inner = build_ref_population([b[1]])[0]
+            models.append(chi.CovariatePopulationModel(
+                inner, chi.LinearCovariateModel(n_cov=b[2])))
+    return models
+
+
+def population_cases(rng):
+    out = []
+    n_ids = 5
+    for spec in POP_SPECS:
+        pm = chi.ComposedPopulationModel(build_ref_population(spec))
+        pm.set_n_ids(n_ids)
+        n_b, n_t = pm.n_hierarchical_parameters(n_ids)
+        n_cov = pm.n_covariates()
+        cov = rng.normal(size=(n_ids, n_cov)) if n_cov else None
+        names = pm.get_parameter_names()
+        top = rng.uniform(0.2, 1.5, n_t)
+        for i, name in enumerate(names):
+            if 'Cov.' in name:
+                top[i] *= 0.05
+        bottom = rng.uniform(0.3, 2.0, n_b)
+        eta = pm.compute_individual_parameters(
+            top, bottom, cov, return_eta=True)
+        psi = pm.compute_individual_parameters(top, eta, cov)
+        score = pm.compute_log_likelihood(top, eta, cov)
+        dlp = rng.normal(size=(n_ids, pm.n_dim()))
+        s1, grad = pm.compute_sensitivities(
+            top, eta, dlogp_dpsi=dlp, reduce=True, covariates=cov)
+        selections = []
+        for m in pm.get_population_models():
+            if isinstance(m, chi.CovariatePopulationModel):
+                pidx, didx = \
+                    m._covariate_model.get_set_population_parameters()
+                selections.append([tolist(pidx), tolist(didx)])
+        out.append({
+            'spec': spec, 'n_ids': n_ids, 'names': names,
+            'selections': selections,
+            'covariates': None if cov is None else tolist(cov),
+            'top': tolist(top), 'bottom': tolist(bottom),
+            'eta': tolist(eta), 'psi': tolist(psi), 'score': float(score),
+            'dlogp_dpsi': tolist(dlp), 'score_s1': float(s1),
+            'grad': tolist(grad), 'n_bottom': int(n_b), 'n_top': int(n_t),
+            'special_dims': [list(map(lambda v: int(v) if not isinstance(
+                v, bool) else v, e)) for e in pm.get_special_dims()[0]]})
+    return out
+
+
+# --------------------------------------------------------------------------
+# log-pdfs on top of the exact ODE solution
+# --------------------------------------------------------------------------
+
+class ExactModel(chi.MechanisticModel):
+    """chi.MechanisticModel whose simulate returns the exact ODE solution."""
+
+    def __init__(self, omodel, events):
+        super(ExactModel, self).__init__()
+        self._m = omodel
+        self._events = events
+        self._sens = False
+
+    def copy(self):
+        return ExactModel(self._m, self._events)
+
+    def enable_sensitivities(self, enabled, parameter_names=None):
+        self._sens = bool(enabled)
+
+    def has_sensitivities(self):
+        return self._sens
+
+    def n_outputs(self):
+        return len(self._m.outputs)
+
+    def n_parameters(self):
+        return self._m.P
+
+    def outputs(self):
+        return list(self._m.outputs)
+
+    def parameters(self):
+        return list(self._m.parameter_names)
+
+    def simulate(self, parameters, times):
+        return ode_exact.simulate(
+            self._m, parameters, times, self._events,
+            sensitivities=self._sens)
+
+
+class IndependentPrior(pints.LogPrior):
+    """Independent Gaussian (kind 0) / log-normal (kind 1) priors."""
+
+    def __init__(self, kinds, locs, scales):
+        self.kinds, self.locs, self.scales = kinds, locs, scales
+
+    def n_parameters(self):
+        return len(self.kinds)
+
+    def evaluateS1(self, x):
+        score = 0.0
+        grad = np.zeros(len(x))
+        for k, (kind, m, s) in enumerate(
+                zip(self.kinds, self.locs, self.scales)):
+            if kind == 0:
+                z = (x[k] - m) / s
+                score += -0.5 * np.log(2 * np.pi) - np.log(s) - 0.5 * z * z
+                grad[k] = -z / s
+            else:
+                z = (np.log(x[k]) - m) / s
+                score += -0.5 * np.log(2 * np.pi) - np.log(s) \
+                    - np.log(x[k]) - 0.5 * z * z
+                grad[k] = -(1 + z / s) / x[k]
+        return score, grad
+
+    def __call__(self, x):
+        return self.evaluateS1(x)[0]
+
+
+def c1_case(rng):
+    """config C1: one-compartment PK, bolus, Gaussian error, 100 times."""
+    omodel = ode_exact.one_compartment(True)
+    events = [(10 / 0.01, 0.0, 0.01, 0.0, 0.0)]
+    times = np.linspace(0.1, 10, 100)
+    psi = np.array([0.0, 2.0, 1.0])
+    y = ode_exact.simulate(omodel, psi, times, events, False)[0]
+    obs = y + 0.1 * rng.normal(size=len(y))
+    ll = chi.LogLikelihood(
+        ExactModel(omodel, events), chi.GaussianErrorModel(), obs, times)
+    prior = IndependentPrior([1, 1, 1, 1], [0.0, np.log(2), 0.0, np.log(.1)],
+                             [1.0, 0.5, 0.5, 0.5])
+    post = chi.LogPosterior(ll, prior)
+    x = np.array([0.3, 2.2, 0.9, 0.12])
+    score, grad = post.evaluateS1(x)
+    return {
+        'model': 'one_compartment_pk_model', 'direct': True,
+        'output': 'central.drug_concentration', 'error': 'gaussian',
+        'events': [list(e) for e in events], 'times': tolist(times),
+        'obs': tolist(obs), 'names': ll.get_parameter_names(),
+        'prior': [prior.kinds, tolist(prior.locs), tolist(prior.scales)],
+        'x': tolist(x), 'score': float(score), 'grad': tolist(grad),
+        'score_call': float(post(x))}
+
+
+def hier_case(rng, n_ids, error, covariates):
+    """configs C2 / C5 at small size."""
+    omodel = ode_exact.two_compartment(True)
+    mu_log = np.log([2.0, 1.0, 5.0, 1.0, 10.0])
+    sigma_log = np.full(5, 0.3)
+    times, events, obs_all = [], [], []
+    eta = rng.normal(size=(n_ids, 5))
+    if error == 'lognormal':
+        em = chi.LogNormalErrorModel()
+        sig = [0.1]
+    else:
+        em = chi.ConstantAndMultiplicativeGaussianErrorModel()
+        sig = [0.05, 0.1]
+    lls = []
+    for i in range(n_ids):
+        t = np.sort(rng.uniform(0.25, 24.0, 8))
+        ev = [(rng.uniform(5, 15) / 1.0, 0.0, 1.0, 8.0, 3.0)]
+        psi = np.concatenate(
+            [[0.0, 0.0], np.exp(mu_log + sigma_log * eta[i])])
+        y = ode_exact.simulate(omodel, psi, t, ev, False)[0]
+        if error == 'lognormal':
+            obs = y * rng.lognormal(-0.005, 0.1, size=len(y))
+        else:
+            obs = np.abs(y + (0.05 + 0.1 * y) * rng.normal(size=len(y)))
+        ll = chi.LogLikelihood(ExactModel(omodel, ev), em, obs, t)
+        ll.set_id('id %d' % i)
+        lls.append(ll)
+        times.append(tolist(t))
+        events.append([list(e) for e in ev])
+        obs_all.append(tolist(obs))
+    names = lls[0].get_parameter_names()
+    if covariates:
+        middle = chi.CovariatePopulationModel(
+            chi.LogNormalModel(n_dim=5, centered=False),
+            chi.LinearCovariateModel(n_cov=2))
+        X = rng.normal(size=(n_ids, 2))
+    else:
+        middle = chi.LogNormalModel(n_dim=5, centered=False)
+        X = None
+    pm = chi.ComposedPopulationModel(
+        [chi.PooledModel(2), middle, chi.PooledModel(len(sig))])
+    pm.set_dim_names(names)
+    hll = chi.HierarchicalLogLikelihood(lls, pm, covariates=X)
+    top_names = hll.get_parameter_names(exclude_bottom_level=True)
+    n_top = len(top_names)
+    top = np.zeros(n_top)
+    kinds, locs, scales = [], [], []
+    for k, name in enumerate(top_names):
+        if 'Cov.' in name:
+            top[k] = 0.03 * rng.normal()
+            kinds.append(0), locs.append(0.0), scales.append(0.5)
+        elif name.startswith('Log mean'):
+            d = names.index(name[len('Log mean '):]) - 2
+            top[k] = mu_log[d]
+            kinds.append(0), locs.append(mu_log[d]), scales.append(1.0)
+        elif name.startswith('Log std.'):
+            top[k] = 0.3
+            kinds.append(1), locs.append(np.log(0.3)), scales.append(0.5)
+        elif 'Sigma' in name:
+            s = sig[0] if ('log' in name or 'base' in name) else sig[-1]
+            top[k] = s
+            kinds.append(1), locs.append(np.log(s)), scales.append(0.5)
+        else:  # pooled initial amounts
+            top[k] = 0.05
+            kinds.append(0), locs.append(0.0), scales.append(1.0)
+    prior = IndependentPrior(kinds, locs, scales)
+    post = chi.HierarchicalLogPosterior(hll, prior)
+    x = np.concatenate([eta.reshape(-1), top])
+    x = x * (1 + 0.02 * rng.normal(size=len(x)))
+    score, grad = post.evaluateS1(x)
+    return {
+        'model': 'two_compartment_pk_model', 'direct': True,
+        'output': 'central.drug_concentration', 'error': error,
+        'n_ids': n_ids, 'times': times, 'events': events, 'obs': obs_all,
+        'covariates': None if X is None else tolist(X),
+        'll_names': names,
+        'names': post.get_parameter_names(include_ids=True),
+        'top_names': top_names,
+        'prior': [kinds, tolist(locs), tolist(scales)],
+        'x': tolist(x), 'score': float(score), 'grad': tolist(grad),
+        'score_call': float(post(x))}
+
+
+def main():
+    rng = np.random.default_rng(20240607)
+    stats_golden = {
+        'error_models': error_model_cases(rng),
+        'population_models': population_cases(rng)}
+    with open(os.path.join(HERE, 'stats_golden.json'), 'w') as f:
+        json.dump(stats_golden, f)
+    hier_golden = {
+        'c1': c1_case(rng),
+        'c2': hier_case(rng, 6, 'lognormal', False),
+        'c5': hier_case(rng, 5, 'cam', True)}
+    with open(os.path.join(HERE, 'hier_golden.json'), 'w') as f:
+        json.dump(hier_golden, f)
+    print('wrote', os.path.join(HERE, 'stats_golden.json'),
+          os.path.join(HERE, 'hier_golden.json'))
+
+
+if __name__ == '__main__':
+    main()

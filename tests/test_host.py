@@ -1,0 +1,316 @@
+"""Host-side logic and the C-ABI library without a GPU."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import chi_b200
+from chi_b200 import _build, _codegen, _lib, _library, _sbml
+from oracle import cport, ode_exact
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE = '/root/reference'
+
+
+def test_library_exports_every_declared_symbol(native_lib):
+    with open(os.path.join(ROOT, 'include', 'chi_b200.h')) as f:
+        header = f.read()
+    declared = set(re.findall(r'\b(chi_b200_[a-z0-9_]+)\s*\(', header))
+    declared.discard('chi_b200_problem')
+    assert declared == set(_lib.exported_symbols())
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert native_lib.chi_b200_abi_version() == 1
+
+
+def test_registry_holds_all_builtin_models(native_lib):
+    with open(os.path.join(_build.GEN, 'index.json')) as f:
+        index = json.load(f)
+    assert native_lib.chi_b200_n_models() >= len(index) == 11
+    for key, info in index.items():
+        idx = native_lib.chi_b200_model_find(key.encode())
+        assert idx >= 0
+        out = np.zeros(8, dtype=np.int32)
+        assert native_lib.chi_b200_model_info(
+            idx, out.ctypes.data_as(_lib.c_i32p)) == 0
+        assert out[0] == len(info['states'])
+        assert out[1] == len(info['constants'])
+        assert out[2] == len(info['outputs'])
+        assert bool(out[3]) == info['linear']
+
+
+def test_generated_sources_are_up_to_date():
+    """The committed gen/*.cuh equal what the code generator emits."""
+    for name, admin, model in _library.builtin_variants():
+        code = _codegen.ModelCode(model)
+        path = os.path.join(_build.GEN, 'model_%s.cuh' % code.key)
+        with open(path) as f:
+            assert f.read() == code.header(), (name, admin)
+
+
+def test_no_cpu_fallback_without_gpu(native_lib):
+    if native_lib.chi_b200_device_count() > 0:
+        pytest.skip('a GPU is present')
+    model = chi_b200.library.ModelLibrary().one_compartment_pk_model()
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        model.simulate([0, 2, 1], [1.0, 2.0])
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        chi_b200.GaussianErrorModel().compute_log_likelihood(
+            [1.0], [1.0], [1.0])
+    pm = chi_b200.LogNormalModel(2)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        pm.compute_log_likelihood([0.1, 0.2, 1, 1], np.ones((3, 2)))
+
+
+def test_parameter_names_and_order():
+    """chi/tests/test_mechanistic_models.py:127-142, 451-481."""
+    lib = chi_b200.library.ModelLibrary()
+    m = lib.tumour_growth_inhibition_model_koch()
+    assert m.parameters() == [
+        'global.tumour_volume', 'global.drug_concentration', 'global.kappa',
+        'global.lambda_0', 'global.lambda_1']
+    assert m.outputs() == ['global.tumour_volume']
+    assert m.n_parameters() == 5 and m.n_outputs() == 1
+    assert not m.supports_dosing()
+    m = lib.one_compartment_pk_model()
+    assert m.outputs() == ['central.drug_concentration']
+    assert m.parameters() == [
+        'central.drug_amount', 'central.size', 'global.elimination_rate']
+    m.set_administration(compartment='central')
+    assert m.parameters() == [
+        'central.drug_amount', 'central.size', 'global.elimination_rate']
+    m.set_administration(compartment='central', direct=False)
+    assert m.parameters() == [
+        'central.drug_amount', 'dose.drug_amount', 'central.size',
+        'dose.absorption_rate', 'global.elimination_rate']
+    assert m.n_parameters() == 5 and m.supports_dosing()
+    m = lib.erlotinib_tumour_growth_inhibition_model()
+    assert m.parameters() == [
+        'central.drug_amount', 'global.tumour_volume', 'central.size',
+        'global.critical_volume', 'global.elimination_rate', 'global.kappa',
+        'global.lambda']
+
+
+def test_administration_and_dosing_regimen_api():
+    """chi/tests/test_mechanistic_models.py:483-593."""
+    m = chi_b200.library.ModelLibrary().one_compartment_pk_model()
+    with pytest.raises(ValueError, match='The route of administration'):
+        m.set_dosing_regimen(dose=1)
+    with pytest.raises(ValueError, match='The model does not'):
+        m.set_administration(compartment='SOME COMP')
+    with pytest.raises(ValueError, match='The drug amount variable'):
+        m.set_administration(compartment='central', amount_var='SOME VAR')
+    with pytest.raises(ValueError, match='The variable <'):
+        m.set_administration(
+            compartment='central', amount_var='drug_concentration')
+    m.set_administration(compartment='central')
+    m.set_dosing_regimen(1, 5)
+    (e,) = m.dosing_regimen().events()
+    assert (e.level(), e.start(), e.period(), e.duration(),
+            e.multiplier()) == (100.0, 5, 0, 0.01, 0)
+    m.set_dosing_regimen(1, 5, 1)
+    (e,) = m.dosing_regimen().events()
+    assert (e.level(), e.duration()) == (1.0, 1)
+    m.set_dosing_regimen(1, 5, period=1)
+    (e,) = m.dosing_regimen().events()
+    assert (e.period(), e.multiplier()) == (1, 0)
+    m.set_dosing_regimen(10, 3, 0.01, 5, 4)
+    (e,) = m.dosing_regimen().events()
+    assert (e.level(), e.start(), e.period(), e.multiplier()) == (
+        1000.0, 3, 5, 4)
+    regimen = chi_b200.blocktrain(period=1, duration=0.1, limit=1)
+    m.set_dosing_regimen(regimen)
+    (e,) = m.dosing_regimen().events()
+    assert (e.level(), e.start(), e.period(), e.duration(),
+            e.multiplier()) == (1, 0, 1, 0.1, 1)
+    assert m.administration() == {'compartment': 'central', 'direct': True}
+
+
+def test_outputs_sensitivities_and_copy_semantics():
+    """Setting outputs / administration disables sensitivities
+    (chi/tests/test_mechanistic_models.py:405-438); copy resets them."""
+    m = chi_b200.library.ModelLibrary().one_compartment_pk_model()
+    m.enable_sensitivities(True)
+    assert m.has_sensitivities()
+    m.set_outputs(['central.drug_amount', 'central.drug_concentration'])
+    assert not m.has_sensitivities() and m.n_outputs() == 2
+    with pytest.raises(KeyError, match='does not exist'):
+        m.set_outputs(['nope.nope'])
+    with pytest.raises(ValueError, match='None of the parameters'):
+        m.enable_sensitivities(True, ['nope'])
+    m.enable_sensitivities(True, ['central.size'])
+    c = m.copy()
+    assert not c.has_sensitivities() and m.has_sensitivities()
+    m.set_output_names({'central.drug_amount': 'A'})
+    assert m.outputs()[0] == 'A'
+    m.set_parameter_names({'central.size': 'V'})
+    assert m.parameters()[1] == 'V'
+    with pytest.raises(TypeError):
+        m.set_parameter_names(['V'])
+
+
+def test_reduced_mechanistic_model_bookkeeping():
+    m = chi_b200.library.ModelLibrary().one_compartment_pk_model()
+    r = chi_b200.ReducedMechanisticModel(m)
+    r.fix_parameters({'central.drug_amount': 0.0})
+    assert r.n_parameters() == 2 and r.n_fixed_parameters() == 1
+    assert r.parameters() == ['central.size', 'global.elimination_rate']
+    r.fix_parameters({'central.drug_amount': None})
+    assert r.n_parameters() == 3
+    with pytest.raises(TypeError):
+        chi_b200.ReducedMechanisticModel('model')
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason='no reference')
+def test_sbml_reader_reproduces_builtin_models():
+    files = {
+        'one_compartment_pk_model':
+            'chi/library/model_library/pk_one_comp.xml',
+        'two_compartment_pk_model':
+            'docs/source/getting_started/code/two_compartment_pk_model.xml',
+        'erlotinib_tumour_growth_inhibition_model':
+            'chi/library/model_library/temporary_full_pkpd_model.xml',
+        'tumour_growth_inhibition_model_koch':
+            'chi/library/model_library/tgi_Koch_2009.xml',
+        'tumour_growth_inhibition_model_koch_reparametrised':
+            'chi/library/model_library/tgi_Koch_2009_reparametrised.xml'}
+    for name, admin, model in _library.builtin_variants():
+        s = _sbml.read_sbml(os.path.join(REFERENCE, files[name]))
+        if admin:
+            state = admin[0] + '.drug_amount'
+            if not admin[1]:
+                state = s.add_dose_compartment(state)
+            s.add_dose_rate(state)
+        assert _codegen.ModelCode(s).key == _codegen.ModelCode(model).key
+    # the docs' compartment-free model: everything lives in `global`
+    s = _sbml.read_sbml(os.path.join(
+        REFERENCE,
+        'docs/source/getting_started/code/one_compartment_pk_model.xml'))
+    assert s.states == ['global.drug_amount']
+    assert sorted(s.constants) == [
+        'global.elimination_rate', 'global.volume']
+    assert list(s.intermediates) == ['global.drug_concentration']
+
+
+def test_population_model_bookkeeping():
+    """SURVEY.md section 8a worked layouts."""
+    pm = chi_b200.ComposedPopulationModel([
+        chi_b200.PooledModel(2), chi_b200.LogNormalModel(5, centered=False),
+        chi_b200.PooledModel(1)])
+    pm.set_n_ids(3)
+    assert pm.n_hierarchical_parameters(3) == (15, 13)
+    assert pm.get_special_dims() == (
+        [[0, 2, 0, 2, True], [7, 8, 12, 13, True]], 3, 0)
+    cpm = chi_b200.ComposedPopulationModel([
+        chi_b200.PooledModel(2),
+        chi_b200.CovariatePopulationModel(
+            chi_b200.LogNormalModel(5, centered=False),
+            chi_b200.LinearCovariateModel(n_cov=2)),
+        chi_b200.PooledModel(2)])
+    cpm.set_n_ids(3)
+    assert cpm.n_hierarchical_parameters(3) == (15, 34)
+    assert cpm.n_covariates() == 2
+    assert len(cpm.get_parameter_names()) == 34
+    het = chi_b200.ComposedPopulationModel([
+        chi_b200.HeterogeneousModel(1), chi_b200.GaussianModel(1)])
+    het.set_n_ids(4)
+    assert het.n_hierarchical_parameters(4) == (4, 6)
+    assert het.get_special_dims() == ([[0, 1, 0, 4, False]], 0, 1)
+    with pytest.raises(TypeError):
+        chi_b200.ComposedPopulationModel(['x'])
+    with pytest.raises(ValueError):
+        chi_b200.LogNormalModel(0)
+
+
+def test_population_sampling_matches_numpy_stream():
+    """sample() draws on the host in the reference's order
+    (chi/_population_models.py:1797-1846, 2678-2732, 793-872)."""
+    pm = chi_b200.ComposedPopulationModel([
+        chi_b200.PooledModel(1), chi_b200.LogNormalModel(2),
+        chi_b200.GaussianModel(1, centered=False)])
+    theta = [3.0, 0.1, 0.2, 0.3, 0.4, 1.0, 2.0]
+    s = pm.sample(theta, n_samples=4, seed=7)
+    rng = np.random.default_rng(7)
+    ref_ln = rng.lognormal(mean=[0.1, 0.2], sigma=[0.3, 0.4], size=(4, 2))
+    ref_g = rng.normal(loc=[0.0], scale=[1.0], size=(4, 1))
+    np.testing.assert_array_equal(s[:, 0], 3.0)
+    np.testing.assert_array_equal(s[:, 1:3], ref_ln)
+    np.testing.assert_array_equal(s[:, 3:], ref_g)
+
+
+def test_error_model_sampling_matches_numpy_stream():
+    """chi/tests/test_error_models.py:284-315 style: seed-pinned draws."""
+    y = np.array([1.0, 2.0, 3.0])
+    s = chi_b200.GaussianErrorModel().sample([0.5], y, n_samples=2, seed=1)
+    ref = y[:, None] + np.random.default_rng(1).normal(0, 0.5, size=(3, 2))
+    np.testing.assert_array_equal(s, ref)
+    s = chi_b200.ConstantAndMultiplicativeGaussianErrorModel().sample(
+        [0.1, 0.2], y, n_samples=2, seed=3)
+    rng = np.random.default_rng(3)
+    b = rng.normal(0, 0.1, size=(3, 2))
+    r = rng.normal(0, 0.2, size=(3, 2))
+    np.testing.assert_array_equal(s, y[:, None] + b + y[:, None] * r)
+    with pytest.raises(ValueError, match='number of provided parameters'):
+        chi_b200.GaussianErrorModel().sample([1, 2], y)
+
+
+def test_log_likelihood_input_validation():
+    """chi/tests/test_log_pdfs.py:1720-1768 message prefixes."""
+    m = chi_b200.library.ModelLibrary().one_compartment_pk_model()
+    em = chi_b200.GaussianErrorModel()
+    with pytest.raises(TypeError, match='The mechanistic model'):
+        chi_b200.LogLikelihood('m', em, [1, 2], [1, 2])
+    with pytest.raises(ValueError, match='One error model has to be'):
+        chi_b200.LogLikelihood(m, [em, em], [1, 2], [1, 2])
+    with pytest.raises(TypeError, match='The error models have to'):
+        chi_b200.LogLikelihood(m, ['e'], [1, 2], [1, 2])
+    with pytest.raises(ValueError, match='Times cannot be negative'):
+        chi_b200.LogLikelihood(m, em, [1, 2], [-1, 2])
+    with pytest.raises(ValueError, match='Times must be increasing'):
+        chi_b200.LogLikelihood(m, em, [1, 2], [2, 1])
+    with pytest.raises(ValueError, match='The observations and times'):
+        chi_b200.LogLikelihood(m, em, [1, 2, 3], [1, 2])
+    ll = chi_b200.LogLikelihood(m, em, [1, 2], [1, 2])
+    assert ll.n_parameters() == 4 and ll.n_observations() == [2]
+    assert ll.get_parameter_names()[-1] == 'Sigma'
+
+
+def test_cpu_port_converges_to_exact_solution():
+    """The host build of the kernel's per-system routine tracks the exact
+    solution as the tolerance tightens (step control sanity, no GPU)."""
+    key = cport.find_key('two_compartment_pk_model', 'central', True)
+    times = np.sort(np.random.default_rng(1).uniform(0.25, 24, 10))
+    reg = [(10.0, 0.0, 1.0, 8.0, 3)]
+    psi = [0, 0, 2, 1, 5, 1, 10]
+    pop = cport.Population(
+        key, ['central.drug_concentration'], None, [times], None, None, [reg])
+    m = ode_exact.two_compartment(True)
+    ye, se = ode_exact.simulate(m, psi, times, reg)
+    prev = None
+    for rtol in (1e-6, 1e-8, 1e-10):
+        y, s, status, nst, nrj = pop.simulate(psi, rtol=rtol, atol=rtol * 0.01)
+        assert status[0] == 0
+        err = np.max(np.abs(y - ye[0]) / np.max(np.abs(ye[0])))
+        scale = np.max(np.abs(se[:, 0, :]), 0)
+        scale[scale == 0] = 1.0   # d/d(central.size) of an amount is zero
+        serr = np.max(np.abs(s - se[:, 0, :]) / scale)
+        assert err < rtol and serr < 2 * rtol
+        assert prev is None or nst[0] > prev
+        prev = nst[0]
+
+
+def test_bench_host_design_matches_synthetic():
+    import bench
+    from chi_b200 import _synthetic
+    t1, e1 = bench.host_design(7, 3, 10, 3)
+    t2, r2 = _synthetic.two_compartment_design(7, 3, 10, 3)
+    for a, b in zip(t1, t2):
+        np.testing.assert_array_equal(a, b)
+    for a, b in zip(e1, r2):
+        np.testing.assert_array_equal(np.array(a), b.as_array())
+    np.testing.assert_array_equal(
+        bench.TWO_CMT_TYPICAL, _synthetic.TWO_CMT_TYPICAL)
