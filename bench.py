@@ -553,8 +553,12 @@ def run_product(args, rank, world, local_rank):
         'peak_source': ('measured in this run: DFMA micro-kernel '
                         '(chi_b200_fp64_peak); MEASURED_PEAKS.json has no '
                         'FP64 figure'),
-        'kernel': 'solve_kernel<two-compartment, G=%d, MC=%d>' % (
-            int(variants[0][vsel]), int(variants[1][vsel])),
+        'kernel': (
+            'solve_stream_kernel<two-compartment, CB=%d> (thread per system, '
+            'columns streamed)' % int(variants[1][vsel])
+            if int(variants[0][vsel]) == 0 else
+            'solve_kernel<two-compartment, G=%d, MC=%d>' % (
+                int(variants[0][vsel]), int(variants[1][vsel]))),
         'kernel_ms': solve_avg_ms, 'kernel_share_of_step':
             solve_ms / dev_ms if dev_ms > 0 else None,
         'flops_per_step_attempt': f_step,

@@ -239,13 +239,14 @@ class ModelCode(object):
         the columns per lane are capped by the state dimension."""
         n, P = self.n, self.n + self.nc
         mc_max = {1: 8, 2: 4, 3: 3}.get(n, 2)
-        out = []
+        # lanes == 0: streamed-columns kernel, `cols` columns per batch
+        out = [(0, 1), (0, 2)]
         for mc in range(min(mc_max, P), 0, -1):
             g = -(-P // mc)
             if g > 32 or any(g == v[0] for v in out):
                 continue
             out.append((g, mc))
-        return out[:4]
+        return out[:5]
 
     def translation_unit(self):
         """Text of the .cu file that instantiates the kernels for this

@@ -63,6 +63,20 @@ constexpr double C65 = -0.6058818238834054e+01;
 
 constexpr double LOG_2PI_HALF = 0.91893853320467274178;
 
+// step-size controller constants
+#ifndef CHI_SAFETY
+#define CHI_SAFETY 0.9f
+#endif
+#ifndef CHI_FACMAX
+#define CHI_FACMAX 5.0f
+#endif
+#ifndef CHI_EDGE_KEEP_H
+#define CHI_EDGE_KEEP_H 0
+#endif
+#ifndef CHI_EDGE_SHRINK
+#define CHI_EDGE_SHRINK 1.0
+#endif
+
 // ---- small dense helpers (fully unrolled, registers only) -----------------
 
 template <int N>
@@ -281,7 +295,8 @@ CHI_HD void solve_system(const SolveArgs& a, const int64_t b, const int sub,
   const int64_t trow = (a.mode == 0) ? a.traj_off[b] : 0;
 
   double t = 0.0;
-  double h = 0.0;        // 0 -> (re)initialise
+  double h = 0.0;
+  double h_full = 0.0;   // last unclipped working step        // 0 -> (re)initialise
   bool after_reject = false;
   int n_acc = 0, n_rej = 0;
   int status = ST_OK;
@@ -362,7 +377,7 @@ CHI_HD void solve_system(const SolveArgs& a, const int64_t b, const int sub,
         ++seg;
         u = a.seg_rate[seg];
         t_edge = (seg + 1 < seg_end) ? a.seg_t[seg + 1] : INFINITY;
-        h = 0.0;
+        h = CHI_EDGE_KEEP_H ? h_full * CHI_EDGE_SHRINK : 0.0;
         continue;
       }
       const double t_stop = fmin(t_rec, t_edge);
@@ -387,6 +402,7 @@ CHI_HD void solve_system(const SolveArgs& a, const int64_t b, const int sub,
 
       // ---- choose the step: hit t_stop exactly ----------------------------
       const double rem = t_stop - t;
+      h_full = h;
       double hs = h;
       bool clipped = false;
       if (rem <= 1.1 * h) {
@@ -485,8 +501,8 @@ CHI_HD void solve_system(const SolveArgs& a, const int64_t b, const int sub,
       if (!(errsq == errsq) || isinf(errsq)) {
         fac = 0.2f;
       } else {
-        fac = 0.9f * fast_powf(fmaxf(errsq, 1e-30f), -0.125f);
-        fac = fminf(fmaxf(fac, 0.2f), 5.0f);
+        fac = CHI_SAFETY * fast_powf(fmaxf(errsq, 1e-30f), -0.125f);
+        fac = fminf(fmaxf(fac, 0.2f), CHI_FACMAX);
       }
       if (accept) {
         t = clipped ? t_stop : t + hs;
@@ -548,9 +564,14 @@ CHI_HD void solve_system(const SolveArgs& a, const int64_t b, const int sub,
   }
 }
 
+}  // namespace chi_b200
+#include "integrator_stream.cuh"
+namespace chi_b200 {
+
 #ifdef __CUDACC__
 
 constexpr int SOLVE_BLOCK = 128;
+constexpr int STREAM_BLOCK = 128;
 
 template <class M, int G, int MC>
 __global__ void __launch_bounds__(SOLVE_BLOCK)
@@ -578,8 +599,42 @@ struct Registrar {
   static inline int32_t cols[NV > 0 ? NV : 1] = {};
   static inline ModelVTable vt = {};
 
+  // Variant<0, CB>: streamed-columns kernel (integrator_stream.cuh)
+  template <int CB>
+  static cudaError_t launch_stream(const SolveArgs& args,
+                                   cudaStream_t stream) {
+    constexpr size_t smem =
+        sizeof(double) * stream_slots<M>() * STREAM_BLOCK;
+    static bool configured = false;
+    if (!configured) {
+      if (smem > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(
+            solve_stream_kernel<M, CB, STREAM_BLOCK>,
+            cudaFuncAttributeMaxDynamicSharedMemorySize,
+            static_cast<int>(smem));
+        if (err != cudaSuccess) return err;
+      }
+      configured = true;
+    }
+    const int64_t blocks = (args.B + STREAM_BLOCK - 1) / STREAM_BLOCK;
+    if (blocks == 0) return cudaSuccess;
+    solve_stream_kernel<M, CB, STREAM_BLOCK>
+        <<<static_cast<unsigned>(blocks), STREAM_BLOCK, smem, stream>>>(args);
+    return cudaGetLastError();
+  }
+
   template <int G, int MC>
   static cudaError_t launch_one(const SolveArgs& args, cudaStream_t stream) {
+    if constexpr (G == 0) {
+      return launch_stream<MC>(args, stream);
+    } else {
+      return launch_lanes<G, MC>(args, stream);
+    }
+  }
+
+  template <int G, int MC>
+  static cudaError_t launch_lanes(const SolveArgs& args,
+                                  cudaStream_t stream) {
     const int64_t spw = 32 / G;
     const int64_t warps = (args.B + spw - 1) / spw;
     const int64_t wpb = SOLVE_BLOCK / 32;
@@ -591,18 +646,19 @@ struct Registrar {
   }
 
   static int pick(const SolveArgs& args, int variant) {
-    if (variant >= 0 && variant < NV &&
-        lanes[variant] * cols[variant] >= args.n_cols)
-      return variant;
+    auto fits = [&](int v) {
+      return lanes[v] == 0 || lanes[v] * cols[v] >= args.n_cols;
+    };
+    if (variant >= 0 && variant < NV && fits(variant)) return variant;
     // default: first variant with enough column slots
     for (int v = 0; v < NV; ++v)
-      if (lanes[v] * cols[v] >= args.n_cols) return v;
+      if (fits(v)) return v;
     return -1;
   }
 
   static cudaError_t launch(const SolveArgs& args, int variant,
                             cudaStream_t stream) {
-    if (!args.with_sens) return launch_one<1, 0>(args, stream);
+    if (!args.with_sens) return launch_lanes<1, 0>(args, stream);
     const int v = pick(args, variant);
     if (v < 0) return cudaErrorInvalidValue;
     cudaError_t err = cudaErrorInvalidValue;
@@ -618,13 +674,34 @@ struct Registrar {
   static cudaError_t describe_one(int* regs, int* block, int* bpsm,
                                   int* local_bytes) {
     cudaFuncAttributes at;
-    cudaError_t err = cudaFuncGetAttributes(&at, solve_kernel<M, G, MC>);
-    if (err != cudaSuccess) return err;
-    *regs = at.numRegs;
-    *block = SOLVE_BLOCK;
-    *local_bytes = static_cast<int>(at.localSizeBytes);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        bpsm, solve_kernel<M, G, MC>, SOLVE_BLOCK, 0);
+    if constexpr (G == 0) {
+      constexpr size_t smem =
+          sizeof(double) * stream_slots<M>() * STREAM_BLOCK;
+      cudaError_t err = cudaFuncGetAttributes(
+          &at, solve_stream_kernel<M, MC, STREAM_BLOCK>);
+      if (err != cudaSuccess) return err;
+      *regs = at.numRegs;
+      *block = STREAM_BLOCK;
+      *local_bytes = static_cast<int>(at.localSizeBytes);
+      if (smem > 48 * 1024) {
+        err = cudaFuncSetAttribute(
+            solve_stream_kernel<M, MC, STREAM_BLOCK>,
+            cudaFuncAttributeMaxDynamicSharedMemorySize,
+            static_cast<int>(smem));
+        if (err != cudaSuccess) return err;
+      }
+      return cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          bpsm, solve_stream_kernel<M, MC, STREAM_BLOCK>, STREAM_BLOCK,
+          smem);
+    } else {
+      cudaError_t err = cudaFuncGetAttributes(&at, solve_kernel<M, G, MC>);
+      if (err != cudaSuccess) return err;
+      *regs = at.numRegs;
+      *block = SOLVE_BLOCK;
+      *local_bytes = static_cast<int>(at.localSizeBytes);
+      return cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          bpsm, solve_kernel<M, G, MC>, SOLVE_BLOCK, 0);
+    }
   }
 
   static cudaError_t describe(int variant, int* regs, int* block, int* bpsm,

@@ -1,0 +1,379 @@
+// chi_b200 -- "streamed columns" variant of the sensitivity solve.
+//
+// Same method and semantics as solve_system<M, G, MC> (integrator.cuh): RODAS4
+// on [y | S] with the exact block-triangular Jacobian, exact hits of dose
+// edges and observation times, fused error model.  What differs is the
+// mapping:
+//
+//   * ONE thread per system (no redundant state column, no shuffles);
+//   * per step the state column runs first and keeps its six stage values
+//     and increments in registers; the sensitivity columns are then streamed
+//     through registers CB at a time (a uniform, non-unrolled loop: every
+//     thread of the block handles column k at the same time, so the loop
+//     adds no divergence and the hot loop stays inside the instruction
+//     cache);
+//   * the sensitivity matrix S (current and candidate) and the gradient
+//     accumulators live in shared memory, slot-major (conflict free):
+//         sm[slot * stride + tid],  slots = 2*P*N + P doubles per thread.
+//
+// Compiles for the host as well (stride = 1, tid = 0) for the CPU port.
+#pragma once
+#include "integrator.cuh"
+
+namespace chi_b200 {
+
+template <class M>
+constexpr int stream_slots() {
+  return 2 * M::P * M::N + M::P;
+}
+
+template <class M, int CB>
+CHI_HD void solve_system_stream(const SolveArgs& a, const int64_t b,
+                                double* sm, const int stride) {
+  using namespace rodas4;
+  constexpr int N = M::N;
+  constexpr int NC = M::NC;
+  constexpr int NCS = M::NCS;
+  constexpr int P = M::P;
+
+  const int id = a.ids ? a.ids[b] : static_cast<int>(b % a.n_ids);
+  const double* xb = a.x + b * a.x_stride;
+  const double* sg = xb + P;
+  const int n_cols = a.with_sens ? a.n_cols : 0;
+  const int n_batches = (n_cols + CB - 1) / CB;
+
+  double y[N], c[NCS];
+#pragma unroll
+  for (int i = 0; i < N; ++i) y[i] = xb[i];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) c[i] = xb[N + i];
+  if (NC == 0) c[0] = 0.0;
+
+  // shared-memory slots: S buffers [2][P][N], gradient accumulators [P]
+  int cur = 0;
+#define CHI_S(buf, k, n) sm[(((buf) * P + (k)) * N + (n)) * stride]
+#define CHI_G(k) sm[(2 * P * N + (k)) * stride]
+  for (int k = 0; k < P; ++k) {
+    const int pk = k < n_cols ? a.col_param[k] : -1;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      CHI_S(0, k, n) = (pk == n) ? 1.0 : 0.0;
+      CHI_S(1, k, n) = 0.0;
+    }
+    CHI_G(k) = 0.0;
+  }
+
+  const bool loglik = a.mode == 1;
+  double ll = 0.0;
+  double dsig[MAX_SIGMA];
+#pragma unroll
+  for (int k = 0; k < MAX_SIGMA; ++k) dsig[k] = 0.0;
+  bool invalid = false;
+  if (loglik) {
+    for (int o = 0; o < a.n_out; ++o) {
+      const int off = a.err_off[o];
+      if (sg[off] <= 0.0) invalid = true;
+      if (a.err_kind[o] == ERR_CAM && sg[off + 1] <= 0.0) invalid = true;
+    }
+  }
+
+  int64_t r = a.rec_off[id];
+  const int64_t r_end = a.rec_off[id + 1];
+  const int64_t r_begin = r;
+  int64_t seg = a.seg_off[id];
+  const int64_t seg_end = a.seg_off[id + 1];
+  double u = (seg < seg_end) ? a.seg_rate[seg] : 0.0;
+  double t_edge = (seg + 1 < seg_end) ? a.seg_t[seg + 1] : INFINITY;
+  const int64_t trow = (a.mode == 0) ? a.traj_off[b] : 0;
+
+  double t = 0.0;
+  double h = 0.0;
+  double h_full = 0.0;   // last unclipped working step
+  bool after_reject = false;
+  int n_acc = 0, n_rej = 0;
+  int status = ST_OK;
+  double J0[N * N];
+  if (M::LINEAR) M::jac(y, c, J0);
+
+  if (!invalid) {
+    while (r < r_end) {
+      const double t_rec = a.rec_t[r];
+      if (t_rec <= t) {
+        // ---- observation record ------------------------------------------
+        const int o = a.rec_out[r];
+        const int oid = a.out_id[o];
+        const double yb = M::out(oid, y, c);
+        double w = 0.0;
+        const int64_t row = trow + (r - r_begin);
+        if (!loglik) {
+          a.traj_y[row] = yb;
+        } else {
+          const int kind = a.err_kind[o];
+          const int off = a.err_off[o];
+          const double yo = a.rec_obs[r];
+          if (kind == ERR_GAUSSIAN) {
+            const double s = sg[off];
+            const double is = 1.0 / s;
+            const double q = (yo - yb) * is;
+            ll -= LOG_2PI_HALF + log(s) + 0.5 * q * q;
+            w = q * is;
+            dsig[off] += (q * q - 1.0) * is;
+          } else if (kind == ERR_LOGNORMAL) {
+            const double s = sg[off];
+            if (yb <= 0.0) invalid = true;
+            const double is = 1.0 / s;
+            const double lo = a.rec_logobs[r];
+            const double q = (lo - log(yb) + 0.5 * s * s) * is;
+            ll -= LOG_2PI_HALF + log(s) + lo + 0.5 * q * q;
+            w = q * is / yb;
+            dsig[off] += -q + (q * q - 1.0) * is;
+          } else {
+            const bool cam = kind == ERR_CAM;
+            const double sb = cam ? sg[off] : 0.0;
+            const double sr = cam ? sg[off + 1] : sg[off];
+            const double st = fma(sr, yb, sb);
+            const double ist = 1.0 / st;
+            const double q = (yo - yb) * ist;
+            ll -= LOG_2PI_HALF + log(st) + 0.5 * q * q;
+            const double q2i = q * q * ist;
+            w = q * ist - sr * ist + sr * q2i;
+            if (cam) {
+              dsig[off] += q2i - ist;
+              dsig[off + 1] += (q2i - ist) * yb;
+            } else {
+              dsig[off] += (q2i - ist) * yb;
+            }
+          }
+        }
+        for (int k = 0; k < n_cols; ++k) {
+          const int pk = a.col_param[k];
+          double s[N], e[NCS];
+#pragma unroll
+          for (int n = 0; n < N; ++n) s[n] = CHI_S(cur, k, n);
+#pragma unroll
+          for (int j = 0; j < NCS; ++j) e[j] = (pk == N + j) ? 1.0 : 0.0;
+          const double dyb = M::dout(oid, y, c, s, e);
+          if (loglik) {
+            CHI_G(k) = fma(w, dyb, CHI_G(k));
+          } else {
+            a.traj_s[row * n_cols + k] = dyb;
+          }
+        }
+        ++r;
+        continue;
+      }
+      if (t_edge <= t) {
+        ++seg;
+        u = a.seg_rate[seg];
+        t_edge = (seg + 1 < seg_end) ? a.seg_t[seg + 1] : INFINITY;
+        h = CHI_EDGE_KEEP_H ? h_full * CHI_EDGE_SHRINK : 0.0;
+        continue;
+      }
+      const double t_stop = fmin(t_rec, t_edge);
+
+      if (h == 0.0) {
+        double f0[N];
+        M::rhs(y, c, u, f0);
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const double sc = a.atol + a.rtol * fabs(y[i]);
+          d0 = fma(y[i] / sc, y[i] / sc, d0);
+          d1 = fma(f0[i] / sc, f0[i] / sc, d1);
+        }
+        d0 = sqrt(d0 / N);
+        d1 = sqrt(d1 / N);
+        h = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        h = fmin(100.0 * h, t_stop - t);
+        after_reject = false;
+      }
+
+      const double rem = t_stop - t;
+      h_full = h;
+      double hs = h;
+      bool clipped = false;
+      if (rem <= 1.1 * h) {
+        hs = rem;
+        clipped = true;
+      } else if (rem < 2.0 * h) {
+        hs = 0.5 * rem;
+      }
+
+      // ---- state column: six stages, values and increments kept ----------
+      if (!M::LINEAR) M::jac(y, c, J0);
+      double Wi[N * N];
+      {
+        double W[N * N];
+        const double fac = 1.0 / (GAMMA * hs);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+          for (int j = 0; j < N; ++j)
+            W[i * N + j] = (i == j ? fac : 0.0) - J0[i * N + j];
+        invert<N>(W, Wi);
+      }
+      const double hinv = 1.0 / hs;
+      double Zy[6][N];
+      double Uy[6][N];
+#define CHI_YSTAGE(I, CNT, a0, a1, a2, a3, a4, c0, c1, c2, c3, c4)           \
+  {                                                                           \
+    double f[N], cy[N], ry[N];                                                \
+    lincomb<CNT, N>(Zy[I], y, Uy, a0, a1, a2, a3, a4);                        \
+    M::rhs(Zy[I], c, u, f);                                                   \
+    lincomb<CNT, N>(cy, nullptr, Uy, c0, c1, c2, c3, c4);                     \
+    _Pragma("unroll") for (int n = 0; n < N; ++n) ry[n] =                     \
+        fma(hinv, cy[n], f[n]);                                               \
+    matvec<N>(Wi, ry, Uy[I]);                                                 \
+  }
+      CHI_YSTAGE(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+      CHI_YSTAGE(1, 1, A21, 0, 0, 0, 0, C21, 0, 0, 0, 0)
+      CHI_YSTAGE(2, 2, A31, A32, 0, 0, 0, C31, C32, 0, 0, 0)
+      CHI_YSTAGE(3, 3, A41, A42, A43, 0, 0, C41, C42, C43, 0, 0)
+      CHI_YSTAGE(4, 4, A51, A52, A53, A54, 0, C51, C52, C53, C54, 0)
+      CHI_YSTAGE(5, 5, A51, A52, A53, A54, 1.0, C61, C62, C63, C64, C65)
+#undef CHI_YSTAGE
+      double yn[N];
+      float errsq;
+      {
+        double s2 = 0.0;
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+          yn[n] = Zy[5][n] + Uy[5][n];
+          const double sc =
+              a.atol + a.rtol * fmax(fabs(y[n]), fabs(yn[n]));
+          const double q = Uy[5][n] / sc;
+          s2 = fma(q, q, s2);
+        }
+        errsq = static_cast<float>(s2 * (1.0 / N));
+      }
+
+      // ---- sensitivity columns, CB at a time --------------------------------
+      const int nxt = 1 - cur;
+      for (int kb = 0; kb < n_batches; ++kb) {
+        double S0[CB][N], Us[CB][6][N], e[CB][NCS];
+#pragma unroll
+        for (int q = 0; q < CB; ++q) {
+          const int k = kb * CB + q;
+          const int pk = k < n_cols ? a.col_param[k] : -1;
+          const int ks = k < P ? k : P - 1;
+#pragma unroll
+          for (int n = 0; n < N; ++n)
+            S0[q][n] = k < n_cols ? CHI_S(cur, ks, n) : 0.0;
+#pragma unroll
+          for (int j = 0; j < NCS; ++j)
+            e[q][j] = (pk == N + j) ? 1.0 : 0.0;
+        }
+#define CHI_SSTAGE(I, CNT, a0, a1, a2, a3, a4, c0, c1, c2, c3, c4)           \
+  {                                                                           \
+    double Ji[N * N];                                                         \
+    if (!M::LINEAR) M::jac(Zy[I], c, Ji);                                     \
+    _Pragma("unroll") for (int q = 0; q < CB; ++q) {                          \
+      double Zs[N], r1[N], r2[N], cs[N], rs[N];                               \
+      lincomb<CNT, N>(Zs, S0[q], Us[q], a0, a1, a2, a3, a4);                  \
+      M::dfdc(Zy[I], c, e[q], r1);                                            \
+      M::hess(y, c, S0[q], e[q], Uy[I], r2);                                  \
+      lincomb<CNT, N>(cs, nullptr, Us[q], c0, c1, c2, c3, c4);                \
+      matvec<N>(M::LINEAR ? J0 : Ji, Zs, rs);                                 \
+      _Pragma("unroll") for (int n = 0; n < N; ++n) rs[n] =                   \
+          fma(hinv, cs[n], rs[n] + r1[n] + r2[n]);                            \
+      matvec<N>(Wi, rs, Us[q][I]);                                            \
+    }                                                                         \
+  }
+        CHI_SSTAGE(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+        CHI_SSTAGE(1, 1, A21, 0, 0, 0, 0, C21, 0, 0, 0, 0)
+        CHI_SSTAGE(2, 2, A31, A32, 0, 0, 0, C31, C32, 0, 0, 0)
+        CHI_SSTAGE(3, 3, A41, A42, A43, 0, 0, C41, C42, C43, 0, 0)
+        CHI_SSTAGE(4, 4, A51, A52, A53, A54, 0, C51, C52, C53, C54, 0)
+        CHI_SSTAGE(5, 5, A51, A52, A53, A54, 1.0, C61, C62, C63, C64, C65)
+#undef CHI_SSTAGE
+#pragma unroll
+        for (int q = 0; q < CB; ++q) {
+          const int k = kb * CB + q;
+          double Sn[N];
+          lincomb<5, N>(Sn, S0[q], Us[q], A51, A52, A53, A54, 1.0);
+          double s2 = 0.0;
+#pragma unroll
+          for (int n = 0; n < N; ++n) {
+            Sn[n] += Us[q][5][n];
+            const double sc =
+                a.atol + a.rtol * fmax(fabs(S0[q][n]), fabs(Sn[n]));
+            const double qq = Us[q][5][n] / sc;
+            s2 = fma(qq, qq, s2);
+          }
+          if (k < n_cols) {
+            errsq = fmaxf(errsq, static_cast<float>(s2 * (1.0 / N)));
+#pragma unroll
+            for (int n = 0; n < N; ++n) CHI_S(nxt, k, n) = Sn[n];
+          }
+        }
+      }
+
+      const bool accept = errsq <= 1.0f;
+      float fac;
+      if (!(errsq == errsq) || isinf(errsq)) {
+        fac = 0.2f;
+      } else {
+        fac = CHI_SAFETY * fast_powf(fmaxf(errsq, 1e-30f), -0.125f);
+        fac = fminf(fmaxf(fac, 0.2f), CHI_FACMAX);
+      }
+      if (accept) {
+        t = clipped ? t_stop : t + hs;
+#pragma unroll
+        for (int n = 0; n < N; ++n) y[n] = yn[n];
+        cur = nxt;
+        if (after_reject) fac = fminf(fac, 1.0f);
+        const double hn = hs * static_cast<double>(fac);
+        h = (hs < h) ? fmax(hn, h) : hn;
+        after_reject = false;
+        ++n_acc;
+      } else {
+        h = hs * static_cast<double>(fminf(fac, 0.9f));
+        after_reject = true;
+        ++n_rej;
+        if (h <= 1e-14 * fmax(fabs(t), 1.0)) {
+          status = (errsq == errsq) ? ST_STEP_UNDERFLOW : ST_NON_FINITE;
+          break;
+        }
+      }
+      if (n_acc + n_rej >= a.max_steps) {
+        status = ST_MAX_STEPS;
+        break;
+      }
+    }
+  }
+
+  a.status[b] = status;
+  if (a.n_steps) a.n_steps[b] = n_acc;
+  if (a.n_rej) a.n_rej[b] = n_rej;
+  if (loglik) {
+    const bool fail = invalid || status != ST_OK;
+    a.ll[b] = fail ? -INFINITY : ll;
+    if (a.with_sens && a.grad) {
+      double* gb = a.grad + b * a.grad_stride;
+      for (int k = 0; k < n_cols; ++k)
+        gb[a.col_param[k]] = fail ? INFINITY : CHI_G(k);
+      for (int k = 0; k < a.n_sigma; ++k)
+        gb[P + k] = fail ? INFINITY : dsig[k];
+    }
+  } else if (status != ST_OK) {
+    for (int64_t q = r; q < r_end; ++q) a.traj_y[trow + (q - r_begin)] = NAN;
+  }
+#undef CHI_S
+#undef CHI_G
+}
+
+#ifdef __CUDACC__
+
+template <class M, int CB, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+solve_stream_kernel(const SolveArgs a) {
+  extern __shared__ double chi_sm[];
+  const int64_t b =
+      static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  solve_system_stream<M, CB>(a, b, chi_sm + threadIdx.x, BLOCK);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace chi_b200

@@ -58,6 +58,9 @@ def lib():
         _lib = ctypes.CDLL(path)
         _lib.chi_port_solve.argtypes = [
             ctypes.c_char_p, ctypes.POINTER(SolveArgs), ctypes.c_int]
+        _lib.chi_port_solve2.argtypes = [
+            ctypes.c_char_p, ctypes.POINTER(SolveArgs), ctypes.c_int,
+            ctypes.c_int]
         assert _lib.chi_port_sizeof_args() == ctypes.sizeof(SolveArgs), (
             _lib.chi_port_sizeof_args(), ctypes.sizeof(SolveArgs))
     return _lib
@@ -163,7 +166,7 @@ class Population(object):
         return a
 
     def loglik(self, x, ids=None, with_grad=True, rtol=1e-8, atol=1e-10,
-               max_steps=100000, n_threads=1):
+               max_steps=100000, n_threads=1, stream_cb=0):
         x = np.ascontiguousarray(x, float)
         if x.ndim == 1:
             x = x[None, :]
@@ -190,13 +193,13 @@ class Population(object):
         a.status = _ptr(status)
         a.n_steps = _ptr(nst)
         a.n_rej = _ptr(nrj)
-        rc = lib().chi_port_solve(self.key.encode(), ctypes.byref(a),
-                                  n_threads)
+        rc = lib().chi_port_solve2(self.key.encode(), ctypes.byref(a),
+                                   n_threads, stream_cb)
         assert rc == 0, rc
         return ll, grad, status, nst, nrj
 
     def simulate(self, psi, ids=None, with_sens=True, rtol=1e-8, atol=1e-10,
-                 max_steps=100000, n_threads=1):
+                 max_steps=100000, n_threads=1, stream_cb=0):
         psi = np.ascontiguousarray(psi, float)
         if psi.ndim == 1:
             psi = psi[None, :]
@@ -225,7 +228,7 @@ class Population(object):
         a.status = _ptr(status)
         a.n_steps = _ptr(nst)
         a.n_rej = _ptr(nrj)
-        rc = lib().chi_port_solve(self.key.encode(), ctypes.byref(a),
-                                  n_threads)
+        rc = lib().chi_port_solve2(self.key.encode(), ctypes.byref(a),
+                                   n_threads, stream_cb)
         assert rc == 0, rc
         return y, s, status, nst, nrj

@@ -24,30 +24,44 @@
 
 using namespace chi_b200;
 
+// stream_cb: 0 = lanes routine (one lane, all columns in "registers"),
+// 1 / 2 = streamed-columns routine with that many columns per batch.
 template <class M>
-static void run_all(const SolveArgs& a, int n_threads) {
+static void run_all(const SolveArgs& a, int n_threads, int stream_cb) {
   (void)n_threads;
 #ifdef _OPENMP
 #pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads)
 #endif
   for (int64_t b = 0; b < a.B; ++b) {
-    if (a.with_sens)
-      solve_system<M, 1, M::P>(a, b, 0, 0, 0, 1u);
-    else
+    if (!a.with_sens) {
       solve_system<M, 1, 0>(a, b, 0, 0, 0, 1u);
+    } else if (stream_cb == 1) {
+      double sm[stream_slots<M>()];
+      solve_system_stream<M, 1>(a, b, sm, 1);
+    } else if (stream_cb == 2) {
+      double sm[stream_slots<M>()];
+      solve_system_stream<M, 2>(a, b, sm, 1);
+    } else {
+      solve_system<M, 1, M::P>(a, b, 0, 0, 0, 1u);
+    }
   }
 }
 
-extern "C" int chi_port_solve(const char* key, const SolveArgs* a,
-                              int n_threads) {
+extern "C" int chi_port_solve2(const char* key, const SolveArgs* a,
+                               int n_threads, int stream_cb) {
 #define CHI_PORT_MODEL(KEY, TYPE)                                            \
   if (std::strcmp(key, KEY) == 0) {                                          \
-    run_all<TYPE>(*a, n_threads);                                            \
+    run_all<TYPE>(*a, n_threads, stream_cb);                                 \
     return 0;                                                                \
   }
   CHI_PORT_MODELS
 #undef CHI_PORT_MODEL
   return -1;
+}
+
+extern "C" int chi_port_solve(const char* key, const SolveArgs* a,
+                              int n_threads) {
+  return chi_port_solve2(key, a, n_threads, 0);
 }
 
 extern "C" int chi_port_sizeof_args(void) { return (int)sizeof(SolveArgs); }
