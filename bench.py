@@ -408,9 +408,11 @@ def run_product(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl')
+        dist.init_process_group(
+            'nccl', device_id=torch.device('cuda', local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    chi_b200.set_default_device(local_rank)
 
     n_total = args.n_ids * (world if args.shard == 'individuals' else 1)
     prob = _synthetic.two_compartment_problem(

@@ -24,5 +24,6 @@ from chi_b200._log_pdfs import (  # noqa: F401
 from chi_b200._priors import (  # noqa: F401
     GaussianLogPrior, LogNormalLogPrior, UniformLogPrior, ComposedLogPrior)
 from chi_b200 import library  # noqa: F401
+from chi_b200._lib import set_default_device  # noqa: F401
 
 __version__ = '0.1.0'

@@ -27,7 +27,7 @@ class ErrorModel(_ErrorModelBase):
 
     _kind = None
     _default_names = None
-    _device = 0
+    _device = None
 
     def __init__(self):
         super(ErrorModel, self).__init__()
@@ -69,8 +69,10 @@ class ErrorModel(_ErrorModelBase):
         pw, p_pw = (None, None)
         if pointwise:
             pw, p_pw = _lib.out_f64(max(n_obs, 1))
+        device = self._device if self._device is not None \
+            else _lib.default_device()
         _lib.check(lib.chi_b200_error_model(
-            self._device, _lib.ERR_KINDS[self._kind], p_sig, n_obs, n_par,
+            device, _lib.ERR_KINDS[self._kind], p_sig, n_obs, n_par,
             p_y, p_s, p_o, 1 if with_grad else 0, p_out, p_pw))
         if pointwise:
             return pw[:n_obs]

@@ -22,6 +22,20 @@ POP_KINDS = {'pooled': 0, 'heterogeneous': 1, 'gaussian': 2, 'lognormal': 3}
 
 _lib = None
 _modules = {}
+_default_device = None
+
+
+def set_default_device(device):
+    """CUDA device used by problems created from now on (one process per
+    GPU: call with LOCAL_RANK)."""
+    global _default_device
+    _default_device = int(device)
+
+
+def default_device():
+    if _default_device is not None:
+        return _default_device
+    return int(os.environ.get('CHI_B200_DEVICE', '0'))
 
 _SIGNATURES = {
     'chi_b200_abi_version': (ctypes.c_int, []),
@@ -210,8 +224,10 @@ _pinned_owner = {}
 class Problem(object):
     """Owner of one ``chi_b200_problem`` handle."""
 
-    def __init__(self, model_id, device=0):
+    def __init__(self, model_id, device=None):
         require_gpu()
+        if device is None:
+            device = default_device()
         self._h = c_vp()
         check(lib().chi_b200_problem_create(
             int(model_id), int(device), ctypes.byref(self._h)))

@@ -59,7 +59,7 @@ class _DeviceLikelihoods(object):
     individual log-likelihoods (one ``chi_b200_problem``)."""
 
     def __init__(self, mechanistic_model, error_kinds, times, observations,
-                 regimens, device=0):
+                 regimens, device=None):
         """times / observations: per individual, per output arrays."""
         if isinstance(mechanistic_model, ReducedMechanisticModel):
             raise NotImplementedError(

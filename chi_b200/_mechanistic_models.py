@@ -157,7 +157,7 @@ class SBMLModel(MechanisticModel):
         self._rtol = DEFAULT_RTOL
         self._atol = DEFAULT_ATOL
         self._max_steps = DEFAULT_MAX_STEPS
-        self._device = 0
+        self._device = None
         self._reset_engine()
         self._set_number_and_names()
 

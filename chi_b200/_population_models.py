@@ -41,7 +41,7 @@ class PopulationModel(_PopulationModelBase):
         self._n_hetero_dims = 0
         self._n_covariates = 0
         self._n_ids = 1
-        self._device = 0
+        self._device = None
         self._dev_cache = None
         if dim_names:
             if len(dim_names) != self._n_dim:
@@ -679,7 +679,7 @@ class ComposedPopulationModel(PopulationModel):
             n_ids = n_ids if n_ids > 1 else pop_model.n_ids()
         self._population_models = population_models
         self._n_ids = n_ids
-        self._device = 0
+        self._device = None
         self._dev_cache = None
         self._n_bottom, self._n_top_cached = self.n_hierarchical_parameters(
             self._n_ids)
