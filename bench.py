@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument('--impl', default='chi_b200',
                     choices=['chi_b200', 'reference'])
     ap.add_argument('--n-ids', type=int, default=1000)
-    ap.add_argument('--chains', type=int, default=128,
+    ap.add_argument('--chains', type=int, default=1024,
                     help='parameter vectors per step and GPU')
     ap.add_argument('--n-doses', type=int, default=3)
     ap.add_argument('--n-obs', type=int, default=10)
@@ -207,7 +207,7 @@ class ReferencePathCPU(object):
     def individual_s1(self, i, x):
         pop = self.pops[i]
         y, s, status, _, _ = pop.simulate(
-            x[:7], rtol=self.rtol, atol=self.atol)
+            x[:7], rtol=self.rtol, atol=self.atol, stream_cb=1)
         return self.stats.lognormal_error_s1(x[7:], y, s, self.obs[i])
 
     def evaluateS1(self, x):
@@ -229,7 +229,7 @@ class ReferencePathCPU(object):
             ids = np.tile(np.arange(self.n_ids, dtype=np.int32), reps)
             t0 = time.perf_counter()
             self.whole.loglik(X, ids=ids, with_grad=True, rtol=self.rtol,
-                              atol=self.atol, n_threads=threads)
+                              atol=self.atol, n_threads=threads, stream_cb=1)
             dt = time.perf_counter() - t0
             t_used += dt
             n_sys += len(X)
@@ -527,7 +527,13 @@ def run_product(args, rank, world, local_rank):
         model_id, info.ctypes.data_as(_lib.c_i32p)))
     n_states = int(info[0])
     n_cols = n_states + int(info[1])
-    f_step = flops_per_step(n_states, n_cols, info)
+    import ctypes
+    inert = ctypes.c_uint32(0)
+    _lib.check(lib.chi_b200_model_inert_mask(model_id, ctypes.byref(inert)))
+    n_inert = bin(inert.value).count('1')
+    # sensitivity columns of constants that do not enter the rhs are
+    # identically zero and are not integrated: they are not counted either
+    f_step = flops_per_step(n_states, n_cols - n_inert, info)
     n_rec = args.n_obs
     flops_launch = (steps_acc + steps_rej) * f_step + \
         n_sys * n_rec * flops_per_record(n_states, n_cols)
@@ -564,6 +570,7 @@ def run_product(args, rank, world, local_rank):
         'kernel_ms': solve_avg_ms, 'kernel_share_of_step':
             solve_ms / dev_ms if dev_ms > 0 else None,
         'flops_per_step_attempt': f_step,
+        'sensitivity_columns_integrated': n_cols - n_inert,
         'steps_per_system': (steps_acc + steps_rej) / max(n_sys, 1),
         'rejected_fraction': steps_rej / max(steps_acc + steps_rej, 1),
         'registers': int(desc[0]), 'blocks_per_sm': int(desc[2]),

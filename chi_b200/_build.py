@@ -131,6 +131,7 @@ def build_core(jobs=None, verbose=False, regenerate=True):
             os.path.join(GEN, 'model_%s.cu' % key),
             os.path.join(OBJ, 'model_%s.o' % key),
             common + [os.path.join(CSRC, 'integrator.cuh'),
+                      os.path.join(CSRC, 'integrator_stream.cuh'),
                       os.path.join(GEN, 'model_%s.cuh' % key)]))
     jobs = jobs or min(len(tasks), os.cpu_count() or 4)
     logs = {}
@@ -162,7 +163,8 @@ def build_model_module(code):
         return so
     obj = os.path.join(OBJ, 'model_%s.o' % code.key)
     _compile(cu, obj, [cuh, os.path.join(CSRC, 'model_api.cuh'),
-                       os.path.join(CSRC, 'integrator.cuh')])
+                       os.path.join(CSRC, 'integrator.cuh'),
+                       os.path.join(CSRC, 'integrator_stream.cuh')])
     _run([nvcc(), '-shared', '-cudart', 'shared', '-o', so, obj,
           '-L' + HERE, '-lchi_b200', '-Xlinker', '-rpath=' + HERE]
          + LINK_FLAGS)

@@ -90,6 +90,11 @@ class ModelCode(object):
         self.fc = f.jacobian(c) if self.nc else sp.zeros(self.n, 0)
         self.fc = self.fc.applyfunc(sp.cancel)
         self.linear = not any(self.J.has(s) for s in y)
+        # constants that do not enter the rhs at all (e.g. compartment sizes
+        # of mass-action PK models): dy/dc_k == 0 identically, only the
+        # output map depends on them
+        self.inert = [all(self.fc[i, k] == 0 for i in range(self.n))
+                      for k in range(self.nc)]
         allowed = set(y) | set(c) | ({u} if u is not None else set())
         stray = f.free_symbols - allowed
         if stray:
@@ -178,6 +183,9 @@ class ModelCode(object):
         a('  static constexpr int NOUT = %d;' % len(self.g))
         a('  static constexpr bool LINEAR = %s;' % (
             'true' if self.linear else 'false'))
+        a('  // bit k: constant k does not enter the rhs (dy/dc_k == 0)')
+        a('  static constexpr unsigned INERT_MASK = 0x%xu;' % sum(
+            (1 << k) for k, flag in enumerate(self.inert) if flag))
         a('  static constexpr int DOSED_STATE = %d;' % (
             self.state_names.index(self.model.dosed_state)
             if self.model.dosed_state else -1))

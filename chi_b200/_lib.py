@@ -48,6 +48,8 @@ _SIGNATURES = {
     'chi_b200_model_find': (ctypes.c_int, [ctypes.c_char_p]),
     'chi_b200_model_info': (ctypes.c_int, [ctypes.c_int, c_i32p]),
     'chi_b200_model_key': (ctypes.c_char_p, [ctypes.c_int]),
+    'chi_b200_model_inert_mask': (
+        ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_uint32)]),
     'chi_b200_model_variants': (
         ctypes.c_int, [ctypes.c_int, c_i32p, c_i32p, c_i32p, ctypes.c_int32]),
     'chi_b200_model_describe': (

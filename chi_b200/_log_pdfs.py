@@ -661,7 +661,11 @@ class HierarchicalLogPosterior(_LogPDFBase):
         """Batched ``__call__``: the prior is evaluated per vector on the
         host (top-level slice only), all likelihoods in one GPU pass."""
         X = np.asarray(X, dtype=float).reshape(-1, self._n_parameters)
-        prior = np.array([self._log_prior(x[self._n_bottom:]) for x in X])
+        if hasattr(self._log_prior, 'evaluateS1_batch'):
+            prior = self._log_prior.evaluateS1_batch(X[:, self._n_bottom:])[0]
+        else:
+            prior = np.array(
+                [self._log_prior(x[self._n_bottom:]) for x in X])
         score = self._log_likelihood.evaluate_batch(X, copy=False)
         score = prior + score
         score[np.isinf(prior)] = prior[np.isinf(prior)]
@@ -672,14 +676,23 @@ class HierarchicalLogPosterior(_LogPDFBase):
         of the page-locked result buffers (valid until the next call)."""
         X = np.asarray(X, dtype=float).reshape(-1, self._n_parameters)
         score, grad = self._log_likelihood.evaluateS1_batch(X, copy=False)
-        for c, x in enumerate(X):
-            p, s = self._log_prior.evaluateS1(x[self._n_bottom:])
-            if np.isinf(p):
-                score[c] = p
-                grad[c] = np.inf
-                continue
-            score[c] += p
-            grad[c, self._n_bottom:] += s
+        if hasattr(self._log_prior, 'evaluateS1_batch'):
+            p, s = self._log_prior.evaluateS1_batch(X[:, self._n_bottom:])
+            bad = np.isinf(p)
+            score += p
+            grad[:, self._n_bottom:] += s
+            if np.any(bad):
+                score[bad] = p[bad]
+                grad[bad] = np.inf
+        else:
+            for c, x in enumerate(X):
+                p, s = self._log_prior.evaluateS1(x[self._n_bottom:])
+                if np.isinf(p):
+                    score[c] = p
+                    grad[c] = np.inf
+                    continue
+                score[c] += p
+                grad[c, self._n_bottom:] += s
         if copy:
             return score.copy(), grad.copy()
         return score, grad

@@ -96,6 +96,33 @@ class UniformLogPrior(_Base):
         return np.random.uniform(self._a, self._b, size=(n, 1))
 
 
+def _batch_1d(prior, x):
+    """Vectorised (score, d score / dx) of a one-dimensional prior over an
+    array of values; used by the batched posterior entry points."""
+    x = np.asarray(x, dtype=float)
+    if isinstance(prior, GaussianLogPrior):
+        z = (x - prior._mean) / prior._sd
+        return (-0.5 * np.log(2 * np.pi) - np.log(prior._sd) - 0.5 * z * z,
+                -z / prior._sd)
+    if isinstance(prior, LogNormalLogPrior):
+        with np.errstate(all='ignore'):
+            z = (np.log(x) - prior._mu) / prior._s
+            score = -0.5 * np.log(2 * np.pi) - np.log(prior._s) - np.log(x) \
+                - 0.5 * z * z
+            grad = -(1 + z / prior._s) / x
+        bad = x <= 0
+        score = np.where(bad, -np.inf, score)
+        grad = np.where(bad, np.inf, grad)
+        return score, grad
+    if isinstance(prior, UniformLogPrior):
+        inside = (x >= prior._a) & (x < prior._b)
+        return (np.where(inside, -np.log(prior._b - prior._a), -np.inf),
+                np.zeros_like(x))
+    out = [prior.evaluateS1(np.array([v])) for v in x]
+    return (np.array([o[0] for o in out]),
+            np.array([np.asarray(o[1]).reshape(-1)[0] for o in out]))
+
+
 class ComposedLogPrior(_Base):
     """``pints.ComposedLogPrior(*priors)``: independent product."""
 
@@ -127,6 +154,25 @@ class ComposedLogPrior(_Base):
             grads.append(np.asarray(g, dtype=float).reshape(-1))
             lo = hi
         return out, np.concatenate(grads)
+
+    def evaluateS1_batch(self, X):
+        """Scores (n,) and gradients (n, n_parameters) of many vectors."""
+        X = np.asarray(X, dtype=float).reshape(-1, self._n)
+        score = np.zeros(len(X))
+        grad = np.empty(X.shape)
+        lo = 0
+        for p in self._priors:
+            if p.n_parameters() != 1:
+                out = [p.evaluateS1(x[lo:lo + p.n_parameters()]) for x in X]
+                score += np.array([o[0] for o in out])
+                grad[:, lo:lo + p.n_parameters()] = np.array(
+                    [o[1] for o in out])
+            else:
+                s, g = _batch_1d(p, X[:, lo])
+                score += s
+                grad[:, lo] = g
+            lo += p.n_parameters()
+        return score, grad
 
     def n_parameters(self):
         return self._n

@@ -575,6 +575,13 @@ int chi_b200_model_info(int model, int32_t info[8]) {
   return 0;
 }
 
+int chi_b200_model_inert_mask(int model, uint32_t* mask) {
+  if (model < 0 || model >= chi_b200_n_models())
+    return fail(-1, "model id out of range");
+  *mask = registry()[model]->inert_mask;
+  return 0;
+}
+
 int chi_b200_model_variants(int model, int32_t* n, int32_t* lanes,
                             int32_t* cols, int32_t capacity) {
   if (model < 0 || model >= chi_b200_n_models())
@@ -668,6 +675,8 @@ int chi_b200_problem_set_outputs(chi_b200_problem* p, int32_t n_out,
     p->err_off[o] = off;
     off += (kind == ERR_CAM) ? 2 : 1;
   }
+  if (err_kinds && off > MAX_SIGMA)
+    return fail(-1, "too many error-model parameters");
   p->n_out = n_out;
   p->n_sigma = err_kinds ? off : 0;
   return 0;

@@ -599,27 +599,48 @@ struct Registrar {
   static inline int32_t cols[NV > 0 ? NV : 1] = {};
   static inline ModelVTable vt = {};
 
-  // Variant<0, CB>: streamed-columns kernel (integrator_stream.cuh)
+  // Variant<0, CB>: streamed-columns persistent kernel
+  // (integrator_stream.cuh)
   template <int CB>
   static cudaError_t launch_stream(const SolveArgs& args,
                                    cudaStream_t stream) {
     constexpr size_t smem =
         sizeof(double) * stream_slots<M>() * STREAM_BLOCK;
-    static bool configured = false;
-    if (!configured) {
+    constexpr int MAX_DEV = 16;
+    static unsigned long long* counters[MAX_DEV] = {};
+    static int resident[MAX_DEV] = {};
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    if (dev < 0 || dev >= MAX_DEV) return cudaErrorInvalidDevice;
+    if (!counters[dev]) {
       if (smem > 48 * 1024) {
-        cudaError_t err = cudaFuncSetAttribute(
+        err = cudaFuncSetAttribute(
             solve_stream_kernel<M, CB, STREAM_BLOCK>,
             cudaFuncAttributeMaxDynamicSharedMemorySize,
             static_cast<int>(smem));
         if (err != cudaSuccess) return err;
       }
-      configured = true;
+      int bpsm = 0, sms = 0;
+      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &bpsm, solve_stream_kernel<M, CB, STREAM_BLOCK>, STREAM_BLOCK,
+          smem);
+      if (err != cudaSuccess) return err;
+      err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (err != cudaSuccess) return err;
+      resident[dev] = bpsm * sms;
+      err = cudaMalloc(&counters[dev], sizeof(unsigned long long));
+      if (err != cudaSuccess) return err;
     }
-    const int64_t blocks = (args.B + STREAM_BLOCK - 1) / STREAM_BLOCK;
-    if (blocks == 0) return cudaSuccess;
+    if (args.B == 0) return cudaSuccess;
+    err = cudaMemsetAsync(counters[dev], 0, sizeof(unsigned long long),
+                          stream);
+    if (err != cudaSuccess) return err;
+    int64_t blocks = (args.B + STREAM_BLOCK - 1) / STREAM_BLOCK;
+    if (blocks > resident[dev]) blocks = resident[dev];
     solve_stream_kernel<M, CB, STREAM_BLOCK>
-        <<<static_cast<unsigned>(blocks), STREAM_BLOCK, smem, stream>>>(args);
+        <<<static_cast<unsigned>(blocks), STREAM_BLOCK, smem, stream>>>(
+            args, counters[dev]);
     return cudaGetLastError();
   }
 
@@ -731,6 +752,7 @@ struct Registrar {
     vt.flops_jac = M::FLOPS_JAC;
     vt.flops_dfdc = M::FLOPS_DFDC;
     vt.flops_hess = M::FLOPS_HESS;
+    vt.inert_mask = M::INERT_MASK;
     vt.n_variants = NV;
     vt.variant_lanes = lanes;
     vt.variant_cols = cols;

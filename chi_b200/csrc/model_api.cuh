@@ -14,7 +14,7 @@ namespace chi_b200 {
 
 constexpr int MAX_OUT = 8;    // outputs selected per problem
 constexpr int MAX_COLS = 32;  // sensitivity columns (mechanistic parameters)
-constexpr int MAX_SIGMA = 2 * MAX_OUT;
+constexpr int MAX_SIGMA = 8;     // error-model parameters per problem
 
 // Error-model kinds (chi/_error_models.py): parameters per kind 1,1,2,1.
 enum ErrKind : int32_t {
@@ -84,6 +84,7 @@ struct ModelVTable {
   const char* key;
   int32_t n_states, n_consts, n_outputs, linear;
   int32_t flops_rhs, flops_jac, flops_dfdc, flops_hess;
+  uint32_t inert_mask;  // constants that do not enter the rhs
   // group geometry of the sensitivity kernel: lanes per system and
   // sensitivity columns per lane (see integrator.cuh)
   int32_t n_variants;

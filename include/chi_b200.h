@@ -78,6 +78,9 @@ int chi_b200_model_find(const char* key);
  * flops_dfdc, flops_hess */
 int chi_b200_model_info(int model, int32_t info[8]);
 const char* chi_b200_model_key(int model);
+/* bit k set: constant k does not enter the rhs (its sensitivity column of the
+ * states is identically zero and is not integrated) */
+int chi_b200_model_inert_mask(int model, uint32_t* mask);
 /* sensitivity kernel variants: lanes per system, columns per lane */
 int chi_b200_model_variants(int model, int32_t* n, int32_t* lanes,
                             int32_t* cols, int32_t capacity);

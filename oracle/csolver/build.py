@@ -30,6 +30,7 @@ def build(force=False):
             f.write(text)
     srcs = [os.path.join(HERE, 'port.cpp'), inc,
             os.path.join(ROOT, 'chi_b200', 'csrc', 'integrator.cuh'),
+            os.path.join(ROOT, 'chi_b200', 'csrc', 'integrator_stream.cuh'),
             os.path.join(ROOT, 'chi_b200', 'csrc', 'model_api.cuh')]
     srcs += [os.path.join(GEN, 'model_%s.cuh' % k) for k in index]
     if not force and os.path.exists(LIB) and all(
