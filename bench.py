@@ -89,20 +89,24 @@ def workload_config(args, n_gpus):
 # --------------------------------------------------------------------------
 
 def flops_per_step(n, n_cols, info):
-    """Algorithmic flops of one RODAS4 step attempt of one system:
-    state column once + n_cols sensitivity columns (FMA = 2)."""
+    """Algorithmic flops of one RODAS4 step attempt of one system: the state
+    column once + the n_cols integrated sensitivity columns (FMA = 2, every
+    other FP64 operation 1)."""
     linear = bool(info[3])
-    f_rhs, f_jac, f_dfdc, f_hess = [int(v) for v in info[4:8]]
+    f_rhs, f_jac, f_col_sum, f_hess_common = [int(v) for v in info[4:8]]
     inv = {1: 2, 2: 12, 3: 51}.get(n, (2 * n ** 3) // 3 + 2 * n * n)
     comb = 2 * n * 15                     # sum_i a_ij U_j, 15 (i, j) pairs
     solve = 6 * n * (2 * n - 1)           # six W^-1 mat-vecs
     state = comb + comb + 6 * 2 * n + 6 * f_rhs + solve
-    sens = comb + comb + 6 * 2 * n + 6 * (
-        n * (2 * n - 1) + f_dfdc + f_hess + 2 * n) + solve
+    # per column: stage combinations, J Z_s, + hinv * combination, solves
+    sens = comb + comb + 6 * 2 * n + 6 * n * (2 * n - 1) + solve
+    # column-specific terms (df/dc_k and its y-derivative) of all columns and
+    # the column-independent second-order term, per stage
+    extra = 6 * (f_col_sum + n_cols * f_hess_common)
     jac = (0 if linear else 7 * f_jac) if n_cols else (
         0 if linear else f_jac)
-    new = (n_cols + 1) * (2 * n * 5 + n + 8 * n)
-    return inv + state + n_cols * sens + jac + new + 10
+    new = (n_cols + 1) * (2 * n * 5 + n + 6 * n)
+    return inv + state + n_cols * sens + extra + jac + new + 10
 
 
 def flops_per_record(n, n_cols):

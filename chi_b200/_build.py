@@ -29,6 +29,8 @@ NVCC_FLAGS = [
     '--expt-relaxed-constexpr', '-Xcudafe', '--diag_suppress=177',
 ]
 LINK_FLAGS = ['-Xlinker', '-rpath=/usr/local/cuda/lib64']
+# extra compile flags for experiments, e.g. CHI_B200_NVCC_FLAGS="-DFOO=1"
+NVCC_FLAGS += os.environ.get('CHI_B200_NVCC_FLAGS', '').split()
 
 
 def nvcc():

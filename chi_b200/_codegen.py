@@ -149,6 +149,36 @@ class ModelCode(object):
         hess_code, fl_hess = _emit_block(
             [('r[%d]' % i, hess[i]) for i in range(n)])
 
+        # column-specialised sensitivity terms (uniform switch on the constant
+        # index): r += (df/dc_k)(y)   and   r += d/dy[J(y) s + (df/dc_k)(y)] v
+        common = [sum((sp.diff(sum((J[i, j] * s_vec[j] for j in range(n)),
+                                   sp.Integer(0)), ylist[l]) * v_vec[l]
+                       for l in range(n)), sp.Integer(0)) for i in range(n)]
+        common = [sp.expand(h) if self.linear else h for h in common]
+
+        def _acc_block(exprs, indent):
+            items = [('r[%d]' % i, sp.Symbol('r[%d]' % i) + e)
+                     for i, e in enumerate(exprs) if e != 0]
+            if not items:
+                return '', 0
+            code, fl = _emit_block(items, indent=indent)
+            return code, fl
+
+        dfdc_cases, hess_cases = [], []
+        self.flops_col = []       # per constant: ops of its extra terms
+        for k in range(nc):
+            e1 = [fc[i, k] for i in range(n)]
+            e2 = [sum((sp.diff(fc[i, k], ylist[l]) * v_vec[l]
+                       for l in range(n)), sp.Integer(0)) for i in range(n)]
+            c1, f1 = _acc_block(e1, '        ')
+            c2, f2 = _acc_block(e2, '        ')
+            dfdc_cases.append(
+                '    if constexpr (K == %d) {\n%s\n    }' % (k, c1))
+            hess_cases.append(
+                '    if constexpr (K == %d) {\n%s\n    }' % (k, c2))
+            self.flops_col.append(f1 + f2)
+        common_code, self.flops_hess_common = _acc_block(common, '    ')
+
         out_cases = []
         dout_cases = []
         for k, g in enumerate(self.g):
@@ -186,6 +216,9 @@ class ModelCode(object):
         a('  // bit k: constant k does not enter the rhs (dy/dc_k == 0)')
         a('  static constexpr unsigned INERT_MASK = 0x%xu;' % sum(
             (1 << k) for k, flag in enumerate(self.inert) if flag))
+        a('  // resident blocks per SM the streamed kernel is compiled for')
+        a('  static constexpr int STREAM_MIN_BLOCKS = %d;' % (
+            3 if (self.linear and n <= 2) else 2))
         a('  static constexpr int DOSED_STATE = %d;' % (
             self.state_names.index(self.model.dosed_state)
             if self.model.dosed_state else -1))
@@ -193,6 +226,12 @@ class ModelCode(object):
         a('  static constexpr int FLOPS_JAC = %d;' % fl_jac)
         a('  static constexpr int FLOPS_DFDC = %d;' % fl_dfdc)
         a('  static constexpr int FLOPS_HESS = %d;' % fl_hess)
+        a('  // ops of the column-specialised terms, summed over the constants'
+          ' that enter the rhs')
+        a('  static constexpr int FLOPS_COL_SUM = %d;' % sum(
+            f for f, flag in zip(self.flops_col, self.inert) if not flag))
+        a('  static constexpr int FLOPS_HESS_COMMON = %d;'
+          % self.flops_hess_common)
         a('  static const char* key() { return "%s"; }' % self.key)
         a('  CHI_HD static void rhs(const double* y, const double* c, '
           'double u, double* f) {')
@@ -215,6 +254,23 @@ class ModelCode(object):
           'const double* s, const double* e, const double* v, double* r) {')
         a('    (void)y; (void)c; (void)s; (void)e; (void)v;')
         a(hess_code)
+        a('  }')
+        a('  // Column-specialised sensitivity terms; K = index of the '
+          'constant,')
+        a('  // K < 0: initial-value column.   r += (df/dc_K)(y)')
+        a('  template <int K>')
+        a('  CHI_HD static void dfdc_col_add(const double* y, '
+          'const double* c, double* r) {')
+        a('    (void)y; (void)c; (void)r;')
+        lines.extend(dfdc_cases)
+        a('  }')
+        a('  // r += d/dy [ J(y) s + (df/dc_K)(y) ] v')
+        a('  template <int K>')
+        a('  CHI_HD static void hess_col_add(const double* y, '
+          'const double* c, const double* s, const double* v, double* r) {')
+        a('    (void)y; (void)c; (void)s; (void)v; (void)r;')
+        a(common_code)
+        lines.extend(hess_cases)
         a('  }')
         a('  CHI_HD static double out(int id, const double* y, '
           'const double* c) {')
@@ -248,7 +304,7 @@ class ModelCode(object):
         n, P = self.n, self.n + self.nc
         mc_max = {1: 8, 2: 4, 3: 3}.get(n, 2)
         # lanes == 0: streamed-columns kernel, `cols` columns per batch
-        out = [(0, 1), (0, 2)]
+        out = [(0, 1)]
         for mc in range(min(mc_max, P), 0, -1):
             g = -(-P // mc)
             if g > 32 or any(g == v[0] for v in out):

@@ -570,8 +570,8 @@ int chi_b200_model_info(int model, int32_t info[8]) {
   info[3] = vt->linear;
   info[4] = vt->flops_rhs;
   info[5] = vt->flops_jac;
-  info[6] = vt->flops_dfdc;
-  info[7] = vt->flops_hess;
+  info[6] = vt->flops_col_sum;
+  info[7] = vt->flops_hess_common;
   return 0;
 }
 

@@ -753,6 +753,8 @@ struct Registrar {
     vt.flops_dfdc = M::FLOPS_DFDC;
     vt.flops_hess = M::FLOPS_HESS;
     vt.inert_mask = M::INERT_MASK;
+    vt.flops_col_sum = M::FLOPS_COL_SUM;
+    vt.flops_hess_common = M::FLOPS_HESS_COMMON;
     vt.n_variants = NV;
     vt.variant_lanes = lanes;
     vt.variant_cols = cols;

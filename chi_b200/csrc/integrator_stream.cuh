@@ -27,6 +27,23 @@ constexpr int stream_slots() {
   return 2 * M::P * M::N + M::P;
 }
 
+// (err / (atol + rtol * max(|z0|, |z1|)))^2 in single precision: the error
+// norm only steers the step size, three digits are plenty, and this keeps two
+// double-precision divisions per column and step off the FP64 pipe.  Values
+// beyond the float range saturate to inf (-> rejection) or flush to zero.
+CHI_HD float err_term(const double err, const double z0, const double z1,
+                      const float atol_f, const float rtol_f) {
+  const float m = fmaxf(fabsf(static_cast<float>(z0)),
+                        fabsf(static_cast<float>(z1)));
+  const float sc = fmaf(rtol_f, m, atol_f);
+#ifdef __CUDA_ARCH__
+  const float q = __fdividef(static_cast<float>(err), sc);
+#else
+  const float q = static_cast<float>(err) / sc;
+#endif
+  return q * q;
+}
+
 // State of one system while it is being integrated.  `init` loads a system,
 // `advance` handles the pending events (observation records, dose edges) and
 // then attempts ONE step, returning true once the system is finished,
@@ -46,7 +63,7 @@ struct StreamSolver {
 
   int64_t b;
   const double* sg;
-  int n_cols, n_batches;
+  int n_cols;
   double y[N], c[NCS];
   int cur;
   bool loglik, invalid, after_reject;
@@ -68,8 +85,8 @@ struct StreamSolver {
     const int id = a.ids ? a.ids[b] : static_cast<int>(b % a.n_ids);
     const double* xb = a.x + b * a.x_stride;
     sg = xb + P;
+    static_assert(CB == 1, "columns are streamed one at a time");
     n_cols = a.with_sens ? a.n_cols : 0;
-    n_batches = (n_cols + CB - 1) / CB;
 #pragma unroll
     for (int i = 0; i < N; ++i) y[i] = xb[i];
 #pragma unroll
@@ -212,6 +229,74 @@ struct StreamSolver {
     }
   }
 
+  // Six RODAS4 stages of sensitivity column k (constant index KC, -1 for an
+  // initial-value column) given the state column's stage values Zy and
+  // increments Uy.  Returns the column's squared scaled error.
+  template <int KC>
+  CHI_HD float column(const int k, const int nxt, const double (&Zy)[6][N],
+                      const double (&Uy)[6][N], const double (&Wi)[N * N],
+                      const double hinv, const float atol_f,
+                      const float rtol_f) {
+    using namespace rodas4;
+    double S0[N], Us[6][N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) S0[n] = CHI_S(cur, k, n);
+#define CHI_SSTAGE(I, CNT, a0, a1, a2, a3, a4, c0, c1, c2, c3, c4)           \
+  {                                                                           \
+    double Ji[N * N];                                                         \
+    if (!M::LINEAR) M::jac(Zy[I], c, Ji);                                     \
+    double Zs[N], cs[N], rs[N];                                               \
+    lincomb<CNT, N>(Zs, S0, Us, a0, a1, a2, a3, a4);                          \
+    lincomb<CNT, N>(cs, nullptr, Us, c0, c1, c2, c3, c4);                     \
+    matvec<N>(M::LINEAR ? J0 : Ji, Zs, rs);                                   \
+    M::template dfdc_col_add<KC>(Zy[I], c, rs);                               \
+    M::template hess_col_add<KC>(y, c, S0, Uy[I], rs);                        \
+    _Pragma("unroll") for (int n = 0; n < N; ++n) rs[n] =                     \
+        fma(hinv, cs[n], rs[n]);                                              \
+    matvec<N>(Wi, rs, Us[I]);                                                 \
+  }
+    CHI_SSTAGE(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+    CHI_SSTAGE(1, 1, A21, 0, 0, 0, 0, C21, 0, 0, 0, 0)
+    CHI_SSTAGE(2, 2, A31, A32, 0, 0, 0, C31, C32, 0, 0, 0)
+    CHI_SSTAGE(3, 3, A41, A42, A43, 0, 0, C41, C42, C43, 0, 0)
+    CHI_SSTAGE(4, 4, A51, A52, A53, A54, 0, C51, C52, C53, C54, 0)
+    CHI_SSTAGE(5, 5, A51, A52, A53, A54, 1.0, C61, C62, C63, C64, C65)
+#undef CHI_SSTAGE
+    double Sn[N];
+    lincomb<5, N>(Sn, S0, Us, A51, A52, A53, A54, 1.0);
+    float s2 = 0.0f;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      Sn[n] += Us[5][n];
+      s2 += err_term(Us[5][n], S0[n], Sn[n], atol_f, rtol_f);
+      CHI_S(nxt, k, n) = Sn[n];
+    }
+    return s2 * (1.0f / N);
+  }
+
+  // Uniform dispatch to the code specialised for constant index kc.  Columns
+  // of constants that do not enter the rhs stay identically zero: nothing to
+  // integrate.
+  template <int K>
+  CHI_HD float dispatch_column(const int kc, const int k, const int nxt,
+                               const double (&Zy)[6][N],
+                               const double (&Uy)[6][N],
+                               const double (&Wi)[N * N], const double hinv,
+                               const float atol_f, const float rtol_f) {
+    if (kc == K) {
+      if constexpr (K >= 0) {
+        if constexpr ((M::INERT_MASK >> K) & 1u) return 0.0f;
+      }
+      return column<K>(k, nxt, Zy, Uy, Wi, hinv, atol_f, rtol_f);
+    }
+    if constexpr (K + 1 < NC) {
+      return dispatch_column<K + 1>(kc, k, nxt, Zy, Uy, Wi, hinv, atol_f,
+                                    rtol_f);
+    } else {
+      return 0.0f;
+    }
+  }
+
   // One step attempt towards the next stop.  Returns true on failure.
   CHI_HD bool step() {
     using namespace rodas4;
@@ -280,87 +365,27 @@ struct StreamSolver {
 #undef CHI_YSTAGE
     double yn[N];
     float errsq;
+    const float atol_f = static_cast<float>(a.atol);
+    const float rtol_f = static_cast<float>(a.rtol);
     {
-      double s2 = 0.0;
+      float s2 = 0.0f;
 #pragma unroll
       for (int n = 0; n < N; ++n) {
         yn[n] = Zy[5][n] + Uy[5][n];
-        const double sc = a.atol + a.rtol * fmax(fabs(y[n]), fabs(yn[n]));
-        const double q = Uy[5][n] / sc;
-        s2 = fma(q, q, s2);
+        s2 += err_term(Uy[5][n], y[n], yn[n], atol_f, rtol_f);
       }
-      errsq = static_cast<float>(s2 * (1.0 / N));
+      errsq = s2 * (1.0f / N);
     }
 
-    // ---- sensitivity columns, CB at a time ----------------------------------
+    // ---- sensitivity columns, streamed one at a time ----------------------
+    // The column's constant index is uniform over the grid, so the dispatch
+    // below is a uniform branch to code specialised for that column.
     const int nxt = 1 - cur;
-    for (int kb = 0; kb < n_batches; ++kb) {
-      // columns of constants that do not enter the rhs stay identically
-      // zero: nothing to integrate (the condition is uniform over the grid)
-      bool skip = true;
-#pragma unroll
-      for (int q = 0; q < CB; ++q) {
-        const int k = kb * CB + q;
-        const int pk = k < n_cols ? a.col_param[k] : -1;
-        if (pk >= 0 && !(pk >= N && ((M::INERT_MASK >> (pk - N)) & 1u)))
-          skip = false;
-      }
-      if (skip) continue;
-      double S0[CB][N], Us[CB][6][N], e[CB][NCS];
-#pragma unroll
-      for (int q = 0; q < CB; ++q) {
-        const int k = kb * CB + q;
-        const int pk = k < n_cols ? a.col_param[k] : -1;
-        const int ks = k < P ? k : P - 1;
-#pragma unroll
-        for (int n = 0; n < N; ++n)
-          S0[q][n] = k < n_cols ? CHI_S(cur, ks, n) : 0.0;
-#pragma unroll
-        for (int j = 0; j < NCS; ++j) e[q][j] = (pk == N + j) ? 1.0 : 0.0;
-      }
-#define CHI_SSTAGE(I, CNT, a0, a1, a2, a3, a4, c0, c1, c2, c3, c4)           \
-  {                                                                           \
-    double Ji[N * N];                                                         \
-    if (!M::LINEAR) M::jac(Zy[I], c, Ji);                                     \
-    _Pragma("unroll") for (int q = 0; q < CB; ++q) {                          \
-      double Zs[N], r1[N], r2[N], cs[N], rs[N];                               \
-      lincomb<CNT, N>(Zs, S0[q], Us[q], a0, a1, a2, a3, a4);                  \
-      M::dfdc(Zy[I], c, e[q], r1);                                            \
-      M::hess(y, c, S0[q], e[q], Uy[I], r2);                                  \
-      lincomb<CNT, N>(cs, nullptr, Us[q], c0, c1, c2, c3, c4);                \
-      matvec<N>(M::LINEAR ? J0 : Ji, Zs, rs);                                 \
-      _Pragma("unroll") for (int n = 0; n < N; ++n) rs[n] =                   \
-          fma(hinv, cs[n], rs[n] + r1[n] + r2[n]);                            \
-      matvec<N>(Wi, rs, Us[q][I]);                                            \
-    }                                                                         \
-  }
-      CHI_SSTAGE(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
-      CHI_SSTAGE(1, 1, A21, 0, 0, 0, 0, C21, 0, 0, 0, 0)
-      CHI_SSTAGE(2, 2, A31, A32, 0, 0, 0, C31, C32, 0, 0, 0)
-      CHI_SSTAGE(3, 3, A41, A42, A43, 0, 0, C41, C42, C43, 0, 0)
-      CHI_SSTAGE(4, 4, A51, A52, A53, A54, 0, C51, C52, C53, C54, 0)
-      CHI_SSTAGE(5, 5, A51, A52, A53, A54, 1.0, C61, C62, C63, C64, C65)
-#undef CHI_SSTAGE
-#pragma unroll
-      for (int q = 0; q < CB; ++q) {
-        const int k = kb * CB + q;
-        double Sn[N];
-        lincomb<5, N>(Sn, S0[q], Us[q], A51, A52, A53, A54, 1.0);
-        double s2 = 0.0;
-#pragma unroll
-        for (int n = 0; n < N; ++n) {
-          Sn[n] += Us[q][5][n];
-          const double sc =
-              a.atol + a.rtol * fmax(fabs(S0[q][n]), fabs(Sn[n]));
-          const double qq = Us[q][5][n] / sc;
-          s2 = fma(qq, qq, s2);
-        }
-        if (k < n_cols) {
-          errsq = fmaxf(errsq, static_cast<float>(s2 * (1.0 / N)));
-#pragma unroll
-          for (int n = 0; n < N; ++n) CHI_S(nxt, k, n) = Sn[n];
-        }
-      }
+    for (int k = 0; k < n_cols; ++k) {
+      const int pk = a.col_param[k];
+      const int kc = pk >= N ? pk - N : -1;
+      errsq = fmaxf(errsq, dispatch_column<-1>(kc, k, nxt, Zy, Uy, Wi, hinv,
+                                               atol_f, rtol_f));
     }
 
     const bool accept = errsq <= 1.0f;
@@ -438,7 +463,7 @@ CHI_HD void solve_system_stream(const SolveArgs& a, const int64_t b,
 // refills itself as soon as its system is finished, so lanes whose systems
 // need fewer steps do not idle and there is no partial last wave.
 template <class M, int CB, int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, M::STREAM_MIN_BLOCKS)
 solve_stream_kernel(const SolveArgs a, unsigned long long* counter) {
   extern __shared__ double chi_sm[];
   StreamSolver<M, CB> s(a, chi_sm + threadIdx.x, BLOCK);

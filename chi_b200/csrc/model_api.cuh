@@ -84,6 +84,7 @@ struct ModelVTable {
   const char* key;
   int32_t n_states, n_consts, n_outputs, linear;
   int32_t flops_rhs, flops_jac, flops_dfdc, flops_hess;
+  int32_t flops_col_sum, flops_hess_common;
   uint32_t inert_mask;  // constants that do not enter the rhs
   // group geometry of the sensitivity kernel: lanes per system and
   // sensitivity columns per lane (see integrator.cuh)

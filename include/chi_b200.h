@@ -74,8 +74,10 @@ int chi_b200_host_free(void* ptr);
  * per model) and register themselves when their shared object is loaded. */
 int chi_b200_n_models(void);
 int chi_b200_model_find(const char* key);
-/* info: n_states, n_consts, n_outputs, linear, flops_rhs, flops_jac,
- * flops_dfdc, flops_hess */
+/* info: n_states, n_consts, n_outputs, linear, and op counts of the generated
+ * code: rhs, Jacobian, the column-specialised sensitivity terms summed over
+ * the constants that enter the rhs, and the column-independent second-order
+ * term (zero for linear models) */
 int chi_b200_model_info(int model, int32_t info[8]);
 const char* chi_b200_model_key(int model);
 /* bit k set: constant k does not enter the rhs (its sensitivity column of the

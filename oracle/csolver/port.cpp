@@ -38,9 +38,6 @@ static void run_all(const SolveArgs& a, int n_threads, int stream_cb) {
     } else if (stream_cb == 1) {
       double sm[stream_slots<M>()];
       solve_system_stream<M, 1>(a, b, sm, 1);
-    } else if (stream_cb == 2) {
-      double sm[stream_slots<M>()];
-      solve_system_stream<M, 2>(a, b, sm, 1);
     } else {
       solve_system<M, 1, M::P>(a, b, 0, 0, 0, 1u);
     }
