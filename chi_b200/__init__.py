@@ -21,6 +21,8 @@ from chi_b200._population_models import (  # noqa: F401
 from chi_b200._log_pdfs import (  # noqa: F401
     LogLikelihood, HierarchicalLogLikelihood, LogPosterior,
     HierarchicalLogPosterior)
+from chi_b200._predictive_models import (  # noqa: F401
+    PredictiveModel, PopulationPredictiveModel)
 from chi_b200._priors import (  # noqa: F401
     GaussianLogPrior, LogNormalLogPrior, UniformLogPrior, ComposedLogPrior)
 from chi_b200 import library  # noqa: F401

@@ -397,6 +397,29 @@ class SBMLModel(MechanisticModel):
         sens = s[:n_t * n_out * n_cols].reshape(n_t, n_out, n_cols).copy()
         return output, sens
 
+    def simulate_batch(self, parameters, times):
+        """Simulates many parameter vectors on the same time grid in one
+        launch (not part of chi's API; used by the predictive models).
+
+        :param parameters: array of shape ``(n_vectors, n_parameters)``.
+        :returns: outputs of shape ``(n_vectors, n_outputs, n_times)`` and
+            the per-vector integrator status.
+        """
+        parameters = np.ascontiguousarray(
+            parameters, dtype=float).reshape(-1, self._n_parameters)
+        times = np.ascontiguousarray(times, dtype=float).reshape(-1)
+        if len(times) == 0:
+            raise IndexError('times must not be empty.')
+        n_t, n_out, n_b = len(times), self._n_outputs, len(parameters)
+        problem = self._configure(times)
+        lib = _lib.lib()
+        a_psi, p_psi = _lib.f64(parameters)
+        y, p_y = _lib.out_f64(n_b * n_t * n_out)
+        status, p_st = _lib.out_i32(n_b)
+        _lib.check(lib.chi_b200_simulate(
+            problem.handle, n_b, None, p_psi, 0, p_y, None, p_st))
+        return y.reshape(n_b, n_t, n_out).transpose(0, 2, 1).copy(), status
+
     def time_unit(self):
         return self._time_unit
 

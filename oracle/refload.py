@@ -24,7 +24,7 @@ REFERENCE_ROOT = os.environ.get('CHI_REFERENCE_ROOT', '/root/reference')
 
 _MODULES = [
     '_covariate_models', '_error_models', '_population_models',
-    '_mechanistic_models', '_log_pdfs']
+    '_mechanistic_models', '_log_pdfs', '_predictive_models']
 
 
 def available():
@@ -90,6 +90,10 @@ def load():
 
     if 'pints' not in sys.modules:
         sys.modules['pints'] = _stub_pints()
+    if 'xarray' not in sys.modules:
+        # only referenced by the posterior/prior predictive classes at call
+        # time; a bare module is enough to import chi/_predictive_models.py
+        sys.modules['xarray'] = types.ModuleType('xarray')
     if 'myokit' not in sys.modules:
         myokit, formats, sbml = _stub_myokit()
         sys.modules['myokit'] = myokit

@@ -591,3 +591,104 @@ def posterior_s1(layout, individual_s1, prior, x, cov=None):
     g = np.array(g, float)
     g[layout.n_bottom:] += sens
     return score + ll, g
+
+
+# --------------------------------------------------------------------------
+# Forward sampling (predictive models)
+# --------------------------------------------------------------------------
+
+def pop_sample(layout, theta, n_samples, rng, cov=None):
+    """PopulationModel.sample: Composed 793-872, Pooled 3005-3037,
+    Gaussian 1797-1846, LogNormal 2678-2732, Covariate 1247-1299
+    (chi/_population_models.py).  Returns (n_samples, n_dim) draws of eta (or
+    of psi for centered models), consuming ``rng`` in the reference's order.
+    Heterogeneous blocks are not supported here."""
+    theta = np.asarray(theta, float)
+    out = np.empty((n_samples, layout.n_dim))
+    cd = ct = cc = 0
+    for b in layout.blocks:
+        nd = block_n_dim(b)
+        nt = block_n_top(b, layout.n_ids)
+        nc = block_n_cov(b)
+        th = theta[ct:ct + nt]
+        kind = b[0]
+        if kind == 'pooled':
+            out[:, cd:cd + nd] = th.reshape(1, -1)
+        elif kind in ('gaussian', 'lognormal'):
+            mu, sigma = th[:nd], th[nd:]
+            if not b[2]:
+                out[:, cd:cd + nd] = rng.normal(
+                    loc=np.zeros(nd), scale=np.ones(nd), size=(n_samples, nd))
+            elif kind == 'gaussian':
+                out[:, cd:cd + nd] = rng.normal(
+                    loc=mu, scale=sigma, size=(n_samples, nd))
+            else:
+                out[:, cd:cd + nd] = rng.lognormal(
+                    mean=mu, sigma=sigma, size=(n_samples, nd))
+        elif kind == 'covariate':
+            inner = b[1]
+            c = np.broadcast_to(cov[:, cc:cc + nc], (n_samples, nc))
+            vt = _covariate_vartheta(b, th, c)
+            for i in range(n_samples):
+                mu, sigma = vt[i, 0], vt[i, 1]
+                if not inner[2]:
+                    out[i, cd:cd + nd] = rng.normal(
+                        loc=np.zeros(nd), scale=np.ones(nd), size=(1, nd))[0]
+                elif inner[0] == 'gaussian':
+                    out[i, cd:cd + nd] = rng.normal(
+                        loc=mu, scale=sigma, size=(1, nd))[0]
+                else:
+                    out[i, cd:cd + nd] = rng.lognormal(
+                        mean=mu, sigma=sigma, size=(1, nd))[0]
+        else:
+            raise NotImplementedError(kind)
+        cd += nd
+        ct += nt
+        cc += nc
+    return out
+
+
+def error_sample(kind, sigma, ybar, rng):
+    """ErrorModel.sample with n_samples = 1 (chi/_error_models.py:469-514,
+    803-847, 1160-1206, 1514-1558) -> (n_times,)."""
+    ybar = np.asarray(ybar, float)
+    shape = (len(ybar), 1)
+    if kind == 'gaussian':
+        return (ybar[:, None] + rng.normal(0, sigma[0], size=shape))[:, 0]
+    if kind == 'lognormal':
+        s = sigma[0]
+        return (ybar[:, None] * rng.lognormal(
+            mean=-s ** 2 / 2, sigma=s, size=shape))[:, 0]
+    if kind == 'cam':
+        base = rng.normal(0, sigma[0], size=shape)
+        rel = rng.normal(0, sigma[1], size=shape)
+        return (ybar[:, None] + base + ybar[:, None] * rel)[:, 0]
+    rel = rng.normal(0, sigma[0], size=shape)
+    return (ybar[:, None] + ybar[:, None] * rel)[:, 0]
+
+
+def population_predictive_sample(layout, simulate, n_mech, error_kinds, theta,
+                                 times, n_samples, seed, cov=None):
+    """PopulationPredictiveModel.sample(return_df=False),
+    chi/_predictive_models.py:951-1037: sample patients, transform to psi,
+    then per patient one forward solve and one noise draw per output.
+    ``simulate(psi)`` -> (n_outputs, n_times).  Returns
+    (n_outputs, n_times, n_samples)."""
+    rng = np.random.default_rng(seed)
+    lay = PopLayout(layout.blocks, n_samples)
+    c = None if cov is None else np.broadcast_to(
+        np.asarray(cov, float).reshape(-1, lay.n_cov), (n_samples, lay.n_cov))
+    patients = pop_sample(lay, theta, n_samples, rng, c)
+    patients = pop_individual_parameters(lay, theta, patients, c)
+    times = np.sort(times)
+    out = np.empty((len(error_kinds), len(times), n_samples))
+    for p, patient in enumerate(patients):
+        ybar = simulate(patient[:n_mech])
+        start = 0
+        for o, kind in enumerate(error_kinds):
+            n_sig = ERROR_MODELS[kind][0]
+            out[o, :, p] = error_sample(
+                kind, patient[n_mech + start:n_mech + start + n_sig],
+                ybar[o], rng)
+            start += n_sig
+    return out

@@ -320,6 +320,76 @@ def hier_case(rng, n_ids, error, covariates):
         'score_call': float(post(x))}
 
 
+def predictive_case(rng, name):
+    """configs C3 / C5 forward sampling at small size:
+    PopulationPredictiveModel.sample(return_df=False)."""
+    if name == 'c3':
+        omodel = ode_exact.tumour_growth_inhibition_pkpd(True)
+        events = [(5 / 0.01, 0.0, 0.01, 1.0, 30.0)]
+        em = chi.LogNormalErrorModel()
+        # [A0, V_T0, size, critical_volume, k_e, kappa, lambda | sigma]
+        pm = chi.ComposedPopulationModel([
+            chi.PooledModel(1), chi.LogNormalModel(1), chi.PooledModel(2),
+            chi.LogNormalModel(3, centered=False), chi.PooledModel(1)])
+        theta = [0.0, np.log(0.2), 0.2, 2.0, 1.0,
+                 np.log(0.5), np.log(0.3), np.log(0.1), 0.2, 0.3, 0.1, 0.1]
+        times = np.arange(0.0, 31.0)
+        X = None
+        n_samples = 6
+        model, direct, output = (
+            'erlotinib_tumour_growth_inhibition_model', True,
+            'global.tumour_volume')
+        error = 'lognormal'
+        spec = [['pooled', 1], ['lognormal', 1, True], ['pooled', 2],
+                ['lognormal', 3, False], ['pooled', 1]]
+    else:
+        omodel = ode_exact.two_compartment(True)
+        events = [(10.0, 0.0, 1.0, 8.0, 3.0)]
+        em = chi.ConstantAndMultiplicativeGaussianErrorModel()
+        pm = chi.ComposedPopulationModel([
+            chi.PooledModel(2),
+            chi.CovariatePopulationModel(
+                chi.LogNormalModel(5, centered=False),
+                chi.LinearCovariateModel(n_cov=2)),
+            chi.PooledModel(2)])
+        n_top = pm.n_parameters()
+        theta = np.zeros(n_top)
+        names = pm.get_parameter_names()
+        mu = np.log([2.0, 1.0, 5.0, 1.0, 10.0])
+        for k, nm in enumerate(names):
+            if 'Cov.' in nm:
+                theta[k] = 0.05 * rng.normal() if nm.startswith(
+                    'Log mean') else 0.0
+            elif nm.startswith('Log mean'):
+                theta[k] = mu[int(nm.split('Dim. ')[1]) - 3]
+            elif nm.startswith('Log std.'):
+                theta[k] = 0.3
+        theta[-2:] = [0.05, 0.1]
+        times = np.array([0.5, 1.0, 2.0, 4.0, 8.5, 12.0, 20.0, 24.0])
+        n_samples = 5
+        X = rng.normal(size=(n_samples, 2))
+        model, direct, output = (
+            'two_compartment_pk_model', True, 'central.drug_concentration')
+        error = 'cam'
+        spec = [['pooled', 2], ['covariate', ['lognormal', 5, False], 2],
+                ['pooled', 2]]
+        theta = list(theta)
+    omodel.set_outputs([output])
+    pred = chi.PredictiveModel(ExactModel(omodel, events), [em])
+    ppm = chi.PopulationPredictiveModel(pred, pm)
+    kwargs = {} if X is None else {'covariates': X}
+    samples = ppm.sample(
+        theta, times, n_samples=n_samples, seed=11, return_df=False,
+        **kwargs)
+    return {
+        'model': model, 'direct': direct, 'output': output, 'error': error,
+        'events': [list(e) for e in events], 'spec': spec,
+        'theta_names': pm.get_parameter_names(), 'theta': tolist(theta),
+        'times': tolist(times), 'n_samples': n_samples, 'seed': 11,
+        'covariates': None if X is None else tolist(X),
+        'samples': tolist(samples)}
+
+
 def main():
     rng = np.random.default_rng(20240607)
     stats_golden = {
@@ -330,7 +400,9 @@ def main():
     hier_golden = {
         'c1': c1_case(rng),
         'c2': hier_case(rng, 6, 'lognormal', False),
-        'c5': hier_case(rng, 5, 'cam', True)}
+        'c5': hier_case(rng, 5, 'cam', True),
+        'predictive_c3': predictive_case(rng, 'c3'),
+        'predictive_c5': predictive_case(rng, 'c5')}
     with open(os.path.join(HERE, 'hier_golden.json'), 'w') as f:
         json.dump(hier_golden, f)
     print('wrote', os.path.join(HERE, 'stats_golden.json'),

@@ -187,3 +187,67 @@ def test_hierarchical_posterior_matches_reference_golden(name):
     assert post(x) == pytest.approx(case['score_call'], rel=1e-8)
     assert post.n_ids() == n_ids
     assert post.get_id(unique=True) == ['id %d' % i for i in range(n_ids)]
+
+
+@pytest.mark.parametrize('name', ['predictive_c3', 'predictive_c5'])
+def test_population_predictive_sample_matches_reference_golden(name):
+    """BASELINE.json configs[2] / [4] forward path at small size:
+    PopulationPredictiveModel.sample(return_df=False), same seed as the
+    reference.  The noise stream is reproduced exactly; the trajectories are
+    integrated at rtol 1e-11, so samples agree to ~1e-9."""
+    case = _load('hier_golden.json')[name]
+    lib = chi_b200.library.ModelLibrary()
+    model = getattr(lib, case['model'])()
+    model.set_administration('central', direct=case['direct'])
+    model.set_outputs([case['output']])
+    reg = chi_b200.DosingRegimen()
+    for ev in case['events']:
+        reg.schedule(*ev)
+    model.set_dosing_regimen(reg)
+    model.set_tolerance(abs_tol=1e-13, rel_tol=1e-11)
+    pred = chi_b200.PredictiveModel(model, [CLASSES[case['error']]()])
+    pm = chi_b200.ComposedPopulationModel(_build_population(case['spec']))
+    names = pm.get_parameter_names()
+    assert sorted(names) == sorted(case['theta_names'])
+    theta = np.array(case['theta'])[
+        [case['theta_names'].index(n) for n in names]]
+    ppm = chi_b200.PopulationPredictiveModel(pred, pm)
+    kwargs = {}
+    if case['covariates'] is not None:
+        kwargs['covariates'] = np.array(case['covariates'])
+    out = ppm.sample(theta, case['times'], n_samples=case['n_samples'],
+                     seed=case['seed'], return_df=False, **kwargs)
+    ref = np.array(case['samples'])
+    assert out.shape == ref.shape
+    # (values that decayed below the integrator's atol = 1e-13 are compared
+    # absolutely)
+    np.testing.assert_allclose(out, ref, rtol=1e-8, atol=1e-12)
+    df = ppm.sample(theta, case['times'], n_samples=case['n_samples'],
+                    seed=case['seed'], **kwargs)
+    assert list(df.columns) == ['ID', 'Time', 'Observable', 'Value']
+    values = df[df['Observable'] == case['output']]['Value'].to_numpy()
+    np.testing.assert_allclose(values, out.flatten(), rtol=1e-15)
+
+
+def test_predictive_model_sample_single_individual():
+    """PredictiveModel.sample: one solve, seed-pinned noise
+    (chi/_predictive_models.py:659-736)."""
+    model = chi_b200.library.ModelLibrary().one_compartment_pk_model()
+    model.set_administration('central')
+    pred = chi_b200.PredictiveModel(model, chi_b200.GaussianErrorModel())
+    pred.set_dosing_regimen(dose=10, start=0, duration=0.01)
+    assert pred.get_parameter_names()[-1] == 'Sigma'
+    times = [3.0, 1.0, 2.0]
+    out = pred.sample([0, 2, 1, 0.1], times, n_samples=4, seed=3,
+                      return_df=False)
+    assert out.shape == (1, 3, 4)
+    ybar = pred.get_submodels()['Mechanistic model'].simulate(
+        [0, 2, 1], np.sort(times))
+    assert np.all(ybar > 0.1)
+    noise = np.random.default_rng(3).normal(0, 0.1, size=(3, 4))
+    np.testing.assert_allclose(out[0], ybar[0][:, None] + noise, rtol=1e-13)
+    df = pred.sample([0, 2, 1, 0.1], times, n_samples=2, seed=3,
+                     include_regimen=True)
+    assert set(df.columns) >= {'ID', 'Time', 'Observable', 'Value'}
+    reg = pred.get_dosing_regimen()
+    assert list(reg['Dose']) == [10.0] and list(reg['Duration']) == [0.01]

@@ -243,3 +243,43 @@ def test_regimen_expansion():
     # indefinite train stops at the horizon
     edges, rates = ode_exact.expand_regimen([(1.0, 0.0, 0.25, 1.0, 0)], 2.5)
     assert len(rates) == 6 and rates[-1] == 0.0
+
+
+def _pred_layout(case):
+    blocks = []
+    for b in case['spec']:
+        if b[0] == 'covariate':
+            names = case['theta_names']
+            cov_names = [n for n in names if 'Cov.' in n][::b[2]]
+            pidx = [0 if n.startswith('Log mean') else 1 for n in cov_names]
+            first = min(int(n.split('Dim. ')[1].split(' ')[0])
+                        for n in cov_names)
+            didx = [int(n.split('Dim. ')[1].split(' ')[0]) - first
+                    for n in cov_names]
+            blocks.append(('covariate', tuple(b[1]), b[2],
+                           np.array(pidx), np.array(didx)))
+        else:
+            blocks.append(tuple(b))
+    return stats.PopLayout(blocks, case['n_samples'])
+
+
+@pytest.mark.parametrize('name', ['predictive_c3', 'predictive_c5'])
+def test_population_predictive_sample_matches_reference_golden(name):
+    """PopulationPredictiveModel.sample(return_df=False) of the unmodified
+    reference (exact ODE plugged in) == oracle restatement, same seed."""
+    case = _load('hier_golden.json')[name]
+    if name == 'predictive_c3':
+        omodel = ode_exact.tumour_growth_inhibition_pkpd(True)
+    else:
+        omodel = ode_exact.two_compartment(True)
+    omodel.set_outputs([case['output']])
+    ev = [tuple(e) for e in case['events']]
+    times = np.array(case['times'])
+
+    def simulate(psi):
+        return ode_exact.simulate(omodel, psi, times, ev, False)
+    out = stats.population_predictive_sample(
+        _pred_layout(case), simulate, omodel.P, [case['error']],
+        np.array(case['theta']), times, case['n_samples'], case['seed'],
+        case['covariates'])
+    np.testing.assert_allclose(out, case['samples'], rtol=1e-12)
