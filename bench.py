@@ -88,24 +88,26 @@ def workload_config(args, n_gpus):
 # flop model ("Algorithmic flops")
 # --------------------------------------------------------------------------
 
-def flops_per_step(n, n_cols, info):
-    """Algorithmic flops of one RODAS4 step attempt of one system: the state
-    column once + the n_cols integrated sensitivity columns (FMA = 2, every
-    other FP64 operation 1)."""
+def flops_per_step(n, n_cols, info, stages=6):
+    """Algorithmic flops of one Rosenbrock step attempt of one system (RODAS4:
+    6 stages, RODAS5: 8): the state column once + the n_cols integrated
+    sensitivity columns (FMA = 2, every other FP64 operation 1)."""
     linear = bool(info[3])
     f_rhs, f_jac, f_col_sum, f_hess_common = [int(v) for v in info[4:8]]
+    s = stages
+    pairs = s * (s - 1) // 2              # (i, j<i) pairs of the stage table
     inv = {1: 2, 2: 12, 3: 51}.get(n, (2 * n ** 3) // 3 + 2 * n * n)
-    comb = 2 * n * 15                     # sum_i a_ij U_j, 15 (i, j) pairs
-    solve = 6 * n * (2 * n - 1)           # six W^-1 mat-vecs
-    state = comb + comb + 6 * 2 * n + 6 * f_rhs + solve
+    comb = 2 * n * pairs                  # sum_j a_ij U_j over all stages
+    solve = s * n * (2 * n - 1)           # s mat-vecs with W^-1
+    state = comb + comb + s * 2 * n + s * f_rhs + solve
     # per column: stage combinations, J Z_s, + hinv * combination, solves
-    sens = comb + comb + 6 * 2 * n + 6 * n * (2 * n - 1) + solve
+    sens = comb + comb + s * 2 * n + s * n * (2 * n - 1) + solve
     # column-specific terms (df/dc_k and its y-derivative) of all columns and
     # the column-independent second-order term, per stage
-    extra = 6 * (f_col_sum + n_cols * f_hess_common)
-    jac = (0 if linear else 7 * f_jac) if n_cols else (
+    extra = s * (f_col_sum + n_cols * f_hess_common)
+    jac = (0 if linear else (s + 1) * f_jac) if n_cols else (
         0 if linear else f_jac)
-    new = (n_cols + 1) * (2 * n * 5 + n + 6 * n)
+    new = (n_cols + 1) * (n + 6 * n)
     return inv + state + n_cols * sens + extra + jac + new + 10
 
 
@@ -211,7 +213,7 @@ class ReferencePathCPU(object):
     def individual_s1(self, i, x):
         pop = self.pops[i]
         y, s, status, _, _ = pop.simulate(
-            x[:7], rtol=self.rtol, atol=self.atol, stream_cb=1)
+            x[:7], rtol=self.rtol, atol=self.atol, stream_cb=5)
         return self.stats.lognormal_error_s1(x[7:], y, s, self.obs[i])
 
     def evaluateS1(self, x):
@@ -233,7 +235,7 @@ class ReferencePathCPU(object):
             ids = np.tile(np.arange(self.n_ids, dtype=np.int32), reps)
             t0 = time.perf_counter()
             self.whole.loglik(X, ids=ids, with_grad=True, rtol=self.rtol,
-                              atol=self.atol, n_threads=threads, stream_cb=1)
+                              atol=self.atol, n_threads=threads, stream_cb=5)
             dt = time.perf_counter() - t0
             t_used += dt
             n_sys += len(X)
@@ -537,7 +539,18 @@ def run_product(args, rank, world, local_rank):
     n_inert = bin(inert.value).count('1')
     # sensitivity columns of constants that do not enter the rhs are
     # identically zero and are not integrated: they are not counted either
-    f_step = flops_per_step(n_states, n_cols - n_inert, info)
+    variants = np.zeros((3, 8), dtype=np.int32)
+    nv = np.zeros(1, dtype=np.int32)
+    lib.chi_b200_model_variants(
+        model_id, nv.ctypes.data_as(_lib.c_i32p),
+        variants[0].ctypes.data_as(_lib.c_i32p),
+        variants[1].ctypes.data_as(_lib.c_i32p), 8)
+    vsel = args.variant if args.variant >= 0 else 0
+    streamed = int(variants[0][vsel]) == 0
+    method = 'RODAS5' if (streamed and int(variants[1][vsel]) == 5) \
+        else 'RODAS4'
+    stages = 8 if method == 'RODAS5' else 6
+    f_step = flops_per_step(n_states, n_cols - n_inert, info, stages)
     n_rec = args.n_obs
     flops_launch = (steps_acc + steps_rej) * f_step + \
         n_sys * n_rec * flops_per_record(n_states, n_cols)
@@ -548,13 +561,6 @@ def run_product(args, rank, world, local_rank):
     solve_avg_ms = solve_ms / max(solve_launches, 1)
     achieved = flops_launch / (solve_avg_ms * 1e-3) * 1e-12
     alg_bytes = n_sys * 8 * (2 * (n_cols + 1) + 2) + n_sys * n_rec * 28
-    variants = np.zeros((3, 8), dtype=np.int32)
-    nv = np.zeros(1, dtype=np.int32)
-    lib.chi_b200_model_variants(
-        model_id, nv.ctypes.data_as(_lib.c_i32p),
-        variants[0].ctypes.data_as(_lib.c_i32p),
-        variants[1].ctypes.data_as(_lib.c_i32p), 8)
-    vsel = args.variant if args.variant >= 0 else 0
     desc = np.zeros(4, dtype=np.int32)
     lib.chi_b200_model_describe(
         model_id, local_rank, vsel, desc.ctypes.data_as(_lib.c_i32p))
@@ -566,14 +572,14 @@ def run_product(args, rank, world, local_rank):
                         '(chi_b200_fp64_peak); MEASURED_PEAKS.json has no '
                         'FP64 figure'),
         'kernel': (
-            'solve_stream_kernel<two-compartment, CB=%d> (thread per system, '
-            'columns streamed)' % int(variants[1][vsel])
-            if int(variants[0][vsel]) == 0 else
+            'solve_stream_kernel<two-compartment, %s> (persistent, thread '
+            'per system, sensitivity columns streamed)' % method
+            if streamed else
             'solve_kernel<two-compartment, G=%d, MC=%d>' % (
                 int(variants[0][vsel]), int(variants[1][vsel]))),
         'kernel_ms': solve_avg_ms, 'kernel_share_of_step':
             solve_ms / dev_ms if dev_ms > 0 else None,
-        'flops_per_step_attempt': f_step,
+        'method': method, 'flops_per_step_attempt': f_step,
         'sensitivity_columns_integrated': n_cols - n_inert,
         'steps_per_system': (steps_acc + steps_rej) / max(n_sys, 1),
         'rejected_fraction': steps_rej / max(steps_acc + steps_rej, 1),

@@ -91,6 +91,9 @@ class _DeviceLikelihoods(object):
         atol, rtol, max_steps = mechanistic_model.tolerance()
         _lib.check(lib.chi_b200_problem_set_tolerances(
             h, rtol, atol, max_steps))
+        if mechanistic_model.kernel_variant() is not None:
+            _lib.check(lib.chi_b200_problem_set_variant(
+                h, mechanistic_model.kernel_variant()))
 
         # records: per individual the (time, output, value) triples sorted by
         # time -- the union grid + masks of chi/_log_pdfs.py:845-883 in

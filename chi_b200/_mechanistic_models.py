@@ -201,6 +201,16 @@ class SBMLModel(MechanisticModel):
     def tolerance(self):
         return self._atol, self._rtol, self._max_steps
 
+    def set_kernel_variant(self, variant):
+        """Selects the sensitivity-kernel variant (index into
+        ``model_code().variants()``; ``None`` = default).  For testing and
+        tuning."""
+        self._variant = None if variant is None else int(variant)
+        self._uploaded = None
+
+    def kernel_variant(self):
+        return getattr(self, '_variant', None)
+
     def set_device(self, device):
         self._device = int(device)
         self._problem = None
@@ -226,7 +236,8 @@ class SBMLModel(MechanisticModel):
         cols = self._sens_columns if self._has_sensitivities else None
         state = (times.tobytes(), tuple(out_ids), events.tobytes(),
                  None if cols is None else tuple(cols),
-                 self._rtol, self._atol, self._max_steps)
+                 self._rtol, self._atol, self._max_steps,
+                 self.kernel_variant())
         if self._uploaded == state:
             return problem
         n_out = len(out_ids)
@@ -240,6 +251,9 @@ class SBMLModel(MechanisticModel):
             problem.handle, len(cols), p_cols))
         _lib.check(lib.chi_b200_problem_set_tolerances(
             problem.handle, self._rtol, self._atol, self._max_steps))
+        _lib.check(lib.chi_b200_problem_set_variant(
+            problem.handle,
+            -1 if self.kernel_variant() is None else self.kernel_variant()))
         n_t = len(times)
         rec_t = np.repeat(times, n_out)
         rec_out = np.tile(np.arange(n_out, dtype=np.int32), n_t)

@@ -27,6 +27,107 @@ constexpr int stream_slots() {
   return 2 * M::P * M::N + M::P;
 }
 
+namespace rodas5 {
+// RODAS5 (Di Marzo 1993; Hairer & Wanner, "Solving ODEs II", sec. VI.4):
+// 8 stages, order 5(4), stiffly accurate, transformed form.  Typed from
+// memory and verified by a convergence-order test (observed order 5.00,
+// embedded estimate ~ h^5; tests/test_host.py).
+constexpr double GAMMA = 0.19;
+constexpr double A21 = 2.0;
+constexpr double A31 = 3.040894194418781;
+constexpr double A32 = 1.041747909077569;
+constexpr double A41 = 2.576417536461461;
+constexpr double A42 = 1.622083060776640;
+constexpr double A43 = -0.9089668560264532;
+constexpr double A51 = 2.760842080225597;
+constexpr double A52 = 1.446624659844071;
+constexpr double A53 = -0.3036980084553738;
+constexpr double A54 = 0.2877498600325443;
+constexpr double A61 = -14.09640773051259;
+constexpr double A62 = 6.925207756232704;
+constexpr double A63 = -41.47510893210728;
+constexpr double A64 = 2.343771018586405;
+constexpr double A65 = 24.13215229196062;
+constexpr double C21 = -10.31323885133993;
+constexpr double C31 = -21.04823117650003;
+constexpr double C32 = -7.234992135176716;
+constexpr double C41 = 32.22751541853323;
+constexpr double C42 = -4.943732386540191;
+constexpr double C43 = 19.44922031041879;
+constexpr double C51 = -20.69865579590063;
+constexpr double C52 = -8.816374604402768;
+constexpr double C53 = 1.260436877740897;
+constexpr double C54 = -0.7495647613787146;
+constexpr double C61 = -46.22004352711257;
+constexpr double C62 = -17.49534862857472;
+constexpr double C63 = -289.6389582892057;
+constexpr double C64 = 93.60855400400906;
+constexpr double C65 = 318.3822534212147;
+constexpr double C71 = 34.20013733472935;
+constexpr double C72 = -14.15535402717690;
+constexpr double C73 = 57.82335640988400;
+constexpr double C74 = 25.83362985412365;
+constexpr double C75 = 1.408950972071624;
+constexpr double C76 = -6.551835421242162;
+constexpr double C81 = 42.57076742291101;
+constexpr double C82 = -13.80770672017997;
+constexpr double C83 = 93.98938432427124;
+constexpr double C84 = 18.77919633714503;
+constexpr double C85 = -31.58359187223370;
+constexpr double C86 = -6.685968952921985;
+constexpr double C87 = -5.810979938412932;
+}  // namespace rodas5
+
+// Stage tables: X(stage, n_previous, a_1..a_7, c_1..c_7)
+#define CHI_RODAS4_TABLE(X)                                                   \
+  X(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)                           \
+  X(1, 1, rodas4::A21, 0, 0, 0, 0, 0, 0, rodas4::C21, 0, 0, 0, 0, 0, 0)       \
+  X(2, 2, rodas4::A31, rodas4::A32, 0, 0, 0, 0, 0, rodas4::C31, rodas4::C32,  \
+    0, 0, 0, 0, 0)                                                            \
+  X(3, 3, rodas4::A41, rodas4::A42, rodas4::A43, 0, 0, 0, 0, rodas4::C41,     \
+    rodas4::C42, rodas4::C43, 0, 0, 0, 0)                                     \
+  X(4, 4, rodas4::A51, rodas4::A52, rodas4::A53, rodas4::A54, 0, 0, 0,        \
+    rodas4::C51, rodas4::C52, rodas4::C53, rodas4::C54, 0, 0, 0)              \
+  X(5, 5, rodas4::A51, rodas4::A52, rodas4::A53, rodas4::A54, 1.0, 0, 0,      \
+    rodas4::C61, rodas4::C62, rodas4::C63, rodas4::C64, rodas4::C65, 0, 0)
+
+#define CHI_RODAS5_TABLE(X)                                                   \
+  X(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)                           \
+  X(1, 1, rodas5::A21, 0, 0, 0, 0, 0, 0, rodas5::C21, 0, 0, 0, 0, 0, 0)       \
+  X(2, 2, rodas5::A31, rodas5::A32, 0, 0, 0, 0, 0, rodas5::C31, rodas5::C32,  \
+    0, 0, 0, 0, 0)                                                            \
+  X(3, 3, rodas5::A41, rodas5::A42, rodas5::A43, 0, 0, 0, 0, rodas5::C41,     \
+    rodas5::C42, rodas5::C43, 0, 0, 0, 0)                                     \
+  X(4, 4, rodas5::A51, rodas5::A52, rodas5::A53, rodas5::A54, 0, 0, 0,        \
+    rodas5::C51, rodas5::C52, rodas5::C53, rodas5::C54, 0, 0, 0)              \
+  X(5, 5, rodas5::A61, rodas5::A62, rodas5::A63, rodas5::A64, rodas5::A65, 0, \
+    0, rodas5::C61, rodas5::C62, rodas5::C63, rodas5::C64, rodas5::C65, 0, 0) \
+  X(6, 6, rodas5::A61, rodas5::A62, rodas5::A63, rodas5::A64, rodas5::A65,    \
+    1.0, 0, rodas5::C71, rodas5::C72, rodas5::C73, rodas5::C74, rodas5::C75,  \
+    rodas5::C76, 0)                                                           \
+  X(7, 7, rodas5::A61, rodas5::A62, rodas5::A63, rodas5::A64, rodas5::A65,    \
+    1.0, 1.0, rodas5::C81, rodas5::C82, rodas5::C83, rodas5::C84,             \
+    rodas5::C85, rodas5::C86, rodas5::C87)
+
+// out = base + sum_{j<CNT} k_j U[j]   (base may be null), up to 7 terms
+template <int CNT, int N>
+CHI_HD void lincomb7(double* out, const double* base, const double (*U)[N],
+                     double k0, double k1, double k2, double k3, double k4,
+                     double k5, double k6) {
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    double v = base ? base[n] : 0.0;
+    if (CNT > 0) v = fma(k0, U[0][n], v);
+    if (CNT > 1) v = fma(k1, U[1][n], v);
+    if (CNT > 2) v = fma(k2, U[2][n], v);
+    if (CNT > 3) v = fma(k3, U[3][n], v);
+    if (CNT > 4) v = fma(k4, U[4][n], v);
+    if (CNT > 5) v = fma(k5, U[5][n], v);
+    if (CNT > 6) v = fma(k6, U[6][n], v);
+    out[n] = v;
+  }
+}
+
 // (err / (atol + rtol * max(|z0|, |z1|)))^2 in single precision: the error
 // norm only steers the step size, three digits are plenty, and this keeps two
 // double-precision divisions per column and step off the FP64 pipe.  Values
@@ -50,8 +151,15 @@ CHI_HD float err_term(const double err, const double z0, const double z1,
 // `finish` writes the results.  Splitting the solve this way lets a
 // persistent kernel refill a lane with the next system as soon as its current
 // one is done (solve_stream_persistent below).
-template <class M, int CB>
+// METHOD_CODE: 1 = RODAS4 (6 stages, order 4(3)), 5 = RODAS5 (8 stages,
+// order 5(4)).
+template <class M, int METHOD_CODE>
 struct StreamSolver {
+  static constexpr bool R5 = METHOD_CODE == 5;
+  static constexpr int NS = R5 ? 8 : 6;          // stages
+  static constexpr double GAMMA = R5 ? rodas5::GAMMA : rodas4::GAMMA;
+  // step-size exponent on err^2: -1/(2 (q+1)), q = order of the estimate
+  static constexpr float EXPO = R5 ? -0.1f : -0.125f;
   static constexpr int N = M::N;
   static constexpr int NC = M::NC;
   static constexpr int NCS = M::NCS;
@@ -85,7 +193,7 @@ struct StreamSolver {
     const int id = a.ids ? a.ids[b] : static_cast<int>(b % a.n_ids);
     const double* xb = a.x + b * a.x_stride;
     sg = xb + P;
-    static_assert(CB == 1, "columns are streamed one at a time");
+    static_assert(METHOD_CODE == 1 || METHOD_CODE == 5, "unknown method");
     n_cols = a.with_sens ? a.n_cols : 0;
 #pragma unroll
     for (int i = 0; i < N; ++i) y[i] = xb[i];
@@ -233,43 +341,42 @@ struct StreamSolver {
   // initial-value column) given the state column's stage values Zy and
   // increments Uy.  Returns the column's squared scaled error.
   template <int KC>
-  CHI_HD float column(const int k, const int nxt, const double (&Zy)[6][N],
-                      const double (&Uy)[6][N], const double (&Wi)[N * N],
+  CHI_HD float column(const int k, const int nxt, const double (&Zy)[NS][N],
+                      const double (&Uy)[NS][N], const double (&Wi)[N * N],
                       const double hinv, const float atol_f,
                       const float rtol_f) {
-    using namespace rodas4;
-    double S0[N], Us[6][N];
+    double S0[N], Us[NS][N], Zl[N];
 #pragma unroll
     for (int n = 0; n < N; ++n) S0[n] = CHI_S(cur, k, n);
-#define CHI_SSTAGE(I, CNT, a0, a1, a2, a3, a4, c0, c1, c2, c3, c4)           \
+#define CHI_SSTAGE(I, CNT, a0, a1, a2, a3, a4, a5, a6, c0, c1, c2, c3, c4,   \
+                   c5, c6)                                                    \
   {                                                                           \
     double Ji[N * N];                                                         \
     if (!M::LINEAR) M::jac(Zy[I], c, Ji);                                     \
-    double Zs[N], cs[N], rs[N];                                               \
-    lincomb<CNT, N>(Zs, S0, Us, a0, a1, a2, a3, a4);                          \
-    lincomb<CNT, N>(cs, nullptr, Us, c0, c1, c2, c3, c4);                     \
-    matvec<N>(M::LINEAR ? J0 : Ji, Zs, rs);                                   \
+    double cs[N], rs[N];                                                      \
+    lincomb7<CNT, N>(Zl, S0, Us, a0, a1, a2, a3, a4, a5, a6);                 \
+    lincomb7<CNT, N>(cs, nullptr, Us, c0, c1, c2, c3, c4, c5, c6);            \
+    matvec<N>(M::LINEAR ? J0 : Ji, Zl, rs);                                   \
     M::template dfdc_col_add<KC>(Zy[I], c, rs);                               \
     M::template hess_col_add<KC>(y, c, S0, Uy[I], rs);                        \
     _Pragma("unroll") for (int n = 0; n < N; ++n) rs[n] =                     \
         fma(hinv, cs[n], rs[n]);                                              \
     matvec<N>(Wi, rs, Us[I]);                                                 \
   }
-    CHI_SSTAGE(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
-    CHI_SSTAGE(1, 1, A21, 0, 0, 0, 0, C21, 0, 0, 0, 0)
-    CHI_SSTAGE(2, 2, A31, A32, 0, 0, 0, C31, C32, 0, 0, 0)
-    CHI_SSTAGE(3, 3, A41, A42, A43, 0, 0, C41, C42, C43, 0, 0)
-    CHI_SSTAGE(4, 4, A51, A52, A53, A54, 0, C51, C52, C53, C54, 0)
-    CHI_SSTAGE(5, 5, A51, A52, A53, A54, 1.0, C61, C62, C63, C64, C65)
+    if constexpr (R5) {
+      CHI_RODAS5_TABLE(CHI_SSTAGE)
+    } else {
+      CHI_RODAS4_TABLE(CHI_SSTAGE)
+    }
 #undef CHI_SSTAGE
-    double Sn[N];
-    lincomb<5, N>(Sn, S0, Us, A51, A52, A53, A54, 1.0);
+    // stiffly accurate: new value = last stage value + last increment, the
+    // last increment is the error estimate
     float s2 = 0.0f;
 #pragma unroll
     for (int n = 0; n < N; ++n) {
-      Sn[n] += Us[5][n];
-      s2 += err_term(Us[5][n], S0[n], Sn[n], atol_f, rtol_f);
-      CHI_S(nxt, k, n) = Sn[n];
+      const double Sn = Zl[n] + Us[NS - 1][n];
+      s2 += err_term(Us[NS - 1][n], S0[n], Sn, atol_f, rtol_f);
+      CHI_S(nxt, k, n) = Sn;
     }
     return s2 * (1.0f / N);
   }
@@ -279,8 +386,8 @@ struct StreamSolver {
   // integrate.
   template <int K>
   CHI_HD float dispatch_column(const int kc, const int k, const int nxt,
-                               const double (&Zy)[6][N],
-                               const double (&Uy)[6][N],
+                               const double (&Zy)[NS][N],
+                               const double (&Uy)[NS][N],
                                const double (&Wi)[N * N], const double hinv,
                                const float atol_f, const float rtol_f) {
     if (kc == K) {
@@ -299,7 +406,6 @@ struct StreamSolver {
 
   // One step attempt towards the next stop.  Returns true on failure.
   CHI_HD bool step() {
-    using namespace rodas4;
     const double t_stop = fmin(a.rec_t[r], t_edge);
 
     if (h == 0.0) {
@@ -344,24 +450,24 @@ struct StreamSolver {
       invert<N>(W, Wi);
     }
     const double hinv = 1.0 / hs;
-    double Zy[6][N];
-    double Uy[6][N];
-#define CHI_YSTAGE(I, CNT, a0, a1, a2, a3, a4, c0, c1, c2, c3, c4)           \
+    double Zy[NS][N];
+    double Uy[NS][N];
+#define CHI_YSTAGE(I, CNT, a0, a1, a2, a3, a4, a5, a6, c0, c1, c2, c3, c4,   \
+                   c5, c6)                                                    \
   {                                                                           \
     double f[N], cy[N], ry[N];                                                \
-    lincomb<CNT, N>(Zy[I], y, Uy, a0, a1, a2, a3, a4);                        \
+    lincomb7<CNT, N>(Zy[I], y, Uy, a0, a1, a2, a3, a4, a5, a6);               \
     M::rhs(Zy[I], c, u, f);                                                   \
-    lincomb<CNT, N>(cy, nullptr, Uy, c0, c1, c2, c3, c4);                     \
+    lincomb7<CNT, N>(cy, nullptr, Uy, c0, c1, c2, c3, c4, c5, c6);            \
     _Pragma("unroll") for (int n = 0; n < N; ++n) ry[n] =                     \
         fma(hinv, cy[n], f[n]);                                               \
     matvec<N>(Wi, ry, Uy[I]);                                                 \
   }
-    CHI_YSTAGE(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
-    CHI_YSTAGE(1, 1, A21, 0, 0, 0, 0, C21, 0, 0, 0, 0)
-    CHI_YSTAGE(2, 2, A31, A32, 0, 0, 0, C31, C32, 0, 0, 0)
-    CHI_YSTAGE(3, 3, A41, A42, A43, 0, 0, C41, C42, C43, 0, 0)
-    CHI_YSTAGE(4, 4, A51, A52, A53, A54, 0, C51, C52, C53, C54, 0)
-    CHI_YSTAGE(5, 5, A51, A52, A53, A54, 1.0, C61, C62, C63, C64, C65)
+    if constexpr (R5) {
+      CHI_RODAS5_TABLE(CHI_YSTAGE)
+    } else {
+      CHI_RODAS4_TABLE(CHI_YSTAGE)
+    }
 #undef CHI_YSTAGE
     double yn[N];
     float errsq;
@@ -371,8 +477,8 @@ struct StreamSolver {
       float s2 = 0.0f;
 #pragma unroll
       for (int n = 0; n < N; ++n) {
-        yn[n] = Zy[5][n] + Uy[5][n];
-        s2 += err_term(Uy[5][n], y[n], yn[n], atol_f, rtol_f);
+        yn[n] = Zy[NS - 1][n] + Uy[NS - 1][n];
+        s2 += err_term(Uy[NS - 1][n], y[n], yn[n], atol_f, rtol_f);
       }
       errsq = s2 * (1.0f / N);
     }
@@ -393,7 +499,7 @@ struct StreamSolver {
     if (!(errsq == errsq) || isinf(errsq)) {
       fac = 0.2f;
     } else {
-      fac = CHI_SAFETY * fast_powf(fmaxf(errsq, 1e-30f), -0.125f);
+      fac = CHI_SAFETY * fast_powf(fmaxf(errsq, 1e-30f), EXPO);
       fac = fminf(fmaxf(fac, 0.2f), CHI_FACMAX);
     }
     if (accept) {

@@ -7,7 +7,7 @@
 #ifdef __CUDACC__
 #define CHI_HD __host__ __device__ __forceinline__
 #else
-#define CHI_HD inline
+#define CHI_HD inline __attribute__((always_inline))
 #endif
 
 namespace chi_b200 {

@@ -25,7 +25,7 @@
 using namespace chi_b200;
 
 // stream_cb: 0 = lanes routine (one lane, all columns in "registers"),
-// 1 / 2 = streamed-columns routine with that many columns per batch.
+// 1 = streamed-columns routine with RODAS4, 5 = with RODAS5.
 template <class M>
 static void run_all(const SolveArgs& a, int n_threads, int stream_cb) {
   (void)n_threads;
@@ -38,6 +38,9 @@ static void run_all(const SolveArgs& a, int n_threads, int stream_cb) {
     } else if (stream_cb == 1) {
       double sm[stream_slots<M>()];
       solve_system_stream<M, 1>(a, b, sm, 1);
+    } else if (stream_cb == 5) {
+      double sm[stream_slots<M>()];
+      solve_system_stream<M, 5>(a, b, sm, 1);
     } else {
       solve_system<M, 1, M::P>(a, b, 0, 0, 0, 1u);
     }

@@ -303,6 +303,41 @@ def test_cpu_port_converges_to_exact_solution():
         prev = nst[0]
 
 
+def test_cpu_port_rodas5_needs_fewer_steps_and_converges():
+    """RODAS5 (order 5(4)) in the host build: converges to the exact solution
+    and needs about half the steps of RODAS4 at the same tolerance."""
+    key = cport.find_key('two_compartment_pk_model', 'central', True)
+    times = np.sort(np.random.default_rng(1).uniform(0.25, 24, 10))
+    reg = [(10.0, 0.0, 1.0, 8.0, 3)]
+    psi = [0, 0, 2, 1, 5, 1, 10]
+    pop = cport.Population(
+        key, ['central.drug_concentration'], None, [times], None, None, [reg])
+    m = ode_exact.two_compartment(True)
+    ye, se = ode_exact.simulate(m, psi, times, reg)
+    scale = np.max(np.abs(se[:, 0, :]), 0)
+    scale[scale == 0] = 1.0
+    errs = {}
+    for rtol in (1e-6, 1e-8, 1e-10):
+        y4, s4, st4, n4, _ = pop.simulate(
+            psi, rtol=rtol, atol=rtol * 0.01, stream_cb=1)
+        y5, s5, st5, n5, _ = pop.simulate(
+            psi, rtol=rtol, atol=rtol * 0.01, stream_cb=5)
+        assert st4[0] == 0 and st5[0] == 0
+        assert n5[0] < 0.65 * n4[0]
+        err = np.max(np.abs(y5 - ye[0]) / np.max(np.abs(ye[0])))
+        serr = np.max(np.abs(s5 - se[:, 0, :]) / scale)
+        assert err < rtol and serr < 2 * rtol
+        errs[rtol] = err
+    # two decades of tolerance buy about two decades of accuracy
+    assert errs[1e-10] < 1e-3 * errs[1e-6]
+    # the streamed and the lane formulation of RODAS4 are the same arithmetic
+    y0, s0, _, n0, _ = pop.simulate(psi, rtol=1e-8, atol=1e-10, stream_cb=0)
+    y1, s1, _, n1, _ = pop.simulate(psi, rtol=1e-8, atol=1e-10, stream_cb=1)
+    assert n0[0] == n1[0]
+    np.testing.assert_allclose(y0, y1, rtol=1e-12)
+    np.testing.assert_allclose(s0, s1, rtol=1e-9, atol=1e-13)
+
+
 def test_bench_host_design_matches_synthetic():
     import bench
     from chi_b200 import _synthetic
