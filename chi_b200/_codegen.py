@@ -172,10 +172,12 @@ class ModelCode(object):
                        for l in range(n)), sp.Integer(0)) for i in range(n)]
             c1, f1 = _acc_block(e1, '        ')
             c2, f2 = _acc_block(e2, '        ')
-            dfdc_cases.append(
-                '    if constexpr (K == %d) {\n%s\n    }' % (k, c1))
-            hess_cases.append(
-                '    if constexpr (K == %d) {\n%s\n    }' % (k, c2))
+            if c1:
+                dfdc_cases.append(
+                    '      case %d: {\n%s\n        break; }' % (k, c1))
+            if c2:
+                hess_cases.append(
+                    '      case %d: {\n%s\n        break; }' % (k, c2))
             self.flops_col.append(f1 + f2)
         common_code, self.flops_hess_common = _acc_block(common, '    ')
 
@@ -255,22 +257,27 @@ class ModelCode(object):
         a('    (void)y; (void)c; (void)s; (void)e; (void)v;')
         a(hess_code)
         a('  }')
-        a('  // Column-specialised sensitivity terms; K = index of the '
-          'constant,')
-        a('  // K < 0: initial-value column.   r += (df/dc_K)(y)')
-        a('  template <int K>')
-        a('  CHI_HD static void dfdc_col_add(const double* y, '
+        a('  // Column-specific sensitivity terms; k = index of the constant '
+          '(uniform')
+        a('  // over the grid), k < 0: initial-value column.  '
+          'r += (df/dc_k)(y)')
+        a('  CHI_HD static void dfdc_col_add(int k, const double* y, '
           'const double* c, double* r) {')
         a('    (void)y; (void)c; (void)r;')
+        a('    switch (k) {')
         lines.extend(dfdc_cases)
+        a('      default: break;')
+        a('    }')
         a('  }')
-        a('  // r += d/dy [ J(y) s + (df/dc_K)(y) ] v')
-        a('  template <int K>')
-        a('  CHI_HD static void hess_col_add(const double* y, '
+        a('  // r += d/dy [ J(y) s + (df/dc_k)(y) ] v')
+        a('  CHI_HD static void hess_col_add(int k, const double* y, '
           'const double* c, const double* s, const double* v, double* r) {')
         a('    (void)y; (void)c; (void)s; (void)v; (void)r;')
         a(common_code)
+        a('    switch (k) {')
         lines.extend(hess_cases)
+        a('      default: break;')
+        a('    }')
         a('  }')
         a('  CHI_HD static double out(int id, const double* y, '
           'const double* c) {')

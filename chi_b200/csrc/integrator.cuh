@@ -679,7 +679,29 @@ struct Registrar {
 
   static cudaError_t launch(const SolveArgs& args, int variant,
                             cudaStream_t stream) {
-    if (!args.with_sens) return launch_lanes<1, 0>(args, stream);
+    if (!args.with_sens) {
+      // forward-only solves run on the same streamed kernel (no columns)
+      // unless a lane-parallel variant was asked for explicitly
+      const bool lanes_forward =
+          variant >= 0 && variant < NV && lanes[variant] != 0;
+      if (lanes_forward) return launch_lanes<1, 0>(args, stream);
+      cudaError_t err = cudaErrorInvalidValue;
+      int idx = 0;
+      int first_stream = -1;
+      for (int v = 0; v < NV; ++v)
+        if (lanes[v] == 0) {
+          first_stream = v;
+          break;
+        }
+      if (variant >= 0 && variant < NV && lanes[variant] == 0)
+        first_stream = variant;
+      if (first_stream < 0) return launch_lanes<1, 0>(args, stream);
+      (void)std::initializer_list<int>{
+          (idx++ == first_stream
+               ? (err = launch_one<Vs::G, Vs::MC>(args, stream), 0)
+               : 0)...};
+      return err;
+    }
     const int v = pick(args, variant);
     if (v < 0) return cudaErrorInvalidValue;
     cudaError_t err = cudaErrorInvalidValue;

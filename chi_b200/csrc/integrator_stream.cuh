@@ -340,8 +340,8 @@ struct StreamSolver {
   // Six RODAS4 stages of sensitivity column k (constant index KC, -1 for an
   // initial-value column) given the state column's stage values Zy and
   // increments Uy.  Returns the column's squared scaled error.
-  template <int KC>
-  CHI_HD float column(const int k, const int nxt, const double (&Zy)[NS][N],
+  CHI_HD float column(const int kc, const int k, const int nxt,
+                      const double (&Zy)[NS][N],
                       const double (&Uy)[NS][N], const double (&Wi)[N * N],
                       const double hinv, const float atol_f,
                       const float rtol_f) {
@@ -357,8 +357,8 @@ struct StreamSolver {
     lincomb7<CNT, N>(Zl, S0, Us, a0, a1, a2, a3, a4, a5, a6);                 \
     lincomb7<CNT, N>(cs, nullptr, Us, c0, c1, c2, c3, c4, c5, c6);            \
     matvec<N>(M::LINEAR ? J0 : Ji, Zl, rs);                                   \
-    M::template dfdc_col_add<KC>(Zy[I], c, rs);                               \
-    M::template hess_col_add<KC>(y, c, S0, Uy[I], rs);                        \
+    M::dfdc_col_add(kc, Zy[I], c, rs);                                        \
+    M::hess_col_add(kc, y, c, S0, Uy[I], rs);                                 \
     _Pragma("unroll") for (int n = 0; n < N; ++n) rs[n] =                     \
         fma(hinv, cs[n], rs[n]);                                              \
     matvec<N>(Wi, rs, Us[I]);                                                 \
@@ -379,29 +379,6 @@ struct StreamSolver {
       CHI_S(nxt, k, n) = Sn;
     }
     return s2 * (1.0f / N);
-  }
-
-  // Uniform dispatch to the code specialised for constant index kc.  Columns
-  // of constants that do not enter the rhs stay identically zero: nothing to
-  // integrate.
-  template <int K>
-  CHI_HD float dispatch_column(const int kc, const int k, const int nxt,
-                               const double (&Zy)[NS][N],
-                               const double (&Uy)[NS][N],
-                               const double (&Wi)[N * N], const double hinv,
-                               const float atol_f, const float rtol_f) {
-    if (kc == K) {
-      if constexpr (K >= 0) {
-        if constexpr ((M::INERT_MASK >> K) & 1u) return 0.0f;
-      }
-      return column<K>(k, nxt, Zy, Uy, Wi, hinv, atol_f, rtol_f);
-    }
-    if constexpr (K + 1 < NC) {
-      return dispatch_column<K + 1>(kc, k, nxt, Zy, Uy, Wi, hinv, atol_f,
-                                    rtol_f);
-    } else {
-      return 0.0f;
-    }
   }
 
   // One step attempt towards the next stop.  Returns true on failure.
@@ -484,14 +461,17 @@ struct StreamSolver {
     }
 
     // ---- sensitivity columns, streamed one at a time ----------------------
-    // The column's constant index is uniform over the grid, so the dispatch
-    // below is a uniform branch to code specialised for that column.
+    // The column's constant index kc is uniform over the grid: the switches
+    // on it inside the generated column terms are uniform branches.
     const int nxt = 1 - cur;
     for (int k = 0; k < n_cols; ++k) {
       const int pk = a.col_param[k];
       const int kc = pk >= N ? pk - N : -1;
-      errsq = fmaxf(errsq, dispatch_column<-1>(kc, k, nxt, Zy, Uy, Wi, hinv,
-                                               atol_f, rtol_f));
+      // columns of constants that do not enter the rhs stay identically
+      // zero: nothing to integrate
+      if (kc >= 0 && ((M::INERT_MASK >> kc) & 1u)) continue;
+      errsq = fmaxf(errsq,
+                    column(kc, k, nxt, Zy, Uy, Wi, hinv, atol_f, rtol_f));
     }
 
     const bool accept = errsq <= 1.0f;
