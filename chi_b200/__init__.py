@@ -25,6 +25,10 @@ from chi_b200._predictive_models import (  # noqa: F401
     PredictiveModel, PopulationPredictiveModel)
 from chi_b200._priors import (  # noqa: F401
     GaussianLogPrior, LogNormalLogPrior, UniformLogPrior, ComposedLogPrior)
+from chi_b200._inference import (  # noqa: F401
+    BatchedSamplingController, HaarioBardenetACMC, HamiltonianMCMC)
+from chi_b200._problems import (  # noqa: F401
+    hierarchical_log_likelihood_from_dataframe)
 from chi_b200 import library  # noqa: F401
 from chi_b200._lib import set_default_device  # noqa: F401
 

@@ -27,6 +27,7 @@ NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
     '-std=c++17', '-Xcompiler', '-fPIC', '-cudart', 'shared',
     '--expt-relaxed-constexpr', '-Xcudafe', '--diag_suppress=177',
+    '-I' + CSRC,
 ]
 LINK_FLAGS = ['-Xlinker', '-rpath=/usr/local/cuda/lib64']
 # extra compile flags for experiments, e.g. CHI_B200_NVCC_FLAGS="-DFOO=1"
@@ -59,14 +60,16 @@ def _digest(paths, extra=''):
     return h.hexdigest()
 
 
-def write_model_sources(code):
-    """Writes gen/model_<key>.cuh/.cu (only when the content changed)."""
-    os.makedirs(GEN, exist_ok=True)
+def write_model_sources(code, directory=None):
+    """Writes model_<key>.cuh/.cu (only when the content changed) into
+    csrc/gen (built-in models) or the given directory."""
+    directory = directory or GEN
+    os.makedirs(directory, exist_ok=True)
     out = []
     for name, text in (
             ('model_%s.cuh' % code.key, code.header()),
             ('model_%s.cu' % code.key, code.translation_unit())):
-        path = os.path.join(GEN, name)
+        path = os.path.join(directory, name)
         old = None
         if os.path.exists(path):
             with open(path) as f:
@@ -159,7 +162,7 @@ def build_model_module(code):
     path of its shared object (which registers itself on load)."""
     os.makedirs(MODULES, exist_ok=True)
     os.makedirs(OBJ, exist_ok=True)
-    cuh, cu = write_model_sources(code)
+    cuh, cu = write_model_sources(code, MODULES)
     so = os.path.join(MODULES, 'libchi_b200_model_%s.so' % code.key)
     if os.path.exists(so):
         return so

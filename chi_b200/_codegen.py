@@ -206,7 +206,7 @@ class ModelCode(object):
         a('// constants: %s' % ', '.join(self.const_names))
         a('// outputs  : %s' % ', '.join(self.output_names))
         a('#pragma once')
-        a('#include "../model_api.cuh"')
+        a('#include "model_api.cuh"')
         a('struct %s {' % name)
         a('  static constexpr int N = %d;' % n)
         a('  static constexpr int NC = %d;' % nc)
@@ -330,5 +330,5 @@ class ModelCode(object):
             '// GENERATED by chi_b200/_codegen.py -- do not edit.\n'
             '#include <initializer_list>\n'
             '#include "model_%s.cuh"\n'
-            '#include "../integrator.cuh"\n'
+            '#include "integrator.cuh"\n'
             'CHI_B200_REGISTER_MODEL(%s, %s)\n' % (self.key, name, vs))

@@ -38,7 +38,9 @@ def build(force=False):
         return LIB
     cmd = ['g++', '-O3', '-std=c++17', '-fPIC', '-shared', '-fopenmp',
            '-ffp-contract=fast', '-march=x86-64-v3',
-           '-I/usr/local/cuda/include', os.path.join(HERE, 'port.cpp'),
+           '-I/usr/local/cuda/include',
+           '-I' + os.path.join(ROOT, 'chi_b200', 'csrc'),
+           os.path.join(HERE, 'port.cpp'),
            '-o', LIB]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE,
                           stderr=subprocess.STDOUT, text=True)
