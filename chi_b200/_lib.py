@@ -65,6 +65,8 @@ _SIGNATURES = {
         ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_double,
                        ctypes.c_int32]),
     'chi_b200_problem_set_variant': (ctypes.c_int, [c_vp, ctypes.c_int32]),
+    'chi_b200_problem_set_fixed_parameters': (
+        ctypes.c_int, [c_vp, ctypes.c_int32, c_i32p, c_f64p]),
     'chi_b200_problem_set_n_ids': (ctypes.c_int, [c_vp, ctypes.c_int64]),
     'chi_b200_problem_upload': (
         ctypes.c_int, [c_vp, ctypes.c_int64, c_i64p, c_f64p, c_f64p, c_i32p,

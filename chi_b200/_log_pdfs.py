@@ -140,6 +140,21 @@ class _DeviceLikelihoods(object):
         _lib.check(_lib.lib().chi_b200_problem_set_sensitivity_columns(
             self.problem.handle, len(columns), p))
 
+    def set_fixed(self, mask, values):
+        """Holds entries of the system vector [psi | sigma] at fixed values
+        (LogLikelihood.fix_parameters).  Sensitivities are then only
+        integrated for the free mechanistic parameters."""
+        mask = np.asarray(mask, dtype=bool)
+        idx = np.flatnonzero(mask).astype(np.int32)
+        a_i, p_i = _lib.i32(idx)
+        a_v, p_v = _lib.f64(np.asarray(values, dtype=float)[mask])
+        _lib.check(_lib.lib().chi_b200_problem_set_fixed_parameters(
+            self.problem.handle, len(idx), p_i, p_v))
+        free_mech = [j for j in range(self.n_mech) if not mask[j]]
+        if free_mech:
+            self.set_sensitivity_columns(free_mech)
+        self.fixed_mask = mask
+
     def simulate(self, psi, ids=None, with_sens=False):
         """Batched ``simulate``: psi (B, n_mech) -> model output at every
         record of every system (concatenated) [and sensitivities]."""
@@ -244,8 +259,60 @@ class LogLikelihood(_LogPDFBase):
         self._n_obs = [len(obs) for obs in observations]
         self._set_error_model_parameter_names()
         self._set_number_and_parameter_names()
+        self._full_parameter_names = list(self._parameter_names)
+        self._fixed_mask = None
+        self._fixed_values = None
         self._id = None
         self._device = None
+
+    def fix_parameters(self, name_value_dict):
+        """Fixes model parameters at the given values and removes them from
+        the parameter vector; ``None`` frees a parameter again
+        (chi/_log_pdfs.py:1029-1073).  Sensitivities are computed for the
+        free parameters only."""
+        try:
+            name_value_dict = dict(name_value_dict)
+        except (TypeError, ValueError):
+            raise ValueError(
+                'The name-value dictionary has to be convertable to a python '
+                'dictionary.')
+        n_full = len(self._full_parameter_names)
+        if self._fixed_mask is None:
+            self._fixed_mask = np.zeros(n_full, dtype=bool)
+            self._fixed_values = np.zeros(n_full)
+        for index, name in enumerate(self._full_parameter_names):
+            if name not in name_value_dict:
+                continue
+            value = name_value_dict[name]
+            if value is None:
+                self._fixed_mask[index] = False
+                continue
+            self._fixed_mask[index] = True
+            self._fixed_values[index] = float(value)
+        if not np.any(self._fixed_mask):
+            self._fixed_mask = None
+            self._fixed_values = None
+        free = np.ones(n_full, dtype=bool) if self._fixed_mask is None \
+            else ~self._fixed_mask
+        self._parameter_names = [
+            n for n, f in zip(self._full_parameter_names, free) if f]
+        self._n_parameters = len(self._parameter_names)
+        self._device = None
+
+    def n_fixed_parameters(self):
+        return 0 if self._fixed_mask is None else int(
+            np.sum(self._fixed_mask))
+
+    def _expand(self, parameters):
+        parameters = np.asarray(parameters, dtype=float).reshape(-1)
+        if len(parameters) != self._n_parameters:
+            raise ValueError(
+                'The number of parameters does not match n_parameters.')
+        if self._fixed_mask is None:
+            return parameters
+        full = self._fixed_values.copy()
+        full[~self._fixed_mask] = parameters
+        return full
 
     # -- device ----------------------------------------------------------------
     def _regimen(self):
@@ -261,12 +328,18 @@ class LogLikelihood(_LogPDFBase):
                 [em._kind for em in self._error_models],
                 [self._output_times], [self._observations],
                 [self._regimen()])
+            if self._fixed_mask is not None:
+                n_mech = self._n_mechanistic_params
+                free_mech = [j for j in range(n_mech)
+                             if not self._fixed_mask[j]]
+                if free_mech:
+                    self._device.set_sensitivity_columns(free_mech)
         return self._device
 
     def __call__(self, parameters):
         """chi/_log_pdfs.py:802-843."""
-        parameters = np.asarray(parameters, dtype=float)
-        ll, _, status = self._get_device().loglik(parameters[None, :])
+        full = self._expand(parameters)
+        ll, _, status = self._get_device().loglik(full[None, :])
         if status[0] != 0:
             _failure_warning(status[0])
             return -np.inf
@@ -274,13 +347,17 @@ class LogLikelihood(_LogPDFBase):
 
     def evaluateS1(self, parameters):
         """chi/_log_pdfs.py:973-1027."""
-        parameters = np.asarray(parameters, dtype=float)
+        full = self._expand(parameters)
         ll, grad, status = self._get_device().loglik(
-            parameters[None, :], with_grad=True)
+            full[None, :], with_grad=True)
         if status[0] != 0:
             _failure_warning(status[0])
-            return -np.inf, np.full(shape=len(parameters), fill_value=np.inf)
-        return float(ll[0]), grad[0].copy()
+            return -np.inf, np.full(
+                shape=self._n_parameters, fill_value=np.inf)
+        grad = grad[0]
+        if self._fixed_mask is not None:
+            grad = grad[~self._fixed_mask]
+        return float(ll[0]), grad.copy()
 
     def _set_error_model_parameter_names(self):
         """chi/_log_pdfs.py:885-909."""
@@ -330,6 +407,13 @@ class LogLikelihood(_LogPDFBase):
         self._id = str(label)
 
 
+def _same_fixed(a, b):
+    if a._fixed_mask is None or b._fixed_mask is None:
+        return a._fixed_mask is None and b._fixed_mask is None
+    return np.array_equal(a._fixed_mask, b._fixed_mask) and np.array_equal(
+        a._fixed_values[a._fixed_mask], b._fixed_values[b._fixed_mask])
+
+
 def _check_structure(log_likelihoods):
     first = log_likelihoods[0]
     key = first._mechanistic_model.model_key()
@@ -338,7 +422,8 @@ def _check_structure(log_likelihoods):
     for ll in log_likelihoods[1:]:
         if ll._mechanistic_model.model_key() != key or \
                 ll._mechanistic_model._output_names != outs or \
-                [em._kind for em in ll._error_models] != kinds:
+                [em._kind for em in ll._error_models] != kinds or \
+                not _same_fixed(first, ll):
             raise ValueError(
                 'The log-likelihoods of a hierarchical model have to be '
                 'structurally identical (same mechanistic model, outputs and '
@@ -388,6 +473,8 @@ class HierarchicalLogLikelihood(object):
             [ll._output_times for ll in log_likelihoods],
             [ll._observations for ll in log_likelihoods],
             [ll._regimen() for ll in log_likelihoods])
+        if first._fixed_mask is not None:
+            device.set_fixed(first._fixed_mask, first._fixed_values)
         self._setup(device, population_model, covariates,
                     first.get_parameter_names(),
                     [ll.get_id() for ll in log_likelihoods])
@@ -395,7 +482,7 @@ class HierarchicalLogLikelihood(object):
     @classmethod
     def from_arrays(cls, mechanistic_model, error_models, times,
                     observations, population_model, regimens=None,
-                    covariates=None, ids=None):
+                    covariates=None, ids=None, fixed_parameters=None):
         """Builds the hierarchical log-likelihood straight from ragged
         arrays (one entry per individual; single output: arrays, multiple
         outputs: lists of arrays) without creating one Python object per
@@ -420,6 +507,11 @@ class HierarchicalLogLikelihood(object):
             template._mechanistic_model,
             [em._kind for em in template._error_models], times, observations,
             regimens)
+        if fixed_parameters:
+            template.fix_parameters(fixed_parameters)
+            if template._fixed_mask is not None:
+                device.set_fixed(
+                    template._fixed_mask, template._fixed_values)
         if population_model.n_covariates() > 0:
             if covariates is None:
                 raise ValueError(
@@ -441,7 +533,9 @@ class HierarchicalLogLikelihood(object):
         self._n_dim = population_model.n_dim()
         self._ll_parameter_names = list(ll_names)
         self._ids = list(ids)
-        if self._n_dim != device.n_dim:
+        n_free = device.n_dim - int(np.sum(
+            getattr(device, 'fixed_mask', np.zeros(1, dtype=bool))))
+        if self._n_dim != n_free:
             raise ValueError(
                 'The dimension of the population model does not match the '
                 'the dimensions of the log-likelihood parameter space.')

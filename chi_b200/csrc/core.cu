@@ -90,6 +90,13 @@ struct PopDesc {
   int32_t n_hdim;
   int32_t n_cov_total;
   int32_t n_red;       // reduced top-level slots (all but heterogeneous)
+  // layout of one system's parameter vector: the population dims are the
+  // free entries, fixed entries carry constants (fix_parameters)
+  int32_t n_sys;                    // length of the system vector
+  int32_t sys_pos[MAX_POP_DIM];     // position of population dim d
+  int32_t n_fixed;
+  int32_t fixed_idx[MAX_POP_DIM];
+  double fixed_val[MAX_POP_DIM];
   PopDim dim[MAX_POP_DIM];
 };
 
@@ -119,6 +126,10 @@ struct chi_b200_problem {
   std::vector<int64_t> h_rec_off;
   DevBuf rec_off, rec_t, rec_obs, rec_logobs, rec_out;
   DevBuf seg_off, seg_t, seg_rate;
+
+  // parameters of the system vector held at fixed values
+  std::vector<int32_t> fixed_idx;
+  std::vector<double> fixed_val;
 
   // population model
   bool has_pop = false;
@@ -188,8 +199,9 @@ __global__ void pop_forward_kernel(PopDesc P, int32_t C, int64_t n_ids,
   const double* xc = x + c * n_params;
   const double* top = xc + n_bottom;
   const double* bot = xc + i * P.n_hdim;
-  double* out = xsys + tid * P.n_dim;
+  double* out = xsys + tid * P.n_sys;
   if (ids) ids[tid] = static_cast<int32_t>(i);
+  for (int f = 0; f < P.n_fixed; ++f) out[P.fixed_idx[f]] = P.fixed_val[f];
   bool bad = false;
   for (int d = 0; d < P.n_dim; ++d) {
     const PopDim& D = P.dim[d];
@@ -213,7 +225,7 @@ __global__ void pop_forward_kernel(PopDesc P, int32_t C, int64_t n_ids,
         psi = exp(fma(sigma, eta, mu));
       }
     }
-    out[d] = psi;
+    out[P.sys_pos[d]] = psi;
     if (eta_out) eta_out[tid * P.n_dim + d] = eta;
   }
   if (bad && popflag) popflag[c] = 1;
@@ -250,7 +262,8 @@ pop_backward_kernel(PopDesc P, int64_t n_ids, int64_t id_begin,
   const double* xc = x + c * n_params;
   const double* top = xc + n_bottom;
   const double* bot = xc + i * P.n_hdim;
-  const double* g_in = dlp ? dlp + (c * n_sh + (live ? k : 0)) * P.n_dim : nullptr;
+  const double* g_in =
+      dlp ? dlp + (c * n_sh + (live ? k : 0)) * P.n_sys : nullptr;
   double* gc = grad ? grad + c * n_params : nullptr;
 
   for (int s = lane; s < n_slots; s += 32) sacc[warp * n_slots + s] = 0.0;
@@ -259,7 +272,7 @@ pop_backward_kernel(PopDesc P, int64_t n_ids, int64_t id_begin,
   double score = (live && ll) ? ll[c * n_sh + k] : 0.0;
   for (int d = 0; d < P.n_dim; ++d) {
     const PopDim& D = P.dim[d];
-    const double dl = (live && g_in) ? g_in[d] : 0.0;
+    const double dl = (live && g_in) ? g_in[P.sys_pos[d]] : 0.0;
     if (D.kind == CHI_B200_POP_POOLED) {
       // PooledModel._shape(reduce=True): d theta = sum_i d ll/d psi_i
       // (chi/_population_models.py:2792-2810)
@@ -714,6 +727,27 @@ int chi_b200_problem_set_n_ids(chi_b200_problem* p, int64_t n_ids) {
   p->n_ids = n_ids;
   p->id_begin = 0;
   p->id_end = n_ids;
+  return 0;
+}
+
+int chi_b200_problem_set_fixed_parameters(chi_b200_problem* p,
+                                          int32_t n_fixed,
+                                          const int32_t* idx,
+                                          const double* values) {
+  if (!p->vt) return fail(-1, "problem has no mechanistic model");
+  const int nd = p->vt->n_states + p->vt->n_consts + p->n_sigma;
+  if (n_fixed < 0 || n_fixed >= nd || n_fixed > MAX_POP_DIM)
+    return fail(-1, "invalid number of fixed parameters");
+  std::vector<int32_t> fi(idx, idx + n_fixed);
+  for (int f = 0; f < n_fixed; ++f) {
+    if (fi[f] < 0 || fi[f] >= nd)
+      return fail(-1, "fixed parameter index out of range");
+    if (f > 0 && fi[f] <= fi[f - 1])
+      return fail(-1, "fixed parameter indices must be increasing");
+  }
+  p->fixed_idx = fi;
+  p->fixed_val.assign(values, values + n_fixed);
+  p->has_pop = false;  // the population layout depends on the fixed set
   return 0;
 }
 
@@ -1230,8 +1264,24 @@ int chi_b200_population_set(chi_b200_problem* p, int32_t n_blocks,
   D.n_cov_total = c0;
   D.n_red = static_cast<int32_t>(p->red_to_top.size());
   p->n_top = top;
-  const int nd_ll =
+  const int n_fixed = p->vt ? static_cast<int>(p->fixed_idx.size()) : 0;
+  const int nd_sys =
       p->vt ? p->vt->n_states + p->vt->n_consts + p->n_sigma : D.n_dim;
+  const int nd_ll = nd_sys - n_fixed;
+  if (nd_sys > MAX_POP_DIM) return fail(-1, "too many system parameters");
+  D.n_sys = nd_sys;
+  D.n_fixed = n_fixed;
+  {
+    std::vector<char> is_fixed(nd_sys, 0);
+    for (int f = 0; f < n_fixed; ++f) {
+      D.fixed_idx[f] = p->fixed_idx[f];
+      D.fixed_val[f] = p->fixed_val[f];
+      is_fixed[p->fixed_idx[f]] = 1;
+    }
+    int d = 0;
+    for (int j = 0; j < nd_sys; ++j)
+      if (!is_fixed[j] && d < MAX_POP_DIM) D.sys_pos[d++] = j;
+  }
   if (D.n_dim != nd_ll)
     return fail(-1,
                 "The dimension of the population model does not match the "
@@ -1274,7 +1324,7 @@ int run_hier(chi_b200_problem* p, int32_t C, const double* d_x,
   const int64_t n_bottom = p->n_ids * D.n_hdim;
   const int64_t n_params = n_bottom + p->n_top;
   const int64_t B = n_sh * C;
-  const int nd = D.n_dim;
+  const int nd = D.n_sys;
   if (B <= 0) return 0;
   CUDA_TRY(p->x.reserve(B * nd * sizeof(double)));
   CUDA_TRY(p->ids.reserve(B * sizeof(int32_t)));
@@ -1411,6 +1461,10 @@ int chi_b200_population_eval(chi_b200_problem* p, const double* top,
                              int32_t with_grad, double* eta, double* psi,
                              double* score, double* grad) {
   if (!p->has_pop) return fail(-1, "no population model set");
+  if (p->pop.n_sys != p->pop.n_dim)
+    return fail(-1,
+                "stand-alone population evaluation is not available on a "
+                "problem with fixed parameters");
   CUDA_TRY(cudaSetDevice(p->device));
   cudaStream_t s = p->stream;
   const PopDesc& D = p->pop;

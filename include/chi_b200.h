@@ -110,6 +110,15 @@ int chi_b200_problem_set_sensitivity_columns(chi_b200_problem* p,
 int chi_b200_problem_set_tolerances(chi_b200_problem* p, double rtol,
                                     double atol, int32_t max_steps);
 int chi_b200_problem_set_variant(chi_b200_problem* p, int32_t variant);
+/* Entries of the per-system parameter vector [psi | sigma] held at fixed
+ * values inside chi_b200_hier_logpdf (LogLikelihood.fix_parameters,
+ * chi/_log_pdfs.py:1029-1073): the population model then spans the free
+ * entries only.  Call after set_outputs and before population_set; indices
+ * increasing. */
+int chi_b200_problem_set_fixed_parameters(chi_b200_problem* p,
+                                          int32_t n_fixed,
+                                          const int32_t* idx,
+                                          const double* values);
 
 /* Static population data.
  *   rec_off[n_ids+1]   observation records of individual i are

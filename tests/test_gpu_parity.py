@@ -602,3 +602,58 @@ def test_dataframe_ingestion_and_batched_sampler():
     out = ctrl.run(n_iterations=5, hyperparameters={
         'n_leapfrog': 3, 'step_size': 0.02})
     assert np.all(np.isfinite(out['log_pdf']))
+
+
+def test_fix_parameters_matches_unfixed_model():
+    """LogLikelihood.fix_parameters (chi/_log_pdfs.py:1029-1073) and its
+    hierarchical counterpart: fixing the initial amounts at 0 must give the
+    score and the gradient of the free parameters of the full model."""
+    from chi_b200 import _synthetic
+    n_ids = 9
+    prob = _synthetic.two_compartment_problem(
+        n_ids, seed=4, n_doses=2, rtol=1e-10, atol=1e-12)
+    full = prob['log_likelihood']
+    x = prob['x0'].copy()
+    n_bottom = 5 * n_ids
+    x[n_bottom:n_bottom + 2] = 0.0          # pooled initial amounts
+    s_full, g_full = full.evaluateS1(x)
+
+    # single individual
+    model = prob['model']
+    reg0 = prob['regimens'][0]
+    m0 = model.copy()
+    m0.set_dosing_regimen(reg0)
+    ll = chi_b200.LogLikelihood(
+        m0, chi_b200.LogNormalErrorModel(), prob['observations'][0],
+        prob['times'][0])
+    psi0 = np.concatenate([[0.0, 0.0], [2.1, 0.9, 4.0, 1.2, 9.0], [0.11]])
+    ref_s, ref_g = ll.evaluateS1(psi0)
+    ll.fix_parameters({'central.drug_amount': 0.0,
+                       'peripheral.drug_amount': 0})
+    assert ll.n_parameters() == 6 and ll.n_fixed_parameters() == 2
+    assert ll.get_parameter_names()[0] == 'central.size'
+    s, g = ll.evaluateS1(psi0[2:])
+    assert s == pytest.approx(ref_s, rel=1e-10)
+    np.testing.assert_allclose(g, ref_g[2:], rtol=1e-7, atol=1e-9)
+    assert ll(psi0[2:]) == pytest.approx(ref_s, rel=1e-8)
+    ll.fix_parameters({'central.drug_amount': None,
+                       'peripheral.drug_amount': None})
+    assert ll.n_parameters() == 8
+
+    # hierarchical: population over the six free parameters only
+    pm = chi_b200.ComposedPopulationModel([
+        chi_b200.LogNormalModel(n_dim=5, centered=False),
+        chi_b200.PooledModel(n_dim=1)])
+    hll = chi_b200.HierarchicalLogLikelihood.from_arrays(
+        model, [chi_b200.LogNormalErrorModel()], prob['times'],
+        prob['observations'], pm, regimens=prob['regimens'],
+        fixed_parameters={'central.drug_amount': 0.0,
+                          'peripheral.drug_amount': 0.0})
+    assert hll.n_parameters() == full.n_parameters() - 2
+    x_fixed = np.concatenate([x[:n_bottom], x[n_bottom + 2:]])
+    s_fix, g_fix = hll.evaluateS1(x_fixed)
+    assert s_fix == pytest.approx(s_full, rel=1e-10)
+    g_ref = np.concatenate([g_full[:n_bottom], g_full[n_bottom + 2:]])
+    np.testing.assert_allclose(
+        g_fix, g_ref, rtol=1e-7, atol=1e-8 * np.max(np.abs(g_ref)))
+    assert hll(x_fixed) == pytest.approx(full(x), rel=1e-10)
