@@ -107,8 +107,10 @@ def flops_per_step(n, n_cols, info, stages=6):
     extra = s * (f_col_sum + n_cols * f_hess_common)
     jac = (0 if linear else (s + 1) * f_jac) if n_cols else (
         0 if linear else f_jac)
-    new = (n_cols + 1) * (n + 6 * n)
-    return inv + state + n_cols * sens + extra + jac + new + 10
+    # new solution = last stage value + last increment; the error norm and
+    # the step-size controller run in FP32 and are not counted
+    new = (n_cols + 1) * n
+    return inv + state + n_cols * sens + extra + jac + new
 
 
 def flops_per_record(n, n_cols):

@@ -220,7 +220,8 @@ class ModelCode(object):
             (1 << k) for k, flag in enumerate(self.inert) if flag))
         a('  // resident blocks per SM the streamed kernel is compiled for')
         a('  static constexpr int STREAM_MIN_BLOCKS = %d;' % (
-            3 if (self.linear and n <= 2) else 2))
+            int(__import__('os').environ.get('CHI_B200_MINB', '0')) or (
+                4 if (self.linear and n <= 2) else 2)))
         a('  static constexpr int DOSED_STATE = %d;' % (
             self.state_names.index(self.model.dosed_state)
             if self.model.dosed_state else -1))

@@ -22,9 +22,12 @@
 
 namespace chi_b200 {
 
+// shared-memory doubles per thread: S (current + candidate), gradient
+// accumulators, the state column's stage values 2..8 (the first is y) and the
+// error-model parameter gradients
 template <class M>
 constexpr int stream_slots() {
-  return 2 * M::P * M::N + M::P;
+  return 2 * M::P * M::N + M::P + 7 * M::N + MAX_SIGMA;
 }
 
 namespace rodas5 {
@@ -176,7 +179,6 @@ struct StreamSolver {
   int cur;
   bool loglik, invalid, after_reject;
   double ll;
-  double dsig[MAX_SIGMA];
   int64_t r, r_end, r_begin, seg, seg_end, trow;
   double u, t_edge, t, h, h_full;
   int n_acc, n_rej, status;
@@ -187,6 +189,8 @@ struct StreamSolver {
 
 #define CHI_S(buf, k, n) sm[(((buf) * P + (k)) * N + (n)) * stride]
 #define CHI_G(k) sm[(2 * P * N + (k)) * stride]
+#define CHI_ZY(i, n) sm[(2 * P * N + P + ((i) - 1) * N + (n)) * stride]
+#define CHI_DSIG(k) sm[(2 * P * N + P + 7 * N + (k)) * stride]
 
   CHI_HD void init(const int64_t system) {
     b = system;
@@ -212,8 +216,7 @@ struct StreamSolver {
     }
     loglik = a.mode == 1;
     ll = 0.0;
-#pragma unroll
-    for (int k = 0; k < MAX_SIGMA; ++k) dsig[k] = 0.0;
+    for (int k = 0; k < MAX_SIGMA; ++k) CHI_DSIG(k) = 0.0;
     invalid = false;
     if (loglik) {
       for (int o = 0; o < a.n_out; ++o) {
@@ -243,8 +246,7 @@ struct StreamSolver {
   // register-resident accumulation into dsig[off] (no dynamic indexing, so
   // the solver state stays in registers)
   CHI_HD void add_dsig(const int off, const double v) {
-#pragma unroll
-    for (int k = 0; k < MAX_SIGMA; ++k) dsig[k] += (k == off) ? v : 0.0;
+    CHI_DSIG(off) += v;
   }
 
   CHI_HD double get_sigma(const int off) const {
@@ -341,7 +343,6 @@ struct StreamSolver {
   // initial-value column) given the state column's stage values Zy and
   // increments Uy.  Returns the column's squared scaled error.
   CHI_HD float column(const int kc, const int k, const int nxt,
-                      const double (&Zy)[NS][N],
                       const double (&Uy)[NS][N], const double (&Wi)[N * N],
                       const double hinv, const float atol_f,
                       const float rtol_f) {
@@ -351,13 +352,15 @@ struct StreamSolver {
 #define CHI_SSTAGE(I, CNT, a0, a1, a2, a3, a4, a5, a6, c0, c1, c2, c3, c4,   \
                    c5, c6)                                                    \
   {                                                                           \
-    double Ji[N * N];                                                         \
-    if (!M::LINEAR) M::jac(Zy[I], c, Ji);                                     \
+    double Ji[N * N], Zyi[N];                                                 \
+    _Pragma("unroll") for (int n = 0; n < N; ++n) Zyi[n] =                    \
+        (I == 0) ? y[n] : CHI_ZY(I, n);                                       \
+    if (!M::LINEAR) M::jac(Zyi, c, Ji);                                       \
     double cs[N], rs[N];                                                      \
     lincomb7<CNT, N>(Zl, S0, Us, a0, a1, a2, a3, a4, a5, a6);                 \
     lincomb7<CNT, N>(cs, nullptr, Us, c0, c1, c2, c3, c4, c5, c6);            \
     matvec<N>(M::LINEAR ? J0 : Ji, Zl, rs);                                   \
-    M::dfdc_col_add(kc, Zy[I], c, rs);                                        \
+    M::dfdc_col_add(kc, Zyi, c, rs);                                          \
     M::hess_col_add(kc, y, c, S0, Uy[I], rs);                                 \
     _Pragma("unroll") for (int n = 0; n < N; ++n) rs[n] =                     \
         fma(hinv, cs[n], rs[n]);                                              \
@@ -427,14 +430,17 @@ struct StreamSolver {
       invert<N>(W, Wi);
     }
     const double hinv = 1.0 / hs;
-    double Zy[NS][N];
     double Uy[NS][N];
+    double Zlast[N];
 #define CHI_YSTAGE(I, CNT, a0, a1, a2, a3, a4, a5, a6, c0, c1, c2, c3, c4,   \
                    c5, c6)                                                    \
   {                                                                           \
     double f[N], cy[N], ry[N];                                                \
-    lincomb7<CNT, N>(Zy[I], y, Uy, a0, a1, a2, a3, a4, a5, a6);               \
-    M::rhs(Zy[I], c, u, f);                                                   \
+    lincomb7<CNT, N>(Zlast, y, Uy, a0, a1, a2, a3, a4, a5, a6);               \
+    if (I > 0) {                                                              \
+      _Pragma("unroll") for (int n = 0; n < N; ++n) CHI_ZY(I, n) = Zlast[n];  \
+    }                                                                         \
+    M::rhs(Zlast, c, u, f);                                                   \
     lincomb7<CNT, N>(cy, nullptr, Uy, c0, c1, c2, c3, c4, c5, c6);            \
     _Pragma("unroll") for (int n = 0; n < N; ++n) ry[n] =                     \
         fma(hinv, cy[n], f[n]);                                               \
@@ -454,7 +460,7 @@ struct StreamSolver {
       float s2 = 0.0f;
 #pragma unroll
       for (int n = 0; n < N; ++n) {
-        yn[n] = Zy[NS - 1][n] + Uy[NS - 1][n];
+        yn[n] = Zlast[n] + Uy[NS - 1][n];
         s2 += err_term(Uy[NS - 1][n], y[n], yn[n], atol_f, rtol_f);
       }
       errsq = s2 * (1.0f / N);
@@ -471,7 +477,7 @@ struct StreamSolver {
       // zero: nothing to integrate
       if (kc >= 0 && ((M::INERT_MASK >> kc) & 1u)) continue;
       errsq = fmaxf(errsq,
-                    column(kc, k, nxt, Zy, Uy, Wi, hinv, atol_f, rtol_f));
+                    column(kc, k, nxt, Uy, Wi, hinv, atol_f, rtol_f));
     }
 
     const bool accept = errsq <= 1.0f;
@@ -519,9 +525,8 @@ struct StreamSolver {
         double* gb = a.grad + b * a.grad_stride;
         for (int k = 0; k < n_cols; ++k)
           gb[a.col_param[k]] = fail ? INFINITY : CHI_G(k);
-#pragma unroll
-        for (int k = 0; k < MAX_SIGMA; ++k)
-          if (k < a.n_sigma) gb[P + k] = fail ? INFINITY : dsig[k];
+        for (int k = 0; k < a.n_sigma; ++k)
+          gb[P + k] = fail ? INFINITY : CHI_DSIG(k);
       }
     } else if (status != ST_OK) {
       for (int64_t q = r; q < r_end; ++q)
@@ -530,6 +535,8 @@ struct StreamSolver {
   }
 #undef CHI_S
 #undef CHI_G
+#undef CHI_ZY
+#undef CHI_DSIG
 };
 
 template <class M, int CB>

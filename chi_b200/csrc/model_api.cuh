@@ -14,7 +14,7 @@ namespace chi_b200 {
 
 constexpr int MAX_OUT = 8;    // outputs selected per problem
 constexpr int MAX_COLS = 32;  // sensitivity columns (mechanistic parameters)
-constexpr int MAX_SIGMA = 8;     // error-model parameters per problem
+constexpr int MAX_SIGMA = 4;     // error-model parameters per problem
 
 // Error-model kinds (chi/_error_models.py): parameters per kind 1,1,2,1.
 enum ErrKind : int32_t {
