@@ -183,8 +183,17 @@ class ModelCode(object):
 
         out_cases = []
         dout_cases = []
+        grad_cases = []
         for k, g in enumerate(self.g):
             gk = g.xreplace(sub)
+            items = [('r', gk)]
+            items += [('gy[%d]' % j, sp.diff(gk, ylist[j]))
+                      for j in range(n)]
+            items += [('gc[%d]' % j, sp.diff(gk, csym[c[j]]))
+                      for j in range(nc)]
+            code, _ = _emit_block(items, indent='        ')
+            grad_cases.append('      case %d: {\n%s\n        break; }' % (
+                k, code))
             code, _ = _emit_block([('r', gk)], indent='        ')
             out_cases.append('      case %d: {\n%s\n        break; }' % (
                 k, code))
@@ -297,6 +306,19 @@ class ModelCode(object):
         a('    double r = 0.0;')
         a('    switch (id) {')
         lines.extend(dout_cases)
+        a('      default: break;')
+        a('    }')
+        a('    return r;')
+        a('  }')
+        a('  // returns g(y, c); gy = dg/dy, gc = dg/dc')
+        a('  CHI_HD static double out_grad(int id, const double* y, '
+          'const double* c, double* gy, double* gc) {')
+        a('    (void)y; (void)c;')
+        a('    double r = 0.0;')
+        a('    for (int j = 0; j < N; ++j) gy[j] = 0.0;')
+        a('    for (int j = 0; j < NCS; ++j) gc[j] = 0.0;')
+        a('    switch (id) {')
+        lines.extend(grad_cases)
         a('      default: break;')
         a('    }')
         a('    return r;')

@@ -71,10 +71,10 @@ constexpr double LOG_2PI_HALF = 0.91893853320467274178;
 #define CHI_FACMAX 5.0f
 #endif
 #ifndef CHI_EDGE_KEEP_H
-#define CHI_EDGE_KEEP_H 0
+#define CHI_EDGE_KEEP_H 1
 #endif
 #ifndef CHI_EDGE_SHRINK
-#define CHI_EDGE_SHRINK 1.0
+#define CHI_EDGE_SHRINK 0.3
 #endif
 
 // ---- small dense helpers (fully unrolled, registers only) -----------------

@@ -24,10 +24,10 @@ namespace chi_b200 {
 
 // shared-memory doubles per thread: S (current + candidate), gradient
 // accumulators, the state column's stage values 2..8 (the first is y) and the
-// error-model parameter gradients
+// error-model parameter gradients, three cold scalars
 template <class M>
 constexpr int stream_slots() {
-  return 2 * M::P * M::N + M::P + 7 * M::N + MAX_SIGMA;
+  return 2 * M::P * M::N + M::P + 7 * M::N + MAX_SIGMA + 3;
 }
 
 namespace rodas5 {
@@ -261,17 +261,16 @@ struct StreamSolver {
   double* sm;
   const int stride;
 
-  int64_t b;
-  const double* sg;
-  int n_cols;
+  // hot state (registers)
   double y[N], c[NCS];
-  int cur;
-  bool loglik, invalid, after_reject;
-  double ll;
-  int64_t r, r_end, r_begin, seg, seg_end, trow;
-  double u, t_edge, t, h, h_full;
-  int n_acc, n_rej, status;
+  double u, t, h, t_stop, ll;
   double J0[N * N];
+  const double* sg;
+  int64_t r;
+  int cur, n_att, status;
+  bool invalid, after_reject;
+  // cold state: only touched when an event is pending
+  int64_t r_end, seg, seg_end;
 
   CHI_HD StreamSolver(const SolveArgs& args, double* smem, int smem_stride)
       : a(args), sm(smem), stride(smem_stride) {}
@@ -280,22 +279,31 @@ struct StreamSolver {
 #define CHI_G(k) sm[(2 * P * N + (k)) * stride]
 #define CHI_ZY(i, n) sm[(2 * P * N + P + ((i) - 1) * N + (n)) * stride]
 #define CHI_DSIG(k) sm[(2 * P * N + P + 7 * N + (k)) * stride]
+// cold per-system scalars kept out of the register file: 0 = system index,
+// 1 = next dose-rate edge, 2 = rejected steps
+#define CHI_COLD(k) sm[(2 * P * N + P + 7 * N + MAX_SIGMA + (k)) * stride]
 
-  CHI_HD void init(const int64_t system) {
-    b = system;
-    const int id = a.ids ? a.ids[b] : static_cast<int>(b % a.n_ids);
+  CHI_HD int n_cols() const { return a.with_sens ? a.n_cols : 0; }
+  CHI_HD bool loglik() const { return a.mode == 1; }
+  CHI_HD int64_t system() const { return static_cast<int64_t>(CHI_COLD(0)); }
+  CHI_HD int individual(const int64_t b) const {
+    return a.ids ? a.ids[b] : static_cast<int>(b % a.n_ids);
+  }
+
+  CHI_HD void init(const int64_t b) {
+    static_assert(METHOD_CODE == 1 || METHOD_CODE == 5, "unknown method");
+    const int id = individual(b);
     const double* xb = a.x + b * a.x_stride;
     sg = xb + P;
-    static_assert(METHOD_CODE == 1 || METHOD_CODE == 5, "unknown method");
-    n_cols = a.with_sens ? a.n_cols : 0;
 #pragma unroll
     for (int i = 0; i < N; ++i) y[i] = xb[i];
 #pragma unroll
     for (int i = 0; i < NC; ++i) c[i] = xb[N + i];
     if (NC == 0) c[0] = 0.0;
     cur = 0;
+    const int nc = n_cols();
     for (int k = 0; k < P; ++k) {
-      const int pk = k < n_cols ? a.col_param[k] : -1;
+      const int pk = k < nc ? a.col_param[k] : -1;
 #pragma unroll
       for (int n = 0; n < N; ++n) {
         CHI_S(0, k, n) = (pk == n) ? 1.0 : 0.0;
@@ -303,11 +311,10 @@ struct StreamSolver {
       }
       CHI_G(k) = 0.0;
     }
-    loglik = a.mode == 1;
     ll = 0.0;
     for (int k = 0; k < MAX_SIGMA; ++k) CHI_DSIG(k) = 0.0;
     invalid = false;
-    if (loglik) {
+    if (loglik()) {
       for (int o = 0; o < a.n_out; ++o) {
         const int off = a.err_off[o];
         if (sg[off] <= 0.0) invalid = true;
@@ -316,40 +323,37 @@ struct StreamSolver {
     }
     r = a.rec_off[id];
     r_end = a.rec_off[id + 1];
-    r_begin = r;
     seg = a.seg_off[id];
     seg_end = a.seg_off[id + 1];
     u = (seg < seg_end) ? a.seg_rate[seg] : 0.0;
-    t_edge = (seg + 1 < seg_end) ? a.seg_t[seg + 1] : INFINITY;
-    trow = (a.mode == 0) ? a.traj_off[b] : 0;
+    CHI_COLD(0) = static_cast<double>(b);
+    CHI_COLD(1) = (seg + 1 < seg_end) ? a.seg_t[seg + 1] : INFINITY;
+    CHI_COLD(2) = 0.0;
     t = 0.0;
+    t_stop = 0.0;   // forces the first pass through the event handler
     h = 0.0;
-    h_full = 0.0;
     after_reject = false;
-    n_acc = 0;
-    n_rej = 0;
+    n_att = 0;
     status = ST_OK;
     if (M::LINEAR) M::jac(y, c, J0);
   }
 
-  // register-resident accumulation into dsig[off] (no dynamic indexing, so
-  // the solver state stays in registers)
   CHI_HD void add_dsig(const int off, const double v) {
     CHI_DSIG(off) += v;
-  }
-
-  CHI_HD double get_sigma(const int off) const {
-    return sg[off];
   }
 
   // observation record r at the current time
   CHI_HD void observe() {
     const int o = a.rec_out[r];
     const int oid = a.out_id[o];
-    const double yb = M::out(oid, y, c);
+    const int nc = n_cols();
+    double gy[N], gc[NCS];
+    const double yb = M::out_grad(oid, y, c, gy, gc);
     double w = 0.0;
-    const int64_t row = trow + (r - r_begin);
-    if (!loglik) {
+    int64_t row = 0;
+    if (!loglik()) {
+      const int64_t b = system();
+      row = a.traj_off[b] + (r - a.rec_off[individual(b)]);
       a.traj_y[row] = yb;
     } else {
       const int kind = a.err_kind[o];
@@ -389,41 +393,49 @@ struct StreamSolver {
         }
       }
     }
-    for (int k = 0; k < n_cols; ++k) {
+    // d ybar / d psi_k = (dg/dy) S_k + dg/dc_k
+    for (int k = 0; k < nc; ++k) {
       const int pk = a.col_param[k];
-      double s[N], e[NCS];
+      double d = 0.0;
 #pragma unroll
-      for (int n = 0; n < N; ++n) s[n] = CHI_S(cur, k, n);
+      for (int j = 0; j < NC; ++j) d = (pk == N + j) ? gc[j] : d;
 #pragma unroll
-      for (int j = 0; j < NCS; ++j) e[j] = (pk == N + j) ? 1.0 : 0.0;
-      const double dyb = M::dout(oid, y, c, s, e);
-      if (loglik) {
-        CHI_G(k) = fma(w, dyb, CHI_G(k));
+      for (int n = 0; n < N; ++n) d = fma(gy[n], CHI_S(cur, k, n), d);
+      if (loglik()) {
+        CHI_G(k) = fma(w, d, CHI_G(k));
       } else {
-        a.traj_s[row * n_cols + k] = dyb;
+        a.traj_s[row * nc + k] = d;
       }
     }
   }
 
   // Handles the events pending at the current time (observation records,
-  // dose-rate edges).  Returns true when the system is finished.
+  // dose-rate edges).  Returns true when the system is finished.  The common
+  // case -- the next stop has not been reached -- is one comparison.
   CHI_HD bool events() {
+    if (t < t_stop) return false;
     if (invalid) return true;
+    double t_edge = CHI_COLD(1);
     for (;;) {
       if (r >= r_end) return true;
-      if (a.rec_t[r] <= t) {
+      const double t_rec = a.rec_t[r];
+      if (t_rec <= t) {
         observe();
+        if (invalid) return true;
         ++r;
         continue;
       }
       if (t_edge <= t) {
-        // dose-rate edge: switch the input, restart the step size
+        // dose-rate edge: switch the input; the step size proposed before
+        // the edge is kept (shrunk), the controller takes it from there
         ++seg;
         u = a.seg_rate[seg];
         t_edge = (seg + 1 < seg_end) ? a.seg_t[seg + 1] : INFINITY;
-        h = CHI_EDGE_KEEP_H ? h_full * CHI_EDGE_SHRINK : 0.0;
+        CHI_COLD(1) = t_edge;
+        h = CHI_EDGE_KEEP_H ? h * CHI_EDGE_SHRINK : 0.0;
         continue;
       }
+      t_stop = fmin(t_rec, t_edge);
       return false;
     }
   }
@@ -475,8 +487,6 @@ struct StreamSolver {
 
   // One step attempt towards the next stop.  Returns true on failure.
   CHI_HD bool step() {
-    const double t_stop = fmin(a.rec_t[r], t_edge);
-
     if (h == 0.0) {
       double f0[N];
       M::rhs(y, c, u, f0);
@@ -495,7 +505,6 @@ struct StreamSolver {
     }
 
     const double rem = t_stop - t;
-    h_full = h;
     double hs = h;
     bool clipped = false;
     if (rem <= 1.1 * h) {
@@ -505,20 +514,19 @@ struct StreamSolver {
       hs = 0.5 * rem;
     }
 
-    // ---- state column: six stages, values and increments kept -------------
+    // ---- state column: stage values and increments kept -------------------
     if (!M::LINEAR) M::jac(y, c, J0);
+    const double hinv = 1.0 / hs;
     double Wi[N * N];
     {
       double W[N * N];
-      const double fac = 1.0 / (GAMMA * hs);
 #pragma unroll
       for (int i = 0; i < N; ++i)
 #pragma unroll
         for (int j = 0; j < N; ++j)
-          W[i * N + j] = (i == j ? fac : 0.0) - J0[i * N + j];
+          W[i * N + j] = (i == j ? hinv * (1.0 / GAMMA) : 0.0) - J0[i * N + j];
       invert<N>(W, Wi);
     }
-    const double hinv = 1.0 / hs;
     double Uy[NS][N];
     double Zlast[N];
 #define CHI_YSTAGE(I, CNT, a0, a1, a2, a3, a4, a5, a6, c0, c1, c2, c3, c4,   \
@@ -559,7 +567,8 @@ struct StreamSolver {
     // The column's constant index kc is uniform over the grid: the switches
     // on it inside the generated column terms are uniform branches.
     const int nxt = 1 - cur;
-    for (int k = 0; k < n_cols; ++k) {
+    const int nc = n_cols();
+    for (int k = 0; k < nc; ++k) {
       const int pk = a.col_param[k];
       const int kc = pk >= N ? pk - N : -1;
       // columns of constants that do not enter the rhs stay identically
@@ -586,17 +595,16 @@ struct StreamSolver {
       const double hn = hs * static_cast<double>(fac);
       h = (hs < h) ? fmax(hn, h) : hn;
       after_reject = false;
-      ++n_acc;
     } else {
       h = hs * static_cast<double>(fminf(fac, 0.9f));
       after_reject = true;
-      ++n_rej;
+      CHI_COLD(2) += 1.0;
       if (h <= 1e-14 * fmax(fabs(t), 1.0)) {
         status = (errsq == errsq) ? ST_STEP_UNDERFLOW : ST_NON_FINITE;
         return true;
       }
     }
-    if (n_acc + n_rej >= a.max_steps) {
+    if (++n_att >= a.max_steps) {
       status = ST_MAX_STEPS;
       return true;
     }
@@ -604,28 +612,32 @@ struct StreamSolver {
   }
 
   CHI_HD void finish() {
+    const int64_t b = system();
+    const int n_rej = static_cast<int>(CHI_COLD(2));
     a.status[b] = status;
-    if (a.n_steps) a.n_steps[b] = n_acc;
+    if (a.n_steps) a.n_steps[b] = n_att - n_rej;
     if (a.n_rej) a.n_rej[b] = n_rej;
-    if (loglik) {
+    if (loglik()) {
       const bool fail = invalid || status != ST_OK;
       a.ll[b] = fail ? -INFINITY : ll;
       if (a.with_sens && a.grad) {
+        const int nc = n_cols();
         double* gb = a.grad + b * a.grad_stride;
-        for (int k = 0; k < n_cols; ++k)
+        for (int k = 0; k < nc; ++k)
           gb[a.col_param[k]] = fail ? INFINITY : CHI_G(k);
         for (int k = 0; k < a.n_sigma; ++k)
           gb[P + k] = fail ? INFINITY : CHI_DSIG(k);
       }
     } else if (status != ST_OK) {
-      for (int64_t q = r; q < r_end; ++q)
-        a.traj_y[trow + (q - r_begin)] = NAN;
+      const int64_t shift = a.traj_off[b] - a.rec_off[individual(b)];
+      for (int64_t q = r; q < r_end; ++q) a.traj_y[shift + q] = NAN;
     }
   }
 #undef CHI_S
 #undef CHI_G
 #undef CHI_ZY
 #undef CHI_DSIG
+#undef CHI_COLD
 };
 
 template <class M, int CB>

@@ -33,7 +33,7 @@ static void run_all(const SolveArgs& a, int n_threads, int stream_cb) {
 #pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads)
 #endif
   for (int64_t b = 0; b < a.B; ++b) {
-    if (!a.with_sens) {
+    if (!a.with_sens && stream_cb == 0) {
       solve_system<M, 1, 0>(a, b, 0, 0, 0, 1u);
     } else if (stream_cb == 1) {
       double sm[stream_slots<M>()];
