@@ -31,6 +31,9 @@ class _Printer(C99CodePrinter):
             return '(1.0/%s)' % self.parenthesize(base, 1000)
         return super(_Printer, self)._print_Pow(expr)
 
+    def _print_rcp(self, expr):
+        return '(1.0/%s)' % self.parenthesize(expr.args[0], 1000)
+
     def _print_Rational(self, expr):
         return '(%d.0/%d.0)' % (expr.p, expr.q)
 
@@ -39,6 +42,23 @@ class _Printer(C99CodePrinter):
 
 
 _printer = _Printer()
+
+
+class rcp(sp.Function):
+    """Reciprocal kept as an opaque function so that it can be shared."""
+    nargs = 1
+
+
+_rcp = rcp
+
+
+def _share_reciprocals(expr):
+    """x**-k -> rcp(x)**k, so that the common-subexpression pass emits one
+    division per distinct denominator and multiplications elsewhere."""
+    expr = sp.sympify(expr)
+    return expr.replace(
+        lambda e: e.is_Pow and e.exp.is_Integer and e.exp.is_negative,
+        lambda e: _rcp(e.base) ** (-e.exp))
 
 
 def _count_flops(exprs):
@@ -50,7 +70,7 @@ def _count_flops(exprs):
 
 def _emit_block(assignments, indent='    '):
     """assignments: list of (lhs string, sympy expr); applies CSE."""
-    exprs = [e for _, e in assignments]
+    exprs = [_share_reciprocals(e) for _, e in assignments]
     repl, reduced = sp.cse(exprs, symbols=sp.numbered_symbols('t_'),
                            optimizations='basic')
     lines = []
@@ -181,6 +201,27 @@ class ModelCode(object):
             self.flops_col.append(f1 + f2)
         common_code, self.flops_hess_common = _acc_block(common, '    ')
 
+        # linear models: (df/dc_k)(y) = D_k y + e_k with D_k, e_k free of y,
+        # so the column terms of a stage are one small matrix-vector product
+        # with data fetched once per column (no switch inside the stages)
+        lin_cases = []
+        if self.linear:
+            for k in range(nc):
+                col = sp.Matrix([fc[i, k] for i in range(n)])
+                Dk = col.jacobian(ylist) if n else sp.zeros(0, 0)
+                ek = (col - Dk * sp.Matrix(ylist)).applyfunc(sp.expand)
+                if any(Dk.has(v) for v in ylist) or any(
+                        ek.has(v) for v in ylist):
+                    raise AssertionError('model is not linear in the states')
+                items = [('D[%d]' % (i * n + j), Dk[i, j])
+                         for i in range(n) for j in range(n) if Dk[i, j] != 0]
+                items += [('e[%d]' % i, ek[i]) for i in range(n)
+                          if ek[i] != 0]
+                if items:
+                    code, _ = _emit_block(items, indent='        ')
+                    lin_cases.append(
+                        '      case %d: {\n%s\n        break; }' % (k, code))
+
         out_cases = []
         dout_cases = []
         grad_cases = []
@@ -286,6 +327,17 @@ class ModelCode(object):
         a(common_code)
         a('    switch (k) {')
         lines.extend(hess_cases)
+        a('      default: break;')
+        a('    }')
+        a('  }')
+        a('  // linear models: (df/dc_k)(y) = D y + e   (k < 0: D = 0, e = 0)')
+        a('  CHI_HD static void col_linear(int k, const double* c, double u, '
+          'double* D, double* e) {')
+        a('    (void)c; (void)u;')
+        a('    for (int j = 0; j < N * N; ++j) D[j] = 0.0;')
+        a('    for (int j = 0; j < N; ++j) e[j] = 0.0;')
+        a('    switch (k) {')
+        lines.extend(lin_cases)
         a('      default: break;')
         a('    }')
         a('  }')

@@ -101,6 +101,8 @@ _SIGNATURES = {
         ctypes.c_int, [c_vp, ctypes.c_int64, ctypes.c_int64]),
     'chi_b200_problem_counters': (ctypes.c_int, [c_vp, c_i64p]),
     'chi_b200_problem_set_timing': (ctypes.c_int, [c_vp, ctypes.c_int32]),
+    'chi_b200_problem_set_snapshot_budget': (
+        ctypes.c_int, [c_vp, ctypes.c_int64]),
     'chi_b200_problem_timings': (ctypes.c_int, [c_vp, c_f64p]),
     'chi_b200_fp64_peak': (ctypes.c_int, [ctypes.c_int32, c_f64p, c_f64p]),
 }

@@ -140,6 +140,13 @@ class _DeviceLikelihoods(object):
         _lib.check(_lib.lib().chi_b200_problem_set_sensitivity_columns(
             self.problem.handle, len(columns), p))
 
+    def set_snapshot_budget(self, n_bytes):
+        """Device memory the deferred observation may use
+        (``chi_b200_problem_set_snapshot_budget``): 0 keeps the error model
+        fused in the solve kernel, -1 restores the default."""
+        _lib.check(_lib.lib().chi_b200_problem_set_snapshot_budget(
+            self.problem.handle, int(n_bytes)))
+
     def set_fixed(self, mask, values):
         """Holds entries of the system vector [psi | sigma] at fixed values
         (LogLikelihood.fix_parameters).  Sensitivities are then only
@@ -638,6 +645,11 @@ class HierarchicalLogLikelihood(object):
         caller all-reduces over the ranks (multi-GPU)."""
         _lib.check(_lib.lib().chi_b200_problem_set_shard(
             self._device.problem.handle, int(id_begin), int(id_end)))
+
+    def set_snapshot_budget(self, n_bytes):
+        """See ``chi_b200_problem_set_snapshot_budget`` (0: observation
+        fused in the solve kernel, -1: default)."""
+        self._device.set_snapshot_budget(n_bytes)
 
     def set_timing(self, enabled):
         _lib.check(_lib.lib().chi_b200_problem_set_timing(

@@ -3,8 +3,10 @@
 // log-pdf pipeline.  See include/chi_b200.h for the contract of every entry
 // point and the reference interface it replaces.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -141,6 +143,11 @@ struct chi_b200_problem {
 
   // scratch
   DevBuf x, ll, grad, status, nst, nrj, ids, traj_off, traj_y, traj_s;
+  // deferred observation (SolveArgs::snap): snapshots of state and
+  // sensitivities at the records; used when they fit the budget
+  DevBuf snap;
+  int64_t max_rec = 0;          // largest number of records of an individual
+  int64_t snap_budget = -1;     // bytes; -1: not determined yet
   DevBuf hx, hscore, hgrad, hstatus, partial, popflag, r2t;
   int64_t counters[4] = {0, 0, 0, 0};
 
@@ -659,7 +666,7 @@ void chi_b200_problem_destroy(chi_b200_problem* p) {
   if (!p) return;
   cudaSetDevice(p->device);
   for (DevBuf* b :
-       {&p->rec_off, &p->rec_t, &p->rec_obs, &p->rec_logobs, &p->rec_out,
+       {&p->snap, &p->rec_off, &p->rec_t, &p->rec_obs, &p->rec_logobs, &p->rec_out,
         &p->seg_off, &p->seg_t, &p->seg_rate, &p->covariates, &p->x, &p->ll,
         &p->grad, &p->status, &p->nst, &p->nrj, &p->ids, &p->traj_off,
         &p->traj_y, &p->traj_s, &p->hx, &p->hscore, &p->hgrad, &p->hstatus,
@@ -779,6 +786,12 @@ int chi_b200_problem_set_timing(chi_b200_problem* p, int32_t enabled) {
   return 0;
 }
 
+int chi_b200_problem_set_snapshot_budget(chi_b200_problem* p, int64_t bytes) {
+  p->snap_budget = bytes;
+  if (bytes == 0) p->snap.release();
+  return 0;
+}
+
 int chi_b200_problem_timings(chi_b200_problem* p, double out[2]) {
   out[0] = p->solve_ms_sum;
   out[1] = static_cast<double>(p->solve_launches);
@@ -887,6 +900,9 @@ int chi_b200_problem_upload(chi_b200_problem* p, int64_t n_ids,
                   t_end, seg_t, seg_rate);
     seg_off[i + 1] = static_cast<int64_t>(seg_t.size());
   }
+  // the streamed kernel keeps record / segment indices as 32-bit integers
+  if (n_rec > INT32_MAX || static_cast<int64_t>(seg_t.size()) > INT32_MAX)
+    return fail(-1, "more than 2^31 - 1 observation records or dose segments");
   CUDA_TRY(upload(p->rec_off, off));
   CUDA_TRY(upload(p->rec_t, t));
   CUDA_TRY(upload(p->rec_obs, obs));
@@ -898,6 +914,9 @@ int chi_b200_problem_upload(chi_b200_problem* p, int64_t n_ids,
   p->n_ids = n_ids;
   p->n_rec = n_rec;
   p->h_rec_off = off;
+  p->max_rec = 0;
+  for (int64_t i = 0; i < n_ids; ++i)
+    p->max_rec = std::max(p->max_rec, off[i + 1] - off[i]);
   p->id_begin = 0;
   p->id_end = n_ids;
   return 0;
@@ -927,7 +946,12 @@ void fill_args(const chi_b200_problem* p, SolveArgs& a) {
   }
   a.n_sigma = p->n_sigma;
   a.n_cols = p->n_cols;
-  for (int i = 0; i < p->n_cols; ++i) a.col_param[i] = p->col_param[i];
+  for (int i = 0; i < MAX_COLS; ++i) a.param_col[i] = -1;
+  for (int i = 0; i < p->n_cols; ++i) {
+    a.col_param[i] = p->col_param[i];
+    if (p->col_param[i] >= 0 && p->col_param[i] < MAX_COLS)
+      a.param_col[p->col_param[i]] = i;
+  }
   a.rtol = p->rtol;
   a.atol = p->atol;
   a.max_steps = p->max_steps;
@@ -954,6 +978,41 @@ int launch_loglik(chi_b200_problem* p, int64_t B, const int32_t* d_ids,
   a.status = d_status;
   a.n_steps = d_nst;
   a.n_rej = d_nrj;
+  a.snap = nullptr;
+  a.snap_rows = 0;
+  a.snap_width = 0;
+  {
+    // deferred observation for the streamed kernels when the snapshots fit
+    const bool streamed =
+        p->variant < 0 || (p->variant < p->vt->n_variants &&
+                           p->vt->variant_lanes[p->variant] == 0);
+    if (p->snap_budget < 0) {
+      const char* env = std::getenv("CHI_B200_SNAP_MB");
+      if (env) {
+        p->snap_budget = static_cast<int64_t>(std::atof(env) * 1048576.0);
+      } else {
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        p->snap_budget = static_cast<int64_t>(free_b / 2);
+      }
+    }
+    const int N = p->vt->n_states;
+    int integrated = 0;
+    if (with_grad)
+      for (int k = 0; k < p->n_cols; ++k) {
+        const int pk = p->col_param[k];
+        if (!(pk >= N && ((p->vt->inert_mask >> (pk - N)) & 1u))) ++integrated;
+      }
+    const int64_t width = static_cast<int64_t>(N) * (1 + integrated);
+    const int64_t bytes = B * p->max_rec * width * 8;
+    if (streamed && p->max_rec > 0 && p->max_rec <= INT32_MAX &&
+        bytes <= p->snap_budget) {
+      CUDA_TRY(p->snap.reserve(static_cast<size_t>(bytes)));
+      a.snap = p->snap.as<double>();
+      a.snap_rows = static_cast<int32_t>(p->max_rec);
+      a.snap_width = static_cast<int32_t>(width);
+    }
+  }
   if (with_grad && p->n_cols < P) {
     // columns without sensitivities read as zero gradient
     const int64_t n = B * a.grad_stride;
@@ -970,7 +1029,7 @@ int launch_loglik(chi_b200_problem* p, int64_t B, const int32_t* d_ids,
     p->solve_ms_sum += ms;
     p->solve_launches += 1;
   }
-  p->counters[3] += 1;
+  p->counters[3] += a.snap ? 2 : 1;
   return 0;
 }
 

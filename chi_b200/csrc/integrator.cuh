@@ -641,7 +641,15 @@ struct Registrar {
     solve_stream_kernel<M, CB, STREAM_BLOCK>
         <<<static_cast<unsigned>(blocks), STREAM_BLOCK, smem, stream>>>(
             args, counters[dev]);
-    return cudaGetLastError();
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    if (args.mode == 1 && args.snap) {
+      // deferred observation: error model and gradient from the snapshots
+      observe_kernel<M><<<static_cast<unsigned>((args.B + 127) / 128), 128, 0,
+                          stream>>>(args);
+      err = cudaGetLastError();
+    }
+    return err;
   }
 
   template <int G, int MC>

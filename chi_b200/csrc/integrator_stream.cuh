@@ -23,11 +23,11 @@
 namespace chi_b200 {
 
 // shared-memory doubles per thread: S (current + candidate), gradient
-// accumulators, the state column's stage values 2..8 (the first is y) and the
-// error-model parameter gradients, three cold scalars
+// accumulators, the state column's stage values 2..8 (the first is y) and
+// seven cold per-system scalars
 template <class M>
 constexpr int stream_slots() {
-  return 2 * M::P * M::N + M::P + 7 * M::N + MAX_SIGMA + 3;
+  return 2 * M::P * M::N + M::P + 7 * M::N + 7;
 }
 
 namespace rodas5 {
@@ -237,6 +237,59 @@ CHI_HD float err_term(const double err, const double z0, const double z1,
   return q * q;
 }
 
+// What one observation contributes under the error model of its output
+// (chi/_error_models.py: compute_log_likelihood / compute_sensitivities of the
+// four models), written once for the fused handler and the deferred kernel.
+struct ErrTerms {
+  double ll;      // log-likelihood without the -log(scale) term
+  double scale;   // the term -log(scale) is accumulated as a product
+  double w;       // d ll / d ybar
+  double ds0, ds1;  // d ll / d sigma (second entry: ConstantAndMultiplicative)
+  bool invalid;   // log-normal model with ybar <= 0
+};
+
+CHI_HD ErrTerms error_terms(const int kind, const double* sg, const double yb,
+                            const double yo, const double lo) {
+  ErrTerms e;
+  e.ds1 = 0.0;
+  e.invalid = false;
+  const double s0 = sg[0];
+  if (kind == ERR_GAUSSIAN) {
+    const double is = 1.0 / s0;
+    const double q = (yo - yb) * is;
+    e.ll = -(LOG_2PI_HALF + 0.5 * q * q);
+    e.scale = s0;
+    e.w = q * is;
+    e.ds0 = (q * q - 1.0) * is;
+  } else if (kind == ERR_LOGNORMAL) {
+    e.invalid = yb <= 0.0;
+    const double is = 1.0 / s0;
+    const double q = (lo - log(yb) + 0.5 * s0 * s0) * is;
+    e.ll = -(LOG_2PI_HALF + lo + 0.5 * q * q);
+    e.scale = s0;
+    e.w = q * is / yb;
+    e.ds0 = (q * q - 1.0) * is - q;
+  } else {
+    const bool cam = kind == ERR_CAM;
+    const double sb = cam ? s0 : 0.0;
+    const double sr = cam ? sg[1] : s0;
+    const double st = fma(sr, yb, sb);
+    const double ist = 1.0 / st;
+    const double q = (yo - yb) * ist;
+    e.ll = -(LOG_2PI_HALF + 0.5 * q * q);
+    e.scale = st;
+    const double q2i = q * q * ist;
+    e.w = q * ist - sr * ist + sr * q2i;
+    if (cam) {
+      e.ds0 = q2i - ist;
+      e.ds1 = (q2i - ist) * yb;
+    } else {
+      e.ds0 = (q2i - ist) * yb;
+    }
+  }
+  return e;
+}
+
 // State of one system while it is being integrated.  `init` loads a system,
 // `advance` handles the pending events (observation records, dose edges) and
 // then attempts ONE step, returning true once the system is finished,
@@ -263,14 +316,11 @@ struct StreamSolver {
 
   // hot state (registers)
   double y[N], c[NCS];
-  double u, t, h, t_stop, ll;
+  double u, t, h, t_stop;
   double J0[N * N];
-  const double* sg;
-  int64_t r;
-  int cur, n_att, status;
+  int cur, n_att;
+  int flags;        // bits 0-7 status, bits 8-31 rejected steps
   bool invalid, after_reject;
-  // cold state: only touched when an event is pending
-  int64_t r_end, seg, seg_end;
 
   CHI_HD StreamSolver(const SolveArgs& args, double* smem, int smem_stride)
       : a(args), sm(smem), stride(smem_stride) {}
@@ -278,13 +328,41 @@ struct StreamSolver {
 #define CHI_S(buf, k, n) sm[(((buf) * P + (k)) * N + (n)) * stride]
 #define CHI_G(k) sm[(2 * P * N + (k)) * stride]
 #define CHI_ZY(i, n) sm[(2 * P * N + P + ((i) - 1) * N + (n)) * stride]
-#define CHI_DSIG(k) sm[(2 * P * N + P + 7 * N + (k)) * stride]
-// cold per-system scalars kept out of the register file: 0 = system index,
-// 1 = next dose-rate edge, 2 = rejected steps
-#define CHI_COLD(k) sm[(2 * P * N + P + 7 * N + MAX_SIGMA + (k)) * stride]
+// Cold per-system scalars, kept out of the register file because they are
+// only touched when an event is pending:
+//   0 system index     1 next dose-rate edge     2 time of the next record
+//   3 fused: log-likelihood; deferred: ints (first record, -)
+//   4 fused: running product of the error scales (its log is taken once)
+//   5 ints: next record, last record     6 ints: segment, last segment
+#define CHI_COLD(k) sm[(2 * P * N + P + 7 * N + (k)) * stride]
+
+  CHI_HD int cold_int(const int k, const int half) const {
+#ifdef __CUDA_ARCH__
+    return reinterpret_cast<const int*>(&CHI_COLD(k))[half];
+#else
+    int v[2];
+    __builtin_memcpy(v, &CHI_COLD(k), 8);
+    return v[half];
+#endif
+  }
+  CHI_HD void set_cold_int(const int k, const int half, const int value) {
+#ifdef __CUDA_ARCH__
+    reinterpret_cast<int*>(&CHI_COLD(k))[half] = value;
+#else
+    int v[2];
+    __builtin_memcpy(v, &CHI_COLD(k), 8);
+    v[half] = value;
+    __builtin_memcpy(&CHI_COLD(k), v, 8);
+#endif
+  }
 
   CHI_HD int n_cols() const { return a.with_sens ? a.n_cols : 0; }
   CHI_HD bool loglik() const { return a.mode == 1; }
+  CHI_HD bool deferred() const { return a.mode == 1 && a.snap != nullptr; }
+  CHI_HD bool want_dsig() const {
+    return a.mode == 1 && a.with_sens && a.grad != nullptr;
+  }
+  CHI_HD int status() const { return flags & 0xff; }
   CHI_HD int64_t system() const { return static_cast<int64_t>(CHI_COLD(0)); }
   CHI_HD int individual(const int64_t b) const {
     return a.ids ? a.ids[b] : static_cast<int>(b % a.n_ids);
@@ -292,9 +370,10 @@ struct StreamSolver {
 
   CHI_HD void init(const int64_t b) {
     static_assert(METHOD_CODE == 1 || METHOD_CODE == 5, "unknown method");
+    static_assert(P <= MAX_COLS, "too many mechanistic parameters");
     const int id = individual(b);
     const double* xb = a.x + b * a.x_stride;
-    sg = xb + P;
+    const double* sg = xb + P;
 #pragma unroll
     for (int i = 0; i < N; ++i) y[i] = xb[i];
 #pragma unroll
@@ -311,8 +390,6 @@ struct StreamSolver {
       }
       CHI_G(k) = 0.0;
     }
-    ll = 0.0;
-    for (int k = 0; k < MAX_SIGMA; ++k) CHI_DSIG(k) = 0.0;
     invalid = false;
     if (loglik()) {
       for (int o = 0; o < a.n_out; ++o) {
@@ -320,90 +397,114 @@ struct StreamSolver {
         if (sg[off] <= 0.0) invalid = true;
         if (a.err_kind[o] == ERR_CAM && sg[off + 1] <= 0.0) invalid = true;
       }
+      if (want_dsig() && !deferred()) {
+        // the error-model gradients accumulate in the output row itself
+        double* gb = a.grad + b * a.grad_stride + P;
+        for (int k = 0; k < a.n_sigma; ++k) gb[k] = 0.0;
+      }
     }
-    r = a.rec_off[id];
-    r_end = a.rec_off[id + 1];
-    seg = a.seg_off[id];
-    seg_end = a.seg_off[id + 1];
+    const int64_t r = a.rec_off[id];
+    const int64_t r_end = a.rec_off[id + 1];
+    const int64_t seg = a.seg_off[id];
+    const int64_t seg_end = a.seg_off[id + 1];
     u = (seg < seg_end) ? a.seg_rate[seg] : 0.0;
     CHI_COLD(0) = static_cast<double>(b);
     CHI_COLD(1) = (seg + 1 < seg_end) ? a.seg_t[seg + 1] : INFINITY;
-    CHI_COLD(2) = 0.0;
+    CHI_COLD(2) = (r < r_end) ? a.rec_t[r] : INFINITY;
+    if (deferred()) {
+      set_cold_int(3, 0, static_cast<int>(r));
+    } else {
+      CHI_COLD(3) = 0.0;
+      CHI_COLD(4) = 1.0;
+    }
+    set_cold_int(5, 0, static_cast<int>(r));
+    set_cold_int(5, 1, static_cast<int>(r_end));
+    set_cold_int(6, 0, static_cast<int>(seg));
+    set_cold_int(6, 1, static_cast<int>(seg_end));
     t = 0.0;
     t_stop = 0.0;   // forces the first pass through the event handler
     h = 0.0;
     after_reject = false;
     n_att = 0;
-    status = ST_OK;
+    flags = ST_OK;
     if (M::LINEAR) M::jac(y, c, J0);
   }
 
-  CHI_HD void add_dsig(const int off, const double v) {
-    CHI_DSIG(off) += v;
+  // ll -= log(scale), deferred: the scales are multiplied up and the
+  // logarithm is taken when the product leaves [1e-270, 1e270] or at the end
+  CHI_HD void add_log_scale(const double scale) {
+    double lp = CHI_COLD(4) * scale;
+    if (!(lp > 1e-270 && lp < 1e270)) {
+      CHI_COLD(3) -= log(lp);
+      lp = 1.0;
+    }
+    CHI_COLD(4) = lp;
   }
 
-  // observation record r at the current time
-  CHI_HD void observe() {
+  // Deferred observation: store the state and the integrated sensitivity
+  // columns of record r; observe_system() below does the rest.
+  CHI_HD void snapshot(const int r) {
+    const int64_t b = system();
+    double* row = a.snap + (b * a.snap_rows + (r - cold_int(3, 0))) *
+                               static_cast<int64_t>(a.snap_width);
+#pragma unroll
+    for (int n = 0; n < N; ++n) row[n] = y[n];
+    const int nc = n_cols();
+    int m = N;
+    for (int k = 0; k < nc; ++k) {
+      const int pk = a.col_param[k];
+      if (pk >= N && ((M::INERT_MASK >> (pk - N)) & 1u)) continue;
+#pragma unroll
+      for (int n = 0; n < N; ++n) row[m + n] = CHI_S(cur, k, n);
+      m += N;
+    }
+  }
+
+  // observation record r at the current time (fused handling)
+  CHI_HD void observe(const int r) {
     const int o = a.rec_out[r];
     const int oid = a.out_id[o];
     const int nc = n_cols();
     double gy[N], gc[NCS];
     const double yb = M::out_grad(oid, y, c, gy, gc);
-    double w = 0.0;
-    int64_t row = 0;
-    if (!loglik()) {
+    if (loglik()) {
       const int64_t b = system();
-      row = a.traj_off[b] + (r - a.rec_off[individual(b)]);
-      a.traj_y[row] = yb;
-    } else {
-      const int kind = a.err_kind[o];
       const int off = a.err_off[o];
-      const double yo = a.rec_obs[r];
-      if (kind == ERR_GAUSSIAN) {
-        const double s = sg[off];
-        const double is = 1.0 / s;
-        const double q = (yo - yb) * is;
-        ll -= LOG_2PI_HALF + log(s) + 0.5 * q * q;
-        w = q * is;
-        add_dsig(off, (q * q - 1.0) * is);
-      } else if (kind == ERR_LOGNORMAL) {
-        const double s = sg[off];
-        if (yb <= 0.0) invalid = true;
-        const double is = 1.0 / s;
-        const double lo = a.rec_logobs[r];
-        const double q = (lo - log(yb) + 0.5 * s * s) * is;
-        ll -= LOG_2PI_HALF + log(s) + lo + 0.5 * q * q;
-        w = q * is / yb;
-        add_dsig(off, -q + (q * q - 1.0) * is);
-      } else {
-        const bool cam = kind == ERR_CAM;
-        const double sb = cam ? sg[off] : 0.0;
-        const double sr = cam ? sg[off + 1] : sg[off];
-        const double st = fma(sr, yb, sb);
-        const double ist = 1.0 / st;
-        const double q = (yo - yb) * ist;
-        ll -= LOG_2PI_HALF + log(st) + 0.5 * q * q;
-        const double q2i = q * q * ist;
-        w = q * ist - sr * ist + sr * q2i;
-        if (cam) {
-          add_dsig(off, q2i - ist);
-          add_dsig(off + 1, (q2i - ist) * yb);
-        } else {
-          add_dsig(off, (q2i - ist) * yb);
-        }
+      const ErrTerms e =
+          error_terms(a.err_kind[o], a.x + b * a.x_stride + P + off, yb,
+                      a.rec_obs[r], a.rec_logobs[r]);
+      if (e.invalid) invalid = true;
+      CHI_COLD(3) += e.ll;
+      add_log_scale(e.scale);
+      if (want_dsig()) {
+        double* dsig = a.grad + b * a.grad_stride + P + off;
+        dsig[0] += e.ds0;
+        if (a.err_kind[o] == ERR_CAM) dsig[1] += e.ds1;
       }
-    }
-    // d ybar / d psi_k = (dg/dy) S_k + dg/dc_k
-    for (int k = 0; k < nc; ++k) {
-      const int pk = a.col_param[k];
-      double d = 0.0;
+      // d ybar / d psi_k = (dg/dy) S_k + dg/dc_k
+      for (int k = 0; k < nc; ++k) {
+        double d = 0.0;
 #pragma unroll
-      for (int j = 0; j < NC; ++j) d = (pk == N + j) ? gc[j] : d;
+        for (int n = 0; n < N; ++n) d = fma(gy[n], CHI_S(cur, k, n), d);
+        CHI_G(k) = fma(e.w, d, CHI_G(k));
+      }
 #pragma unroll
-      for (int n = 0; n < N; ++n) d = fma(gy[n], CHI_S(cur, k, n), d);
-      if (loglik()) {
-        CHI_G(k) = fma(w, d, CHI_G(k));
-      } else {
+      for (int j = 0; j < NC; ++j) {
+        const int k = a.param_col[N + j];
+        if (gc[j] != 0.0 && k >= 0 && k < nc)
+          CHI_G(k) = fma(e.w, gc[j], CHI_G(k));
+      }
+    } else {
+      const int64_t b = system();
+      const int64_t row = a.traj_off[b] + (r - a.rec_off[individual(b)]);
+      a.traj_y[row] = yb;
+      for (int k = 0; k < nc; ++k) {
+        const int pk = a.col_param[k];
+        double d = 0.0;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) d = (pk == N + j) ? gc[j] : d;
+#pragma unroll
+        for (int n = 0; n < N; ++n) d = fma(gy[n], CHI_S(cur, k, n), d);
         a.traj_s[row * nc + k] = d;
       }
     }
@@ -415,56 +516,96 @@ struct StreamSolver {
   CHI_HD bool events() {
     if (t < t_stop) return false;
     if (invalid) return true;
+    int r = cold_int(5, 0);
+    const int r_end = cold_int(5, 1);
     double t_edge = CHI_COLD(1);
+    double t_rec = CHI_COLD(2);
     for (;;) {
       if (r >= r_end) return true;
-      const double t_rec = a.rec_t[r];
       if (t_rec <= t) {
-        observe();
-        if (invalid) return true;
+        // fetch the next record's time while this one is processed
+        const double t_next = (r + 1 < r_end) ? a.rec_t[r + 1] : INFINITY;
+        if (deferred()) {
+          snapshot(r);
+        } else {
+          observe(r);
+          if (invalid) return true;
+        }
         ++r;
+        t_rec = t_next;
         continue;
       }
       if (t_edge <= t) {
         // dose-rate edge: switch the input; the step size proposed before
         // the edge is kept (shrunk), the controller takes it from there
-        ++seg;
+        const int seg = cold_int(6, 0) + 1;
+        set_cold_int(6, 0, seg);
         u = a.seg_rate[seg];
-        t_edge = (seg + 1 < seg_end) ? a.seg_t[seg + 1] : INFINITY;
-        CHI_COLD(1) = t_edge;
+        t_edge = (seg + 1 < cold_int(6, 1)) ? a.seg_t[seg + 1] : INFINITY;
         h = CHI_EDGE_KEEP_H ? h * CHI_EDGE_SHRINK : 0.0;
         continue;
       }
+      set_cold_int(5, 0, r);
+      CHI_COLD(1) = t_edge;
+      CHI_COLD(2) = t_rec;
       t_stop = fmin(t_rec, t_edge);
       return false;
     }
   }
 
-  // Six RODAS4 stages of sensitivity column k (constant index KC, -1 for an
-  // initial-value column) given the state column's stage values Zy and
-  // increments Uy.  Returns the column's squared scaled error.
+  // All stages of sensitivity column k (constant index kc, -1 for an
+  // initial-value column) given what the state column left behind; returns
+  // the column's squared scaled error.
+  //   nonlinear models: stage values Zy (shared memory) and increments Uy;
+  //     the column-specific terms are selected by a uniform switch per stage.
+  //   linear models: (df/dc_k)(Z) + d/dy[...] U = D_k (Zy + Uy) + e_k with
+  //     D_k, e_k fetched once per column, and V = Zy + Uy was stored by the
+  //     state column (V0 for the first stage), so neither Uy nor the model
+  //     constants are live here.
   CHI_HD float column(const int kc, const int k, const int nxt,
-                      const double (&Uy)[NS][N], const double (&Wi)[N * N],
-                      const double hinv, const float atol_f,
-                      const float rtol_f) {
+                      const double (&Uy)[NS][N], const double (&V0)[N],
+                      const double (&Wi)[N * N], const double hinv,
+                      const float atol_f, const float rtol_f) {
     double S0[N], Us[NS][N], Zl[N];
 #pragma unroll
     for (int n = 0; n < N; ++n) S0[n] = CHI_S(cur, k, n);
+    double DK[N * N], ek[N];
+    if (M::LINEAR) M::col_linear(kc, c, u, DK, ek);
 #define CHI_SSTAGE(I, CNT, a0, a1, a2, a3, a4, a5, a6, c0, c1, c2, c3, c4,   \
                    c5, c6)                                                    \
   {                                                                           \
-    double Ji[N * N], Zyi[N];                                                 \
-    _Pragma("unroll") for (int n = 0; n < N; ++n) Zyi[n] =                    \
-        (I == 0) ? y[n] : CHI_ZY(I, n);                                       \
-    if (!M::LINEAR) M::jac(Zyi, c, Ji);                                       \
     double cs[N], rs[N];                                                      \
-    lincomb7<CNT, N>(Zl, S0, Us, a0, a1, a2, a3, a4, a5, a6);                 \
-    lincomb7<CNT, N>(cs, nullptr, Us, c0, c1, c2, c3, c4, c5, c6);            \
-    matvec<N>(M::LINEAR ? J0 : Ji, Zl, rs);                                   \
-    M::dfdc_col_add(kc, Zyi, c, rs);                                          \
-    M::hess_col_add(kc, y, c, S0, Uy[I], rs);                                 \
-    _Pragma("unroll") for (int n = 0; n < N; ++n) rs[n] =                     \
-        fma(hinv, cs[n], rs[n]);                                              \
+    if (M::LINEAR) {                                                          \
+      double V[N];                                                            \
+      _Pragma("unroll") for (int n = 0; n < N; ++n) V[n] =                    \
+          (I == 0) ? V0[n] : CHI_ZY(I, n);                                    \
+      _Pragma("unroll") for (int n = 0; n < N; ++n) {                         \
+        double acc = ek[n];                                                   \
+        _Pragma("unroll") for (int m = 0; m < N; ++m) acc =                   \
+            fma(DK[n * N + m], V[m], acc);                                    \
+        rs[n] = acc;                                                          \
+      }                                                                       \
+      lincomb7<CNT, N>(Zl, S0, Us, a0, a1, a2, a3, a4, a5, a6);               \
+      lincomb7<CNT, N>(cs, nullptr, Us, c0, c1, c2, c3, c4, c5, c6);          \
+      _Pragma("unroll") for (int n = 0; n < N; ++n) {                         \
+        double acc = rs[n];                                                   \
+        _Pragma("unroll") for (int m = 0; m < N; ++m) acc =                   \
+            fma(J0[n * N + m], Zl[m], acc);                                   \
+        rs[n] = fma(hinv, cs[n], acc);                                        \
+      }                                                                       \
+    } else {                                                                  \
+      double Ji[N * N], Zyi[N];                                               \
+      _Pragma("unroll") for (int n = 0; n < N; ++n) Zyi[n] =                  \
+          (I == 0) ? y[n] : CHI_ZY(I, n);                                     \
+      M::jac(Zyi, c, Ji);                                                     \
+      lincomb7<CNT, N>(Zl, S0, Us, a0, a1, a2, a3, a4, a5, a6);               \
+      lincomb7<CNT, N>(cs, nullptr, Us, c0, c1, c2, c3, c4, c5, c6);          \
+      matvec<N>(Ji, Zl, rs);                                                  \
+      M::dfdc_col_add(kc, Zyi, c, rs);                                        \
+      M::hess_col_add(kc, y, c, S0, Uy[I], rs);                               \
+      _Pragma("unroll") for (int n = 0; n < N; ++n) rs[n] =                   \
+          fma(hinv, cs[n], rs[n]);                                            \
+    }                                                                         \
     matvec<N>(Wi, rs, Us[I]);                                                 \
   }
     if constexpr (R5) {
@@ -528,20 +669,22 @@ struct StreamSolver {
       invert<N>(W, Wi);
     }
     double Uy[NS][N];
-    double Zlast[N];
+    double Zlast[N], V0[N];
 #define CHI_YSTAGE(I, CNT, a0, a1, a2, a3, a4, a5, a6, c0, c1, c2, c3, c4,   \
                    c5, c6)                                                    \
   {                                                                           \
     double f[N], cy[N], ry[N];                                                \
     lincomb7<CNT, N>(Zlast, y, Uy, a0, a1, a2, a3, a4, a5, a6);               \
-    if (I > 0) {                                                              \
-      _Pragma("unroll") for (int n = 0; n < N; ++n) CHI_ZY(I, n) = Zlast[n];  \
-    }                                                                         \
     M::rhs(Zlast, c, u, f);                                                   \
     lincomb7<CNT, N>(cy, nullptr, Uy, c0, c1, c2, c3, c4, c5, c6);            \
     _Pragma("unroll") for (int n = 0; n < N; ++n) ry[n] =                     \
         fma(hinv, cy[n], f[n]);                                               \
     matvec<N>(Wi, ry, Uy[I]);                                                 \
+    /* what the sensitivity columns need of this stage */                     \
+    _Pragma("unroll") for (int n = 0; n < N; ++n) {                           \
+      const double v = M::LINEAR ? Zlast[n] + Uy[I][n] : Zlast[n];            \
+      if (I == 0) V0[n] = v; else CHI_ZY(I, n) = v;                           \
+    }                                                                         \
   }
     if constexpr (R5) {
       CHI_RODAS5_TABLE(CHI_YSTAGE)
@@ -574,8 +717,13 @@ struct StreamSolver {
       // columns of constants that do not enter the rhs stay identically
       // zero: nothing to integrate
       if (kc >= 0 && ((M::INERT_MASK >> kc) & 1u)) continue;
+#ifdef __CUDA_ARCH__
+      // keep the coefficient loads inside the column body: hoisted out of the
+      // loop they would occupy a hundred registers
+      asm volatile("" ::: "memory");
+#endif
       errsq = fmaxf(errsq,
-                    column(kc, k, nxt, Uy, Wi, hinv, atol_f, rtol_f));
+                    column(kc, k, nxt, Uy, V0, Wi, hinv, atol_f, rtol_f));
     }
 
     const bool accept = errsq <= 1.0f;
@@ -598,14 +746,14 @@ struct StreamSolver {
     } else {
       h = hs * static_cast<double>(fminf(fac, 0.9f));
       after_reject = true;
-      CHI_COLD(2) += 1.0;
+      flags += 0x100;
       if (h <= 1e-14 * fmax(fabs(t), 1.0)) {
-        status = (errsq == errsq) ? ST_STEP_UNDERFLOW : ST_NON_FINITE;
+        flags |= (errsq == errsq) ? ST_STEP_UNDERFLOW : ST_NON_FINITE;
         return true;
       }
     }
     if (++n_att >= a.max_steps) {
-      status = ST_MAX_STEPS;
+      flags |= ST_MAX_STEPS;
       return true;
     }
     return false;
@@ -613,30 +761,32 @@ struct StreamSolver {
 
   CHI_HD void finish() {
     const int64_t b = system();
-    const int n_rej = static_cast<int>(CHI_COLD(2));
-    a.status[b] = status;
+    const int n_rej = static_cast<int>(static_cast<unsigned>(flags) >> 8);
+    a.status[b] = status();
     if (a.n_steps) a.n_steps[b] = n_att - n_rej;
     if (a.n_rej) a.n_rej[b] = n_rej;
+    if (deferred()) return;   // observe_system() writes ll and the gradient
     if (loglik()) {
-      const bool fail = invalid || status != ST_OK;
-      a.ll[b] = fail ? -INFINITY : ll;
+      const bool fail = invalid || status() != ST_OK;
+      a.ll[b] = fail ? -INFINITY : CHI_COLD(3) - log(CHI_COLD(4));
       if (a.with_sens && a.grad) {
         const int nc = n_cols();
         double* gb = a.grad + b * a.grad_stride;
         for (int k = 0; k < nc; ++k)
           gb[a.col_param[k]] = fail ? INFINITY : CHI_G(k);
-        for (int k = 0; k < a.n_sigma; ++k)
-          gb[P + k] = fail ? INFINITY : CHI_DSIG(k);
+        if (fail)
+          for (int k = 0; k < a.n_sigma; ++k) gb[P + k] = INFINITY;
       }
-    } else if (status != ST_OK) {
+    } else if (status() != ST_OK) {
+      const int r_end = cold_int(5, 1);
       const int64_t shift = a.traj_off[b] - a.rec_off[individual(b)];
-      for (int64_t q = r; q < r_end; ++q) a.traj_y[shift + q] = NAN;
+      for (int64_t q = cold_int(5, 0); q < r_end; ++q)
+        a.traj_y[shift + q] = NAN;
     }
   }
 #undef CHI_S
 #undef CHI_G
 #undef CHI_ZY
-#undef CHI_DSIG
 #undef CHI_COLD
 };
 
@@ -651,7 +801,96 @@ CHI_HD void solve_system_stream(const SolveArgs& a, const int64_t b,
   s.finish();
 }
 
+// Deferred observation of one system: output map, error model, log-likelihood
+// and gradient from the snapshots the solve left behind (SolveArgs::snap).
+// Same arithmetic as StreamSolver::observe, but every lane of a warp is busy:
+// inside the solve this work ran with one or two active lanes per warp.
+template <class M>
+CHI_HD void observe_system(const SolveArgs& a, const int64_t b) {
+  constexpr int N = M::N, NC = M::NC, NCS = M::NCS, P = M::P;
+  const int id = a.ids ? a.ids[b] : static_cast<int>(b % a.n_ids);
+  const double* xb = a.x + b * a.x_stride;
+  const double* sg = xb + P;
+  const int nc = a.with_sens ? a.n_cols : 0;
+  bool fail = a.status[b] != ST_OK;
+  for (int o = 0; o < a.n_out; ++o) {
+    const int off = a.err_off[o];
+    if (sg[off] <= 0.0) fail = true;
+    if (a.err_kind[o] == ERR_CAM && sg[off + 1] <= 0.0) fail = true;
+  }
+  double c[NCS];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) c[i] = xb[N + i];
+  if (NC == 0) c[0] = 0.0;
+  double ll = 0.0, lp = 1.0;
+  double G[P], dsig[MAX_SIGMA];
+#pragma unroll
+  for (int k = 0; k < P; ++k) G[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < MAX_SIGMA; ++k) dsig[k] = 0.0;
+  if (!fail) {
+    const int64_t r0 = a.rec_off[id], r1 = a.rec_off[id + 1];
+    const double* row = a.snap + b * a.snap_rows *
+                                     static_cast<int64_t>(a.snap_width);
+    for (int64_t r = r0; r < r1; ++r, row += a.snap_width) {
+      const int o = a.rec_out[r];
+      const int off = a.err_off[o];
+      double y[N], gy[N], gc[NCS];
+#pragma unroll
+      for (int n = 0; n < N; ++n) y[n] = row[n];
+      const double yb = M::out_grad(a.out_id[o], y, c, gy, gc);
+      const ErrTerms e = error_terms(a.err_kind[o], sg + off, yb,
+                                     a.rec_obs[r], a.rec_logobs[r]);
+      if (e.invalid) fail = true;
+      ll += e.ll;
+      lp *= e.scale;
+      if (!(lp > 1e-270 && lp < 1e270)) {
+        ll -= log(lp);
+        lp = 1.0;
+      }
+#pragma unroll
+      for (int k = 0; k < MAX_SIGMA; ++k) {
+        dsig[k] += (k == off) ? e.ds0 : 0.0;
+        dsig[k] += (k == off + 1) ? e.ds1 : 0.0;
+      }
+      int m = N;
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+        if (k < nc) {
+          const int pk = a.col_param[k];
+          double d = 0.0;
+#pragma unroll
+          for (int j = 0; j < NC; ++j) d = (pk == N + j) ? gc[j] : d;
+          if (!(pk >= N && ((M::INERT_MASK >> (pk - N)) & 1u))) {
+#pragma unroll
+            for (int n = 0; n < N; ++n) d = fma(gy[n], row[m + n], d);
+            m += N;
+          }
+          G[k] = fma(e.w, d, G[k]);
+        }
+      }
+    }
+  }
+  a.ll[b] = fail ? -INFINITY : ll - log(lp);
+  if (a.with_sens && a.grad) {
+    double* gb = a.grad + b * a.grad_stride;
+#pragma unroll
+    for (int k = 0; k < P; ++k)
+      if (k < nc) gb[a.col_param[k]] = fail ? INFINITY : G[k];
+#pragma unroll
+    for (int k = 0; k < MAX_SIGMA; ++k)
+      if (k < a.n_sigma) gb[P + k] = fail ? INFINITY : dsig[k];
+  }
+}
+
 #ifdef __CUDACC__
+
+template <class M>
+__global__ void __launch_bounds__(128)
+observe_kernel(const SolveArgs a) {
+  const int64_t b = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (b < a.B) observe_system<M>(a, b);
+}
 
 // Persistent kernel: every lane pulls systems from a global counter and
 // refills itself as soon as its system is finished, so lanes whose systems

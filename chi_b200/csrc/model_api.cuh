@@ -61,6 +61,7 @@ struct SolveArgs {
 
   int32_t n_cols;            // sensitivity columns
   int32_t col_param[MAX_COLS];  // mechanistic parameter index of each column
+  int32_t param_col[MAX_COLS];  // inverse map: column of parameter p, or -1
 
   int32_t mode;              // 0: simulate (write trajectories); 1: log-likelihood
   int32_t with_sens;
@@ -77,6 +78,15 @@ struct SolveArgs {
   int32_t* status;           // [B]
   int32_t* n_steps;          // [B] accepted steps (may be null)
   int32_t* n_rej;            // [B] rejected steps (may be null)
+
+  // Deferred observation (streamed kernel, mode 1).  When `snap` is set the
+  // solve kernel only stores the state and the integrated sensitivity columns
+  // at every observation record, [B][snap_rows][snap_width] doubles, and a
+  // second, fully convergent kernel evaluates output map, error model and
+  // gradient from these snapshots.  Null: everything is fused in the solve.
+  double* snap;
+  int32_t snap_rows;         // rows per system (max records per individual)
+  int32_t snap_width;        // N * (1 + integrated columns)
 };
 
 // What a compiled model contributes to the registry of the core library.

@@ -207,6 +207,17 @@ int chi_b200_problem_counters(chi_b200_problem* p, int64_t out[4]);
  * since timing was enabled. */
 int chi_b200_problem_set_timing(chi_b200_problem* p, int32_t enabled);
 int chi_b200_problem_timings(chi_b200_problem* p, double out[2]);
+/* Deferred observation.  By default the streamed solve kernel only stores
+ * the state and the integrated sensitivity columns at every observation
+ * record (B x max records x N (1 + columns) doubles of device memory) and a
+ * second kernel evaluates the output map, the error model
+ * (chi/_error_models.py:288-330, 631-674, 983-1026, 1342-1385) and the
+ * gradient from these snapshots; inside the solve that work runs with one or
+ * two active lanes per warp.  The snapshots are used when they fit `bytes`
+ * (default: half of the free device memory at the first evaluation, or
+ * CHI_B200_SNAP_MB); 0 keeps the observation fused in the solve kernel,
+ * -1 restores the default. */
+int chi_b200_problem_set_snapshot_budget(chi_b200_problem* p, int64_t bytes);
 /* measured FP64 FMA throughput of the device (DFMA micro-kernel) */
 int chi_b200_fp64_peak(int32_t device, double* tflops, double* sm_clock_mhz);
 

@@ -36,12 +36,15 @@ class SolveArgs(ctypes.Structure):
         ('n_sigma', ctypes.c_int32),
         ('n_cols', ctypes.c_int32),
         ('col_param', ctypes.c_int32 * MAX_COLS),
+        ('param_col', ctypes.c_int32 * MAX_COLS),
         ('mode', ctypes.c_int32), ('with_sens', ctypes.c_int32),
         ('rtol', ctypes.c_double), ('atol', ctypes.c_double),
         ('max_steps', ctypes.c_int32),
         ('traj_off', _vp), ('traj_y', _vp), ('traj_s', _vp),
         ('ll', _vp), ('grad', _vp), ('grad_stride', ctypes.c_int32),
         ('status', _vp), ('n_steps', _vp), ('n_rej', _vp),
+        ('snap', _vp), ('snap_rows', ctypes.c_int32),
+        ('snap_width', ctypes.c_int32),
     ]
 
 
@@ -58,6 +61,8 @@ def lib():
         _lib = ctypes.CDLL(path)
         _lib.chi_port_solve.argtypes = [
             ctypes.c_char_p, ctypes.POINTER(SolveArgs), ctypes.c_int]
+        _lib.chi_port_snap_width.argtypes = [
+            ctypes.c_char_p, ctypes.POINTER(SolveArgs)]
         _lib.chi_port_solve2.argtypes = [
             ctypes.c_char_p, ctypes.POINTER(SolveArgs), ctypes.c_int,
             ctypes.c_int]
@@ -161,12 +166,18 @@ class Population(object):
                 off += N_SIGMA[self.err_kind[o]]
         a.n_sigma = off
         a.n_cols = self.P
+        for k in range(MAX_COLS):
+            a.param_col[k] = -1
         for k in range(self.P):
             a.col_param[k] = k
+            a.param_col[k] = k
         return a
 
     def loglik(self, x, ids=None, with_grad=True, rtol=1e-8, atol=1e-10,
-               max_steps=100000, n_threads=1, stream_cb=0):
+               max_steps=100000, n_threads=1, stream_cb=0, deferred=None):
+        """``deferred``: evaluate the observations from snapshots after the
+        solve (SolveArgs::snap), the streamed routines' default on the GPU;
+        False keeps them fused in the solve."""
         x = np.ascontiguousarray(x, float)
         if x.ndim == 1:
             x = x[None, :]
@@ -193,6 +204,17 @@ class Population(object):
         a.status = _ptr(status)
         a.n_steps = _ptr(nst)
         a.n_rej = _ptr(nrj)
+        if deferred is None:
+            deferred = stream_cb != 0
+        snap = None
+        if deferred and stream_cb != 0:
+            width = lib().chi_port_snap_width(
+                self.key.encode(), ctypes.byref(a))
+            rows = int(np.max(np.diff(self.rec_off))) if self.n_ids else 0
+            snap = np.full(B * max(rows, 1) * width, np.nan)
+            a.snap = _ptr(snap)
+            a.snap_rows = rows
+            a.snap_width = width
         rc = lib().chi_port_solve2(self.key.encode(), ctypes.byref(a),
                                    n_threads, stream_cb)
         assert rc == 0, rc

@@ -44,7 +44,28 @@ static void run_all(const SolveArgs& a, int n_threads, int stream_cb) {
     } else {
       solve_system<M, 1, M::P>(a, b, 0, 0, 0, 1u);
     }
+    if (stream_cb != 0 && a.mode == 1 && a.snap) observe_system<M>(a, b);
   }
+}
+
+// doubles per snapshot row for these arguments (SolveArgs::snap_width)
+template <class M>
+static int snap_width(const SolveArgs& a) {
+  int integrated = 0;
+  if (a.with_sens)
+    for (int k = 0; k < a.n_cols; ++k) {
+      const int pk = a.col_param[k];
+      if (!(pk >= M::N && ((M::INERT_MASK >> (pk - M::N)) & 1u))) ++integrated;
+    }
+  return M::N * (1 + integrated);
+}
+
+extern "C" int chi_port_snap_width(const char* key, const SolveArgs* a) {
+#define CHI_PORT_MODEL(KEY, TYPE)                                            \
+  if (std::strcmp(key, KEY) == 0) return snap_width<TYPE>(*a);
+  CHI_PORT_MODELS
+#undef CHI_PORT_MODEL
+  return -1;
 }
 
 extern "C" int chi_port_solve2(const char* key, const SolveArgs* a,

@@ -657,3 +657,41 @@ def test_fix_parameters_matches_unfixed_model():
     np.testing.assert_allclose(
         g_fix, g_ref, rtol=1e-7, atol=1e-8 * np.max(np.abs(g_ref)))
     assert hll(x_fixed) == pytest.approx(full(x), rel=1e-10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('error', ['lognormal', 'cam', 'gaussian'])
+def test_deferred_and_fused_observation_agree(error):
+    """The streamed kernel either evaluates the error model inside the solve
+    (fused) or stores snapshots at the records and evaluates them in a second
+    kernel (deferred, the default): same arithmetic, same results -- also for
+    failed systems and non-positive outputs."""
+    from chi_b200 import _synthetic
+    prob = _synthetic.two_compartment_problem(
+        n_ids=37, seed=3, n_obs=7, n_doses=2, error=error)
+    ll = prob['log_likelihood']
+    rng = np.random.default_rng(5)
+    X = prob['x0'][None, :] * (1 + 0.02 * rng.normal(size=(6, len(prob['x0']))))
+    X[4, -1] = -0.1                      # invalid sigma -> -inf
+    res = {}
+    for name, budget in (('deferred', -1), ('fused', 0)):
+        ll.set_snapshot_budget(budget)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            s, g = ll.evaluateS1_batch(X)
+            res[name] = (np.array(s), np.array(g), np.array(
+                ll.evaluate_batch(X)))
+        launches = int(ll.counters()[3])
+        res[name + '_launches'] = launches
+    ll.set_snapshot_budget(-1)
+    assert res['deferred_launches'] == res['fused_launches'] + 1
+    sd, gd, fd = res['deferred']
+    sf, gf, ff = res['fused']
+    assert sd[4] == -np.inf and sf[4] == -np.inf
+    ok = np.isfinite(sf)
+    assert ok.sum() == 5
+    np.testing.assert_allclose(sd[ok], sf[ok], rtol=1e-13)
+    np.testing.assert_allclose(
+        gd[ok], gf[ok], rtol=1e-11, atol=1e-11 * np.max(np.abs(gf[ok])))
+    np.testing.assert_allclose(fd[ok], ff[ok], rtol=1e-13)
+    assert np.array_equal(gd[4], gf[4], equal_nan=True)
