@@ -97,11 +97,17 @@ def flops_per_step(n, n_cols, info, stages=6):
     s = stages
     pairs = s * (s - 1) // 2              # (i, j<i) pairs of the stage table
     inv = {1: 2, 2: 12, 3: 51}.get(n, (2 * n ** 3) // 3 + 2 * n * n)
-    comb = 2 * n * pairs                  # sum_j a_ij U_j over all stages
+    comb_c = 2 * n * pairs                # sum_j c_ij U_j over all stages
+    # stage values sum_j a_ij U_j: the last rows of the stiffly accurate
+    # methods repeat the row before them plus one unit entry, i.e. they are
+    # the previous stage value plus the previous increment (n additions)
+    incr = 2 if s == 8 else 1
+    pairs_a = (s - incr) * (s - incr - 1) // 2
+    comb_a = 2 * n * pairs_a + incr * n
     solve = s * n * (2 * n - 1)           # s mat-vecs with W^-1
-    state = comb + comb + s * 2 * n + s * f_rhs + solve
+    state = comb_a + comb_c + s * 2 * n + s * f_rhs + solve
     # per column: stage combinations, J Z_s, + hinv * combination, solves
-    sens = comb + comb + s * 2 * n + s * n * (2 * n - 1) + solve
+    sens = comb_a + comb_c + s * 2 * n + s * n * (2 * n - 1) + solve
     # column-specific terms (df/dc_k and its y-derivative) of all columns and
     # the column-independent second-order term, per stage
     extra = s * (f_col_sum + n_cols * f_hess_common)

@@ -22,12 +22,20 @@
 
 namespace chi_b200 {
 
-// shared-memory doubles per thread: S (current + candidate), gradient
-// accumulators, the state column's stage values 2..8 (the first is y) and
-// seven cold per-system scalars
+// shared-memory doubles per thread: S of the integrated columns (current +
+// candidate), gradient accumulators, the state column's stage values 2..8
+// (the first is y), seven cold per-system scalars and the model constants
+template <class M>
+constexpr int stream_integrated() {
+  // parameters whose sensitivity column is integrated: all but the constants
+  // that do not enter the rhs (their columns are identically zero)
+  int n = M::P;
+  for (int k = 0; k < M::NC; ++k) n -= (M::INERT_MASK >> k) & 1u;
+  return n;
+}
 template <class M>
 constexpr int stream_slots() {
-  return 2 * M::P * M::N + M::P + 7 * M::N + 7;
+  return 2 * stream_integrated<M>() * M::N + M::P + 7 * M::N + 7 + M::NCS;
 }
 
 namespace rodas5 {
@@ -170,36 +178,39 @@ static __constant__ double C87 = -5.810979938412932;
 #define CHI_R5(x) rodas5::x
 #endif
 
-// Stage tables: X(stage, n_previous, a_1..a_7, c_1..c_7)
+// Stage tables: X(stage, n_previous, incremental, a_1..a_7, c_1..c_7).
+// "incremental": the stage value is the previous stage value plus the previous
+// increment (the last rows of the stiffly accurate methods repeat the row
+// before them with one more unit entry), so it costs N additions instead of a
+// full combination.
 #define CHI_RODAS4_TABLE(X)                                                   \
-  X(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)                           \
-  X(1, 1, CHI_R4(A21), 0, 0, 0, 0, 0, 0, CHI_R4(C21), 0, 0, 0, 0, 0, 0)       \
-  X(2, 2, CHI_R4(A31), CHI_R4(A32), 0, 0, 0, 0, 0, CHI_R4(C31), CHI_R4(C32),  \
-    0, 0, 0, 0, 0)                                                            \
-  X(3, 3, CHI_R4(A41), CHI_R4(A42), CHI_R4(A43), 0, 0, 0, 0, CHI_R4(C41),     \
+  X(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)                        \
+  X(1, 1, 0, CHI_R4(A21), 0, 0, 0, 0, 0, 0, CHI_R4(C21), 0, 0, 0, 0, 0, 0)    \
+  X(2, 2, 0, CHI_R4(A31), CHI_R4(A32), 0, 0, 0, 0, 0, CHI_R4(C31),            \
+    CHI_R4(C32), 0, 0, 0, 0, 0)                                               \
+  X(3, 3, 0, CHI_R4(A41), CHI_R4(A42), CHI_R4(A43), 0, 0, 0, 0, CHI_R4(C41),  \
     CHI_R4(C42), CHI_R4(C43), 0, 0, 0, 0)                                     \
-  X(4, 4, CHI_R4(A51), CHI_R4(A52), CHI_R4(A53), CHI_R4(A54), 0, 0, 0,        \
+  X(4, 4, 0, CHI_R4(A51), CHI_R4(A52), CHI_R4(A53), CHI_R4(A54), 0, 0, 0,     \
     CHI_R4(C51), CHI_R4(C52), CHI_R4(C53), CHI_R4(C54), 0, 0, 0)              \
-  X(5, 5, CHI_R4(A51), CHI_R4(A52), CHI_R4(A53), CHI_R4(A54), 1.0, 0, 0,      \
-    CHI_R4(C61), CHI_R4(C62), CHI_R4(C63), CHI_R4(C64), CHI_R4(C65), 0, 0)
+  X(5, 5, 1, 0, 0, 0, 0, 0, 0, 0, CHI_R4(C61), CHI_R4(C62), CHI_R4(C63),      \
+    CHI_R4(C64), CHI_R4(C65), 0, 0)
 
 #define CHI_RODAS5_TABLE(X)                                                   \
-  X(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)                           \
-  X(1, 1, CHI_R5(A21), 0, 0, 0, 0, 0, 0, CHI_R5(C21), 0, 0, 0, 0, 0, 0)       \
-  X(2, 2, CHI_R5(A31), CHI_R5(A32), 0, 0, 0, 0, 0, CHI_R5(C31), CHI_R5(C32),  \
-    0, 0, 0, 0, 0)                                                            \
-  X(3, 3, CHI_R5(A41), CHI_R5(A42), CHI_R5(A43), 0, 0, 0, 0, CHI_R5(C41),     \
+  X(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)                        \
+  X(1, 1, 0, CHI_R5(A21), 0, 0, 0, 0, 0, 0, CHI_R5(C21), 0, 0, 0, 0, 0, 0)    \
+  X(2, 2, 0, CHI_R5(A31), CHI_R5(A32), 0, 0, 0, 0, 0, CHI_R5(C31),            \
+    CHI_R5(C32), 0, 0, 0, 0, 0)                                               \
+  X(3, 3, 0, CHI_R5(A41), CHI_R5(A42), CHI_R5(A43), 0, 0, 0, 0, CHI_R5(C41),  \
     CHI_R5(C42), CHI_R5(C43), 0, 0, 0, 0)                                     \
-  X(4, 4, CHI_R5(A51), CHI_R5(A52), CHI_R5(A53), CHI_R5(A54), 0, 0, 0,        \
+  X(4, 4, 0, CHI_R5(A51), CHI_R5(A52), CHI_R5(A53), CHI_R5(A54), 0, 0, 0,     \
     CHI_R5(C51), CHI_R5(C52), CHI_R5(C53), CHI_R5(C54), 0, 0, 0)              \
-  X(5, 5, CHI_R5(A61), CHI_R5(A62), CHI_R5(A63), CHI_R5(A64), CHI_R5(A65), 0, \
-    0, CHI_R5(C61), CHI_R5(C62), CHI_R5(C63), CHI_R5(C64), CHI_R5(C65), 0, 0) \
-  X(6, 6, CHI_R5(A61), CHI_R5(A62), CHI_R5(A63), CHI_R5(A64), CHI_R5(A65),    \
-    1.0, 0, CHI_R5(C71), CHI_R5(C72), CHI_R5(C73), CHI_R5(C74), CHI_R5(C75),  \
-    CHI_R5(C76), 0)                                                           \
-  X(7, 7, CHI_R5(A61), CHI_R5(A62), CHI_R5(A63), CHI_R5(A64), CHI_R5(A65),    \
-    1.0, 1.0, CHI_R5(C81), CHI_R5(C82), CHI_R5(C83), CHI_R5(C84),             \
-    CHI_R5(C85), CHI_R5(C86), CHI_R5(C87))
+  X(5, 5, 0, CHI_R5(A61), CHI_R5(A62), CHI_R5(A63), CHI_R5(A64), CHI_R5(A65), \
+    0, 0, CHI_R5(C61), CHI_R5(C62), CHI_R5(C63), CHI_R5(C64), CHI_R5(C65), 0, \
+    0)                                                                        \
+  X(6, 6, 1, 0, 0, 0, 0, 0, 0, 0, CHI_R5(C71), CHI_R5(C72), CHI_R5(C73),      \
+    CHI_R5(C74), CHI_R5(C75), CHI_R5(C76), 0)                                 \
+  X(7, 7, 1, 0, 0, 0, 0, 0, 0, 0, CHI_R5(C81), CHI_R5(C82), CHI_R5(C83),      \
+    CHI_R5(C84), CHI_R5(C85), CHI_R5(C86), CHI_R5(C87))
 
 // out = base + sum_{j<CNT} k_j U[j]   (base may be null), up to 7 terms
 template <int CNT, int N>
@@ -315,7 +326,7 @@ struct StreamSolver {
   const int stride;
 
   // hot state (registers)
-  double y[N], c[NCS];
+  double y[N];
   double u, t, h, t_stop;
   double J0[N * N];
   int cur, n_att;
@@ -325,16 +336,31 @@ struct StreamSolver {
   CHI_HD StreamSolver(const SolveArgs& args, double* smem, int smem_stride)
       : a(args), sm(smem), stride(smem_stride) {}
 
-#define CHI_S(buf, k, n) sm[(((buf) * P + (k)) * N + (n)) * stride]
-#define CHI_G(k) sm[(2 * P * N + (k)) * stride]
-#define CHI_ZY(i, n) sm[(2 * P * N + P + ((i) - 1) * N + (n)) * stride]
+  static constexpr int PI = stream_integrated<M>();
+// S is stored for the integrated columns only; `m` is the column's rank
+// among them (the loops over the columns carry it along)
+#define CHI_S(buf, m, n) sm[(((buf) * PI + (m)) * N + (n)) * stride]
+#define CHI_G(k) sm[(2 * PI * N + (k)) * stride]
+#define CHI_ZY(i, n) sm[(2 * PI * N + P + ((i) - 1) * N + (n)) * stride]
 // Cold per-system scalars, kept out of the register file because they are
 // only touched when an event is pending:
 //   0 system index     1 next dose-rate edge     2 time of the next record
 //   3 fused: log-likelihood; deferred: ints (first record, -)
 //   4 fused: running product of the error scales (its log is taken once)
 //   5 ints: next record, last record     6 ints: segment, last segment
-#define CHI_COLD(k) sm[(2 * P * N + P + 7 * N + (k)) * stride]
+#define CHI_COLD(k) sm[(2 * PI * N + P + 7 * N + (k)) * stride]
+// the model constants: needed by the state column and the event handlers,
+// not by the sensitivity columns of a linear model -- kept here and loaded
+// where used so that they do not occupy registers across the column loop
+#define CHI_C(j) sm[(2 * PI * N + P + 7 * N + 7 + (j)) * stride]
+
+  CHI_HD static bool inert(const int pk) {
+    return pk >= N && ((M::INERT_MASK >> (pk - N)) & 1u);
+  }
+  CHI_HD void load_constants(double (&c)[NCS]) const {
+#pragma unroll
+    for (int j = 0; j < NCS; ++j) c[j] = CHI_C(j);
+  }
 
   CHI_HD int cold_int(const int k, const int half) const {
 #ifdef __CUDA_ARCH__
@@ -376,19 +402,25 @@ struct StreamSolver {
     const double* sg = xb + P;
 #pragma unroll
     for (int i = 0; i < N; ++i) y[i] = xb[i];
+    double c[NCS];
 #pragma unroll
     for (int i = 0; i < NC; ++i) c[i] = xb[N + i];
     if (NC == 0) c[0] = 0.0;
+#pragma unroll
+    for (int j = 0; j < NCS; ++j) CHI_C(j) = c[j];
     cur = 0;
     const int nc = n_cols();
-    for (int k = 0; k < P; ++k) {
-      const int pk = k < nc ? a.col_param[k] : -1;
+    for (int k = 0, m = 0; k < P; ++k) {
+      CHI_G(k) = 0.0;
+      if (k >= nc) continue;
+      const int pk = a.col_param[k];
+      if (inert(pk)) continue;
 #pragma unroll
       for (int n = 0; n < N; ++n) {
-        CHI_S(0, k, n) = (pk == n) ? 1.0 : 0.0;
-        CHI_S(1, k, n) = 0.0;
+        CHI_S(0, m, n) = (pk == n) ? 1.0 : 0.0;
+        CHI_S(1, m, n) = 0.0;
       }
-      CHI_G(k) = 0.0;
+      ++m;
     }
     invalid = false;
     if (loglik()) {
@@ -450,13 +482,11 @@ struct StreamSolver {
 #pragma unroll
     for (int n = 0; n < N; ++n) row[n] = y[n];
     const int nc = n_cols();
-    int m = N;
-    for (int k = 0; k < nc; ++k) {
-      const int pk = a.col_param[k];
-      if (pk >= N && ((M::INERT_MASK >> (pk - N)) & 1u)) continue;
+    for (int k = 0, m = 0; k < nc; ++k) {
+      if (inert(a.col_param[k])) continue;
 #pragma unroll
-      for (int n = 0; n < N; ++n) row[m + n] = CHI_S(cur, k, n);
-      m += N;
+      for (int n = 0; n < N; ++n) row[N + m * N + n] = CHI_S(cur, m, n);
+      ++m;
     }
   }
 
@@ -465,7 +495,8 @@ struct StreamSolver {
     const int o = a.rec_out[r];
     const int oid = a.out_id[o];
     const int nc = n_cols();
-    double gy[N], gc[NCS];
+    double c[NCS], gy[N], gc[NCS];
+    load_constants(c);
     const double yb = M::out_grad(oid, y, c, gy, gc);
     if (loglik()) {
       const int64_t b = system();
@@ -482,11 +513,13 @@ struct StreamSolver {
         if (a.err_kind[o] == ERR_CAM) dsig[1] += e.ds1;
       }
       // d ybar / d psi_k = (dg/dy) S_k + dg/dc_k
-      for (int k = 0; k < nc; ++k) {
+      for (int k = 0, m = 0; k < nc; ++k) {
+        if (inert(a.col_param[k])) continue;
         double d = 0.0;
 #pragma unroll
-        for (int n = 0; n < N; ++n) d = fma(gy[n], CHI_S(cur, k, n), d);
+        for (int n = 0; n < N; ++n) d = fma(gy[n], CHI_S(cur, m, n), d);
         CHI_G(k) = fma(e.w, d, CHI_G(k));
+        ++m;
       }
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
@@ -498,13 +531,16 @@ struct StreamSolver {
       const int64_t b = system();
       const int64_t row = a.traj_off[b] + (r - a.rec_off[individual(b)]);
       a.traj_y[row] = yb;
-      for (int k = 0; k < nc; ++k) {
+      for (int k = 0, m = 0; k < nc; ++k) {
         const int pk = a.col_param[k];
         double d = 0.0;
 #pragma unroll
         for (int j = 0; j < NC; ++j) d = (pk == N + j) ? gc[j] : d;
+        if (!inert(pk)) {
 #pragma unroll
-        for (int n = 0; n < N; ++n) d = fma(gy[n], CHI_S(cur, k, n), d);
+          for (int n = 0; n < N; ++n) d = fma(gy[n], CHI_S(cur, m, n), d);
+          ++m;
+        }
         a.traj_s[row * nc + k] = d;
       }
     }
@@ -562,17 +598,18 @@ struct StreamSolver {
   //     D_k, e_k fetched once per column, and V = Zy + Uy was stored by the
   //     state column (V0 for the first stage), so neither Uy nor the model
   //     constants are live here.
-  CHI_HD float column(const int kc, const int k, const int nxt,
-                      const double (&Uy)[NS][N], const double (&V0)[N],
+  CHI_HD float column(const int kc, const int m, const int nxt,
+                      const double (&c)[NCS], const double (&Uy)[NS][N],
+                      const double (&V0)[N],
                       const double (&Wi)[N * N], const double hinv,
                       const float atol_f, const float rtol_f) {
     double S0[N], Us[NS][N], Zl[N];
 #pragma unroll
-    for (int n = 0; n < N; ++n) S0[n] = CHI_S(cur, k, n);
+    for (int n = 0; n < N; ++n) S0[n] = CHI_S(cur, m, n);
     double DK[N * N], ek[N];
     if (M::LINEAR) M::col_linear(kc, c, u, DK, ek);
-#define CHI_SSTAGE(I, CNT, a0, a1, a2, a3, a4, a5, a6, c0, c1, c2, c3, c4,   \
-                   c5, c6)                                                    \
+#define CHI_SSTAGE(I, CNT, INCR, a0, a1, a2, a3, a4, a5, a6, c0, c1, c2, c3,  \
+                   c4, c5, c6)                                                \
   {                                                                           \
     double cs[N], rs[N];                                                      \
     if (M::LINEAR) {                                                          \
@@ -585,7 +622,12 @@ struct StreamSolver {
             fma(DK[n * N + m], V[m], acc);                                    \
         rs[n] = acc;                                                          \
       }                                                                       \
-      lincomb7<CNT, N>(Zl, S0, Us, a0, a1, a2, a3, a4, a5, a6);               \
+      if (INCR) {                                                             \
+        _Pragma("unroll") for (int n = 0; n < N; ++n) Zl[n] +=                \
+            Us[I > 0 ? I - 1 : 0][n];                                         \
+      } else {                                                                \
+        lincomb7<CNT, N>(Zl, S0, Us, a0, a1, a2, a3, a4, a5, a6);             \
+      }                                                                       \
       lincomb7<CNT, N>(cs, nullptr, Us, c0, c1, c2, c3, c4, c5, c6);          \
       _Pragma("unroll") for (int n = 0; n < N; ++n) {                         \
         double acc = rs[n];                                                   \
@@ -598,7 +640,12 @@ struct StreamSolver {
       _Pragma("unroll") for (int n = 0; n < N; ++n) Zyi[n] =                  \
           (I == 0) ? y[n] : CHI_ZY(I, n);                                     \
       M::jac(Zyi, c, Ji);                                                     \
-      lincomb7<CNT, N>(Zl, S0, Us, a0, a1, a2, a3, a4, a5, a6);               \
+      if (INCR) {                                                             \
+        _Pragma("unroll") for (int n = 0; n < N; ++n) Zl[n] +=                \
+            Us[I > 0 ? I - 1 : 0][n];                                         \
+      } else {                                                                \
+        lincomb7<CNT, N>(Zl, S0, Us, a0, a1, a2, a3, a4, a5, a6);             \
+      }                                                                       \
       lincomb7<CNT, N>(cs, nullptr, Us, c0, c1, c2, c3, c4, c5, c6);          \
       matvec<N>(Ji, Zl, rs);                                                  \
       M::dfdc_col_add(kc, Zyi, c, rs);                                        \
@@ -621,13 +668,15 @@ struct StreamSolver {
     for (int n = 0; n < N; ++n) {
       const double Sn = Zl[n] + Us[NS - 1][n];
       s2 += err_term(Us[NS - 1][n], S0[n], Sn, atol_f, rtol_f);
-      CHI_S(nxt, k, n) = Sn;
+      CHI_S(nxt, m, n) = Sn;
     }
     return s2 * (1.0f / N);
   }
 
   // One step attempt towards the next stop.  Returns true on failure.
   CHI_HD bool step() {
+    double c[NCS];
+    load_constants(c);
     if (h == 0.0) {
       double f0[N];
       M::rhs(y, c, u, f0);
@@ -670,11 +719,16 @@ struct StreamSolver {
     }
     double Uy[NS][N];
     double Zlast[N], V0[N];
-#define CHI_YSTAGE(I, CNT, a0, a1, a2, a3, a4, a5, a6, c0, c1, c2, c3, c4,   \
-                   c5, c6)                                                    \
+#define CHI_YSTAGE(I, CNT, INCR, a0, a1, a2, a3, a4, a5, a6, c0, c1, c2, c3,  \
+                   c4, c5, c6)                                                \
   {                                                                           \
     double f[N], cy[N], ry[N];                                                \
-    lincomb7<CNT, N>(Zlast, y, Uy, a0, a1, a2, a3, a4, a5, a6);               \
+    if (INCR) {                                                               \
+      _Pragma("unroll") for (int n = 0; n < N; ++n) Zlast[n] +=               \
+          Uy[I > 0 ? I - 1 : 0][n];                                           \
+    } else {                                                                  \
+      lincomb7<CNT, N>(Zlast, y, Uy, a0, a1, a2, a3, a4, a5, a6);             \
+    }                                                                         \
     M::rhs(Zlast, c, u, f);                                                   \
     lincomb7<CNT, N>(cy, nullptr, Uy, c0, c1, c2, c3, c4, c5, c6);            \
     _Pragma("unroll") for (int n = 0; n < N; ++n) ry[n] =                     \
@@ -692,16 +746,19 @@ struct StreamSolver {
       CHI_RODAS4_TABLE(CHI_YSTAGE)
     }
 #undef CHI_YSTAGE
-    double yn[N];
     float errsq;
     const float atol_f = static_cast<float>(a.atol);
     const float rtol_f = static_cast<float>(a.rtol);
     {
+      // the candidate solution yn = last stage value + last increment; for
+      // linear models that is what the last stage left in CHI_ZY(NS - 1, .),
+      // it is fetched from there after the column loop
       float s2 = 0.0f;
 #pragma unroll
       for (int n = 0; n < N; ++n) {
-        yn[n] = Zlast[n] + Uy[NS - 1][n];
-        s2 += err_term(Uy[NS - 1][n], y[n], yn[n], atol_f, rtol_f);
+        const double yn = Zlast[n] + Uy[NS - 1][n];
+        if (!M::LINEAR) Zlast[n] = yn;
+        s2 += err_term(Uy[NS - 1][n], y[n], yn, atol_f, rtol_f);
       }
       errsq = s2 * (1.0f / N);
     }
@@ -711,19 +768,15 @@ struct StreamSolver {
     // on it inside the generated column terms are uniform branches.
     const int nxt = 1 - cur;
     const int nc = n_cols();
-    for (int k = 0; k < nc; ++k) {
+    for (int k = 0, m = 0; k < nc; ++k) {
       const int pk = a.col_param[k];
       const int kc = pk >= N ? pk - N : -1;
       // columns of constants that do not enter the rhs stay identically
       // zero: nothing to integrate
-      if (kc >= 0 && ((M::INERT_MASK >> kc) & 1u)) continue;
-#ifdef __CUDA_ARCH__
-      // keep the coefficient loads inside the column body: hoisted out of the
-      // loop they would occupy a hundred registers
-      asm volatile("" ::: "memory");
-#endif
+      if (inert(pk)) continue;
       errsq = fmaxf(errsq,
-                    column(kc, k, nxt, Uy, V0, Wi, hinv, atol_f, rtol_f));
+                    column(kc, m, nxt, c, Uy, V0, Wi, hinv, atol_f, rtol_f));
+      ++m;
     }
 
     const bool accept = errsq <= 1.0f;
@@ -737,7 +790,8 @@ struct StreamSolver {
     if (accept) {
       t = clipped ? t_stop : t + hs;
 #pragma unroll
-      for (int n = 0; n < N; ++n) y[n] = yn[n];
+      for (int n = 0; n < N; ++n)
+        y[n] = M::LINEAR ? CHI_ZY(NS - 1, n) : Zlast[n];
       cur = nxt;
       if (after_reject) fac = fminf(fac, 1.0f);
       const double hn = hs * static_cast<double>(fac);
@@ -788,6 +842,7 @@ struct StreamSolver {
 #undef CHI_G
 #undef CHI_ZY
 #undef CHI_COLD
+#undef CHI_C
 };
 
 template <class M, int CB>
