@@ -24,7 +24,8 @@ namespace chi_b200 {
 
 // shared-memory doubles per thread: S of the integrated columns (current +
 // candidate), gradient accumulators, the state column's stage values 2..8
-// (the first is y), seven cold per-system scalars and the model constants
+// (the first is y), seven cold per-system scalars, the model constants and
+// the state
 template <class M>
 constexpr int stream_integrated() {
   // parameters whose sensitivity column is integrated: all but the constants
@@ -35,7 +36,8 @@ constexpr int stream_integrated() {
 }
 template <class M>
 constexpr int stream_slots() {
-  return 2 * stream_integrated<M>() * M::N + M::P + 7 * M::N + 7 + M::NCS;
+  return 2 * stream_integrated<M>() * M::N + M::P + 7 * M::N + 7 + M::NCS +
+         M::N;
 }
 
 namespace rodas5 {
@@ -326,7 +328,6 @@ struct StreamSolver {
   const int stride;
 
   // hot state (registers)
-  double y[N];
   double u, t, h, t_stop;
   double J0[N * N];
   int cur, n_att;
@@ -353,6 +354,8 @@ struct StreamSolver {
 // not by the sensitivity columns of a linear model -- kept here and loaded
 // where used so that they do not occupy registers across the column loop
 #define CHI_C(j) sm[(2 * PI * N + P + 7 * N + 7 + (j)) * stride]
+// ... and the state itself
+#define CHI_Y(n) sm[(2 * PI * N + P + 7 * N + 7 + NCS + (n)) * stride]
 
   CHI_HD static bool inert(const int pk) {
     return pk >= N && ((M::INERT_MASK >> (pk - N)) & 1u);
@@ -360,6 +363,10 @@ struct StreamSolver {
   CHI_HD void load_constants(double (&c)[NCS]) const {
 #pragma unroll
     for (int j = 0; j < NCS; ++j) c[j] = CHI_C(j);
+  }
+  CHI_HD void load_state(double (&y)[N]) const {
+#pragma unroll
+    for (int n = 0; n < N; ++n) y[n] = CHI_Y(n);
   }
 
   CHI_HD int cold_int(const int k, const int half) const {
@@ -400,8 +407,11 @@ struct StreamSolver {
     const int id = individual(b);
     const double* xb = a.x + b * a.x_stride;
     const double* sg = xb + P;
+    double y[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) y[i] = xb[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) CHI_Y(i) = y[i];
     double c[NCS];
 #pragma unroll
     for (int i = 0; i < NC; ++i) c[i] = xb[N + i];
@@ -480,7 +490,7 @@ struct StreamSolver {
     double* row = a.snap + (b * a.snap_rows + (r - cold_int(3, 0))) *
                                static_cast<int64_t>(a.snap_width);
 #pragma unroll
-    for (int n = 0; n < N; ++n) row[n] = y[n];
+    for (int n = 0; n < N; ++n) row[n] = CHI_Y(n);
     const int nc = n_cols();
     for (int k = 0, m = 0; k < nc; ++k) {
       if (inert(a.col_param[k])) continue;
@@ -495,7 +505,8 @@ struct StreamSolver {
     const int o = a.rec_out[r];
     const int oid = a.out_id[o];
     const int nc = n_cols();
-    double c[NCS], gy[N], gc[NCS];
+    double y[N], c[NCS], gy[N], gc[NCS];
+    load_state(y);
     load_constants(c);
     const double yb = M::out_grad(oid, y, c, gy, gc);
     if (loglik()) {
@@ -599,7 +610,8 @@ struct StreamSolver {
   //     state column (V0 for the first stage), so neither Uy nor the model
   //     constants are live here.
   CHI_HD float column(const int kc, const int m, const int nxt,
-                      const double (&c)[NCS], const double (&Uy)[NS][N],
+                      const double (&y)[N], const double (&c)[NCS],
+                      const double (&Uy)[NS][N],
                       const double (&V0)[N],
                       const double (&Wi)[N * N], const double hinv,
                       const float atol_f, const float rtol_f) {
@@ -675,7 +687,8 @@ struct StreamSolver {
 
   // One step attempt towards the next stop.  Returns true on failure.
   CHI_HD bool step() {
-    double c[NCS];
+    double y[N], c[NCS];
+    load_state(y);
     load_constants(c);
     if (h == 0.0) {
       double f0[N];
@@ -775,7 +788,8 @@ struct StreamSolver {
       // zero: nothing to integrate
       if (inert(pk)) continue;
       errsq = fmaxf(errsq,
-                    column(kc, m, nxt, c, Uy, V0, Wi, hinv, atol_f, rtol_f));
+                    column(kc, m, nxt, y, c, Uy, V0, Wi, hinv, atol_f,
+                           rtol_f));
       ++m;
     }
 
@@ -791,7 +805,7 @@ struct StreamSolver {
       t = clipped ? t_stop : t + hs;
 #pragma unroll
       for (int n = 0; n < N; ++n)
-        y[n] = M::LINEAR ? CHI_ZY(NS - 1, n) : Zlast[n];
+        CHI_Y(n) = M::LINEAR ? CHI_ZY(NS - 1, n) : Zlast[n];
       cur = nxt;
       if (after_reject) fac = fminf(fac, 1.0f);
       const double hn = hs * static_cast<double>(fac);
@@ -843,6 +857,7 @@ struct StreamSolver {
 #undef CHI_ZY
 #undef CHI_COLD
 #undef CHI_C
+#undef CHI_Y
 };
 
 template <class M, int CB>
