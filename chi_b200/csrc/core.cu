@@ -947,10 +947,17 @@ void fill_args(const chi_b200_problem* p, SolveArgs& a) {
   a.n_sigma = p->n_sigma;
   a.n_cols = p->n_cols;
   for (int i = 0; i < MAX_COLS; ++i) a.param_col[i] = -1;
+  a.n_int = 0;
   for (int i = 0; i < p->n_cols; ++i) {
-    a.col_param[i] = p->col_param[i];
-    if (p->col_param[i] >= 0 && p->col_param[i] < MAX_COLS)
-      a.param_col[p->col_param[i]] = i;
+    const int pk = p->col_param[i];
+    a.col_param[i] = pk;
+    if (pk >= 0 && pk < MAX_COLS) a.param_col[pk] = i;
+    const int N = p->vt->n_states;
+    if (!(pk >= N && ((p->vt->inert_mask >> (pk - N)) & 1u))) {
+      a.int_col[a.n_int] = i;
+      a.int_param[a.n_int] = pk;
+      ++a.n_int;
+    }
   }
   a.rtol = p->rtol;
   a.atol = p->atol;
@@ -997,12 +1004,7 @@ int launch_loglik(chi_b200_problem* p, int64_t B, const int32_t* d_ids,
       }
     }
     const int N = p->vt->n_states;
-    int integrated = 0;
-    if (with_grad)
-      for (int k = 0; k < p->n_cols; ++k) {
-        const int pk = p->col_param[k];
-        if (!(pk >= N && ((p->vt->inert_mask >> (pk - N)) & 1u))) ++integrated;
-      }
+    const int integrated = with_grad ? a.n_int : 0;
     const int64_t width = static_cast<int64_t>(N) * (1 + integrated);
     const int64_t bytes = B * p->max_rec * width * 8;
     if (streamed && p->max_rec > 0 && p->max_rec <= INT32_MAX &&

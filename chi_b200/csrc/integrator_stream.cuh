@@ -346,7 +346,7 @@ struct StreamSolver {
 // Cold per-system scalars, kept out of the register file because they are
 // only touched when an event is pending:
 //   0 system index     1 next dose-rate edge     2 time of the next record
-//   3 fused: log-likelihood; deferred: ints (first record, -)
+//   3 fused: log-likelihood; deferred: snapshot write position (two ints)
 //   4 fused: running product of the error scales (its log is taken once)
 //   5 ints: next record, last record     6 ints: segment, last segment
 #define CHI_COLD(k) sm[(2 * PI * N + P + 7 * N + (k)) * stride]
@@ -390,6 +390,7 @@ struct StreamSolver {
   }
 
   CHI_HD int n_cols() const { return a.with_sens ? a.n_cols : 0; }
+  CHI_HD int n_int() const { return a.with_sens ? a.n_int : 0; }
   CHI_HD bool loglik() const { return a.mode == 1; }
   CHI_HD bool deferred() const { return a.mode == 1 && a.snap != nullptr; }
   CHI_HD bool want_dsig() const {
@@ -420,17 +421,15 @@ struct StreamSolver {
     for (int j = 0; j < NCS; ++j) CHI_C(j) = c[j];
     cur = 0;
     const int nc = n_cols();
-    for (int k = 0, m = 0; k < P; ++k) {
-      CHI_G(k) = 0.0;
-      if (k >= nc) continue;
-      const int pk = a.col_param[k];
-      if (inert(pk)) continue;
+    for (int k = 0; k < P; ++k) CHI_G(k) = 0.0;
+    const int ni = n_int();
+    for (int m = 0; m < ni; ++m) {
+      const int pk = a.int_param[m];
 #pragma unroll
       for (int n = 0; n < N; ++n) {
         CHI_S(0, m, n) = (pk == n) ? 1.0 : 0.0;
         CHI_S(1, m, n) = 0.0;
       }
-      ++m;
     }
     invalid = false;
     if (loglik()) {
@@ -454,7 +453,9 @@ struct StreamSolver {
     CHI_COLD(1) = (seg + 1 < seg_end) ? a.seg_t[seg + 1] : INFINITY;
     CHI_COLD(2) = (r < r_end) ? a.rec_t[r] : INFINITY;
     if (deferred()) {
-      set_cold_int(3, 0, static_cast<int>(r));
+      const int64_t pos = b * a.snap_rows * static_cast<int64_t>(a.snap_width);
+      set_cold_int(3, 0, static_cast<int>(pos & 0xffffffff));
+      set_cold_int(3, 1, static_cast<int>(pos >> 32));
     } else {
       CHI_COLD(3) = 0.0;
       CHI_COLD(4) = 1.0;
@@ -483,21 +484,26 @@ struct StreamSolver {
     CHI_COLD(4) = lp;
   }
 
-  // Deferred observation: store the state and the integrated sensitivity
-  // columns of record r; observe_system() below does the rest.
-  CHI_HD void snapshot(const int r) {
-    const int64_t b = system();
-    double* row = a.snap + (b * a.snap_rows + (r - cold_int(3, 0))) *
-                               static_cast<int64_t>(a.snap_width);
+  // Deferred observation: append the state and the integrated sensitivity
+  // columns to the system's snapshot rows; observe_system() does the rest.
+  CHI_HD void snapshot() {
+    const int64_t pos =
+        (static_cast<int64_t>(cold_int(3, 1)) << 32) |
+        static_cast<int64_t>(static_cast<unsigned>(cold_int(3, 0)));
+    double* row = a.snap + pos;
 #pragma unroll
     for (int n = 0; n < N; ++n) row[n] = CHI_Y(n);
-    const int nc = n_cols();
-    for (int k = 0, m = 0; k < nc; ++k) {
-      if (inert(a.col_param[k])) continue;
+    const int ni = n_int();
 #pragma unroll
-      for (int n = 0; n < N; ++n) row[N + m * N + n] = CHI_S(cur, m, n);
-      ++m;
+    for (int m = 0; m < PI; ++m) {
+      if (m < ni) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) row[N + m * N + n] = CHI_S(cur, m, n);
+      }
     }
+    const int64_t next = pos + a.snap_width;
+    set_cold_int(3, 0, static_cast<int>(next & 0xffffffff));
+    set_cold_int(3, 1, static_cast<int>(next >> 32));
   }
 
   // observation record r at the current time (fused handling)
@@ -524,13 +530,13 @@ struct StreamSolver {
         if (a.err_kind[o] == ERR_CAM) dsig[1] += e.ds1;
       }
       // d ybar / d psi_k = (dg/dy) S_k + dg/dc_k
-      for (int k = 0, m = 0; k < nc; ++k) {
-        if (inert(a.col_param[k])) continue;
+      const int ni = n_int();
+      for (int m = 0; m < ni; ++m) {
+        const int k = a.int_col[m];
         double d = 0.0;
 #pragma unroll
         for (int n = 0; n < N; ++n) d = fma(gy[n], CHI_S(cur, m, n), d);
         CHI_G(k) = fma(e.w, d, CHI_G(k));
-        ++m;
       }
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
@@ -573,7 +579,7 @@ struct StreamSolver {
         // fetch the next record's time while this one is processed
         const double t_next = (r + 1 < r_end) ? a.rec_t[r + 1] : INFINITY;
         if (deferred()) {
-          snapshot(r);
+          snapshot();
         } else {
           observe(r);
           if (invalid) return true;
@@ -780,17 +786,15 @@ struct StreamSolver {
     // The column's constant index kc is uniform over the grid: the switches
     // on it inside the generated column terms are uniform branches.
     const int nxt = 1 - cur;
-    const int nc = n_cols();
-    for (int k = 0, m = 0; k < nc; ++k) {
-      const int pk = a.col_param[k];
+    // (columns of constants that do not enter the rhs stay identically zero
+    // and are not in the list)
+    const int ni = n_int();
+    for (int m = 0; m < ni; ++m) {
+      const int pk = a.int_param[m];
       const int kc = pk >= N ? pk - N : -1;
-      // columns of constants that do not enter the rhs stay identically
-      // zero: nothing to integrate
-      if (inert(pk)) continue;
       errsq = fmaxf(errsq,
                     column(kc, m, nxt, y, c, Uy, V0, Wi, hinv, atol_f,
                            rtol_f));
-      ++m;
     }
 
     const bool accept = errsq <= 1.0f;

@@ -62,6 +62,11 @@ struct SolveArgs {
   int32_t n_cols;            // sensitivity columns
   int32_t col_param[MAX_COLS];  // mechanistic parameter index of each column
   int32_t param_col[MAX_COLS];  // inverse map: column of parameter p, or -1
+  // the columns that are integrated (all but those of constants that do not
+  // enter the rhs), in column order: column index and parameter index
+  int32_t n_int;
+  int32_t int_col[MAX_COLS];
+  int32_t int_param[MAX_COLS];
 
   int32_t mode;              // 0: simulate (write trajectories); 1: log-likelihood
   int32_t with_sens;

@@ -37,6 +37,9 @@ class SolveArgs(ctypes.Structure):
         ('n_cols', ctypes.c_int32),
         ('col_param', ctypes.c_int32 * MAX_COLS),
         ('param_col', ctypes.c_int32 * MAX_COLS),
+        ('n_int', ctypes.c_int32),
+        ('int_col', ctypes.c_int32 * MAX_COLS),
+        ('int_param', ctypes.c_int32 * MAX_COLS),
         ('mode', ctypes.c_int32), ('with_sens', ctypes.c_int32),
         ('rtol', ctypes.c_double), ('atol', ctypes.c_double),
         ('max_steps', ctypes.c_int32),
@@ -61,6 +64,8 @@ def lib():
         _lib = ctypes.CDLL(path)
         _lib.chi_port_solve.argtypes = [
             ctypes.c_char_p, ctypes.POINTER(SolveArgs), ctypes.c_int]
+        _lib.chi_port_fill_integrated.argtypes = [
+            ctypes.c_char_p, ctypes.POINTER(SolveArgs)]
         _lib.chi_port_snap_width.argtypes = [
             ctypes.c_char_p, ctypes.POINTER(SolveArgs)]
         _lib.chi_port_solve2.argtypes = [
@@ -171,6 +176,7 @@ class Population(object):
         for k in range(self.P):
             a.col_param[k] = k
             a.param_col[k] = k
+        lib().chi_port_fill_integrated(self.key.encode(), ctypes.byref(a))
         return a
 
     def loglik(self, x, ids=None, with_grad=True, rtol=1e-8, atol=1e-10,

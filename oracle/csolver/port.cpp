@@ -48,16 +48,33 @@ static void run_all(const SolveArgs& a, int n_threads, int stream_cb) {
   }
 }
 
+// fills SolveArgs::n_int / int_col / int_param from col_param
+template <class M>
+static int fill_integrated(SolveArgs& a) {
+  a.n_int = 0;
+  for (int k = 0; k < a.n_cols; ++k) {
+    const int pk = a.col_param[k];
+    if (!(pk >= M::N && ((M::INERT_MASK >> (pk - M::N)) & 1u))) {
+      a.int_col[a.n_int] = k;
+      a.int_param[a.n_int] = pk;
+      ++a.n_int;
+    }
+  }
+  return 0;
+}
+
+extern "C" int chi_port_fill_integrated(const char* key, SolveArgs* a) {
+#define CHI_PORT_MODEL(KEY, TYPE)                                            \
+  if (std::strcmp(key, KEY) == 0) return fill_integrated<TYPE>(*a);
+  CHI_PORT_MODELS
+#undef CHI_PORT_MODEL
+  return -1;
+}
+
 // doubles per snapshot row for these arguments (SolveArgs::snap_width)
 template <class M>
 static int snap_width(const SolveArgs& a) {
-  int integrated = 0;
-  if (a.with_sens)
-    for (int k = 0; k < a.n_cols; ++k) {
-      const int pk = a.col_param[k];
-      if (!(pk >= M::N && ((M::INERT_MASK >> (pk - M::N)) & 1u))) ++integrated;
-    }
-  return M::N * (1 + integrated);
+  return M::N * (1 + (a.with_sens ? a.n_int : 0));
 }
 
 extern "C" int chi_port_snap_width(const char* key, const SolveArgs* a) {
