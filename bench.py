@@ -119,6 +119,22 @@ def flops_per_step(n, n_cols, info, stages=6):
     return inv + state + n_cols * sens + extra + jac + new
 
 
+def _ncu_traffic(args):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the solve
+    kernel, taken from profiles/solve_kernel_traffic.json (written from an
+    `ncu --set full` capture of the default workload); None for any other
+    workload or when the file is missing."""
+    path = os.path.join(ROOT, 'profiles', 'solve_kernel_traffic.json')
+    try:
+        with open(path) as f:
+            rec = json.load(f)
+    except (OSError, ValueError):
+        return None
+    same = all(rec.get(k) == getattr(args, k) for k in (
+        'n_ids', 'chains', 'n_obs', 'n_doses', 'rtol', 'atol'))
+    return rec.get('dram_bytes_per_launch') if same else None
+
+
 def flops_per_record(n, n_cols):
     """Output map, its directional derivatives and the error model."""
     return 3 + n_cols * (2 * n + 3) + 25 + 2 * n_cols
@@ -403,7 +419,7 @@ def run_reference(args, rank, world):
             'sample': (
                 'full evaluateS1 of the %d-individual model repeated for '
                 '%.1f s on %d processes (one per core): Python loop '
-                'over individuals, one compiled RODAS4+sensitivities solve '
+                'over individuals, one compiled RODAS5+sensitivities solve '
                 'per individual, numpy error and population models '
                 '(oracle/stats.py, oracle/csolver)' % (
                     n_ids, per_step, cores))},
@@ -575,7 +591,9 @@ def run_product(args, rank, world, local_rank):
     roofline = {
         'bound': 'fp64', 'achieved': achieved, 'peak': float(peak[0]),
         'unit': 'TFLOP/s', 'frac': achieved / float(peak[0]),
-        'traffic': None,
+        # DRAM bytes per launch (read + write) of the solve kernel from the
+        # committed `ncu --set full` capture of this workload, if present
+        'traffic': _ncu_traffic(args),
         'peak_source': ('measured in this run: DFMA micro-kernel '
                         '(chi_b200_fp64_peak); MEASURED_PEAKS.json has no '
                         'FP64 figure'),

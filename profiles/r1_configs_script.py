@@ -37,3 +37,9 @@ ll = chi_b200.LogLikelihood(m1, chi_b200.GaussianErrorModel(), y1, t1)
 lp = chi_b200.LogPosterior(ll, chi_b200.ComposedLogPrior(*[chi_b200.LogNormalLogPrior(0,1)]*4))
 dt,_ = timeit(lambda: lp.evaluateS1([0.3,2.0,1.0,0.1]), n=50, warm=3)
 print('C1: LogPosterior.evaluateS1 latency (1 individual, 100 times): %.3f ms' % (dt*1e3))
+# C4: 1024 chains x 500 individuals, forward only (__call__ semantics of an MCMC iteration)
+prob4 = _synthetic.two_compartment_problem(500, seed=0, n_doses=3, rtol=1e-6, atol=1e-8)
+post4 = prob4['log_posterior']
+X4 = np.tile(prob4['x0'], (1024, 1)) * (1 + 0.001 * np.random.default_rng(0).normal(size=(1024, len(prob4['x0']))))
+dt, s4 = timeit(lambda: post4.evaluate_batch(X4), n=5, warm=2)
+print('C4: HierarchicalLogPosterior.evaluate_batch, 1024 chains x 500 individuals: %.2f ms per MCMC iteration = %.0f evals/s = %.2e ODE solves/s, finite %s' % (dt*1e3, 1024/dt, 1024*500/dt, np.isfinite(np.asarray(s4)).all()))
