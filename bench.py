@@ -526,6 +526,9 @@ def run_product(args, rank, world, local_rank):
 
     evals = args.steps * C * (world if args.shard == 'chains' else 1)
     value = evals / (dev_ms * 1e-3)
+    copied_cols = n_params
+    if args.shard == 'individuals' and world > 1:
+        copied_cols = n_top + (n_bottom // n_total) * args.n_ids
 
     # step counters of the last step (host API call gives them)
     score_h, _ = ll.evaluateS1_batch(np.array(X_host), copy=False)
@@ -535,12 +538,17 @@ def run_product(args, rank, world, local_rank):
     steps_acc, steps_rej = int(cnt[1]), int(cnt[2])
 
     # ---- end to end through the public API ---------------------------------
+    api = post
+    if dist is not None and args.shard == 'individuals':
+        # shard evaluation + the all-reduce of [score | d theta] + host prior
+        from chi_b200._distributed import ShardedHierarchicalLogPosterior
+        api = ShardedHierarchicalLogPosterior(post, gather_bottom=False)
     for _ in range(max(1, args.warmup)):
-        post.evaluateS1_batch(X_host, copy=False)
+        api.evaluateS1_batch(X_host, copy=False)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        s, g = post.evaluateS1_batch(X_host, copy=False)
+        s, g = api.evaluateS1_batch(X_host, copy=False)
         _ = float(s[0])
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -652,8 +660,10 @@ def run_product(args, rank, world, local_rank):
             'data': 'synthetic', 'config': workload_config(args, world),
             'e2e': {
                 'value': e2e_value, 'unit': UNIT,
-                'h2d_bytes_per_step': int(C * n_params * 8),
-                'd2h_bytes_per_step': int(C * (n_params + 1) * 8 + C * 4),
+                # with a shard set only the shard's bottom-level block and
+                # the top-level entries travel (chi_b200_hier_logpdf)
+                'h2d_bytes_per_step': int(C * copied_cols * 8),
+                'd2h_bytes_per_step': int(C * (copied_cols + 1) * 8 + C * 4),
                 'ms_per_step': e2e_s * 1e3 / args.steps},
             'gpu_launches': launches,
             'system_solves_per_s': value * n_total if args.shard == 'chains'

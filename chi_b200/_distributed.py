@@ -78,9 +78,10 @@ class ShardedHierarchicalLogPosterior(object):
         if self._partial_fn is not None:
             return self._partial_fn(X, self._begin, self._end)
         if with_grad:
-            return self._ll.evaluateS1_batch(X)
-        score = self._ll.evaluate_batch(X)
-        return score, np.zeros((len(score), self._n_params))
+            # page-locked result buffers; entries of other shards are zero
+            return self._ll.evaluateS1_batch(X, copy=False)
+        score = self._ll.evaluate_batch(X, copy=False)
+        return score, None
 
     def _all_reduce(self, array):
         import torch
@@ -91,28 +92,49 @@ class ShardedHierarchicalLogPosterior(object):
         self._dist.all_reduce(t, group=self._group)
         return t.cpu().numpy() if backend == 'nccl' else t.numpy()
 
-    def evaluateS1_batch(self, X, with_grad=True):
+    def _add_prior(self, X, score, grad):
+        top = X[:, self._n_bottom:]
+        if hasattr(self._prior, 'evaluateS1_batch'):
+            p, s = self._prior.evaluateS1_batch(top)
+        else:
+            ps = [self._prior.evaluateS1(x) for x in top]
+            p = np.array([q[0] for q in ps], dtype=float)
+            s = np.array([q[1] for q in ps], dtype=float)
+        bad = np.isinf(p)
+        score += np.where(bad, 0.0, p)
+        score[bad] = p[bad]
+        if grad is not None:
+            grad[:, self._n_bottom:] += np.where(bad[:, None], 0.0, s)
+            grad[bad] = np.inf
+
+    def evaluateS1_batch(self, X, with_grad=True, copy=True):
+        """Scores and gradients of the parameter vectors ``X``.  With
+        ``gather_bottom=False`` every rank's gradient holds the reduced
+        top-level entries and its own individuals' bottom-level entries (the
+        others are zero); with ``copy=False`` the arrays are the page-locked
+        result buffers of the likelihood, valid until the next evaluation."""
         X = np.asarray(X, dtype=float).reshape(-1, self._n_params)
         score, grad = self._partials(X, with_grad)
-        score = np.array(score, dtype=float)
-        grad = np.array(grad, dtype=float)
-        if self._gather_bottom and with_grad:
+        if self._partial_fn is not None or copy:
+            score = np.array(score, dtype=float)
+            grad = None if grad is None else np.array(grad, dtype=float)
+        if grad is None:
+            score[:] = self._all_reduce(
+                np.ascontiguousarray(score.reshape(-1, 1)))[:, 0]
+            grad_out = None
+        elif self._gather_bottom:
             # bottom blocks are disjoint: a sum is a concatenation
-            buf = np.ascontiguousarray(np.hstack([score[:, None], grad]))
-            buf = self._all_reduce(buf)
-            score, grad = buf[:, 0].copy(), buf[:, 1:].copy()
+            buf = self._all_reduce(
+                np.ascontiguousarray(np.hstack([score[:, None], grad])))
+            score[:] = buf[:, 0]
+            grad[:] = buf[:, 1:]
+            grad_out = grad
         else:
             buf = self._all_reduce(pack_partials(score, grad, self._n_bottom))
             unpack_partials(buf, score, grad, self._n_bottom)
-        for c, x in enumerate(X):
-            p, s = self._prior.evaluateS1(x[self._n_bottom:])
-            if np.isinf(p):
-                score[c] = p
-                grad[c] = np.inf
-                continue
-            score[c] += p
-            grad[c, self._n_bottom:] += s
-        return score, grad
+            grad_out = grad
+        self._add_prior(X, score, grad if grad is not None else None)
+        return score, grad_out
 
     def evaluate_batch(self, X):
         return self.evaluateS1_batch(X, with_grad=False)[0]

@@ -578,9 +578,12 @@ class HierarchicalLogLikelihood(object):
         if cache is None or cache[0] < C or (with_grad and cache[3] is None):
             score = _lib.pinned_empty((C,))
             status = _lib.pinned_empty((C,), np.int32)
-            grad = _lib.pinned_empty((C, self._n_parameters)) \
-                if with_grad else (cache[3] if cache and cache[0] >= C
-                                   else None)
+            grad = (cache[3] if cache and cache[0] >= C else None)
+            if with_grad:
+                # zero-filled: with a shard set only the shard's columns are
+                # written, the other individuals' entries stay zero
+                grad = _lib.pinned_empty((C, self._n_parameters))
+                grad[...] = 0.0
             cache = (C, score, status, grad)
             self._pinned = cache
         _, score, status, grad = cache
@@ -645,6 +648,7 @@ class HierarchicalLogLikelihood(object):
         caller all-reduces over the ranks (multi-GPU)."""
         _lib.check(_lib.lib().chi_b200_problem_set_shard(
             self._device.problem.handle, int(id_begin), int(id_end)))
+        self._pinned = None   # result buffers are re-created zero-filled
 
     def set_snapshot_budget(self, n_bytes):
         """See ``chi_b200_problem_set_snapshot_budget`` (0: observation

@@ -1473,15 +1473,35 @@ int chi_b200_hier_logpdf(chi_b200_problem* p, int32_t C, const double* x,
   CUDA_TRY(p->hx.reserve(C * n_params * sizeof(double)));
   CUDA_TRY(p->hscore.reserve(C * sizeof(double)));
   CUDA_TRY(p->hstatus.reserve(C * sizeof(int32_t)));
-  if (with_grad) {
-    CUDA_TRY(p->hgrad.reserve(C * n_params * sizeof(double)));
-    // entries of individuals outside this shard stay zero
-    if (p->id_end - p->id_begin != p->n_ids)
-      CUDA_TRY(cudaMemsetAsync(p->hgrad.ptr, 0,
-                               C * n_params * sizeof(double), s));
+  if (with_grad) CUDA_TRY(p->hgrad.reserve(C * n_params * sizeof(double)));
+  // With a shard set only the shard's block of bottom-level parameters and
+  // the top-level parameters travel (the same two column blocks of the
+  // gradient come back): an individuals-sharded rank of an 8-GPU job moves an
+  // eighth of the bytes.
+  const bool sharded = p->id_end - p->id_begin != p->n_ids;
+  const int64_t n_bottom = p->n_ids * p->pop.n_hdim;
+  const size_t pitch = static_cast<size_t>(n_params) * sizeof(double);
+  const size_t off_b = static_cast<size_t>(p->id_begin) * p->pop.n_hdim;
+  const size_t w_b = static_cast<size_t>(p->id_end - p->id_begin) *
+                     p->pop.n_hdim * sizeof(double);
+  const size_t w_t = static_cast<size_t>(p->n_top) * sizeof(double);
+  if (!sharded) {
+    CUDA_TRY(cudaMemcpyAsync(p->hx.ptr, x, C * pitch, cudaMemcpyHostToDevice,
+                             s));
+  } else {
+    if (w_b)
+      CUDA_TRY(cudaMemcpy2DAsync(p->hx.as<double>() + off_b, pitch, x + off_b,
+                                 pitch, w_b, C, cudaMemcpyHostToDevice, s));
+    if (w_t)
+      CUDA_TRY(cudaMemcpy2DAsync(p->hx.as<double>() + n_bottom, pitch,
+                                 x + n_bottom, pitch, w_t, C,
+                                 cudaMemcpyHostToDevice, s));
+    // top-level entries that belong to individuals of other shards
+    // (heterogeneous dimensions) read as zero
+    if (with_grad && w_t)
+      CUDA_TRY(cudaMemset2DAsync(p->hgrad.as<double>() + n_bottom, pitch, 0,
+                                 w_t, C, s));
   }
-  CUDA_TRY(cudaMemcpyAsync(p->hx.ptr, x, C * n_params * sizeof(double),
-                           cudaMemcpyHostToDevice, s));
   p->counters[3] = 0;
   int rc = run_hier(p, C, p->hx.as<double>(), with_grad,
                     p->hscore.as<double>(),
@@ -1491,10 +1511,21 @@ int chi_b200_hier_logpdf(chi_b200_problem* p, int32_t C, const double* x,
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(score, p->hscore.ptr, C * sizeof(double),
                            cudaMemcpyDeviceToHost, s));
-  if (with_grad && grad)
-    CUDA_TRY(cudaMemcpyAsync(grad, p->hgrad.ptr,
-                             C * n_params * sizeof(double),
-                             cudaMemcpyDeviceToHost, s));
+  if (with_grad && grad) {
+    if (!sharded) {
+      CUDA_TRY(cudaMemcpyAsync(grad, p->hgrad.ptr, C * pitch,
+                               cudaMemcpyDeviceToHost, s));
+    } else {
+      if (w_b)
+        CUDA_TRY(cudaMemcpy2DAsync(grad + off_b, pitch,
+                                   p->hgrad.as<double>() + off_b, pitch, w_b,
+                                   C, cudaMemcpyDeviceToHost, s));
+      if (w_t)
+        CUDA_TRY(cudaMemcpy2DAsync(grad + n_bottom, pitch,
+                                   p->hgrad.as<double>() + n_bottom, pitch,
+                                   w_t, C, cudaMemcpyDeviceToHost, s));
+    }
+  }
   if (status)
     CUDA_TRY(cudaMemcpyAsync(status, p->hstatus.ptr, C * sizeof(int32_t),
                              cudaMemcpyDeviceToHost, s));

@@ -185,7 +185,10 @@ int chi_b200_population_eval(chi_b200_problem* p, const double* top,
 /* ---- hierarchical log-likelihood over C parameter vectors --------------- */
 /* x: [C][n_bottom + n_top]; score: [C]; grad: [C][n_bottom + n_top];
  * status: [C] (max over the chain's systems). id range [id_begin, id_end) is
- * the shard of individuals evaluated by this call (multi-GPU). */
+ * the shard of individuals evaluated by this call (multi-GPU).  With a shard
+ * set, only the shard's block of bottom-level entries and the top-level
+ * entries of x are read, and only those two column blocks of grad are
+ * written (partial sums for the top level); the rest of grad is untouched. */
 int chi_b200_hier_logpdf(chi_b200_problem* p, int32_t C, const double* x,
                          int32_t with_grad, double* score, double* grad,
                          int32_t* status);

@@ -695,3 +695,45 @@ def test_deferred_and_fused_observation_agree(error):
         gd[ok], gf[ok], rtol=1e-11, atol=1e-11 * np.max(np.abs(gf[ok])))
     np.testing.assert_allclose(fd[ok], ff[ok], rtol=1e-13)
     assert np.array_equal(gd[4], gf[4], equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_individual_shards_sum_to_the_full_evaluation():
+    """Multi-GPU individuals-sharded mode on one device: the partial scores
+    and top-level gradients of two shards add up to the unsharded result, each
+    shard returns its own block of the bottom-level gradient and leaves the
+    other individuals' entries zero (chi_b200_problem_set_shard; only the
+    shard's column blocks are copied)."""
+    from chi_b200 import _synthetic
+    from chi_b200._distributed import shard_bounds
+    prob = _synthetic.two_compartment_problem(
+        n_ids=23, seed=11, n_obs=6, n_doses=2, error='cam', covariates=True)
+    ll = prob['log_likelihood']
+    n_params = len(prob['x0'])
+    n_top = ll.n_parameters(exclude_bottom_level=True)
+    n_bottom = n_params - n_top
+    n_hdim = n_bottom // 23
+    rng = np.random.default_rng(2)
+    X = prob['x0'][None, :] * (1 + 0.02 * rng.normal(size=(3, n_params)))
+    full_s, full_g = ll.evaluateS1_batch(X)
+    full_f = ll.evaluate_batch(X)
+    tot_s = np.zeros(3)
+    tot_f = np.zeros(3)
+    tot_g = np.zeros_like(full_g)
+    for rank in range(2):
+        b, e = shard_bounds(23, rank, 2)
+        ll.set_shard(b, e)
+        s, g = ll.evaluateS1_batch(X)
+        tot_f += ll.evaluate_batch(X)
+        outside = np.ones(n_bottom, dtype=bool)
+        outside[b * n_hdim:e * n_hdim] = False
+        assert np.all(g[:, :n_bottom][:, outside] == 0.0)
+        tot_s += s
+        tot_g += g
+    ll.set_shard(0, 23)
+    np.testing.assert_allclose(tot_s, full_s, rtol=1e-12)
+    np.testing.assert_allclose(tot_f, full_f, rtol=1e-12)
+    np.testing.assert_allclose(
+        tot_g, full_g, rtol=1e-10, atol=1e-10 * np.max(np.abs(full_g)))
+    s, g = ll.evaluateS1_batch(X)
+    np.testing.assert_allclose(g, full_g, rtol=1e-13)
