@@ -17,7 +17,8 @@ from chi_b200._covariate_models import (  # noqa: F401
     CovariateModel, LinearCovariateModel)
 from chi_b200._population_models import (  # noqa: F401
     PopulationModel, PooledModel, HeterogeneousModel, GaussianModel,
-    LogNormalModel, ComposedPopulationModel, CovariatePopulationModel)
+    LogNormalModel, TruncatedGaussianModel, ComposedPopulationModel,
+    CovariatePopulationModel)
 from chi_b200._log_pdfs import (  # noqa: F401
     LogLikelihood, HierarchicalLogLikelihood, LogPosterior,
     HierarchicalLogPosterior)

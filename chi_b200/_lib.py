@@ -18,7 +18,8 @@ c_f64p = ctypes.POINTER(ctypes.c_double)
 c_vp = ctypes.c_void_p
 
 ERR_KINDS = {'gaussian': 0, 'lognormal': 1, 'cam': 2, 'multiplicative': 3}
-POP_KINDS = {'pooled': 0, 'heterogeneous': 1, 'gaussian': 2, 'lognormal': 3}
+POP_KINDS = {'pooled': 0, 'heterogeneous': 1, 'gaussian': 2, 'lognormal': 3,
+             'truncated_gaussian': 4}
 
 _lib = None
 _modules = {}

@@ -101,7 +101,7 @@ class PopulationModel(_PopulationModelBase):
         cols = []
         d = 0
         for b in self._blocks():
-            if b[0] in ('gaussian', 'lognormal'):
+            if b[0] in ('gaussian', 'lognormal', 'truncated_gaussian'):
                 cols += list(range(d, d + b[1]))
             d += b[1]
         return cols
@@ -209,7 +209,7 @@ class PopulationModel(_PopulationModelBase):
         t_red = t_full = 0
         for b in self._blocks():
             nt = _block_n_top(b, n_ids)
-            if b[0] in ('gaussian', 'lognormal'):
+            if b[0] in ('gaussian', 'lognormal', 'truncated_gaussian'):
                 dtheta[t_full:t_full + nt] = dtop[t_red:t_red + nt]
             t_red += nt
             t_full += nt
@@ -425,6 +425,62 @@ class LogNormalModel(_DensityModel):
         return rng.lognormal(mean=mus, sigma=sigmas, size=sample_shape)
 
 
+class TruncatedGaussianModel(_DensityModel):
+    """Gaussian population truncated at zero,
+    chi/_population_models.py:3500-3939.  Always centered: the bottom-level
+    parameters are the individual parameters themselves; sigma <= 0 or a
+    negative individual parameter scores -inf (3557-3558, 3656-3658)."""
+    _kind = 'truncated_gaussian'
+
+    def __init__(self, n_dim=1, dim_names=None):
+        super(TruncatedGaussianModel, self).__init__(
+            n_dim, dim_names, centered=True)
+
+    def _default_parameter_names(self):
+        return ['Mu'] * self._n_dim + ['Sigma'] * self._n_dim
+
+    def get_mean_and_std(self, parameters):
+        """chi/_population_models.py:3771-3821."""
+        from scipy.stats import norm
+        parameters = np.asarray(parameters)
+        if parameters.ndim != 2:
+            n_parameters = len(parameters) // self._n_dim
+            parameters = parameters.reshape(n_parameters, self._n_dim)
+        mus = parameters[0]
+        sigmas = parameters[1]
+        if np.any(sigmas < 0):
+            raise ValueError('The standard deviation cannot be negative.')
+        f = norm.pdf(mus / sigmas) / (1 - norm.cdf(-mus / sigmas))
+        # (the reference allocates (n_parameters, n_dim) and leaves all but
+        # the first two rows uninitialised; the documented shape is returned)
+        return np.vstack([
+            mus + sigmas * f,
+            np.sqrt(sigmas**2 * (1 - mus / sigmas * f - f**2))])
+
+    def sample(self, parameters, n_samples=None, seed=None, *args, **kwargs):
+        """chi/_population_models.py:3863-3919.  Like the reference this
+        draws ``truncnorm.rvs(a=0, b=inf, loc=mu, scale=sigma)`` from numpy's
+        global generator seeded with ``seed`` (scipy's ``a`` is in standard
+        units, so the draws are truncated at ``mu``; reproduced as is for
+        seed-level parity)."""
+        from scipy.stats import truncnorm
+        parameters = self._sample_parameters(parameters)
+        if n_samples is None:
+            n_samples = 1
+        sample_shape = (int(n_samples), self._n_dim)
+        mus = parameters[0]
+        sigmas = parameters[1]
+        if np.any(sigmas < 0):
+            raise ValueError(
+                'A truncated Gaussian distribution only accepts strictly '
+                'positive standard deviations.')
+        if isinstance(seed, np.random.Generator):
+            seed = seed.integers(low=0, high=1E6)
+        np.random.seed(seed)
+        return truncnorm.rvs(
+            a=0, b=np.inf, loc=mus, scale=sigmas, size=sample_shape)
+
+
 class PooledModel(PopulationModel):
     """chi/_population_models.py:2759-3061."""
     _kind = 'pooled'
@@ -535,7 +591,8 @@ class CovariatePopulationModel(PopulationModel):
                 'The population model cannot be an instance of a '
                 'chi.ComposedPopulationModel. Please compose multiple '
                 'covariate models instead.')
-        if not isinstance(population_model, _DensityModel):
+        if not isinstance(population_model, _DensityModel) or isinstance(
+                population_model, TruncatedGaussianModel):
             raise TypeError(
                 'chi_b200 supports covariate models over GaussianModel and '
                 'LogNormalModel only.')

@@ -222,7 +222,12 @@ __global__ void pop_forward_kernel(PopDesc P, int32_t C, int64_t n_ids,
       double mu, sigma;
       pop_mu_sigma(D, top, cov, P.n_cov_total, i, mu, sigma);
       if (sigma < 0.0) bad = true;
-      if (D.centered) {
+      // truncated Gaussian: sigma <= 0 or a negative individual parameter
+      // is -inf (chi/_population_models.py:3557-3558, 3656-3658)
+      if (D.kind == CHI_B200_POP_TRUNCATED_GAUSSIAN &&
+          (sigma <= 0.0 || eta < 0.0))
+        bad = true;
+      if (D.centered || D.kind == CHI_B200_POP_TRUNCATED_GAUSSIAN) {
         psi = eta;
       } else if (sigma < 0.0) {
         psi = NAN;
@@ -299,7 +304,19 @@ pop_backward_kernel(PopDesc P, int64_t n_ids, int64_t id_begin,
         eta = bot[D.hcol];
       }
       double s_i, deta, dmu, dsg;
-      if (!D.centered) {
+      if (D.kind == CHI_B200_POP_TRUNCATED_GAUSSIAN) {
+        // chi/_population_models.py:3560-3565, 3616-3627:
+        // 1 - Phi(-mu/sigma) with Phi(x) = (1 + erf(x / sqrt 2)) / 2
+        const double var = sigma * sigma;
+        const double r = eta - mu;
+        const double z = mu / sigma;
+        const double tail = 1.0 - 0.5 * (1.0 + erf(-z * M_SQRT1_2));
+        const double pdf = exp(-0.5 * z * z) * 0.39894228040143267794;
+        s_i = -(0.5 * log(2.0 * M_PI * var) + r * r / (2.0 * var) + log(tail));
+        deta = -r / var + dl;
+        dmu = (r / sigma - pdf / tail) / sigma;
+        dsg = (-1.0 + r * r / var + pdf * z / tail) / sigma;
+      } else if (!D.centered) {
         // chi/_population_models.py:1474-1493 (Gaussian),
         // 2306-2339 (LogNormal)
         s_i = -(0.5 * LOG_2PI + 0.5 * eta * eta);
@@ -1275,7 +1292,9 @@ int chi_b200_population_set(chi_b200_problem* p, int32_t n_blocks,
         q.het_stride = nd;
         q.het_off = j;
       } else if (kind[b] == CHI_B200_POP_GAUSSIAN ||
-                 kind[b] == CHI_B200_POP_LOGNORMAL) {
+                 kind[b] == CHI_B200_POP_LOGNORMAL ||
+                 kind[b] == CHI_B200_POP_TRUNCATED_GAUSSIAN) {
+        if (kind[b] == CHI_B200_POP_TRUNCATED_GAUSSIAN) q.centered = 1;
         q.hcol = h0 + j;
         q.top0 = static_cast<int32_t>(top + j);
         q.top1 = static_cast<int32_t>(top + nd + j);
@@ -1283,7 +1302,8 @@ int chi_b200_population_set(chi_b200_problem* p, int32_t n_blocks,
         return fail(-1, "unknown population block kind");
       }
     }
-    if (kind[b] == CHI_B200_POP_GAUSSIAN || kind[b] == CHI_B200_POP_LOGNORMAL) {
+    if (kind[b] == CHI_B200_POP_GAUSSIAN || kind[b] == CHI_B200_POP_LOGNORMAL ||
+        kind[b] == CHI_B200_POP_TRUNCATED_GAUSSIAN) {
       // reduced slots in theta order: mu_1..mu_d, sigma_1..sigma_d, betas
       for (int j = 0; j < nd; ++j) {
         D.dim[d0 + j].red_mu = static_cast<int32_t>(p->red_to_top.size());

@@ -52,6 +52,8 @@ extern "C" {
 #define CHI_B200_POP_HETEROGENEOUS 1
 #define CHI_B200_POP_GAUSSIAN 2
 #define CHI_B200_POP_LOGNORMAL 3
+/* TruncatedGaussianModel (chi/_population_models.py:3500-3939), always centered */
+#define CHI_B200_POP_TRUNCATED_GAUSSIAN 4
 
 /* per-system status words */
 #define CHI_B200_ST_OK 0

@@ -240,6 +240,7 @@ def loglikelihood_s1(simulate, n_mech, error_kinds, obs, masks, x,
 #   ('hetero', n_dim)
 #   ('gaussian', n_dim, centered)
 #   ('lognormal', n_dim, centered)
+#   ('truncgauss', n_dim, True)      TruncatedGaussianModel, always centered
 #   ('covariate', inner_block, n_cov, pidx, didx)   inner: gaussian/lognormal
 # theta layout per block follows the reference's get_parameter_names():
 #   pooled: [n_dim]; hetero: [n_ids*n_dim] id-major; gaussian/lognormal:
@@ -267,7 +268,7 @@ def block_n_top(b, n_ids):
         return b[1]
     if kind == 'hetero':
         return n_ids * b[1]
-    if kind in ('gaussian', 'lognormal'):
+    if kind in ('gaussian', 'lognormal', 'truncgauss'):
         return 2 * b[1]
     if kind == 'covariate':
         return block_n_top(b[1], n_ids) + len(b[3]) * b[2]
@@ -397,6 +398,8 @@ def _density_block(inner, mu, sigma, obs, dlp):
     """
     kind, d, centered = inner
     n_ids = len(obs)
+    if kind == 'truncgauss':
+        return _truncated_gaussian_block(d, mu, sigma, obs, dlp)
     if np.any(sigma < 0):
         return -np.inf, np.full((n_ids, d), np.nan), \
             np.full((n_ids, 2, d), np.nan)
@@ -433,6 +436,44 @@ def _density_block(inner, mu, sigma, obs, dlp):
             dth[:, 1] = (-1 + (lo - mu) ** 2 / var) / np.sqrt(var)
         if np.isnan(score):
             score = -np.inf
+        if dlp is not None:
+            dbot = dbot + dlp
+    return score, dbot, dth
+
+
+def _norm_cdf(x):
+    """Phi(x) = (1 + erf(x / sqrt 2)) / 2, chi/_population_models.py (module
+    level helper used by TruncatedGaussianModel)."""
+    from scipy.special import erf
+    return (1 + erf(np.asarray(x, float) / np.sqrt(2))) / 2
+
+
+def _norm_pdf(x):
+    return np.exp(-np.asarray(x, float) ** 2 / 2) / np.sqrt(2 * np.pi)
+
+
+def _truncated_gaussian_block(d, mu, sigma, obs, dlp):
+    """TruncatedGaussianModel: compute_log_likelihood 3629-3660 with
+    _compute_log_likelihood 3542-3571, compute_sensitivities 3703-3769 with
+    _compute_sensitivities 3592-3627 (chi/_population_models.py)."""
+    n_ids = len(obs)
+    nan_b = np.full((n_ids, d), np.nan)
+    nan_t = np.full((n_ids, 2, d), np.nan)
+    if np.any(sigma <= 0) or np.any(obs < 0):
+        return -np.inf, nan_b, nan_t
+    with np.errstate(divide='ignore', invalid='ignore'):
+        tail = 1 - _norm_cdf(-mu / sigma)
+        score = -np.sum(
+            np.log(2 * np.pi * sigma ** 2) / 2
+            + (obs - mu) ** 2 / (2 * sigma ** 2)
+            + np.log(tail) * np.ones((n_ids, d)))
+        if np.isnan(score) or np.isinf(score):
+            return -np.inf, nan_b, nan_t
+        dbot = (mu - obs) / sigma ** 2 * np.ones((n_ids, d))
+        dth = np.empty((n_ids, 2, d))
+        dth[:, 0] = ((obs - mu) / sigma - _norm_pdf(mu / sigma) / tail) / sigma
+        dth[:, 1] = (-1 + (obs - mu) ** 2 / sigma ** 2
+                     + _norm_pdf(mu / sigma) * mu / sigma / tail) / sigma
         if dlp is not None:
             dbot = dbot + dlp
     return score, dbot, dth

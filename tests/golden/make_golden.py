@@ -84,6 +84,47 @@ POP_SPECS = [
 ]
 
 
+def truncated_gaussian_cases(rng):
+    """TruncatedGaussianModel stand-alone (the reference does not implement
+    compute_individual_parameters for it, so it cannot sit inside a
+    ComposedPopulationModel there): log-likelihood, sensitivities in both
+    shapes, moments and seeded samples."""
+    out = []
+    for n_dim, n_ids in ((1, 7), (3, 5)):
+        pm = chi.TruncatedGaussianModel(n_dim=n_dim)
+        theta = np.concatenate([rng.uniform(-0.5, 2.0, n_dim),
+                                rng.uniform(0.3, 1.5, n_dim)])
+        obs = rng.uniform(0.05, 3.0, (n_ids, n_dim))
+        dlp = rng.normal(size=(n_ids, n_dim))
+        ll = pm.compute_log_likelihood(theta, obs)
+        s_r, g_r = pm.compute_sensitivities(
+            theta, obs, dlogp_dpsi=dlp.copy(), reduce=True)
+        s_f, dpsi, dtheta = pm.compute_sensitivities(
+            theta, obs, dlogp_dpsi=dlp.copy(), flattened=True)
+        neg = obs.copy()
+        neg[0, 0] = -0.1
+        bad = theta.copy()
+        bad[n_dim] = 0.0
+        out.append({
+            'n_dim': n_dim, 'n_ids': n_ids, 'names': pm.get_parameter_names(),
+            'theta': tolist(theta), 'obs': tolist(obs),
+            'dlogp_dpsi': tolist(dlp), 'll': float(ll),
+            # the reference allocates d theta with n_parameters = 2 n_dim
+            # rows per individual and fills the first two (mu, sigma); only
+            # those are kept
+            'score_reduced': float(s_r),
+            'grad_reduced': tolist(g_r[:n_ids * n_dim + 2 * n_dim]),
+            'score_flat': float(s_f), 'dpsi': tolist(dpsi),
+            'dtheta': tolist(np.asarray(dtheta).reshape(
+                -1, n_dim)[:2].flatten()),
+            'll_negative_obs': float(pm.compute_log_likelihood(theta, neg)),
+            'll_zero_sigma': float(pm.compute_log_likelihood(bad, obs)),
+            # the reference allocates (n_parameters, n_dim) and fills two rows
+            'mean_and_std': tolist(pm.get_mean_and_std(theta)[:2]),
+            'samples_seed3': tolist(pm.sample(theta, n_samples=4, seed=3))})
+    return out
+
+
 def build_ref_population(spec):
     models = []
     for b in spec:
@@ -405,8 +446,12 @@ def main():
         'predictive_c5': predictive_case(rng, 'c5')}
     with open(os.path.join(HERE, 'hier_golden.json'), 'w') as f:
         json.dump(hier_golden, f)
+    rng2 = np.random.default_rng(20241020)
+    with open(os.path.join(HERE, 'stats_golden_extra.json'), 'w') as f:
+        json.dump({'truncated_gaussian': truncated_gaussian_cases(rng2)}, f)
     print('wrote', os.path.join(HERE, 'stats_golden.json'),
-          os.path.join(HERE, 'hier_golden.json'))
+          os.path.join(HERE, 'hier_golden.json'),
+          os.path.join(HERE, 'stats_golden_extra.json'))
 
 
 if __name__ == '__main__':

@@ -104,6 +104,37 @@ def test_population_models_match_reference_golden_on_device():
             atol=1e-13 * max(1.0, np.max(np.abs(ref))))
 
 
+def test_truncated_gaussian_matches_reference_golden_on_device():
+    """TruncatedGaussianModel (chi/_population_models.py:3500-3939) against
+    the reference's own outputs, stand-alone as the reference supports it."""
+    for case in _load('stats_golden_extra.json')['truncated_gaussian']:
+        d, n_ids = case['n_dim'], case['n_ids']
+        pm = chi_b200.TruncatedGaussianModel(n_dim=d)
+        assert pm.get_parameter_names() == case['names']
+        theta = np.array(case['theta'])
+        obs = np.array(case['obs'])
+        dlp = np.array(case['dlogp_dpsi'])
+        assert pm.compute_log_likelihood(theta, obs) == pytest.approx(
+            case['ll'], rel=1e-12)
+        s, g = pm.compute_sensitivities(
+            theta, obs, dlogp_dpsi=dlp, reduce=True)
+        assert s == pytest.approx(case['score_reduced'], rel=1e-12)
+        np.testing.assert_allclose(
+            g, case['grad_reduced'], rtol=1e-11,
+            atol=1e-13 * np.max(np.abs(case['grad_reduced'])))
+        neg = obs.copy()
+        neg[0, 0] = -0.1
+        assert pm.compute_log_likelihood(theta, neg) == -np.inf
+        bad = theta.copy()
+        bad[d] = 0.0
+        assert pm.compute_log_likelihood(bad, obs) == -np.inf
+        np.testing.assert_allclose(
+            pm.get_mean_and_std(theta), case['mean_and_std'], rtol=1e-13)
+        np.testing.assert_allclose(
+            pm.sample(theta, n_samples=4, seed=3), case['samples_seed3'],
+            rtol=1e-13)
+
+
 def _prior(spec):
     kinds, locs, scales = spec
     priors = []

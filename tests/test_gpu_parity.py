@@ -283,6 +283,7 @@ def test_log_likelihood_invalid_sigma_and_failure_convention():
 def _pop_cases(n_ids):
     G, L, P, H = (chi_b200.GaussianModel, chi_b200.LogNormalModel,
                   chi_b200.PooledModel, chi_b200.HeterogeneousModel)
+    T = chi_b200.TruncatedGaussianModel
     C = chi_b200.CovariatePopulationModel
     Lin = chi_b200.LinearCovariateModel
     return [
@@ -300,6 +301,11 @@ def _pop_cases(n_ids):
          [('covariate', ('gaussian', 2, True), 1), ('lognormal', 1, True)]),
         ([C(L(2, centered=True), Lin(n_cov=3)), H(2, n_ids=n_ids)],
          [('covariate', ('lognormal', 2, True), 3), ('hetero', 2)]),
+        # TruncatedGaussianModel inside a composed model (the reference only
+        # supports it stand-alone; here it is a centered block like any other)
+        ([P(1), T(3), L(1, centered=False)],
+         [('pooled', 1), ('truncgauss', 3, True), ('lognormal', 1, False)]),
+        ([T(2)], [('truncgauss', 2, True)]),
     ]
 
 

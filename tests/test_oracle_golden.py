@@ -283,3 +283,32 @@ def test_population_predictive_sample_matches_reference_golden(name):
         np.array(case['theta']), times, case['n_samples'], case['seed'],
         case['covariates'])
     np.testing.assert_allclose(out, case['samples'], rtol=1e-12)
+
+
+def test_truncated_gaussian_matches_reference_golden():
+    """TruncatedGaussianModel (chi/_population_models.py:3500-3939), stand-
+    alone as the reference supports it: log-likelihood, reduced and flat
+    sensitivities, -inf rules."""
+    for case in _load('stats_golden_extra.json')['truncated_gaussian']:
+        d, n_ids = case['n_dim'], case['n_ids']
+        lay = stats.PopLayout([('truncgauss', d, True)], n_ids)
+        theta = np.array(case['theta'])
+        obs = np.array(case['obs'])
+        dlp = np.array(case['dlogp_dpsi'])
+        assert stats.pop_log_likelihood(lay, theta, obs) == pytest.approx(
+            case['ll'], rel=1e-13)
+        s, g = stats.pop_sensitivities_reduced(lay, theta, obs, dlp)
+        assert s == pytest.approx(case['score_reduced'], rel=1e-13)
+        np.testing.assert_allclose(
+            g, case['grad_reduced'], rtol=1e-12, atol=1e-13)
+        # flat form: d psi (n_ids, d) and d theta summed over individuals
+        np.testing.assert_allclose(
+            g[:n_ids * d].reshape(n_ids, d), case['dpsi'], rtol=1e-12)
+        neg = obs.copy()
+        neg[0, 0] = -0.1
+        assert stats.pop_log_likelihood(lay, theta, neg) == -np.inf
+        bad = theta.copy()
+        bad[d] = 0.0
+        assert stats.pop_log_likelihood(lay, bad, obs) == -np.inf
+        assert case['ll_negative_obs'] == -np.inf
+        assert case['ll_zero_sigma'] == -np.inf
