@@ -743,3 +743,30 @@ def test_individual_shards_sum_to_the_full_evaluation():
         tot_g, full_g, rtol=1e-10, atol=1e-10 * np.max(np.abs(full_g)))
     s, g = ll.evaluateS1_batch(X)
     np.testing.assert_allclose(g, full_g, rtol=1e-13)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['tgi_direct_daily', 'two_cmt_indirect_indefinite'])
+def test_log_likelihood_nonlinear_and_indirect_models(name):
+    """LogLikelihood.evaluateS1 of the nonlinear erlotinib TGI model (30 daily
+    doses) and the 3-state indirectly dosed two-compartment model against the
+    oracle (exact / DOP853 solution + numpy error model), through both
+    observation paths of the streamed kernel."""
+    model, omodel, psi, times = _build(name)
+    model.set_tolerance(**TIGHT)
+    times = times[times > 0]
+    rng = np.random.default_rng(4)
+    y_ref, _ = ode_exact.simulate(omodel, psi, times, _events(model))
+    obs = np.abs(y_ref[0] * np.exp(0.1 * rng.normal(size=len(times)))) + 1e-6
+    ll = chi_b200.LogLikelihood(
+        model, chi_b200.LogNormalErrorModel(), obs, times)
+    x = np.array(list(psi) + [0.15])
+    _, f_s1 = _oracle_individual(
+        omodel, 'lognormal', times, obs, _events(model), len(psi))
+    score_ref, grad_ref = f_s1(x)
+    for budget in (-1, 0):
+        ll._get_device().set_snapshot_budget(budget)
+        score, grad = ll.evaluateS1(x)
+        assert score == pytest.approx(score_ref, rel=1e-8)
+        np.testing.assert_allclose(
+            grad, grad_ref, rtol=2e-6, atol=2e-6 * np.max(np.abs(grad_ref)))
