@@ -645,6 +645,8 @@ def run_product(args, rank, world, local_rank):
                 'one compiled solve with sensitivities per individual, numpy '
                 'error/population models (oracle/stats.py + oracle/csolver)'
                 % (args.n_ids, args.cpu_seconds, cores)),
+            # what one chain of the reference gets (one process on one core)
+            'per_core_value': v / cores,
             'openmp_no_python_value': omp,
             'gpu_vs_cpu_score_rel_diff': float(
                 abs(sc - (score_h0 + prob['log_prior'](

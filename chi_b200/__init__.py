@@ -12,7 +12,7 @@ from chi_b200._mechanistic_models import (  # noqa: F401
 from chi_b200._error_models import (  # noqa: F401
     ErrorModel, GaussianErrorModel, LogNormalErrorModel,
     ConstantAndMultiplicativeGaussianErrorModel,
-    MultiplicativeGaussianErrorModel)
+    MultiplicativeGaussianErrorModel, ReducedErrorModel)
 from chi_b200._covariate_models import (  # noqa: F401
     CovariateModel, LinearCovariateModel)
 from chi_b200._population_models import (  # noqa: F401

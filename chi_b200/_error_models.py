@@ -184,3 +184,113 @@ class MultiplicativeGaussianErrorModel(ErrorModel):
         rel_samples = rng.normal(loc=0, scale=parameters[0], size=shape)
         model_output = np.expand_dims(model_output, axis=1)
         return model_output + model_output * rel_samples
+
+
+class ReducedErrorModel(object):
+    """Error model with some parameters held at fixed values
+    (chi/_error_models.py:1583-1906).  The wrapped model does the arithmetic
+    (on the device); this class scatters the free parameters into the full
+    parameter vector and drops the fixed entries from the gradient
+    (1729-1750)."""
+
+    def __init__(self, error_model):
+        if not isinstance(error_model, ErrorModel):
+            raise ValueError(
+                'The error model has to be an instance of a '
+                'chi.ErrorModel')
+        self._error_model = error_model
+        self._n_parameters = error_model.n_parameters()
+        self._parameter_names = error_model.get_parameter_names()
+        self._fixed_mask = None
+        self._fixed_values = None
+
+    # -- parameter bookkeeping ------------------------------------------------
+    def _full(self, parameters):
+        if self._fixed_mask is None:
+            return parameters
+        self._fixed_values[~self._fixed_mask] = parameters
+        return self._fixed_values
+
+    def fix_parameters(self, name_value_dict):
+        """chi/_error_models.py:1752-1796: ``{name: value}`` fixes, ``{name:
+        None}`` frees a parameter."""
+        try:
+            name_value_dict = dict(name_value_dict)
+        except (TypeError, ValueError):
+            raise ValueError(
+                'The name-value dictionary has to be convertable to a python '
+                'dictionary.')
+        mask = np.zeros(self._n_parameters, dtype=bool) \
+            if self._fixed_mask is None else self._fixed_mask
+        values = np.empty(self._n_parameters) \
+            if self._fixed_values is None else self._fixed_values
+        for index, name in enumerate(self._parameter_names):
+            if name not in name_value_dict:
+                continue
+            value = name_value_dict[name]
+            mask[index] = value is not None
+            values[index] = np.nan if value is None else value
+        if not np.any(mask):
+            mask = values = None
+        self._fixed_mask, self._fixed_values = mask, values
+
+    def get_error_model(self):
+        return self._error_model
+
+    def get_parameter_names(self):
+        names = list(self._parameter_names)
+        if self._fixed_mask is not None:
+            names = [n for n, f in zip(names, self._fixed_mask) if not f]
+        return names
+
+    def n_fixed_parameters(self):
+        return 0 if self._fixed_mask is None else int(np.sum(self._fixed_mask))
+
+    def n_parameters(self):
+        return self._n_parameters - self.n_fixed_parameters()
+
+    def set_parameter_names(self, names=None):
+        """chi/_error_models.py:1872-1906."""
+        if names is None:
+            self._error_model.set_parameter_names(None)
+            self._parameter_names = self._error_model.get_parameter_names()
+            return None
+        if len(names) != self.n_parameters():
+            raise ValueError('Length of names does not match n_parameters.')
+        for name in names:
+            if len(name) > 50:
+                raise ValueError(
+                    'Parameter names cannot exceed 50 characters.')
+        names = [str(label) for label in names]
+        full = list(self._parameter_names)
+        free = [i for i in range(self._n_parameters)
+                if self._fixed_mask is None or not self._fixed_mask[i]]
+        for i, name in zip(free, names):
+            full[i] = name
+        self._error_model.set_parameter_names(full)
+        self._parameter_names = full
+
+    # -- evaluation -----------------------------------------------------------
+    def compute_log_likelihood(self, parameters, model_output, observations):
+        return self._error_model.compute_log_likelihood(
+            self._full(parameters), model_output, observations)
+
+    def compute_pointwise_ll(self, parameters, model_output, observations):
+        return self._error_model.compute_pointwise_ll(
+            self._full(parameters), model_output, observations)
+
+    def compute_sensitivities(
+            self, parameters, model_output, model_sensitivities, observations):
+        score, sens = self._error_model.compute_sensitivities(
+            self._full(parameters), model_output, model_sensitivities,
+            observations)
+        if self._fixed_mask is None:
+            return score, sens
+        n_mechanistic = np.asarray(model_sensitivities).shape[1]
+        keep = np.ones(n_mechanistic + self._n_parameters, dtype=bool)
+        keep[n_mechanistic:] = ~self._fixed_mask
+        return score, sens[keep]
+
+    def sample(self, parameters, model_output, n_samples=None, seed=None):
+        return self._error_model.sample(
+            self._full(parameters), model_output, n_samples, seed)

@@ -84,6 +84,39 @@ POP_SPECS = [
 ]
 
 
+def reduced_error_model_cases(rng):
+    """ReducedErrorModel (chi/_error_models.py:1583-1906) over the CAM model
+    with 'Sigma rel.' fixed, and over the Gaussian model with nothing fixed."""
+    out = []
+    n_obs, n_par = 8, 4
+    ybar = rng.uniform(0.5, 3.0, n_obs)
+    obs = rng.uniform(0.5, 3.0, n_obs)
+    sens = rng.normal(size=(n_obs, n_par))
+    for kind, em, fixed, free in (
+            ('cam', chi.ConstantAndMultiplicativeGaussianErrorModel(),
+             {'Sigma rel.': 0.15}, [0.4]),
+            ('cam', chi.ConstantAndMultiplicativeGaussianErrorModel(),
+             {'Sigma base': 0.2}, [0.3]),
+            ('gaussian', chi.GaussianErrorModel(), {}, [0.7])):
+        rem = chi.ReducedErrorModel(em)
+        if fixed:
+            rem.fix_parameters(fixed)
+        ll, grad = rem.compute_sensitivities(
+            np.array(free), ybar, sens, obs)
+        out.append({
+            'kind': kind, 'fixed': fixed, 'free': free,
+            'names': rem.get_parameter_names(),
+            'n_parameters': rem.n_parameters(),
+            'n_fixed': rem.n_fixed_parameters(),
+            'ybar': tolist(ybar), 'obs': tolist(obs), 'sens': tolist(sens),
+            'll': float(ll), 'grad': tolist(grad),
+            'll_call': float(rem.compute_log_likelihood(
+                np.array(free), ybar, obs)),
+            'sample_seed5': tolist(rem.sample(
+                np.array(free), ybar, n_samples=2, seed=5))})
+    return out
+
+
 def truncated_gaussian_cases(rng):
     """TruncatedGaussianModel stand-alone (the reference does not implement
     compute_individual_parameters for it, so it cannot sit inside a
@@ -448,7 +481,8 @@ def main():
         json.dump(hier_golden, f)
     rng2 = np.random.default_rng(20241020)
     with open(os.path.join(HERE, 'stats_golden_extra.json'), 'w') as f:
-        json.dump({'truncated_gaussian': truncated_gaussian_cases(rng2)}, f)
+        json.dump({'truncated_gaussian': truncated_gaussian_cases(rng2),
+                   'reduced_error_model': reduced_error_model_cases(rng2)}, f)
     print('wrote', os.path.join(HERE, 'stats_golden.json'),
           os.path.join(HERE, 'hier_golden.json'),
           os.path.join(HERE, 'stats_golden_extra.json'))

@@ -282,3 +282,33 @@ def test_predictive_model_sample_single_individual():
     assert set(df.columns) >= {'ID', 'Time', 'Observable', 'Value'}
     reg = pred.get_dosing_regimen()
     assert list(reg['Dose']) == [10.0] and list(reg['Duration']) == [0.01]
+
+
+def test_reduced_error_model_matches_reference_golden_on_device():
+    """ReducedErrorModel (chi/_error_models.py:1583-1906): fixed parameters
+    are scattered into the full vector and dropped from the gradient."""
+    ctor = {'cam': chi_b200.ConstantAndMultiplicativeGaussianErrorModel,
+            'gaussian': chi_b200.GaussianErrorModel}
+    for case in _load('stats_golden_extra.json')['reduced_error_model']:
+        rem = chi_b200.ReducedErrorModel(ctor[case['kind']]())
+        if case['fixed']:
+            rem.fix_parameters(case['fixed'])
+        assert rem.get_parameter_names() == case['names']
+        assert rem.n_parameters() == case['n_parameters']
+        assert rem.n_fixed_parameters() == case['n_fixed']
+        free = np.array(case['free'])
+        ybar, obs = np.array(case['ybar']), np.array(case['obs'])
+        sens = np.array(case['sens'])
+        ll, grad = rem.compute_sensitivities(free, ybar, sens, obs)
+        assert ll == pytest.approx(case['ll'], rel=1e-12)
+        np.testing.assert_allclose(
+            grad, case['grad'], rtol=1e-11,
+            atol=1e-13 * np.max(np.abs(case['grad'])))
+        assert rem.compute_log_likelihood(free, ybar, obs) == pytest.approx(
+            case['ll_call'], rel=1e-12)
+        np.testing.assert_allclose(
+            rem.sample(free, ybar, n_samples=2, seed=5),
+            case['sample_seed5'], rtol=1e-13)
+        if case['fixed']:
+            rem.fix_parameters({k: None for k in case['fixed']})
+            assert rem.n_fixed_parameters() == 0
