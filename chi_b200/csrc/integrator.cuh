@@ -65,7 +65,7 @@ constexpr double LOG_2PI_HALF = 0.91893853320467274178;
 
 // step-size controller constants
 #ifndef CHI_SAFETY
-#define CHI_SAFETY 0.9f
+#define CHI_SAFETY 0.95f
 #endif
 #ifndef CHI_FACMAX
 #define CHI_FACMAX 5.0f
