@@ -70,6 +70,13 @@ constexpr double LOG_2PI_HALF = 0.91893853320467274178;
 #ifndef CHI_FACMAX
 #define CHI_FACMAX 5.0f
 #endif
+// a step that would end within this factor of the proposed size from the
+// next stop (observation record, dose edge) is stretched to hit it; has to
+// stay below 1/0.9 (a rejected step shrinks by at least 0.9, and the retry
+// must not be stretched back to the same size)
+#ifndef CHI_CLIP_STRETCH
+#define CHI_CLIP_STRETCH 1.1
+#endif
 #ifndef CHI_EDGE_KEEP_H
 #define CHI_EDGE_KEEP_H 1
 #endif

@@ -716,7 +716,7 @@ struct StreamSolver {
     const double rem = t_stop - t;
     double hs = h;
     bool clipped = false;
-    if (rem <= 1.1 * h) {
+    if (rem <= CHI_CLIP_STRETCH * h) {
       hs = rem;
       clipped = true;
     } else if (rem < 2.0 * h) {
