@@ -615,6 +615,7 @@ struct StreamSolver {
   //     D_k, e_k fetched once per column, and V = Zy + Uy was stored by the
   //     state column (V0 for the first stage), so neither Uy nor the model
   //     constants are live here.
+  template <bool HAS_TERMS>
   CHI_HD float column(const int kc, const int m, const int nxt,
                       const double (&y)[N], const double (&c)[NCS],
                       const double (&Uy)[NS][N],
@@ -624,8 +625,10 @@ struct StreamSolver {
     double S0[N], Us[NS][N], Zl[N];
 #pragma unroll
     for (int n = 0; n < N; ++n) S0[n] = CHI_S(cur, m, n);
+    // HAS_TERMS = false: initial-value column of a linear model, D_k = 0 and
+    // e_k = 0 (no column-specific work at all)
     double DK[N * N], ek[N];
-    if (M::LINEAR) M::col_linear(kc, c, u, DK, ek);
+    if (M::LINEAR && HAS_TERMS) M::col_linear(kc, c, u, DK, ek);
 #define CHI_SSTAGE(I, CNT, INCR, a0, a1, a2, a3, a4, a5, a6, c0, c1, c2, c3,  \
                    c4, c5, c6)                                                \
   {                                                                           \
@@ -635,9 +638,12 @@ struct StreamSolver {
       _Pragma("unroll") for (int n = 0; n < N; ++n) V[n] =                    \
           (I == 0) ? V0[n] : CHI_ZY(I, n);                                    \
       _Pragma("unroll") for (int n = 0; n < N; ++n) {                         \
-        double acc = ek[n];                                                   \
-        _Pragma("unroll") for (int m = 0; m < N; ++m) acc =                   \
-            fma(DK[n * N + m], V[m], acc);                                    \
+        double acc = 0.0;                                                     \
+        if (HAS_TERMS) {                                                      \
+          acc = ek[n];                                                        \
+          _Pragma("unroll") for (int m = 0; m < N; ++m) acc =                 \
+              fma(DK[n * N + m], V[m], acc);                                  \
+        }                                                                     \
         rs[n] = acc;                                                          \
       }                                                                       \
       if (INCR) {                                                             \
@@ -789,12 +795,20 @@ struct StreamSolver {
     // (columns of constants that do not enter the rhs stay identically zero
     // and are not in the list)
     const int ni = n_int();
-    for (int m = 0; m < ni; ++m) {
+    int m = 0;
+    if (M::LINEAR) {
+      // initial-value columns first (they lead the list): no column terms
+      for (; m < ni && a.int_param[m] < N; ++m)
+        errsq = fmaxf(errsq,
+                      column<false>(-1, m, nxt, y, c, Uy, V0, Wi, hinv,
+                                    atol_f, rtol_f));
+    }
+    for (; m < ni; ++m) {
       const int pk = a.int_param[m];
       const int kc = pk >= N ? pk - N : -1;
       errsq = fmaxf(errsq,
-                    column(kc, m, nxt, y, c, Uy, V0, Wi, hinv, atol_f,
-                           rtol_f));
+                    column<true>(kc, m, nxt, y, c, Uy, V0, Wi, hinv, atol_f,
+                                 rtol_f));
     }
 
     const bool accept = errsq <= 1.0f;
