@@ -77,6 +77,11 @@ constexpr double LOG_2PI_HALF = 0.91893853320467274178;
 #ifndef CHI_CLIP_STRETCH
 #define CHI_CLIP_STRETCH 1.1
 #endif
+// first step size of the streamed solver, as a fraction of the distance to
+// the first stop
+#ifndef CHI_H0_FRACTION
+#define CHI_H0_FRACTION 0.01
+#endif
 #ifndef CHI_EDGE_KEEP_H
 #define CHI_EDGE_KEEP_H 1
 #endif
@@ -390,20 +395,9 @@ CHI_HD void solve_system(const SolveArgs& a, const int64_t b, const int sub,
       const double t_stop = fmin(t_rec, t_edge);
 
       if (h == 0.0) {
-        // initial step size (Hairer's d0/d1 heuristic, first half)
-        double f0[N];
-        M::rhs(y, c, u, f0);
-        double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-          const double sc = a.atol + a.rtol * fabs(y[i]);
-          d0 = fma(y[i] / sc, y[i] / sc, d0);
-          d1 = fma(f0[i] / sc, f0[i] / sc, d1);
-        }
-        d0 = sqrt(d0 / N);
-        d1 = sqrt(d1 / N);
-        h = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-        h = fmin(100.0 * h, t_stop - t);
+        // first step: a fraction of the distance to the first stop (same
+        // policy as the streamed solver, integrator_stream.cuh)
+        h = CHI_H0_FRACTION * (t_stop - t);
         after_reject = false;
       }
 
@@ -412,7 +406,7 @@ CHI_HD void solve_system(const SolveArgs& a, const int64_t b, const int sub,
       h_full = h;
       double hs = h;
       bool clipped = false;
-      if (rem <= 1.1 * h) {
+      if (rem <= CHI_CLIP_STRETCH * h) {
         hs = rem;
         clipped = true;
       } else if (rem < 2.0 * h) {

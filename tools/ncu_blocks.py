@@ -7,7 +7,17 @@ rep = sys.argv[1]; thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.3
 txt = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'],
                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
-hdr = rows[1]; data = rows[2:]
+# a report may hold several kernels: take the one with the most samples
+starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name'] + [len(rows)]
+best = None
+for a, b in zip(starts[:-1], starts[1:]):
+    hdr = rows[a + 1]
+    seg = [r for r in rows[a + 2:b] if len(r) == len(hdr)]
+    n = sum(int(r[hdr.index('# Samples')]) for r in seg)
+    if best is None or n > best[0]:
+        best = (n, rows[a][1], hdr, seg)
+print(best[1][:100])
+hdr, data = best[2], best[3]
 iA = hdr.index('Source'); iI = hdr.index('Instructions Executed')
 iT = hdr.index('Avg. Threads Executed'); iS = hdr.index('# Samples')
 tots = sum(int(r[iS]) for r in data); tot = sum(int(r[iI]) for r in data)
