@@ -91,17 +91,34 @@ constexpr double LOG_2PI_HALF = 0.91893853320467274178;
 
 // ---- small dense helpers (fully unrolled, registers only) -----------------
 
+// 1/x for the step size and the determinant of W: the hardware's 20-bit
+// reciprocal seed and two Newton steps, without the special-case branch of
+// the IEEE division (x is a step size or a determinant of order 1/h^N: finite,
+// non-zero and far from the exponent range's ends; a non-finite x produces a
+// non-finite result, which the error test rejects).  Accurate to ~1 ulp.
+CHI_HD double rcp_newton(const double x) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+#else
+  return 1.0 / x;
+#endif
+}
+
 template <int N>
 CHI_HD void invert(const double* A, double* Ai);
 
 template <>
 CHI_HD void invert<1>(const double* A, double* Ai) {
-  Ai[0] = 1.0 / A[0];
+  Ai[0] = rcp_newton(A[0]);
 }
 
 template <>
 CHI_HD void invert<2>(const double* A, double* Ai) {
-  const double r = 1.0 / (A[0] * A[3] - A[1] * A[2]);
+  const double r = rcp_newton(A[0] * A[3] - A[1] * A[2]);
   Ai[0] = A[3] * r;
   Ai[1] = -A[1] * r;
   Ai[2] = -A[2] * r;
@@ -113,7 +130,7 @@ CHI_HD void invert<3>(const double* A, double* Ai) {
   const double c00 = A[4] * A[8] - A[5] * A[7];
   const double c01 = A[5] * A[6] - A[3] * A[8];
   const double c02 = A[3] * A[7] - A[4] * A[6];
-  const double r = 1.0 / (A[0] * c00 + A[1] * c01 + A[2] * c02);
+  const double r = rcp_newton(A[0] * c00 + A[1] * c01 + A[2] * c02);
   Ai[0] = c00 * r;
   Ai[1] = (A[2] * A[7] - A[1] * A[8]) * r;
   Ai[2] = (A[1] * A[5] - A[2] * A[4]) * r;

@@ -725,7 +725,7 @@ struct StreamSolver {
 
     // ---- state column: stage values and increments kept -------------------
     if (!M::LINEAR) M::jac(y, c, J0);
-    const double hinv = 1.0 / hs;
+    const double hinv = rcp_newton(hs);
     double Wi[N * N];
     {
       double W[N * N];
