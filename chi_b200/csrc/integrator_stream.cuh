@@ -1,20 +1,28 @@
-// chi_b200 -- "streamed columns" variant of the sensitivity solve.
+// chi_b200 -- "streamed columns" sensitivity solve (the default kernels).
 //
-// Same method and semantics as solve_system<M, G, MC> (integrator.cuh): RODAS4
-// on [y | S] with the exact block-triangular Jacobian, exact hits of dose
-// edges and observation times, fused error model.  What differs is the
-// mapping:
+// Same method family and semantics as solve_system<M, G, MC> (integrator.cuh):
+// a stiffly accurate Rosenbrock method (RODAS5 by default, RODAS4 as a
+// variant) on [y | S] with the exact block-triangular Jacobian, exact hits of
+// dose edges and observation times.  What differs is the mapping:
 //
-//   * ONE thread per system (no redundant state column, no shuffles);
-//   * per step the state column runs first and keeps its six stage values
-//     and increments in registers; the sensitivity columns are then streamed
-//     through registers CB at a time (a uniform, non-unrolled loop: every
-//     thread of the block handles column k at the same time, so the loop
-//     adds no divergence and the hot loop stays inside the instruction
-//     cache);
-//   * the sensitivity matrix S (current and candidate) and the gradient
-//     accumulators live in shared memory, slot-major (conflict free):
-//         sm[slot * stride + tid],  slots = 2*P*N + P doubles per thread.
+//   * ONE thread per system (no redundant state column, no shuffles), in a
+//     persistent grid whose lanes refill themselves from a global counter;
+//   * per step the state column runs first; the sensitivity columns are then
+//     streamed through registers one at a time in a uniform, non-unrolled
+//     loop (every thread of the grid handles the same column at the same
+//     time: no divergence, and the hot loop stays inside the instruction
+//     cache).  Linear models take a branch-free column body that needs only
+//     V_i = Z_i + U_i of the state column (shared memory);
+//   * S of the integrated columns (current and candidate), the stage values,
+//     the state, the model constants and the per-system scalars that only the
+//     event handler touches live in shared memory, slot-major (conflict
+//     free): sm[slot * stride + tid], stream_slots<M>() doubles per thread --
+//     the kernel then fits 128 registers without spills at 4 blocks per SM;
+//   * at an observation record the thread only stores a snapshot of y and S
+//     (SolveArgs::snap); observe_system / observe_kernel evaluate output map,
+//     error model and gradient afterwards with all lanes busy.  Without a
+//     snapshot buffer the same arithmetic (error_terms) runs fused in the
+//     event handler.
 //
 // Compiles for the host as well (stride = 1, tid = 0) for the CPU port.
 #pragma once
@@ -304,11 +312,12 @@ CHI_HD ErrTerms error_terms(const int kind, const double* sg, const double yb,
 }
 
 // State of one system while it is being integrated.  `init` loads a system,
-// `advance` handles the pending events (observation records, dose edges) and
-// then attempts ONE step, returning true once the system is finished,
-// `finish` writes the results.  Splitting the solve this way lets a
-// persistent kernel refill a lane with the next system as soon as its current
-// one is done (solve_stream_persistent below).
+// `events` handles what is pending at the current time (observation records,
+// dose edges) and returns true once the system is finished, `step` attempts
+// ONE step, `finish` writes the results.  Splitting the solve this way lets
+// the persistent kernel refill a lane with the next system as soon as its
+// current one is done, and re-join the warp between the (divergent) event
+// handling and the (expensive) step (solve_stream_kernel below).
 // METHOD_CODE: 1 = RODAS4 (6 stages, order 4(3)), 5 = RODAS5 (8 stages,
 // order 5(4)).
 template <class M, int METHOD_CODE>
