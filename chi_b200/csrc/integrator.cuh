@@ -59,6 +59,17 @@ constexpr double C62 = -0.7981132988064893e+01;
 constexpr double C63 = -0.3152159432874371e+02;
 constexpr double C64 = 0.1631930543123136e+02;
 constexpr double C65 = -0.6058818238834054e+01;
+// D_ij = A_ij / gamma + C_ij (see integrator_stream.cuh)
+constexpr double D21 = A21 / GAMMA + C21;
+constexpr double D31 = A31 / GAMMA + C31;
+constexpr double D32 = A32 / GAMMA + C32;
+constexpr double D41 = A41 / GAMMA + C41;
+constexpr double D42 = A42 / GAMMA + C42;
+constexpr double D43 = A43 / GAMMA + C43;
+constexpr double D51 = A51 / GAMMA + C51;
+constexpr double D52 = A52 / GAMMA + C52;
+constexpr double D53 = A53 / GAMMA + C53;
+constexpr double D54 = A54 / GAMMA + C54;
 }  // namespace rodas4
 
 constexpr double LOG_2PI_HALF = 0.91893853320467274178;

@@ -97,6 +97,23 @@ constexpr double C84 = 18.77919633714503;
 constexpr double C85 = -31.58359187223370;
 constexpr double C86 = -6.685968952921985;
 constexpr double C87 = -5.810979938412932;
+// D_ij = A_ij / gamma + C_ij: for linear models J Z + (C/h) U collapses into
+// one combination (StreamSolver::column)
+constexpr double D21 = A21 / GAMMA + C21;
+constexpr double D31 = A31 / GAMMA + C31;
+constexpr double D32 = A32 / GAMMA + C32;
+constexpr double D41 = A41 / GAMMA + C41;
+constexpr double D42 = A42 / GAMMA + C42;
+constexpr double D43 = A43 / GAMMA + C43;
+constexpr double D51 = A51 / GAMMA + C51;
+constexpr double D52 = A52 / GAMMA + C52;
+constexpr double D53 = A53 / GAMMA + C53;
+constexpr double D54 = A54 / GAMMA + C54;
+constexpr double D61 = A61 / GAMMA + C61;
+constexpr double D62 = A62 / GAMMA + C62;
+constexpr double D63 = A63 / GAMMA + C63;
+constexpr double D64 = A64 / GAMMA + C64;
+constexpr double D65 = A65 / GAMMA + C65;
 }  // namespace rodas5
 
 
@@ -132,6 +149,16 @@ static __constant__ double C62 = -0.7981132988064893e+01;
 static __constant__ double C63 = -0.3152159432874371e+02;
 static __constant__ double C64 = 0.1631930543123136e+02;
 static __constant__ double C65 = -0.6058818238834054e+01;
+static __constant__ double D21 = rodas4::D21;
+static __constant__ double D31 = rodas4::D31;
+static __constant__ double D32 = rodas4::D32;
+static __constant__ double D41 = rodas4::D41;
+static __constant__ double D42 = rodas4::D42;
+static __constant__ double D43 = rodas4::D43;
+static __constant__ double D51 = rodas4::D51;
+static __constant__ double D52 = rodas4::D52;
+static __constant__ double D53 = rodas4::D53;
+static __constant__ double D54 = rodas4::D54;
 }  // namespace rodas4d
 namespace rodas5d {
 static __constant__ double GAMMA = 0.19;
@@ -178,6 +205,21 @@ static __constant__ double C84 = 18.77919633714503;
 static __constant__ double C85 = -31.58359187223370;
 static __constant__ double C86 = -6.685968952921985;
 static __constant__ double C87 = -5.810979938412932;
+static __constant__ double D21 = rodas5::D21;
+static __constant__ double D31 = rodas5::D31;
+static __constant__ double D32 = rodas5::D32;
+static __constant__ double D41 = rodas5::D41;
+static __constant__ double D42 = rodas5::D42;
+static __constant__ double D43 = rodas5::D43;
+static __constant__ double D51 = rodas5::D51;
+static __constant__ double D52 = rodas5::D52;
+static __constant__ double D53 = rodas5::D53;
+static __constant__ double D54 = rodas5::D54;
+static __constant__ double D61 = rodas5::D61;
+static __constant__ double D62 = rodas5::D62;
+static __constant__ double D63 = rodas5::D63;
+static __constant__ double D64 = rodas5::D64;
+static __constant__ double D65 = rodas5::D65;
 }  // namespace rodas5d
 #endif
 #ifdef __CUDA_ARCH__
@@ -216,6 +258,43 @@ static __constant__ double C87 = -5.810979938412932;
     CHI_R5(C51), CHI_R5(C52), CHI_R5(C53), CHI_R5(C54), 0, 0, 0)              \
   X(5, 5, 0, CHI_R5(A61), CHI_R5(A62), CHI_R5(A63), CHI_R5(A64), CHI_R5(A65), \
     0, 0, CHI_R5(C61), CHI_R5(C62), CHI_R5(C63), CHI_R5(C64), CHI_R5(C65), 0, \
+    0)                                                                        \
+  X(6, 6, 1, 0, 0, 0, 0, 0, 0, 0, CHI_R5(C71), CHI_R5(C72), CHI_R5(C73),      \
+    CHI_R5(C74), CHI_R5(C75), CHI_R5(C76), 0)                                 \
+  X(7, 7, 1, 0, 0, 0, 0, 0, 0, 0, CHI_R5(C81), CHI_R5(C82), CHI_R5(C83),      \
+    CHI_R5(C84), CHI_R5(C85), CHI_R5(C86), CHI_R5(C87))
+
+// Tables of the linear-model column body: X(stage, n_previous, incremental,
+// a_1..a_7, m_1..m_7) with m = D (= A / gamma + C) for the ordinary stages and
+// m = C for the incremental ones.  For a linear model J is the matrix inside
+// W = I/(gamma h) - J, so W^-1 J Z = W^-1 Z / (gamma h) - Z and the stage
+// equation  U_i = W^-1 (J Z_i + (1/h) sum_j C_ij U_j + b_i)  becomes
+//     U_i = W^-1 ( (1/h) (Z_i / gamma + sum_j C_ij U_j) + b_i ) - Z_i,
+// where Z_i / gamma + sum_j C_ij U_j = S / gamma + sum_j D_ij U_j is ONE
+// combination: no product with J, one combination less per stage.
+#define CHI_RODAS4_LIN_TABLE(X)                                               \
+  X(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)                        \
+  X(1, 1, 0, CHI_R4(A21), 0, 0, 0, 0, 0, 0, CHI_R4(D21), 0, 0, 0, 0, 0, 0)    \
+  X(2, 2, 0, CHI_R4(A31), CHI_R4(A32), 0, 0, 0, 0, 0, CHI_R4(D31),            \
+    CHI_R4(D32), 0, 0, 0, 0, 0)                                               \
+  X(3, 3, 0, CHI_R4(A41), CHI_R4(A42), CHI_R4(A43), 0, 0, 0, 0, CHI_R4(D41),  \
+    CHI_R4(D42), CHI_R4(D43), 0, 0, 0, 0)                                     \
+  X(4, 4, 0, CHI_R4(A51), CHI_R4(A52), CHI_R4(A53), CHI_R4(A54), 0, 0, 0,     \
+    CHI_R4(D51), CHI_R4(D52), CHI_R4(D53), CHI_R4(D54), 0, 0, 0)              \
+  X(5, 5, 1, 0, 0, 0, 0, 0, 0, 0, CHI_R4(C61), CHI_R4(C62), CHI_R4(C63),      \
+    CHI_R4(C64), CHI_R4(C65), 0, 0)
+
+#define CHI_RODAS5_LIN_TABLE(X)                                               \
+  X(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)                        \
+  X(1, 1, 0, CHI_R5(A21), 0, 0, 0, 0, 0, 0, CHI_R5(D21), 0, 0, 0, 0, 0, 0)    \
+  X(2, 2, 0, CHI_R5(A31), CHI_R5(A32), 0, 0, 0, 0, 0, CHI_R5(D31),            \
+    CHI_R5(D32), 0, 0, 0, 0, 0)                                               \
+  X(3, 3, 0, CHI_R5(A41), CHI_R5(A42), CHI_R5(A43), 0, 0, 0, 0, CHI_R5(D41),  \
+    CHI_R5(D42), CHI_R5(D43), 0, 0, 0, 0)                                     \
+  X(4, 4, 0, CHI_R5(A51), CHI_R5(A52), CHI_R5(A53), CHI_R5(A54), 0, 0, 0,     \
+    CHI_R5(D51), CHI_R5(D52), CHI_R5(D53), CHI_R5(D54), 0, 0, 0)              \
+  X(5, 5, 0, CHI_R5(A61), CHI_R5(A62), CHI_R5(A63), CHI_R5(A64), CHI_R5(A65), \
+    0, 0, CHI_R5(D61), CHI_R5(D62), CHI_R5(D63), CHI_R5(D64), CHI_R5(D65), 0, \
     0)                                                                        \
   X(6, 6, 1, 0, 0, 0, 0, 0, 0, 0, CHI_R5(C71), CHI_R5(C72), CHI_R5(C73),      \
     CHI_R5(C74), CHI_R5(C75), CHI_R5(C76), 0)                                 \
@@ -638,61 +717,76 @@ struct StreamSolver {
     // e_k = 0 (no column-specific work at all)
     double DK[N * N], ek[N];
     if (M::LINEAR && HAS_TERMS) M::col_linear(kc, c, u, DK, ek);
+#define CHI_LSTAGE(I, CNT, INCR, a0, a1, a2, a3, a4, a5, a6, m0, m1, m2, m3,  \
+                   m4, m5, m6)                                                \
+  {                                                                           \
+    /* linear model, see CHI_RODAS5_LIN_TABLE */                              \
+    double ms[N], rs[N];                                                      \
+    if (INCR) {                                                               \
+      _Pragma("unroll") for (int n = 0; n < N; ++n) Zl[n] +=                  \
+          Us[I > 0 ? I - 1 : 0][n];                                           \
+      lincomb7<CNT, N>(ms, nullptr, Us, m0, m1, m2, m3, m4, m5, m6);          \
+      _Pragma("unroll") for (int n = 0; n < N; ++n) ms[n] =                   \
+          fma(1.0 / GAMMA, Zl[n], ms[n]);                                     \
+    } else {                                                                  \
+      lincomb7<CNT, N>(Zl, S0, Us, a0, a1, a2, a3, a4, a5, a6);               \
+      lincomb7<CNT, N>(ms, S0g, Us, m0, m1, m2, m3, m4, m5, m6);              \
+    }                                                                         \
+    _Pragma("unroll") for (int n = 0; n < N; ++n) {                           \
+      double acc = 0.0;                                                       \
+      if (HAS_TERMS) {                                                        \
+        acc = ek[n];                                                          \
+        _Pragma("unroll") for (int q = 0; q < N; ++q) acc = fma(              \
+            DK[n * N + q], (I == 0) ? V0[q] : CHI_ZY(I, q), acc);             \
+      }                                                                       \
+      rs[n] = fma(hinv, ms[n], acc);                                          \
+    }                                                                         \
+    _Pragma("unroll") for (int n = 0; n < N; ++n) {                           \
+      double acc = -Zl[n];                                                    \
+      _Pragma("unroll") for (int q = 0; q < N; ++q) acc =                     \
+          fma(Wi[n * N + q], rs[q], acc);                                     \
+      Us[I][n] = acc;                                                         \
+    }                                                                         \
+  }
 #define CHI_SSTAGE(I, CNT, INCR, a0, a1, a2, a3, a4, a5, a6, c0, c1, c2, c3,  \
                    c4, c5, c6)                                                \
   {                                                                           \
     double cs[N], rs[N];                                                      \
-    if (M::LINEAR) {                                                          \
-      double V[N];                                                            \
-      _Pragma("unroll") for (int n = 0; n < N; ++n) V[n] =                    \
-          (I == 0) ? V0[n] : CHI_ZY(I, n);                                    \
-      _Pragma("unroll") for (int n = 0; n < N; ++n) {                         \
-        double acc = 0.0;                                                     \
-        if (HAS_TERMS) {                                                      \
-          acc = ek[n];                                                        \
-          _Pragma("unroll") for (int m = 0; m < N; ++m) acc =                 \
-              fma(DK[n * N + m], V[m], acc);                                  \
-        }                                                                     \
-        rs[n] = acc;                                                          \
-      }                                                                       \
-      if (INCR) {                                                             \
-        _Pragma("unroll") for (int n = 0; n < N; ++n) Zl[n] +=                \
-            Us[I > 0 ? I - 1 : 0][n];                                         \
-      } else {                                                                \
-        lincomb7<CNT, N>(Zl, S0, Us, a0, a1, a2, a3, a4, a5, a6);             \
-      }                                                                       \
-      lincomb7<CNT, N>(cs, nullptr, Us, c0, c1, c2, c3, c4, c5, c6);          \
-      _Pragma("unroll") for (int n = 0; n < N; ++n) {                         \
-        double acc = rs[n];                                                   \
-        _Pragma("unroll") for (int m = 0; m < N; ++m) acc =                   \
-            fma(J0[n * N + m], Zl[m], acc);                                   \
-        rs[n] = fma(hinv, cs[n], acc);                                        \
-      }                                                                       \
+    double Ji[N * N], Zyi[N];                                                 \
+    _Pragma("unroll") for (int n = 0; n < N; ++n) Zyi[n] =                    \
+        (I == 0) ? y[n] : CHI_ZY(I, n);                                       \
+    M::jac(Zyi, c, Ji);                                                       \
+    if (INCR) {                                                               \
+      _Pragma("unroll") for (int n = 0; n < N; ++n) Zl[n] +=                  \
+          Us[I > 0 ? I - 1 : 0][n];                                           \
     } else {                                                                  \
-      double Ji[N * N], Zyi[N];                                               \
-      _Pragma("unroll") for (int n = 0; n < N; ++n) Zyi[n] =                  \
-          (I == 0) ? y[n] : CHI_ZY(I, n);                                     \
-      M::jac(Zyi, c, Ji);                                                     \
-      if (INCR) {                                                             \
-        _Pragma("unroll") for (int n = 0; n < N; ++n) Zl[n] +=                \
-            Us[I > 0 ? I - 1 : 0][n];                                         \
-      } else {                                                                \
-        lincomb7<CNT, N>(Zl, S0, Us, a0, a1, a2, a3, a4, a5, a6);             \
-      }                                                                       \
-      lincomb7<CNT, N>(cs, nullptr, Us, c0, c1, c2, c3, c4, c5, c6);          \
-      matvec<N>(Ji, Zl, rs);                                                  \
-      M::dfdc_col_add(kc, Zyi, c, rs);                                        \
-      M::hess_col_add(kc, y, c, S0, Uy[I], rs);                               \
-      _Pragma("unroll") for (int n = 0; n < N; ++n) rs[n] =                   \
-          fma(hinv, cs[n], rs[n]);                                            \
+      lincomb7<CNT, N>(Zl, S0, Us, a0, a1, a2, a3, a4, a5, a6);               \
     }                                                                         \
+    lincomb7<CNT, N>(cs, nullptr, Us, c0, c1, c2, c3, c4, c5, c6);            \
+    matvec<N>(Ji, Zl, rs);                                                    \
+    M::dfdc_col_add(kc, Zyi, c, rs);                                          \
+    M::hess_col_add(kc, y, c, S0, Uy[I], rs);                                 \
+    _Pragma("unroll") for (int n = 0; n < N; ++n) rs[n] =                     \
+        fma(hinv, cs[n], rs[n]);                                              \
     matvec<N>(Wi, rs, Us[I]);                                                 \
   }
-    if constexpr (R5) {
-      CHI_RODAS5_TABLE(CHI_SSTAGE)
+    if constexpr (M::LINEAR) {
+      double S0g[N];
+#pragma unroll
+      for (int n = 0; n < N; ++n) S0g[n] = S0[n] * (1.0 / GAMMA);
+      if constexpr (R5) {
+        CHI_RODAS5_LIN_TABLE(CHI_LSTAGE)
+      } else {
+        CHI_RODAS4_LIN_TABLE(CHI_LSTAGE)
+      }
     } else {
-      CHI_RODAS4_TABLE(CHI_SSTAGE)
+      if constexpr (R5) {
+        CHI_RODAS5_TABLE(CHI_SSTAGE)
+      } else {
+        CHI_RODAS4_TABLE(CHI_SSTAGE)
+      }
     }
+#undef CHI_LSTAGE
 #undef CHI_SSTAGE
     // stiffly accurate: new value = last stage value + last increment, the
     // last increment is the error estimate
