@@ -105,9 +105,21 @@ def flops_per_step(n, n_cols, info, stages=6):
     pairs_a = (s - incr) * (s - incr - 1) // 2
     comb_a = 2 * n * pairs_a + incr * n
     solve = s * n * (2 * n - 1)           # s mat-vecs with W^-1
-    state = comb_a + comb_c + s * 2 * n + s * f_rhs + solve
-    # per column: stage combinations, J Z_s, + hinv * combination, solves
-    sens = comb_a + comb_c + s * 2 * n + s * n * (2 * n - 1) + solve
+    if linear:
+        # J is the matrix inside W = I/(gamma h) - J, so W^-1 J Z =
+        # W^-1 Z/(gamma h) - Z: no product with J and no rhs evaluation per
+        # stage; Z/gamma + sum_j C_ij U_j is one combination with
+        # D = A/gamma + C for the ordinary stages and the C combination plus
+        # n FMAs for the incremental ones
+        pairs_ci = pairs - pairs_a        # c entries of the incremental rows
+        comb_m = 2 * n * pairs_a + 2 * n * pairs_ci + incr * 2 * n + n
+        stage_lin = s * 2 * n + s * 2 * n * n     # + hinv * m, W^-1 (.) - Z
+        state = comb_a + comb_m + stage_lin + f_rhs
+        sens = comb_a + comb_m + stage_lin
+    else:
+        state = comb_a + comb_c + s * 2 * n + s * f_rhs + solve
+        # per column: stage combinations, J Z_s, + hinv * combination, solves
+        sens = comb_a + comb_c + s * 2 * n + s * n * (2 * n - 1) + solve
     # column-specific terms (df/dc_k and its y-derivative) of all columns and
     # the column-independent second-order term, per stage
     extra = s * (f_col_sum + n_cols * f_hess_common)

@@ -862,11 +862,53 @@ struct StreamSolver {
       if (I == 0) V0[n] = v; else CHI_ZY(I, n) = v;                           \
     }                                                                         \
   }
-    if constexpr (R5) {
-      CHI_RODAS5_TABLE(CHI_YSTAGE)
+    // linear models, same identity as in the columns (CHI_RODAS5_LIN_TABLE):
+    // f(Z) = J Z + f(0), so U_i = V_i - Z_i with
+    // V_i = W^-1 ((1/h)(Z_i/gamma + sum_j C_ij U_j) + f(0)) -- and V_i is
+    // exactly what the sensitivity columns need of this stage
+#define CHI_YLSTAGE(I, CNT, INCR, a0, a1, a2, a3, a4, a5, a6, m0, m1, m2, m3, \
+                    m4, m5, m6)                                               \
+  {                                                                           \
+    double my[N], ry[N], V[N];                                                \
+    if (INCR) {                                                               \
+      _Pragma("unroll") for (int n = 0; n < N; ++n) Zlast[n] +=               \
+          Uy[I > 0 ? I - 1 : 0][n];                                           \
+      lincomb7<CNT, N>(my, nullptr, Uy, m0, m1, m2, m3, m4, m5, m6);          \
+      _Pragma("unroll") for (int n = 0; n < N; ++n) my[n] =                   \
+          fma(1.0 / GAMMA, Zlast[n], my[n]);                                  \
+    } else {                                                                  \
+      lincomb7<CNT, N>(Zlast, y, Uy, a0, a1, a2, a3, a4, a5, a6);             \
+      lincomb7<CNT, N>(my, yg, Uy, m0, m1, m2, m3, m4, m5, m6);               \
+    }                                                                         \
+    _Pragma("unroll") for (int n = 0; n < N; ++n) ry[n] =                     \
+        fma(hinv, my[n], f0[n]);                                              \
+    matvec<N>(Wi, ry, V);                                                     \
+    _Pragma("unroll") for (int n = 0; n < N; ++n) {                           \
+      Uy[I][n] = V[n] - Zlast[n];                                             \
+      if (I == 0) V0[n] = V[n]; else CHI_ZY(I, n) = V[n];                     \
+    }                                                                         \
+  }
+    if constexpr (M::LINEAR) {
+      double f0[N], yg[N], zero[N];
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        zero[n] = 0.0;
+        yg[n] = y[n] * (1.0 / GAMMA);
+      }
+      M::rhs(zero, c, u, f0);
+      if constexpr (R5) {
+        CHI_RODAS5_LIN_TABLE(CHI_YLSTAGE)
+      } else {
+        CHI_RODAS4_LIN_TABLE(CHI_YLSTAGE)
+      }
     } else {
-      CHI_RODAS4_TABLE(CHI_YSTAGE)
+      if constexpr (R5) {
+        CHI_RODAS5_TABLE(CHI_YSTAGE)
+      } else {
+        CHI_RODAS4_TABLE(CHI_YSTAGE)
+      }
     }
+#undef CHI_YLSTAGE
 #undef CHI_YSTAGE
     float errsq;
     const float atol_f = static_cast<float>(a.atol);
