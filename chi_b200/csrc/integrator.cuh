@@ -336,8 +336,9 @@ CHI_HD void solve_system(const SolveArgs& a, const int64_t b, const int sub,
 
   double t = 0.0;
   double h = 0.0;
-  double h_full = 0.0;   // last unclipped working step        // 0 -> (re)initialise
   bool after_reject = false;
+  int edge_kind = 0;            // dose edge whose first step is pending
+  float h_mem_up = 0.0f, h_mem_down = 0.0f;
   int n_acc = 0, n_rej = 0;
   int status = ST_OK;
   double J0[N * N];
@@ -415,9 +416,17 @@ CHI_HD void solve_system(const SolveArgs& a, const int64_t b, const int sub,
       if (t_edge <= t) {
         // ---- dose-rate edge: switch the input, restart the step size -----
         ++seg;
+        const double u_old = u;
         u = a.seg_rate[seg];
         t_edge = (seg + 1 < seg_end) ? a.seg_t[seg + 1] : INFINITY;
-        h = CHI_EDGE_KEEP_H ? h_full * CHI_EDGE_SHRINK : 0.0;
+        {
+          // restart from the first accepted step after the previous edge of
+          // this kind, if there was one (same policy as the streamed solver)
+          edge_kind = (fabs(u) > fabs(u_old)) ? 1 : 2;
+          const float hm = edge_kind == 1 ? h_mem_up : h_mem_down;
+          h = (hm > 0.0f) ? fmin(static_cast<double>(hm), h)
+                          : (CHI_EDGE_KEEP_H ? h * CHI_EDGE_SHRINK : 0.0);
+        }
         continue;
       }
       const double t_stop = fmin(t_rec, t_edge);
@@ -431,7 +440,6 @@ CHI_HD void solve_system(const SolveArgs& a, const int64_t b, const int sub,
 
       // ---- choose the step: hit t_stop exactly ----------------------------
       const double rem = t_stop - t;
-      h_full = h;
       double hs = h;
       bool clipped = false;
       if (rem <= CHI_CLIP_STRETCH * h) {
@@ -541,6 +549,9 @@ CHI_HD void solve_system(const SolveArgs& a, const int64_t b, const int sub,
         for (int m = 0; m < MC; ++m)
 #pragma unroll
           for (int n = 0; n < N; ++n) S[m][n] = Sn[m][n];
+        if (edge_kind == 1) h_mem_up = static_cast<float>(hs);
+        if (edge_kind == 2) h_mem_down = static_cast<float>(hs);
+        edge_kind = 0;
         if (after_reject) fac = fminf(fac, 1.0f);
         const double hn = hs * static_cast<double>(fac);
         // a step shortened to hit a stop must not shrink the working step
