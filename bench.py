@@ -88,7 +88,7 @@ def workload_config(args, n_gpus):
 # flop model ("Algorithmic flops")
 # --------------------------------------------------------------------------
 
-def flops_per_step(n, n_cols, info, stages=6):
+def flops_per_step(n, n_cols, info, stages=6, n_init=0):
     """Algorithmic flops of one Rosenbrock step attempt of one system (RODAS4:
     6 stages, RODAS5: 8): the state column once + the n_cols integrated
     sensitivity columns (FMA = 2, every other FP64 operation 1)."""
@@ -113,9 +113,13 @@ def flops_per_step(n, n_cols, info, stages=6):
         # n FMAs for the incremental ones
         pairs_ci = pairs - pairs_a        # c entries of the incremental rows
         comb_m = 2 * n * pairs_a + 2 * n * pairs_ci + incr * 2 * n + n
-        stage_lin = s * 2 * n + s * 2 * n * n     # + hinv * m, W^-1 (.) - Z
-        state = comb_a + comb_m + stage_lin + f_rhs
-        sens = comb_a + comb_m + stage_lin
+        # state column and the n_init initial-value columns (no column
+        # terms): U = (W^-1/h) m + W^-1 f(0) - Z, with W^-1/h and W^-1 f(0)
+        # formed once per step; columns of constants: (1/h) m + b, W^-1(.) - Z
+        plain = comb_a + comb_m + s * 2 * n * n
+        state = plain + f_rhs + n * n + n * (2 * n - 1)
+        sens = plain + s * 2 * n
+        state -= min(n_init, n_cols) * s * 2 * n   # term-free columns
     else:
         state = comb_a + comb_c + s * 2 * n + s * f_rhs + solve
         # per column: stage combinations, J Z_s, + hinv * combination, solves
@@ -594,7 +598,8 @@ def run_product(args, rank, world, local_rank):
     method = 'RODAS5' if (streamed and int(variants[1][vsel]) == 5) \
         else 'RODAS4'
     stages = 8 if method == 'RODAS5' else 6
-    f_step = flops_per_step(n_states, n_cols - n_inert, info, stages)
+    f_step = flops_per_step(n_states, n_cols - n_inert, info, stages,
+                            n_init=n_states)
     n_rec = args.n_obs
     flops_launch = (steps_acc + steps_rej) * f_step + \
         n_sys * n_rec * flops_per_record(n_states, n_cols)

@@ -737,8 +737,9 @@ struct StreamSolver {
                       const double (&y)[N], const double (&c)[NCS],
                       const double (&Uy)[NS][N],
                       const double (&V0)[N],
-                      const double (&Wi)[N * N], const double hinv,
-                      const float atol_f, const float rtol_f) {
+                      const double (&Wi)[N * N], const double (&Wh)[N * N],
+                      const double hinv, const float atol_f,
+                      const float rtol_f) {
     double S0[N], Us[NS][N], Zl[N];
 #pragma unroll
     for (int n = 0; n < N; ++n) S0[n] = CHI_S(cur, m, n);
@@ -761,20 +762,28 @@ struct StreamSolver {
       lincomb7<CNT, N>(Zl, S0, Us, a0, a1, a2, a3, a4, a5, a6);               \
       lincomb7<CNT, N>(ms, S0g, Us, m0, m1, m2, m3, m4, m5, m6);              \
     }                                                                         \
-    _Pragma("unroll") for (int n = 0; n < N; ++n) {                           \
-      double acc = 0.0;                                                       \
-      if (HAS_TERMS) {                                                        \
-        acc = ek[n];                                                          \
+    if (HAS_TERMS) {                                                          \
+      _Pragma("unroll") for (int n = 0; n < N; ++n) {                         \
+        double acc = ek[n];                                                   \
         _Pragma("unroll") for (int q = 0; q < N; ++q) acc = fma(              \
             DK[n * N + q], (I == 0) ? V0[q] : CHI_ZY(I, q), acc);             \
+        rs[n] = fma(hinv, ms[n], acc);                                        \
       }                                                                       \
-      rs[n] = fma(hinv, ms[n], acc);                                          \
-    }                                                                         \
-    _Pragma("unroll") for (int n = 0; n < N; ++n) {                           \
-      double acc = -Zl[n];                                                    \
-      _Pragma("unroll") for (int q = 0; q < N; ++q) acc =                     \
-          fma(Wi[n * N + q], rs[q], acc);                                     \
-      Us[I][n] = acc;                                                         \
+      _Pragma("unroll") for (int n = 0; n < N; ++n) {                         \
+        double acc = -Zl[n];                                                  \
+        _Pragma("unroll") for (int q = 0; q < N; ++q) acc =                   \
+            fma(Wi[n * N + q], rs[q], acc);                                   \
+        Us[I][n] = acc;                                                       \
+      }                                                                       \
+    } else {                                                                  \
+      /* no column terms: U = (W^-1 / h) m - Z */                             \
+      (void)rs;                                                               \
+      _Pragma("unroll") for (int n = 0; n < N; ++n) {                         \
+        double acc = -Zl[n];                                                  \
+        _Pragma("unroll") for (int q = 0; q < N; ++q) acc =                   \
+            fma(Wh[n * N + q], ms[q], acc);                                   \
+        Us[I][n] = acc;                                                       \
+      }                                                                       \
     }                                                                         \
   }
 #define CHI_SSTAGE(I, CNT, INCR, a0, a1, a2, a3, a4, a5, a6, c0, c1, c2, c3,  \
@@ -868,6 +877,9 @@ struct StreamSolver {
           W[i * N + j] = (i == j ? hinv * (1.0 / GAMMA) : 0.0) - J0[i * N + j];
       invert<N>(W, Wi);
     }
+    double Wh[N * N];
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) Wh[i] = hinv * Wi[i];
     double Uy[NS][N];
     double Zlast[N], V0[N];
 #define CHI_YSTAGE(I, CNT, INCR, a0, a1, a2, a3, a4, a5, a6, c0, c1, c2, c3,  \
@@ -909,9 +921,13 @@ struct StreamSolver {
       lincomb7<CNT, N>(Zlast, y, Uy, a0, a1, a2, a3, a4, a5, a6);             \
       lincomb7<CNT, N>(my, yg, Uy, m0, m1, m2, m3, m4, m5, m6);               \
     }                                                                         \
-    _Pragma("unroll") for (int n = 0; n < N; ++n) ry[n] =                     \
-        fma(hinv, my[n], f0[n]);                                              \
-    matvec<N>(Wi, ry, V);                                                     \
+    (void)ry;                                                                 \
+    _Pragma("unroll") for (int n = 0; n < N; ++n) {                           \
+      double acc = Wf0[n];                                                    \
+      _Pragma("unroll") for (int q = 0; q < N; ++q) acc =                     \
+          fma(Wh[n * N + q], my[q], acc);                                     \
+      V[n] = acc;                                                             \
+    }                                                                         \
     _Pragma("unroll") for (int n = 0; n < N; ++n) {                           \
       Uy[I][n] = V[n] - Zlast[n];                                             \
       if (I == 0) V0[n] = V[n]; else CHI_ZY(I, n) = V[n];                     \
@@ -925,6 +941,9 @@ struct StreamSolver {
         yg[n] = y[n] * (1.0 / GAMMA);
       }
       M::rhs(zero, c, u, f0);
+      // V_i = (W^-1 / h) m_i + W^-1 f(0)
+      double Wf0[N];
+      matvec<N>(Wi, f0, Wf0);
       if constexpr (R5) {
         CHI_RODAS5_LIN_TABLE(CHI_YLSTAGE)
       } else {
@@ -968,15 +987,15 @@ struct StreamSolver {
       // initial-value columns first (they lead the list): no column terms
       for (; m < ni && a.int_param[m] < N; ++m)
         errsq = fmaxf(errsq,
-                      column<false>(-1, m, nxt, y, c, Uy, V0, Wi, hinv,
+                      column<false>(-1, m, nxt, y, c, Uy, V0, Wi, Wh, hinv,
                                     atol_f, rtol_f));
     }
     for (; m < ni; ++m) {
       const int pk = a.int_param[m];
       const int kc = pk >= N ? pk - N : -1;
       errsq = fmaxf(errsq,
-                    column<true>(kc, m, nxt, y, c, Uy, V0, Wi, hinv, atol_f,
-                                 rtol_f));
+                    column<true>(kc, m, nxt, y, c, Uy, V0, Wi, Wh, hinv,
+                                 atol_f, rtol_f));
     }
 
     const bool accept = errsq <= 1.0f;
