@@ -930,7 +930,8 @@ struct StreamSolver {
     }                                                                         \
     _Pragma("unroll") for (int n = 0; n < N; ++n) {                           \
       Uy[I][n] = V[n] - Zlast[n];                                             \
-      if (I == 0) V0[n] = V[n]; else CHI_ZY(I, n) = V[n];                     \
+      if (I == 0) V0[n] = V[n];                                               \
+      else if (need_v || I == NS - 1) CHI_ZY(I, n) = V[n];                    \
     }                                                                         \
   }
     if constexpr (M::LINEAR) {
@@ -941,6 +942,9 @@ struct StreamSolver {
         yg[n] = y[n] * (1.0 / GAMMA);
       }
       M::rhs(zero, c, u, f0);
+      // the columns read V_i from shared memory; a forward-only solve only
+      // needs the last one (the new state)
+      const bool need_v = n_int() > 0;
       // V_i = (W^-1 / h) m_i + W^-1 f(0)
       double Wf0[N];
       matvec<N>(Wi, f0, Wf0);
