@@ -161,37 +161,125 @@ def flops_per_record(n, n_cols):
 # --------------------------------------------------------------------------
 
 class ClockSampler(object):
+    """Samples SM clock and throttle reasons of one GPU while the timed
+    region runs: NVML in a thread (a sample every few ms, so even a 100 ms
+    region is covered), `nvidia-smi -lms` only when NVML is unavailable.
+    `start()` is called before the warm-up so that start-up cost stays out
+    of the timed region; samples count from `mark()` on."""
     FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,'
               'clocks_event_reasons.active,'
               'clocks_event_reasons.hw_slowdown,'
               'clocks_event_reasons.hw_thermal_slowdown,'
               'clocks_event_reasons.sw_thermal_slowdown,'
               'clocks_event_reasons.sw_power_cap')
+    PERIOD_S = 0.004
 
     def __init__(self, device):
         self.device = device
         self.proc = None
-        self.lines = []
+        self.nvml = None
+        self.handle = None
+        self.samples = []          # (t, sm_mhz, reasons bitmask)
+        self.lines = []            # (t, nvidia-smi csv line)
+        self.t_mark = None
+        self.smax = None
+        self.running = False
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        handle = None
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.device).uuid)
+            if not uuid.startswith('GPU-'):
+                uuid = 'GPU-' + uuid
+            handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            handle = None
+        if handle is None:
+            index = self.device
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+            ids = [v for v in visible.split(',') if v.strip()]
+            if ids and ids[min(index, len(ids) - 1)].strip().isdigit():
+                index = int(ids[index])
+            handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        return pynvml, handle
 
     def start(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.smax = float(self.nvml.nvmlDeviceGetMaxClockInfo(
+                self.handle, self.nvml.NVML_CLOCK_SM))
+            self.running = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.device),
                  '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits',
-                 '-lms', '100'], stdout=subprocess.PIPE,
+                 '-lms', '20'], stdout=subprocess.PIPE,
                 stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """The timed region starts now."""
+        self.t_mark = time.perf_counter()
+
+    def _poll(self):
+        nv = self.nvml
+        while self.running:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                try:
+                    why = nv.nvmlDeviceGetCurrentClocksEventReasons(
+                        self.handle)
+                except Exception:
+                    why = nv.nvmlDeviceGetCurrentClocksThrottleReasons(
+                        self.handle)
+                self.samples.append((time.perf_counter(), float(sm),
+                                     int(why)))
+            except Exception:
+                pass
+            time.sleep(self.PERIOD_S)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self):
+        t_mark = self.t_mark if self.t_mark is not None else 0.0
+        if self.nvml is not None:
+            self.running = False
+            self.thread.join(timeout=1)
+            nv = self.nvml
+            flags = (
+                ('hw_slowdown', nv.nvmlClocksThrottleReasonHwSlowdown),
+                ('hw_thermal_slowdown',
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ('sw_thermal_slowdown',
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                ('sw_power_cap', nv.nvmlClocksThrottleReasonSwPowerCap))
+            inside = [s for s in self.samples if s[0] >= t_mark]
+            reasons = set()
+            for _, _, why in inside:
+                for name, bit in flags:
+                    if why & bit:
+                        reasons.add(name)
+            sm = [s[1] for s in inside]
+            return {
+                'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': self.smax, 'samples': len(sm),
+                'reasons': sorted(reasons), 'source': 'nvml'}
         if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'samples': 0,
+                    'reasons': [], 'source': None}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -200,7 +288,9 @@ class ClockSampler(object):
         sm, smax, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
                  'sw_power_cap']
-        for line in self.lines:
+        for t, line in self.lines:
+            if t < t_mark:
+                continue
             parts = [p.strip() for p in line.split(',')]
             if len(parts) < 9:
                 continue
@@ -215,7 +305,8 @@ class ClockSampler(object):
         return {
             'sm_mhz': float(np.median(sm)) if sm else None,
             'sm_max_mhz': float(np.max(smax)) if smax else None,
-            'samples': len(sm), 'reasons': sorted(reasons)}
+            'samples': len(sm), 'reasons': sorted(reasons),
+            'source': 'nvidia-smi'}
 
 
 # --------------------------------------------------------------------------
@@ -506,18 +597,19 @@ def run_product(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident timing ------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
     barrier()
     ll.set_timing(True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True),
            torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches = 0
     steps_acc = steps_rej = 0
     counters = np.zeros(4, dtype=np.int64)
     barrier()
+    sampler.mark()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()                      # L2 flush, outside the event pair
