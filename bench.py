@@ -106,20 +106,24 @@ def flops_per_step(n, n_cols, info, stages=6, n_init=0):
     comb_a = 2 * n * pairs_a + incr * n
     solve = s * n * (2 * n - 1)           # s mat-vecs with W^-1
     if linear:
-        # J is the matrix inside W = I/(gamma h) - J, so W^-1 J Z =
-        # W^-1 Z/(gamma h) - Z: no product with J and no rhs evaluation per
-        # stage; Z/gamma + sum_j C_ij U_j is one combination with
-        # D = A/gamma + C for the ordinary stages and the C combination plus
-        # n FMAs for the incremental ones
-        pairs_ci = pairs - pairs_a        # c entries of the incremental rows
-        comb_m = 2 * n * pairs_a + 2 * n * pairs_ci + incr * 2 * n + n
-        # state column and the n_init initial-value columns (no column
-        # terms): U = (W^-1/h) m + W^-1 f(0) - Z, with W^-1/h and W^-1 f(0)
-        # formed once per step; columns of constants: (1/h) m + b, W^-1(.) - Z
-        plain = comb_a + comb_m + s * 2 * n * n
-        state = plain + f_rhs + n * n + n * (2 * n - 1)
-        sens = plain + s * 2 * n
-        state -= min(n_init, n_cols) * s * 2 * n   # term-free columns
+        # k-stage form (integrator_stream.cuh, K constants): per stage ONE
+        # combination arg = z + sum_j K_ij kappa_j and
+        # kappa = E arg + W^-1 g, E = W^-1 J formed once per step.  RODAS5:
+        # K72 = 0 and row 8 = row 7 + two entries -> 22 of the 28 pairs
+        pairs_k = 22 if s == 8 else pairs
+        comb_k = 2 * n * pairs_k
+        mv = n * (2 * n - 1)              # one N x N product
+        # state column: kappa = E arg + W^-1 f(0) (FMAs throughout),
+        # V = arg + kappa per stage; f(0), W^-1 f(0) and E once per step
+        state = comb_k + s * 2 * n * n + s * n + f_rhs + mv + n * mv
+        # initial-value columns: kappa = E arg; the last two V's
+        plain = comb_k + s * mv + 2 * n
+        # columns of constants: + W^-1 (D_k V + e_k) per stage, the sparse
+        # D_k V + e_k itself is in `extra` below (the kernel multiplies
+        # W^-1 D_k out once per step and executes a dense product instead:
+        # slightly more than is counted here)
+        sens = plain + s * (mv + n)
+        state -= min(n_init, n_cols) * s * (mv + n)   # term-free columns
     else:
         state = comb_a + comb_c + s * 2 * n + s * f_rhs + solve
         # per column: stage combinations, J Z_s, + hinv * combination, solves
@@ -129,7 +133,8 @@ def flops_per_step(n, n_cols, info, stages=6, n_init=0):
     extra = s * (f_col_sum + n_cols * f_hess_common)
     jac = (0 if linear else (s + 1) * f_jac) if n_cols else (
         0 if linear else f_jac)
-    # new solution = last stage value + last increment; the error norm and
+    # new solution = last stage value + last increment (nonlinear) / error
+    # estimate = difference of the last two V's (linear); the error norm and
     # the step-size controller run in FP32 and are not counted
     new = (n_cols + 1) * n
     return inv + state + n_cols * sens + extra + jac + new

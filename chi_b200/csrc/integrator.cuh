@@ -59,17 +59,24 @@ constexpr double C62 = -0.7981132988064893e+01;
 constexpr double C63 = -0.3152159432874371e+02;
 constexpr double C64 = 0.1631930543123136e+02;
 constexpr double C65 = -0.6058818238834054e+01;
-// D_ij = A_ij / gamma + C_ij (see integrator_stream.cuh)
-constexpr double D21 = A21 / GAMMA + C21;
-constexpr double D31 = A31 / GAMMA + C31;
-constexpr double D32 = A32 / GAMMA + C32;
-constexpr double D41 = A41 / GAMMA + C41;
-constexpr double D42 = A42 / GAMMA + C42;
-constexpr double D43 = A43 / GAMMA + C43;
-constexpr double D51 = A51 / GAMMA + C51;
-constexpr double D52 = A52 / GAMMA + C52;
-constexpr double D53 = A53 / GAMMA + C53;
-constexpr double D54 = A54 / GAMMA + C54;
+// K_ij = (alpha_ij + gamma_ij) / gamma of the method in its original k-stage
+// form (tools/derive_kform.py derives them from the a, C tables above): the
+// stages of a LINEAR system need one combination each (integrator_stream.cuh)
+constexpr double K21 = 0.1268;
+constexpr double K31 = 0.04988880902896939;
+constexpr double K32 = 0.20411119097103052;
+constexpr double K41 = 4.7841506773549481;
+constexpr double K42 = 0.7099789456713099;
+constexpr double K43 = -4.1189296230262583;
+constexpr double K51 = 9.7145350618679512;
+constexpr double K52 = -1.5309949350591384;
+constexpr double K53 = -7.4228813237183214;
+constexpr double K54 = 2.239341196909505;
+constexpr double K61 = 1.3937770851442061;
+constexpr double K62 = 0.8520544876475948;
+constexpr double K63 = -0.61641013064927383;
+constexpr double K64 = 1.8852831175659833;
+constexpr double K65 = -0.5147045597085135;
 }  // namespace rodas4
 
 constexpr double LOG_2PI_HALF = 0.91893853320467274178;

@@ -97,23 +97,38 @@ constexpr double C84 = 18.77919633714503;
 constexpr double C85 = -31.58359187223370;
 constexpr double C86 = -6.685968952921985;
 constexpr double C87 = -5.810979938412932;
-// D_ij = A_ij / gamma + C_ij: for linear models J Z + (C/h) U collapses into
-// one combination (StreamSolver::column)
-constexpr double D21 = A21 / GAMMA + C21;
-constexpr double D31 = A31 / GAMMA + C31;
-constexpr double D32 = A32 / GAMMA + C32;
-constexpr double D41 = A41 / GAMMA + C41;
-constexpr double D42 = A42 / GAMMA + C42;
-constexpr double D43 = A43 / GAMMA + C43;
-constexpr double D51 = A51 / GAMMA + C51;
-constexpr double D52 = A52 / GAMMA + C52;
-constexpr double D53 = A53 / GAMMA + C53;
-constexpr double D54 = A54 / GAMMA + C54;
-constexpr double D61 = A61 / GAMMA + C61;
-constexpr double D62 = A62 / GAMMA + C62;
-constexpr double D63 = A63 / GAMMA + C63;
-constexpr double D64 = A64 / GAMMA + C64;
-constexpr double D65 = A65 / GAMMA + C65;
+// K_ij = (alpha_ij + gamma_ij) / gamma of the method in its original k-stage
+// form, derived from the a, C tables above (tools/derive_kform.py).  For a
+// LINEAR system z' = J z + g the stage equations collapse to
+//     kappa_i = E arg_i + W^-1 g_i,   arg_i = z + sum_j K_ij kappa_j,
+//     E = W^-1 J,  W = I / (gamma h) - J,  kappa_i = gamma k_i,
+// i.e. ONE combination and one product per stage; arg_i + kappa_i equals
+// Z_i + U_i of the transformed form, the new solution is arg_8 + kappa_8 and
+// the embedded one arg_7 + kappa_7.  K72 = K82 = 0 (to rounding of the
+// tables), and row 8 repeats row 7 in its first five entries:
+//     arg_8 = arg_7 + (K86 - K76) kappa_6 + K87 kappa_7.
+constexpr double K21 = 0.0404846182454133;
+constexpr double K31 = -0.30594588947147515;
+constexpr double K32 = -0.33290059660600704;
+constexpr double K41 = 3.7240608400705508;
+constexpr double K42 = -3.147526073234625;
+constexpr double K43 = 2.7863850029531169;
+constexpr double K51 = -0.18407908723123721;
+constexpr double K52 = -1.014987413588082;
+constexpr double K53 = 0.47283992697435224;
+constexpr double K54 = 0.14533255537058853;
+constexpr double K61 = 39.922429989489724;
+constexpr double K62 = -81.969800437891473;
+constexpr double K63 = -46.391615240042746;
+constexpr double K64 = 8.0773631411899189;
+constexpr double K65 = 84.624780441991413;
+constexpr double K71 = 2.4452730732036673;
+constexpr double K73 = -9.0574079412504045;
+constexpr double K74 = 1.5318316952410377;
+constexpr double K75 = 9.5883097975785527;
+constexpr double K76 = -0.24484873003601078;
+constexpr double K8D6 = 0.10408618829845701;   // K86 - K76
+constexpr double K87 = -0.10408618829845708;
 }  // namespace rodas5
 
 
@@ -149,16 +164,21 @@ static __constant__ double C62 = -0.7981132988064893e+01;
 static __constant__ double C63 = -0.3152159432874371e+02;
 static __constant__ double C64 = 0.1631930543123136e+02;
 static __constant__ double C65 = -0.6058818238834054e+01;
-static __constant__ double D21 = rodas4::D21;
-static __constant__ double D31 = rodas4::D31;
-static __constant__ double D32 = rodas4::D32;
-static __constant__ double D41 = rodas4::D41;
-static __constant__ double D42 = rodas4::D42;
-static __constant__ double D43 = rodas4::D43;
-static __constant__ double D51 = rodas4::D51;
-static __constant__ double D52 = rodas4::D52;
-static __constant__ double D53 = rodas4::D53;
-static __constant__ double D54 = rodas4::D54;
+static __constant__ double K21 = rodas4::K21;
+static __constant__ double K31 = rodas4::K31;
+static __constant__ double K32 = rodas4::K32;
+static __constant__ double K41 = rodas4::K41;
+static __constant__ double K42 = rodas4::K42;
+static __constant__ double K43 = rodas4::K43;
+static __constant__ double K51 = rodas4::K51;
+static __constant__ double K52 = rodas4::K52;
+static __constant__ double K53 = rodas4::K53;
+static __constant__ double K54 = rodas4::K54;
+static __constant__ double K61 = rodas4::K61;
+static __constant__ double K62 = rodas4::K62;
+static __constant__ double K63 = rodas4::K63;
+static __constant__ double K64 = rodas4::K64;
+static __constant__ double K65 = rodas4::K65;
 }  // namespace rodas4d
 namespace rodas5d {
 static __constant__ double GAMMA = 0.19;
@@ -205,21 +225,28 @@ static __constant__ double C84 = 18.77919633714503;
 static __constant__ double C85 = -31.58359187223370;
 static __constant__ double C86 = -6.685968952921985;
 static __constant__ double C87 = -5.810979938412932;
-static __constant__ double D21 = rodas5::D21;
-static __constant__ double D31 = rodas5::D31;
-static __constant__ double D32 = rodas5::D32;
-static __constant__ double D41 = rodas5::D41;
-static __constant__ double D42 = rodas5::D42;
-static __constant__ double D43 = rodas5::D43;
-static __constant__ double D51 = rodas5::D51;
-static __constant__ double D52 = rodas5::D52;
-static __constant__ double D53 = rodas5::D53;
-static __constant__ double D54 = rodas5::D54;
-static __constant__ double D61 = rodas5::D61;
-static __constant__ double D62 = rodas5::D62;
-static __constant__ double D63 = rodas5::D63;
-static __constant__ double D64 = rodas5::D64;
-static __constant__ double D65 = rodas5::D65;
+static __constant__ double K21 = rodas5::K21;
+static __constant__ double K31 = rodas5::K31;
+static __constant__ double K32 = rodas5::K32;
+static __constant__ double K41 = rodas5::K41;
+static __constant__ double K42 = rodas5::K42;
+static __constant__ double K43 = rodas5::K43;
+static __constant__ double K51 = rodas5::K51;
+static __constant__ double K52 = rodas5::K52;
+static __constant__ double K53 = rodas5::K53;
+static __constant__ double K54 = rodas5::K54;
+static __constant__ double K61 = rodas5::K61;
+static __constant__ double K62 = rodas5::K62;
+static __constant__ double K63 = rodas5::K63;
+static __constant__ double K64 = rodas5::K64;
+static __constant__ double K65 = rodas5::K65;
+static __constant__ double K71 = rodas5::K71;
+static __constant__ double K73 = rodas5::K73;
+static __constant__ double K74 = rodas5::K74;
+static __constant__ double K75 = rodas5::K75;
+static __constant__ double K76 = rodas5::K76;
+static __constant__ double K8D6 = rodas5::K8D6;
+static __constant__ double K87 = rodas5::K87;
 }  // namespace rodas5d
 #endif
 #ifdef __CUDA_ARCH__
@@ -264,42 +291,50 @@ static __constant__ double D65 = rodas5::D65;
   X(7, 7, 1, 0, 0, 0, 0, 0, 0, 0, CHI_R5(C81), CHI_R5(C82), CHI_R5(C83),      \
     CHI_R5(C84), CHI_R5(C85), CHI_R5(C86), CHI_R5(C87))
 
-// Tables of the linear-model column body: X(stage, n_previous, incremental,
-// a_1..a_7, m_1..m_7) with m = D (= A / gamma + C) for the ordinary stages and
-// m = C for the incremental ones.  For a linear model J is the matrix inside
-// W = I/(gamma h) - J, so W^-1 J Z = W^-1 Z / (gamma h) - Z and the stage
-// equation  U_i = W^-1 (J Z_i + (1/h) sum_j C_ij U_j + b_i)  becomes
-//     U_i = W^-1 ( (1/h) (Z_i / gamma + sum_j C_ij U_j) + b_i ) - Z_i,
-// where Z_i / gamma + sum_j C_ij U_j = S / gamma + sum_j D_ij U_j is ONE
-// combination: no product with J, one combination less per stage.
-#define CHI_RODAS4_LIN_TABLE(X)                                               \
-  X(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)                        \
-  X(1, 1, 0, CHI_R4(A21), 0, 0, 0, 0, 0, 0, CHI_R4(D21), 0, 0, 0, 0, 0, 0)    \
-  X(2, 2, 0, CHI_R4(A31), CHI_R4(A32), 0, 0, 0, 0, 0, CHI_R4(D31),            \
-    CHI_R4(D32), 0, 0, 0, 0, 0)                                               \
-  X(3, 3, 0, CHI_R4(A41), CHI_R4(A42), CHI_R4(A43), 0, 0, 0, 0, CHI_R4(D41),  \
-    CHI_R4(D42), CHI_R4(D43), 0, 0, 0, 0)                                     \
-  X(4, 4, 0, CHI_R4(A51), CHI_R4(A52), CHI_R4(A53), CHI_R4(A54), 0, 0, 0,     \
-    CHI_R4(D51), CHI_R4(D52), CHI_R4(D53), CHI_R4(D54), 0, 0, 0)              \
-  X(5, 5, 1, 0, 0, 0, 0, 0, 0, 0, CHI_R4(C61), CHI_R4(C62), CHI_R4(C63),      \
-    CHI_R4(C64), CHI_R4(C65), 0, 0)
+// Tables of the linear-model bodies (k-stage form, see the K constants):
+// X(stage, first, count, skip, k_1..k_7):
+//     arg = (first == 0 ? z : arg of the previous stage)
+//           + sum_{first <= j < count, bit j of skip clear} k_j kappa_j.
+#define CHI_RODAS4_K_TABLE(X)                                                 \
+  X(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)                                          \
+  X(1, 0, 1, 0, CHI_R4(K21), 0, 0, 0, 0, 0, 0)                                \
+  X(2, 0, 2, 0, CHI_R4(K31), CHI_R4(K32), 0, 0, 0, 0, 0)                      \
+  X(3, 0, 3, 0, CHI_R4(K41), CHI_R4(K42), CHI_R4(K43), 0, 0, 0, 0)            \
+  X(4, 0, 4, 0, CHI_R4(K51), CHI_R4(K52), CHI_R4(K53), CHI_R4(K54), 0, 0, 0)  \
+  X(5, 0, 5, 0, CHI_R4(K61), CHI_R4(K62), CHI_R4(K63), CHI_R4(K64),           \
+    CHI_R4(K65), 0, 0)
 
-#define CHI_RODAS5_LIN_TABLE(X)                                               \
-  X(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)                        \
-  X(1, 1, 0, CHI_R5(A21), 0, 0, 0, 0, 0, 0, CHI_R5(D21), 0, 0, 0, 0, 0, 0)    \
-  X(2, 2, 0, CHI_R5(A31), CHI_R5(A32), 0, 0, 0, 0, 0, CHI_R5(D31),            \
-    CHI_R5(D32), 0, 0, 0, 0, 0)                                               \
-  X(3, 3, 0, CHI_R5(A41), CHI_R5(A42), CHI_R5(A43), 0, 0, 0, 0, CHI_R5(D41),  \
-    CHI_R5(D42), CHI_R5(D43), 0, 0, 0, 0)                                     \
-  X(4, 4, 0, CHI_R5(A51), CHI_R5(A52), CHI_R5(A53), CHI_R5(A54), 0, 0, 0,     \
-    CHI_R5(D51), CHI_R5(D52), CHI_R5(D53), CHI_R5(D54), 0, 0, 0)              \
-  X(5, 5, 0, CHI_R5(A61), CHI_R5(A62), CHI_R5(A63), CHI_R5(A64), CHI_R5(A65), \
-    0, 0, CHI_R5(D61), CHI_R5(D62), CHI_R5(D63), CHI_R5(D64), CHI_R5(D65), 0, \
-    0)                                                                        \
-  X(6, 6, 1, 0, 0, 0, 0, 0, 0, 0, CHI_R5(C71), CHI_R5(C72), CHI_R5(C73),      \
-    CHI_R5(C74), CHI_R5(C75), CHI_R5(C76), 0)                                 \
-  X(7, 7, 1, 0, 0, 0, 0, 0, 0, 0, CHI_R5(C81), CHI_R5(C82), CHI_R5(C83),      \
-    CHI_R5(C84), CHI_R5(C85), CHI_R5(C86), CHI_R5(C87))
+#define CHI_RODAS5_K_TABLE(X)                                                 \
+  X(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)                                          \
+  X(1, 0, 1, 0, CHI_R5(K21), 0, 0, 0, 0, 0, 0)                                \
+  X(2, 0, 2, 0, CHI_R5(K31), CHI_R5(K32), 0, 0, 0, 0, 0)                      \
+  X(3, 0, 3, 0, CHI_R5(K41), CHI_R5(K42), CHI_R5(K43), 0, 0, 0, 0)            \
+  X(4, 0, 4, 0, CHI_R5(K51), CHI_R5(K52), CHI_R5(K53), CHI_R5(K54), 0, 0, 0)  \
+  X(5, 0, 5, 0, CHI_R5(K61), CHI_R5(K62), CHI_R5(K63), CHI_R5(K64),           \
+    CHI_R5(K65), 0, 0)                                                        \
+  X(6, 0, 6, 2, CHI_R5(K71), 0, CHI_R5(K73), CHI_R5(K74), CHI_R5(K75),        \
+    CHI_R5(K76), 0)                                                           \
+  X(7, 5, 7, 0, 0, 0, 0, 0, 0, CHI_R5(K8D6), CHI_R5(K87))
+
+// out = base + sum_{FIRST <= j < CNT, bit j of SKIP clear} k_j K[j]; `out`
+// may alias `base`
+template <int FIRST, int CNT, int SKIP, int N>
+CHI_HD void lincombk(double* out, const double* base, const double (*K)[N],
+                     double k0, double k1, double k2, double k3, double k4,
+                     double k5, double k6) {
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    double v = base[n];
+    if (FIRST <= 0 && CNT > 0 && !(SKIP & 1)) v = fma(k0, K[0][n], v);
+    if (FIRST <= 1 && CNT > 1 && !(SKIP & 2)) v = fma(k1, K[1][n], v);
+    if (FIRST <= 2 && CNT > 2 && !(SKIP & 4)) v = fma(k2, K[2][n], v);
+    if (FIRST <= 3 && CNT > 3 && !(SKIP & 8)) v = fma(k3, K[3][n], v);
+    if (FIRST <= 4 && CNT > 4 && !(SKIP & 16)) v = fma(k4, K[4][n], v);
+    if (FIRST <= 5 && CNT > 5 && !(SKIP & 32)) v = fma(k5, K[5][n], v);
+    if (FIRST <= 6 && CNT > 6 && !(SKIP & 64)) v = fma(k6, K[6][n], v);
+    out[n] = v;
+  }
+}
 
 // out = base + sum_{j<CNT} k_j U[j]   (base may be null), up to 7 terms
 template <int CNT, int N>
@@ -728,16 +763,20 @@ struct StreamSolver {
   // the column's squared scaled error.
   //   nonlinear models: stage values Zy (shared memory) and increments Uy;
   //     the column-specific terms are selected by a uniform switch per stage.
-  //   linear models: (df/dc_k)(Z) + d/dy[...] U = D_k (Zy + Uy) + e_k with
-  //     D_k, e_k fetched once per column, and V = Zy + Uy was stored by the
-  //     state column (V0 for the first stage), so neither Uy nor the model
-  //     constants are live here.
+  //   linear models (k-stage form, see the K constants): the augmented system
+  //     is linear with the block-triangular Jacobian [[J, 0], [D_k, J]], so
+  //         kappa_i = E arg_i + W^-1 (D_k V_i + e_k),   E = W^-1 J,
+  //     with V_i = arg_i^y + kappa_i^y stored by the state column (V0 for the
+  //     first stage) and D_k, e_k fetched once per column and multiplied
+  //     through by W^-1 once per step: a stage is one combination and two
+  //     N x N products, and neither the state column's increments nor the
+  //     model constants are live here.
   template <bool HAS_TERMS>
   CHI_HD float column(const int kc, const int m, const int nxt,
                       const double (&y)[N], const double (&c)[NCS],
                       const double (&Uy)[NS][N],
                       const double (&V0)[N],
-                      const double (&Wi)[N * N], const double (&Wh)[N * N],
+                      const double (&Wi)[N * N], const double (&E)[N * N],
                       const double hinv, const float atol_f,
                       const float rtol_f) {
     double S0[N], Us[NS][N], Zl[N];
@@ -745,45 +784,44 @@ struct StreamSolver {
     for (int n = 0; n < N; ++n) S0[n] = CHI_S(cur, m, n);
     // HAS_TERMS = false: initial-value column of a linear model, D_k = 0 and
     // e_k = 0 (no column-specific work at all)
-    double DK[N * N], ek[N];
-    if (M::LINEAR && HAS_TERMS) M::col_linear(kc, c, u, DK, ek);
-#define CHI_LSTAGE(I, CNT, INCR, a0, a1, a2, a3, a4, a5, a6, m0, m1, m2, m3,  \
-                   m4, m5, m6)                                                \
+    double WD[N * N], We[N], Vp[N];
+    if (M::LINEAR && HAS_TERMS) {
+      double DK[N * N], ek[N];
+      M::col_linear(kc, c, u, DK, ek);
+      matvec<N>(Wi, ek, We);
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          double acc = Wi[i * N] * DK[j];
+#pragma unroll
+          for (int q = 1; q < N; ++q)
+            acc = fma(Wi[i * N + q], DK[q * N + j], acc);
+          WD[i * N + j] = acc;
+        }
+    }
+#define CHI_KSTAGE(I, FIRST, CNT, SKIP, k0, k1, k2, k3, k4, k5, k6)           \
   {                                                                           \
-    /* linear model, see CHI_RODAS5_LIN_TABLE */                              \
-    double ms[N], rs[N];                                                      \
-    if (INCR) {                                                               \
-      _Pragma("unroll") for (int n = 0; n < N; ++n) Zl[n] +=                  \
-          Us[I > 0 ? I - 1 : 0][n];                                           \
-      lincomb7<CNT, N>(ms, nullptr, Us, m0, m1, m2, m3, m4, m5, m6);          \
-      _Pragma("unroll") for (int n = 0; n < N; ++n) ms[n] =                   \
-          fma(1.0 / GAMMA, Zl[n], ms[n]);                                     \
-    } else {                                                                  \
-      lincomb7<CNT, N>(Zl, S0, Us, a0, a1, a2, a3, a4, a5, a6);               \
-      lincomb7<CNT, N>(ms, S0g, Us, m0, m1, m2, m3, m4, m5, m6);              \
-    }                                                                         \
-    if (HAS_TERMS) {                                                          \
-      _Pragma("unroll") for (int n = 0; n < N; ++n) {                         \
-        double acc = ek[n];                                                   \
+    lincombk<FIRST, CNT, SKIP, N>(Zl, FIRST == 0 ? S0 : Zl, Us, k0, k1, k2,   \
+                                  k3, k4, k5, k6);                            \
+    _Pragma("unroll") for (int n = 0; n < N; ++n) {                           \
+      double acc;                                                             \
+      if (HAS_TERMS) {                                                        \
+        acc = We[n];                                                          \
         _Pragma("unroll") for (int q = 0; q < N; ++q) acc = fma(              \
-            DK[n * N + q], (I == 0) ? V0[q] : CHI_ZY(I, q), acc);             \
-        rs[n] = fma(hinv, ms[n], acc);                                        \
-      }                                                                       \
-      _Pragma("unroll") for (int n = 0; n < N; ++n) {                         \
-        double acc = -Zl[n];                                                  \
+            WD[n * N + q], (I == 0) ? V0[q] : CHI_ZY(I, q), acc);             \
         _Pragma("unroll") for (int q = 0; q < N; ++q) acc =                   \
-            fma(Wi[n * N + q], rs[q], acc);                                   \
-        Us[I][n] = acc;                                                       \
+            fma(E[n * N + q], Zl[q], acc);                                    \
+      } else {                                                                \
+        acc = E[n * N] * Zl[0];                                               \
+        _Pragma("unroll") for (int q = 1; q < N; ++q) acc =                   \
+            fma(E[n * N + q], Zl[q], acc);                                    \
       }                                                                       \
-    } else {                                                                  \
-      /* no column terms: U = (W^-1 / h) m - Z */                             \
-      (void)rs;                                                               \
-      _Pragma("unroll") for (int n = 0; n < N; ++n) {                         \
-        double acc = -Zl[n];                                                  \
-        _Pragma("unroll") for (int q = 0; q < N; ++q) acc =                   \
-            fma(Wh[n * N + q], ms[q], acc);                                   \
-        Us[I][n] = acc;                                                       \
-      }                                                                       \
+      Us[I][n] = acc;                                                         \
+    }                                                                         \
+    if (I == NS - 2) {                                                        \
+      _Pragma("unroll") for (int n = 0; n < N; ++n) Vp[n] =                   \
+          Zl[n] + Us[I][n];                                                   \
     }                                                                         \
   }
 #define CHI_SSTAGE(I, CNT, INCR, a0, a1, a2, a3, a4, a5, a6, c0, c1, c2, c3,  \
@@ -809,13 +847,10 @@ struct StreamSolver {
     matvec<N>(Wi, rs, Us[I]);                                                 \
   }
     if constexpr (M::LINEAR) {
-      double S0g[N];
-#pragma unroll
-      for (int n = 0; n < N; ++n) S0g[n] = S0[n] * (1.0 / GAMMA);
       if constexpr (R5) {
-        CHI_RODAS5_LIN_TABLE(CHI_LSTAGE)
+        CHI_RODAS5_K_TABLE(CHI_KSTAGE)
       } else {
-        CHI_RODAS4_LIN_TABLE(CHI_LSTAGE)
+        CHI_RODAS4_K_TABLE(CHI_KSTAGE)
       }
     } else {
       if constexpr (R5) {
@@ -824,15 +859,17 @@ struct StreamSolver {
         CHI_RODAS4_TABLE(CHI_SSTAGE)
       }
     }
-#undef CHI_LSTAGE
+#undef CHI_KSTAGE
 #undef CHI_SSTAGE
-    // stiffly accurate: new value = last stage value + last increment, the
-    // last increment is the error estimate
+    // stiffly accurate: new value = last stage value + last increment; the
+    // error estimate is the last increment (transformed form) or the
+    // difference to the value after the stage before (k-stage form)
     float s2 = 0.0f;
 #pragma unroll
     for (int n = 0; n < N; ++n) {
       const double Sn = Zl[n] + Us[NS - 1][n];
-      s2 += err_term(Us[NS - 1][n], S0[n], Sn, atol_f, rtol_f);
+      const double en = M::LINEAR ? Sn - Vp[n] : Us[NS - 1][n];
+      s2 += err_term(en, S0[n], Sn, atol_f, rtol_f);
       CHI_S(nxt, m, n) = Sn;
     }
     return s2 * (1.0f / N);
@@ -877,11 +914,21 @@ struct StreamSolver {
           W[i * N + j] = (i == j ? hinv * (1.0 / GAMMA) : 0.0) - J0[i * N + j];
       invert<N>(W, Wi);
     }
-    double Wh[N * N];
+    // E = W^-1 J (= (I - gamma h J)^-1 - I, without the cancellation), used
+    // by the linear-model bodies
+    double E[N * N];
 #pragma unroll
-    for (int i = 0; i < N * N; ++i) Wh[i] = hinv * Wi[i];
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double acc = Wi[i * N] * J0[j];
+#pragma unroll
+        for (int q = 1; q < N; ++q)
+          acc = fma(Wi[i * N + q], J0[q * N + j], acc);
+        E[i * N + j] = acc;
+      }
     double Uy[NS][N];
-    double Zlast[N], V0[N];
+    double Zlast[N], V0[N], Vp[N];
 #define CHI_YSTAGE(I, CNT, INCR, a0, a1, a2, a3, a4, a5, a6, c0, c1, c2, c3,  \
                    c4, c5, c6)                                                \
   {                                                                           \
@@ -903,55 +950,41 @@ struct StreamSolver {
       if (I == 0) V0[n] = v; else CHI_ZY(I, n) = v;                           \
     }                                                                         \
   }
-    // linear models, same identity as in the columns (CHI_RODAS5_LIN_TABLE):
-    // f(Z) = J Z + f(0), so U_i = V_i - Z_i with
-    // V_i = W^-1 ((1/h)(Z_i/gamma + sum_j C_ij U_j) + f(0)) -- and V_i is
-    // exactly what the sensitivity columns need of this stage
-#define CHI_YLSTAGE(I, CNT, INCR, a0, a1, a2, a3, a4, a5, a6, m0, m1, m2, m3, \
-                    m4, m5, m6)                                               \
+    // linear models, k-stage form (see the K constants): f(Z) = J Z + f(0),
+    //     kappa_i = E arg_i + W^-1 f(0),   V_i = arg_i + kappa_i,
+    // and V_i is exactly what the sensitivity columns need of this stage; the
+    // last one is the candidate solution, the one before the embedded one
+#define CHI_YKSTAGE(I, FIRST, CNT, SKIP, k0, k1, k2, k3, k4, k5, k6)          \
   {                                                                           \
-    double my[N], ry[N], V[N];                                                \
-    if (INCR) {                                                               \
-      _Pragma("unroll") for (int n = 0; n < N; ++n) Zlast[n] +=               \
-          Uy[I > 0 ? I - 1 : 0][n];                                           \
-      lincomb7<CNT, N>(my, nullptr, Uy, m0, m1, m2, m3, m4, m5, m6);          \
-      _Pragma("unroll") for (int n = 0; n < N; ++n) my[n] =                   \
-          fma(1.0 / GAMMA, Zlast[n], my[n]);                                  \
-    } else {                                                                  \
-      lincomb7<CNT, N>(Zlast, y, Uy, a0, a1, a2, a3, a4, a5, a6);             \
-      lincomb7<CNT, N>(my, yg, Uy, m0, m1, m2, m3, m4, m5, m6);               \
-    }                                                                         \
-    (void)ry;                                                                 \
+    lincombk<FIRST, CNT, SKIP, N>(Zlast, FIRST == 0 ? y : Zlast, Uy, k0, k1,  \
+                                  k2, k3, k4, k5, k6);                        \
     _Pragma("unroll") for (int n = 0; n < N; ++n) {                           \
       double acc = Wf0[n];                                                    \
       _Pragma("unroll") for (int q = 0; q < N; ++q) acc =                     \
-          fma(Wh[n * N + q], my[q], acc);                                     \
-      V[n] = acc;                                                             \
+          fma(E[n * N + q], Zlast[q], acc);                                   \
+      Uy[I][n] = acc;                                                         \
     }                                                                         \
     _Pragma("unroll") for (int n = 0; n < N; ++n) {                           \
-      Uy[I][n] = V[n] - Zlast[n];                                             \
-      if (I == 0) V0[n] = V[n];                                               \
-      else if (need_v || I == NS - 1) CHI_ZY(I, n) = V[n];                    \
+      const double V = Zlast[n] + Uy[I][n];                                   \
+      if (I == 0) V0[n] = V;                                                  \
+      else if (need_v || I == NS - 1) CHI_ZY(I, n) = V;                       \
+      if (I == NS - 2) Vp[n] = V;                                             \
     }                                                                         \
   }
     if constexpr (M::LINEAR) {
-      double f0[N], yg[N], zero[N];
+      double f0[N], zero[N];
 #pragma unroll
-      for (int n = 0; n < N; ++n) {
-        zero[n] = 0.0;
-        yg[n] = y[n] * (1.0 / GAMMA);
-      }
+      for (int n = 0; n < N; ++n) zero[n] = 0.0;
       M::rhs(zero, c, u, f0);
       // the columns read V_i from shared memory; a forward-only solve only
       // needs the last one (the new state)
       const bool need_v = n_int() > 0;
-      // V_i = (W^-1 / h) m_i + W^-1 f(0)
       double Wf0[N];
       matvec<N>(Wi, f0, Wf0);
       if constexpr (R5) {
-        CHI_RODAS5_LIN_TABLE(CHI_YLSTAGE)
+        CHI_RODAS5_K_TABLE(CHI_YKSTAGE)
       } else {
-        CHI_RODAS4_LIN_TABLE(CHI_YLSTAGE)
+        CHI_RODAS4_K_TABLE(CHI_YKSTAGE)
       }
     } else {
       if constexpr (R5) {
@@ -960,7 +993,7 @@ struct StreamSolver {
         CHI_RODAS4_TABLE(CHI_YSTAGE)
       }
     }
-#undef CHI_YLSTAGE
+#undef CHI_YKSTAGE
 #undef CHI_YSTAGE
     float errsq;
     const float atol_f = static_cast<float>(a.atol);
@@ -973,8 +1006,9 @@ struct StreamSolver {
 #pragma unroll
       for (int n = 0; n < N; ++n) {
         const double yn = Zlast[n] + Uy[NS - 1][n];
+        const double en = M::LINEAR ? yn - Vp[n] : Uy[NS - 1][n];
         if (!M::LINEAR) Zlast[n] = yn;
-        s2 += err_term(Uy[NS - 1][n], y[n], yn, atol_f, rtol_f);
+        s2 += err_term(en, y[n], yn, atol_f, rtol_f);
       }
       errsq = s2 * (1.0f / N);
     }
@@ -991,14 +1025,14 @@ struct StreamSolver {
       // initial-value columns first (they lead the list): no column terms
       for (; m < ni && a.int_param[m] < N; ++m)
         errsq = fmaxf(errsq,
-                      column<false>(-1, m, nxt, y, c, Uy, V0, Wi, Wh, hinv,
+                      column<false>(-1, m, nxt, y, c, Uy, V0, Wi, E, hinv,
                                     atol_f, rtol_f));
     }
     for (; m < ni; ++m) {
       const int pk = a.int_param[m];
       const int kc = pk >= N ? pk - N : -1;
       errsq = fmaxf(errsq,
-                    column<true>(kc, m, nxt, y, c, Uy, V0, Wi, Wh, hinv,
+                    column<true>(kc, m, nxt, y, c, Uy, V0, Wi, E, hinv,
                                  atol_f, rtol_f));
     }
 
