@@ -63,6 +63,9 @@ def parse_args():
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--spread', type=float, default=0.01,
+                    help='relative spread of the parameter vectors of one '
+                         'step around the data-generating values')
     return ap.parse_args()
 
 
@@ -79,6 +82,7 @@ def workload_config(args, n_gpus):
         'n_ids': args.n_ids, 'chains_per_step_per_gpu': args.chains,
         'n_obs': args.n_obs, 'n_doses': args.n_doses,
         'rtol': args.rtol, 'atol': args.atol,
+        'parameter_spread': args.spread,
         'parallelism': '%s-sharded x%d' % (args.shard, n_gpus),
         'l2': 'flushed between timed steps (256 MiB write)',
     }
@@ -577,7 +581,7 @@ def run_product(args, rank, world, local_rank):
         rank if args.shard == 'chains' else 0))
     X_host = _lib.pinned_empty((C, n_params))
     X_host[:] = prob['x0'][None, :] * (
-        1.0 + 0.01 * rng.normal(size=(C, n_params)))
+        1.0 + args.spread * rng.normal(size=(C, n_params)))
     d_x = torch.from_numpy(np.array(X_host)).to(dev)
     d_score = torch.empty(C, dtype=torch.float64, device=dev)
     d_grad = torch.zeros(C, n_params, dtype=torch.float64, device=dev)

@@ -1209,9 +1209,22 @@ observe_kernel(const SolveArgs a) {
   if (b < a.B) observe_system<M>(a, b);
 }
 
-// Persistent kernel: every lane pulls systems from a global counter and
-// refills itself as soon as its system is finished, so lanes whose systems
-// need fewer steps do not idle and there is no partial last wave.
+// Persistent kernel: the lanes pull systems from a global counter, in the
+// work order of SolveArgs::order_inner.  With refill_wait = 0 every lane
+// refills itself as soon as its system is finished (lanes whose systems need
+// fewer steps do not idle); with a warp's worth of parameter vectors per
+// individual the warp refills as a whole instead, which keeps its lanes --
+// same individual, same stops -- in phase.  No partial last wave either way.
+
+// work item -> system (SolveArgs::order_inner)
+__device__ __forceinline__ int64_t stream_system_of(const SolveArgs& a,
+                                                    const unsigned long long w) {
+  if (a.order_inner <= 1) return static_cast<int64_t>(w);
+  const unsigned long long q = w / static_cast<unsigned>(a.order_inner);
+  const unsigned long long r = w - q * static_cast<unsigned>(a.order_inner);
+  return static_cast<int64_t>(r * static_cast<unsigned>(a.order_stride) + q);
+}
+
 template <class M, int CB, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, M::STREAM_MIN_BLOCKS)
 solve_stream_kernel(const SolveArgs a, unsigned long long* counter) {
@@ -1219,18 +1232,38 @@ solve_stream_kernel(const SolveArgs a, unsigned long long* counter) {
   StreamSolver<M, CB> s(a, chi_sm + threadIdx.x, BLOCK);
   bool active = false;
   bool exhausted = false;
+  int waited = 0;
+  const unsigned long long total = static_cast<unsigned long long>(a.B);
   for (;;) {
-    if (!active && !exhausted) {
-      const unsigned long long b = atomicAdd(counter, 1ull);
-      if (b >= static_cast<unsigned long long>(a.B)) {
+    // Refill.  A warp whose lanes are all done takes 32 consecutive work
+    // items at once; a single idle lane waits up to `refill_wait` iterations
+    // for the rest of its warp (which keeps the lanes in phase when they
+    // integrate the same individual, SolveArgs::order_inner) and then takes
+    // the next item on its own.  refill_wait = 0: no waiting.
+    if (!__any_sync(0xffffffffu, active)) {
+      unsigned long long base = 0;
+      if ((threadIdx.x & 31) == 0) base = atomicAdd(counter, 32ull);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= total) break;
+      const unsigned long long w = base + (threadIdx.x & 31);
+      if (w < total) {
+        s.init(stream_system_of(a, w));
+        active = true;
+      } else {
+        exhausted = true;
+      }
+      waited = 0;
+    } else if (!active && !exhausted &&
+               (waited < a.refill_wait ? (++waited, false) : true)) {
+      const unsigned long long w = atomicAdd(counter, 1ull);
+      if (w >= total) {
         exhausted = true;
       } else {
-        s.init(static_cast<int64_t>(b));
+        s.init(stream_system_of(a, w));
         active = true;
       }
+      waited = 0;
     }
-    // all 32 lanes stay in the loop until the warp has no work left
-    if (!__any_sync(0xffffffffu, active)) break;
     bool done = active ? s.events() : true;
     // the vote is the convergence point: lanes that refilled or handled an
     // event re-join the others here, so the (expensive) step below is

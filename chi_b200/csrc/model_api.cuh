@@ -92,6 +92,20 @@ struct SolveArgs {
   double* snap;
   int32_t snap_rows;         // rows per system (max records per individual)
   int32_t snap_width;        // N * (1 + integrated columns)
+
+  // Order in which the persistent kernel hands out the systems.  With
+  // order_inner = C > 1 and order_stride = n (systems laid out chain-major,
+  // b = chain * n + individual) work item w is system
+  //     b = (w % C) * n + w / C,
+  // i.e. the lanes of a warp integrate the SAME individual under different
+  // parameter vectors: same dose edges and observation times, so the lanes
+  // reach their stops in (nearly) the same iterations and the event handler
+  // runs with many active lanes instead of one or two.  0: b = w.
+  int32_t order_inner, order_stride;
+  // iterations an idle lane waits for the rest of its warp to finish before
+  // it refills on its own (a warp whose lanes are all idle always refills as
+  // a whole, 32 consecutive work items); 0: no waiting
+  int32_t refill_wait;
 };
 
 // What a compiled model contributes to the registry of the core library.

@@ -48,6 +48,8 @@ class SolveArgs(ctypes.Structure):
         ('status', _vp), ('n_steps', _vp), ('n_rej', _vp),
         ('snap', _vp), ('snap_rows', ctypes.c_int32),
         ('snap_width', ctypes.c_int32),
+        ('order_inner', ctypes.c_int32), ('order_stride', ctypes.c_int32),
+        ('refill_wait', ctypes.c_int32),
     ]
 
 
