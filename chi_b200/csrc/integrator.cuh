@@ -680,14 +680,15 @@ struct Registrar {
       if (err != cudaSuccess) return err;
     }
     if (args.B == 0) return cudaSuccess;
-    err = cudaMemsetAsync(counters[dev], 0, sizeof(unsigned long long),
-                          stream);
+    unsigned long long* counter =
+        args.work_counter ? args.work_counter : counters[dev];
+    err = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return err;
     int64_t blocks = (args.B + STREAM_BLOCK - 1) / STREAM_BLOCK;
     if (blocks > resident[dev]) blocks = resident[dev];
     solve_stream_kernel<M, CB, STREAM_BLOCK>
         <<<static_cast<unsigned>(blocks), STREAM_BLOCK, smem, stream>>>(
-            args, counters[dev]);
+            args, counter);
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     if (args.mode == 1 && args.snap) {

@@ -106,6 +106,9 @@ struct SolveArgs {
   // it refills on its own (a warp whose lanes are all idle always refills as
   // a whole, 32 consecutive work items); 0: no waiting
   int32_t refill_wait;
+  // work counter of the persistent kernel (one per launch that may be in
+  // flight at a time); null: the launcher's own per-device counter
+  unsigned long long* work_counter;
 };
 
 // What a compiled model contributes to the registry of the core library.

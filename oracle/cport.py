@@ -49,7 +49,7 @@ class SolveArgs(ctypes.Structure):
         ('snap', _vp), ('snap_rows', ctypes.c_int32),
         ('snap_width', ctypes.c_int32),
         ('order_inner', ctypes.c_int32), ('order_stride', ctypes.c_int32),
-        ('refill_wait', ctypes.c_int32),
+        ('refill_wait', ctypes.c_int32), ('work_counter', _vp),
     ]
 
 
