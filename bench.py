@@ -96,7 +96,8 @@ def flops_per_step(n, n_cols, info, stages=6, n_init=0):
     """Algorithmic flops of one Rosenbrock step attempt of one system (RODAS4:
     6 stages, RODAS5: 8): the state column once + the n_cols integrated
     sensitivity columns (FMA = 2, every other FP64 operation 1)."""
-    linear = bool(info[3])
+    linear = bool(info[3] & 1)
+    rank1 = bool(info[3] & 2)
     f_rhs, f_jac, f_col_sum, f_hess_common = [int(v) for v in info[4:8]]
     s = stages
     pairs = s * (s - 1) // 2              # (i, j<i) pairs of the stage table
@@ -127,14 +128,21 @@ def flops_per_step(n, n_cols, info, stages=6, n_init=0):
         # W^-1 D_k out once per step and executes a dense product instead:
         # slightly more than is counted here)
         sens = plain + s * (mv + n)
-        state -= min(n_init, n_cols) * s * (mv + n)   # term-free columns
+        if rank1:
+            # every D_k has one non-zero column q: D_k V + e_k = d_k V[q] +
+            # e_k, so a stage adds (W^-1 d_k) V[q] + W^-1 e_k (n FMAs), with
+            # W^-1 d_k and W^-1 e_k formed once per step; nothing of the
+            # column terms is left for `extra`
+            sens = plain + s * 2 * n + 2 * mv
+        state -= min(n_init, n_cols) * (sens - plain)   # term-free columns
     else:
         state = comb_a + comb_c + s * 2 * n + s * f_rhs + solve
         # per column: stage combinations, J Z_s, + hinv * combination, solves
         sens = comb_a + comb_c + s * 2 * n + s * n * (2 * n - 1) + solve
     # column-specific terms (df/dc_k and its y-derivative) of all columns and
     # the column-independent second-order term, per stage
-    extra = s * (f_col_sum + n_cols * f_hess_common)
+    extra = 0 if (linear and rank1) else \
+        s * (f_col_sum + n_cols * f_hess_common)
     jac = (0 if linear else (s + 1) * f_jac) if n_cols else (
         0 if linear else f_jac)
     # new solution = last stage value + last increment (nonlinear) / error

@@ -205,6 +205,11 @@ class ModelCode(object):
         # so the column terms of a stage are one small matrix-vector product
         # with data fetched once per column (no switch inside the stages)
         lin_cases = []
+        # ... and when every D_k has at most one non-zero column q_k (a
+        # constant that multiplies one state, the mass-action case),
+        # (df/dc_k)(y) = d_k y[q_k] + e_k: a scalar times a vector per stage
+        r1_cases = []
+        col_rank1 = bool(self.linear)
         if self.linear:
             for k in range(nc):
                 col = sp.Matrix([fc[i, k] for i in range(n)])
@@ -221,6 +226,23 @@ class ModelCode(object):
                     code, _ = _emit_block(items, indent='        ')
                     lin_cases.append(
                         '      case %d: {\n%s\n        break; }' % (k, code))
+                nzcols = [j for j in range(n)
+                          if any(Dk[i, j] != 0 for i in range(n))]
+                if len(nzcols) > 1:
+                    col_rank1 = False
+                elif col_rank1:
+                    q = nzcols[0] if nzcols else 0
+                    items = [('d[%d]' % i, Dk[i, q]) for i in range(n)
+                             if nzcols and Dk[i, q] != 0]
+                    items += [('e[%d]' % i, ek[i]) for i in range(n)
+                              if ek[i] != 0]
+                    if items:
+                        code, _ = _emit_block(items, indent='        ')
+                        r1_cases.append(
+                            '      case %d: {\n%s\n        q = %d;\n'
+                            '        break; }' % (k, code, q))
+        if not col_rank1:
+            r1_cases = []
 
         out_cases = []
         dout_cases = []
@@ -340,6 +362,22 @@ class ModelCode(object):
         lines.extend(lin_cases)
         a('      default: break;')
         a('    }')
+        a('  }')
+        a('  // linear models whose D_k all have at most one non-zero column:')
+        a('  // (df/dc_k)(y) = d y[q] + e, returns q')
+        a('  static constexpr bool COL_RANK1 = %s;' % (
+            'true' if col_rank1 else 'false'))
+        a('  CHI_HD static int col_rank1(int k, const double* c, double u, '
+          'double* d, double* e) {')
+        a('    (void)c; (void)u;')
+        a('    for (int j = 0; j < N; ++j) d[j] = 0.0;')
+        a('    for (int j = 0; j < N; ++j) e[j] = 0.0;')
+        a('    int q = 0;')
+        a('    switch (k) {')
+        lines.extend(r1_cases)
+        a('      default: break;')
+        a('    }')
+        a('    return q;')
         a('  }')
         a('  CHI_HD static double out(int id, const double* y, '
           'const double* c) {')

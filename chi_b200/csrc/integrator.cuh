@@ -825,7 +825,8 @@ struct Registrar {
     vt.n_states = M::N;
     vt.n_consts = M::NC;
     vt.n_outputs = M::NOUT;
-    vt.linear = M::LINEAR ? 1 : 0;
+    // bit 0: linear in the states; bit 1: rank-one column terms (COL_RANK1)
+    vt.linear = (M::LINEAR ? 1 : 0) | ((M::LINEAR && M::COL_RANK1) ? 2 : 0);
     vt.flops_rhs = M::FLOPS_RHS;
     vt.flops_jac = M::FLOPS_JAC;
     vt.flops_dfdc = M::FLOPS_DFDC;

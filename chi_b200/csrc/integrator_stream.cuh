@@ -784,32 +784,54 @@ struct StreamSolver {
     for (int n = 0; n < N; ++n) S0[n] = CHI_S(cur, m, n);
     // HAS_TERMS = false: initial-value column of a linear model, D_k = 0 and
     // e_k = 0 (no column-specific work at all)
-    double WD[N * N], We[N], Vp[N];
+    // COL_RANK1: every D_k has a single non-zero column q (the constant
+    // multiplies one state), D_k V = d_k V[q]: W^-1 d_k once per step, one
+    // shared-memory load and N FMAs per stage instead of N and N^2
+    constexpr bool R1 = M::LINEAR && M::COL_RANK1;
+    double WD[R1 ? N : N * N], We[N], Vp[N];
+    int q1 = 0;
+    double v0 = V0[0];
     if (M::LINEAR && HAS_TERMS) {
-      double DK[N * N], ek[N];
-      M::col_linear(kc, c, u, DK, ek);
-      matvec<N>(Wi, ek, We);
+      if constexpr (R1) {
+        double dk[N], ek[N];
+        q1 = M::col_rank1(kc, c, u, dk, ek);
+        matvec<N>(Wi, ek, We);
+        matvec<N>(Wi, dk, WD);
 #pragma unroll
-      for (int i = 0; i < N; ++i)
+        for (int j = 1; j < N; ++j) v0 = (q1 == j) ? V0[j] : v0;
+      } else {
+        double DK[N * N], ek[N];
+        M::col_linear(kc, c, u, DK, ek);
+        matvec<N>(Wi, ek, We);
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-          double acc = Wi[i * N] * DK[j];
+        for (int i = 0; i < N; ++i)
 #pragma unroll
-          for (int q = 1; q < N; ++q)
-            acc = fma(Wi[i * N + q], DK[q * N + j], acc);
-          WD[i * N + j] = acc;
-        }
+          for (int j = 0; j < N; ++j) {
+            double acc = Wi[i * N] * DK[j];
+#pragma unroll
+            for (int q = 1; q < N; ++q)
+              acc = fma(Wi[i * N + q], DK[q * N + j], acc);
+            WD[i * N + j] = acc;
+          }
+      }
     }
 #define CHI_KSTAGE(I, FIRST, CNT, SKIP, k0, k1, k2, k3, k4, k5, k6)           \
   {                                                                           \
     lincombk<FIRST, CNT, SKIP, N>(Zl, FIRST == 0 ? S0 : Zl, Us, k0, k1, k2,   \
                                   k3, k4, k5, k6);                            \
+    double vq = 0.0;                                                          \
+    if (HAS_TERMS && R1) vq = (I == 0) ? v0 : CHI_ZY(I, q1);                  \
     _Pragma("unroll") for (int n = 0; n < N; ++n) {                           \
       double acc;                                                             \
       if (HAS_TERMS) {                                                        \
-        acc = We[n];                                                          \
-        _Pragma("unroll") for (int q = 0; q < N; ++q) acc = fma(              \
-            WD[n * N + q], (I == 0) ? V0[q] : CHI_ZY(I, q), acc);             \
+        if (R1) {                                                             \
+          acc = fma(WD[n], vq, We[n]);                                        \
+        } else {                                                              \
+          acc = We[n];                                                        \
+          _Pragma("unroll") for (int q = 0; q < N; ++q) acc = fma(            \
+              WD[(R1 ? 0 : n * N) + q], (I == 0) ? V0[q] : CHI_ZY(I, q),      \
+              acc);                                                           \
+        }                                                                     \
         _Pragma("unroll") for (int q = 0; q < N; ++q) acc =                   \
             fma(E[n * N + q], Zl[q], acc);                                    \
       } else {                                                                \

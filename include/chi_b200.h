@@ -76,7 +76,9 @@ int chi_b200_host_free(void* ptr);
  * per model) and register themselves when their shared object is loaded. */
 int chi_b200_n_models(void);
 int chi_b200_model_find(const char* key);
-/* info: n_states, n_consts, n_outputs, linear, and op counts of the generated
+/* info: n_states, n_consts, n_outputs, linear (bit 0: rhs linear in the
+ * states; bit 1: every constant's column term has a single non-zero column,
+ * the mass-action case), and op counts of the generated
  * code: rhs, Jacobian, the column-specialised sensitivity terms summed over
  * the constants that enter the rhs, and the column-independent second-order
  * term (zero for linear models) */
