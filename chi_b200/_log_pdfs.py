@@ -770,16 +770,41 @@ class HierarchicalLogPosterior(_LogPDFBase):
         sensitivities[self._n_bottom:] += sens
         return score, sensitivities
 
+    def _prior_batch(self, top, with_grad):
+        """Prior (and its gradient) of every row of ``top`` on the host."""
+        if hasattr(self._log_prior, 'evaluateS1_batch'):
+            p, s = self._log_prior.evaluateS1_batch(top)
+            return p, (s if with_grad else None)
+        if not with_grad:
+            return np.array([self._log_prior(x) for x in top]), None
+        p = np.empty(len(top))
+        s = np.empty(top.shape)
+        for c, x in enumerate(top):
+            p[c], s[c] = self._log_prior.evaluateS1(x)
+        return p, s
+
+    def _prior_async(self, X, with_grad):
+        """Starts the host prior on a worker thread so that it runs while the
+        calling thread waits for the GPU inside the (GIL-free) library call;
+        returns a future."""
+        pool = getattr(HierarchicalLogPosterior, '_pool', None)
+        if pool is None:
+            import concurrent.futures
+            pool = concurrent.futures.ThreadPoolExecutor(
+                1, thread_name_prefix='chi_b200-prior')
+            HierarchicalLogPosterior._pool = pool
+        return pool.submit(self._prior_batch, X[:, self._n_bottom:], with_grad)
+
     def evaluate_batch(self, X, copy=True):
         """Batched ``__call__``: the prior is evaluated per vector on the
-        host (top-level slice only), all likelihoods in one GPU pass."""
+        host (top-level slice only, concurrently with the GPU pass), all
+        likelihoods in one GPU pass."""
         X = np.asarray(X, dtype=float).reshape(-1, self._n_parameters)
-        if hasattr(self._log_prior, 'evaluateS1_batch'):
-            prior = self._log_prior.evaluateS1_batch(X[:, self._n_bottom:])[0]
-        else:
-            prior = np.array(
-                [self._log_prior(x[self._n_bottom:]) for x in X])
-        score = self._log_likelihood.evaluate_batch(X, copy=False)
+        future = self._prior_async(X, False)
+        try:
+            score = self._log_likelihood.evaluate_batch(X, copy=False)
+        finally:
+            prior = future.result()[0]
         score = prior + score
         score[np.isinf(prior)] = prior[np.isinf(prior)]
         return score
@@ -788,24 +813,20 @@ class HierarchicalLogPosterior(_LogPDFBase):
         """Batched ``evaluateS1``.  With ``copy=False`` the results are views
         of the page-locked result buffers (valid until the next call)."""
         X = np.asarray(X, dtype=float).reshape(-1, self._n_parameters)
-        score, grad = self._log_likelihood.evaluateS1_batch(X, copy=False)
-        if hasattr(self._log_prior, 'evaluateS1_batch'):
-            p, s = self._log_prior.evaluateS1_batch(X[:, self._n_bottom:])
-            bad = np.isinf(p)
-            score += p
-            grad[:, self._n_bottom:] += s
-            if np.any(bad):
-                score[bad] = p[bad]
-                grad[bad] = np.inf
-        else:
-            for c, x in enumerate(X):
-                p, s = self._log_prior.evaluateS1(x[self._n_bottom:])
-                if np.isinf(p):
-                    score[c] = p
-                    grad[c] = np.inf
-                    continue
-                score[c] += p
-                grad[c, self._n_bottom:] += s
+        future = self._prior_async(X, True)
+        try:
+            score, grad = self._log_likelihood.evaluateS1_batch(
+                X, copy=False)
+        finally:
+            p, s = future.result()
+        bad = np.isinf(p)
+        score += p
+        if np.any(bad):
+            s = np.where(bad[:, None], 0.0, s)
+        grad[:, self._n_bottom:] += s
+        if np.any(bad):
+            score[bad] = p[bad]
+            grad[bad] = np.inf
         if copy:
             return score.copy(), grad.copy()
         return score, grad
