@@ -192,7 +192,16 @@ int chi_b200_population_eval(chi_b200_problem* p, const double* top,
  * the shard of individuals evaluated by this call (multi-GPU).  With a shard
  * set, only the shard's block of bottom-level entries and the top-level
  * entries of x are read, and only those two column blocks of grad are
- * written (partial sums for the top level); the rest of grad is untouched. */
+ * written (partial sums for the top level); the rest of grad is untouched.
+ * The host-buffer entry point evaluates large batches in chunks on two
+ * streams so that the copies overlap the solves (environment
+ * CHI_B200_CHUNKS forces the number of chunks, 1 = one pass); page-locked
+ * host buffers are needed for the overlap, not for correctness.  The call
+ * returns when all results are in the caller's buffers.
+ * With at least 32 vectors the persistent solve kernel hands the systems out
+ * individual-major, one individual per warp (CHI_B200_ORDER = smallest C for
+ * which it does, 0 = never; CHI_B200_REFILL_WAIT = iterations an idle lane
+ * waits for its warp before it refills alone); results do not depend on it. */
 int chi_b200_hier_logpdf(chi_b200_problem* p, int32_t C, const double* x,
                          int32_t with_grad, double* score, double* grad,
                          int32_t* status);
