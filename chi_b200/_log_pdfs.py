@@ -655,6 +655,15 @@ class HierarchicalLogLikelihood(object):
         fused in the solve kernel, -1: default)."""
         self._device.set_snapshot_budget(n_bytes)
 
+    def set_batching(self, n_chunks=-1, order_min_vectors=-1, refill_wait=-1):
+        """See ``chi_b200_problem_set_batching``: how a batch of parameter
+        vectors is worked through (chunks of the host entry point, work order
+        and refill policy of the solve kernel); -1 keeps the default.  The
+        results do not depend on it."""
+        _lib.check(_lib.lib().chi_b200_problem_set_batching(
+            self._device.problem.handle, int(n_chunks),
+            int(order_min_vectors), int(refill_wait)))
+
     def set_timing(self, enabled):
         _lib.check(_lib.lib().chi_b200_problem_set_timing(
             self._device.problem.handle, 1 if enabled else 0))

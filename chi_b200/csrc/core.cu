@@ -113,6 +113,8 @@ struct chi_b200_problem {
   // the work counters of the solve launches that may be in flight together
   cudaStream_t stream2 = nullptr;
   DevBuf work_counters;
+  // chi_b200_problem_set_batching: -1 = default (environment, then built-in)
+  int32_t cfg_chunks = -1, cfg_order = -1, cfg_wait = -1;
 
   // configuration
   int32_t n_out = 0;
@@ -816,6 +818,15 @@ int chi_b200_problem_set_snapshot_budget(chi_b200_problem* p, int64_t bytes) {
   return 0;
 }
 
+int chi_b200_problem_set_batching(chi_b200_problem* p, int32_t n_chunks,
+                                  int32_t order_min_vectors,
+                                  int32_t refill_wait) {
+  p->cfg_chunks = n_chunks;
+  p->cfg_order = order_min_vectors;
+  p->cfg_wait = refill_wait;
+  return 0;
+}
+
 int chi_b200_problem_timings(chi_b200_problem* p, double out[2]) {
   out[0] = p->solve_ms_sum;
   out[1] = static_cast<double>(p->solve_launches);
@@ -1057,12 +1068,14 @@ int launch_loglik(chi_b200_problem* p, int64_t B, const int32_t* d_ids,
       const char* e = std::getenv("CHI_B200_REFILL_WAIT");
       return e ? std::atoi(e) : -1;
     }();
-    const bool ordered = min_inner > 0 && order_inner >= min_inner;
+    const int min_vectors = p->cfg_order >= 0 ? p->cfg_order : min_inner;
+    const int wait = p->cfg_wait >= 0 ? p->cfg_wait : wait_env;
+    const bool ordered = min_vectors > 0 && order_inner >= min_vectors;
     if (ordered) {
       a.order_inner = order_inner;
       a.order_stride = order_stride;
     }
-    a.refill_wait = wait_env >= 0 ? wait_env : (ordered ? INT32_MAX : 0);
+    a.refill_wait = wait >= 0 ? wait : (ordered ? INT32_MAX : 0);
   }
   {
     // deferred observation for the streamed kernels when the snapshots fit
@@ -1589,7 +1602,9 @@ int chi_b200_hier_logpdf(chi_b200_problem* p, int32_t C, const double* x,
     return e ? std::atoi(e) : 0;
   }();
   int n_chunks = 1;
-  if (chunks_env > 0) {
+  if (p->cfg_chunks > 0) {
+    n_chunks = p->cfg_chunks;
+  } else if (chunks_env > 0) {
     n_chunks = chunks_env;
   } else if (!p->timing && C >= 128 &&
              static_cast<size_t>(C) * (sharded ? w_b + w_t : pitch) >=

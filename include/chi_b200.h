@@ -234,6 +234,16 @@ int chi_b200_problem_timings(chi_b200_problem* p, double out[2]);
  * CHI_B200_SNAP_MB); 0 keeps the observation fused in the solve kernel,
  * -1 restores the default. */
 int chi_b200_problem_set_snapshot_budget(chi_b200_problem* p, int64_t bytes);
+/* How a batch of parameter vectors is worked through (see
+ * chi_b200_hier_logpdf): number of chunks of the host-buffer entry point,
+ * smallest number of vectors for which the solve kernel hands the systems out
+ * individual-major (0: never), and the iterations an idle lane waits for its
+ * warp before it refills alone.  -1 for any of them: the default (which the
+ * CHI_B200_CHUNKS / CHI_B200_ORDER / CHI_B200_REFILL_WAIT environment
+ * variables override).  Results do not depend on these settings. */
+int chi_b200_problem_set_batching(chi_b200_problem* p, int32_t n_chunks,
+                                  int32_t order_min_vectors,
+                                  int32_t refill_wait);
 /* measured FP64 FMA throughput of the device (DFMA micro-kernel) */
 int chi_b200_fp64_peak(int32_t device, double* tflops, double* sm_clock_mhz);
 

@@ -746,6 +746,53 @@ def test_individual_shards_sum_to_the_full_evaluation():
 
 
 @pytest.mark.gpu
+def test_results_do_not_depend_on_how_the_batch_is_worked_through():
+    """Chunks of the host entry point on two streams, individual-major work
+    order and whole-warp refill of the persistent solve kernel
+    (chi_b200_problem_set_batching) only change the schedule: every system
+    runs the same arithmetic and every vector's reduction keeps its order, so
+    scores and gradients are bit-identical to the plain pass -- with and
+    without a shard of individuals, with and without gradient."""
+    from chi_b200 import _synthetic
+    n_ids = 37
+    prob = _synthetic.two_compartment_problem(
+        n_ids=n_ids, seed=5, n_obs=7, n_doses=3, rtol=1e-6, atol=1e-8)
+    ll = prob['log_likelihood']
+    n_params = len(prob['x0'])
+    rng = np.random.default_rng(4)
+    C = 77   # not a multiple of the warp size or of the chunk count
+    X = prob['x0'][None, :] * (1 + 0.05 * rng.normal(size=(C, n_params)))
+    X[5, -1] = -0.1       # invalid sigma: -inf score, inf gradient
+    ll.set_batching(n_chunks=1, order_min_vectors=0, refill_wait=0)
+    with np.errstate(all='ignore'):
+        ref_s, ref_g = ll.evaluateS1_batch(X)
+        ref_f = ll.evaluate_batch(X)
+    assert np.isneginf(ref_s[5]) and np.all(np.isfinite(np.delete(ref_s, 5)))
+    settings = [(3, 0, 0), (1, 32, -1), (1, 32, 0), (1, 32, 5), (4, 32, -1),
+                (8, 16, 2), (-1, -1, -1)]
+    for chunks, order, wait in settings:
+        ll.set_batching(chunks, order, wait)
+        with np.errstate(all='ignore'):
+            s, g = ll.evaluateS1_batch(X)
+            f = ll.evaluate_batch(X)
+        np.testing.assert_array_equal(s, ref_s)
+        np.testing.assert_array_equal(g, ref_g)
+        np.testing.assert_array_equal(f, ref_f)
+    # the same under a shard of individuals (column blocks copied per chunk)
+    ll.set_shard(11, 30)
+    ll.set_batching(1, 0, 0)
+    with np.errstate(all='ignore'):
+        sh_s, sh_g = ll.evaluateS1_batch(X)
+    ll.set_batching(4, 32, -1)
+    with np.errstate(all='ignore'):
+        s, g = ll.evaluateS1_batch(X)
+    np.testing.assert_array_equal(s, sh_s)
+    np.testing.assert_array_equal(g, sh_g)
+    ll.set_shard(0, n_ids)
+    ll.set_batching()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize('name', ['tgi_direct_daily', 'two_cmt_indirect_indefinite'])
 def test_log_likelihood_nonlinear_and_indirect_models(name):
     """LogLikelihood.evaluateS1 of the nonlinear erlotinib TGI model (30 daily
