@@ -349,3 +349,82 @@ def test_bench_host_design_matches_synthetic():
         np.testing.assert_array_equal(np.array(a), b.as_array())
     np.testing.assert_array_equal(
         bench.TWO_CMT_TYPICAL, _synthetic.TWO_CMT_TYPICAL)
+
+
+def test_k_stage_tables_follow_from_the_transformed_tables():
+    """The K_ij constants of the linear-model bodies (k-stage form,
+    chi_b200/csrc/integrator_stream.cuh) are (alpha + Gamma_offdiag) / gamma
+    of the same method whose transformed tables (a_ij, C_ij, gamma) the
+    nonlinear bodies use: re-derive them (tools/derive_kform.py) and compare;
+    also the structure the RODAS5 body relies on -- K72 = K82 = 0, row 8 = row
+    7 + two entries -- and that one k-form step of a random linear system
+    reproduces the transformed form."""
+    import importlib.util
+    import mpmath as mp
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location(
+        'derive_kform', os.path.join(root, 'tools', 'derive_kform.py'))
+    dk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(dk)
+    for name, path, s in (
+            ('rodas4', 'chi_b200/csrc/integrator.cuh', 6),
+            ('rodas5', 'chi_b200/csrc/integrator_stream.cuh', 8)):
+        vals = dk.read_namespace(os.path.join(root, path), name)
+        g, alpha, G, beta = dk.derive(vals, s)
+        K = np.array([[float(beta[i, j] / g) for j in range(s)]
+                      for i in range(s)])
+        typed = np.zeros((s, s))
+        for i in range(1, s):
+            for j in range(i):
+                key = 'K%d%d' % (i + 1, j + 1)
+                if key in vals:
+                    typed[i, j] = float(vals[key])
+        if name == 'rodas5':
+            assert abs(K[6, 1]) < 1e-13 and abs(K[7, 1]) < 1e-13
+            np.testing.assert_allclose(K[7, :5], K[6, :5], atol=1e-13)
+            typed[7, :5] = typed[6, :5]
+            typed[7, 5] = typed[6, 5] + float(vals['K8D6'])
+            K[6, 1] = K[7, 1] = 0.0
+        np.testing.assert_allclose(typed, K, rtol=1e-13, atol=1e-14)
+        # one step of z' = J z + f0, transformed form vs k-stage form
+        a = np.zeros((s, s))
+        C = np.zeros((s, s))
+        for i in range(1, s):
+            have = ('A%d1' % (i + 1)) in vals
+            for j in range(i):
+                C[i, j] = float(vals['C%d%d' % (i + 1, j + 1)])
+                a[i, j] = float(vals['A%d%d' % (i + 1, j + 1)]) if have \
+                    else (a[i - 1, j] if j < i - 1 else 1.0)
+        rng = np.random.default_rng(0)
+        n, h, gam = 3, 0.37, float(g)
+        J = rng.normal(size=(n, n))
+        f0 = rng.normal(size=n)
+        y = rng.normal(size=n)
+        Wi = np.linalg.inv(np.eye(n) / (gam * h) - J)
+        U = np.zeros((s, n))
+        for i in range(s):
+            Z = y + a[i, :i] @ U[:i]
+            U[i] = Wi @ (J @ Z + f0 + (C[i, :i] @ U[:i]) / h)
+        y_new, err = Z + U[s - 1], U[s - 1]
+        E = Wi @ J
+        kap = np.zeros((s, n))
+        V = np.zeros((s, n))
+        for i in range(s):
+            arg = y + typed[i, :i] @ kap[:i]
+            kap[i] = E @ arg + Wi @ f0
+            V[i] = arg + kap[i]
+        np.testing.assert_allclose(V[s - 1], y_new, rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(V[s - 1] - V[s - 2], err, atol=1e-12)
+
+
+def test_flop_model_of_the_bench_counts_the_k_stage_form():
+    """bench.flops_per_step for the two-compartment model (DESIGN.md,
+    'Algorithmic flops'): N = 2, 5 integrated columns of which 2 are
+    initial-value columns; info = chi_b200_model_info."""
+    import bench
+    info = np.array([2, 5, 4, 3, 6, 3, 10, 0])   # linear, rank-one terms
+    assert bench.flops_per_step(2, 5, info, stages=8, n_init=2) == 1048
+    assert bench.flops_per_step(2, 0, info, stages=8, n_init=2) == 206
+    dense = info.copy()
+    dense[3] = 1                                  # linear, dense column terms
+    assert bench.flops_per_step(2, 5, dense, stages=8, n_init=2) == 1188
