@@ -56,6 +56,21 @@ class SolveArgs(ctypes.Structure):
 _lib = None
 
 
+def _configure(port):
+    port.chi_port_solve.argtypes = [
+        ctypes.c_char_p, ctypes.POINTER(SolveArgs), ctypes.c_int]
+    port.chi_port_fill_integrated.argtypes = [
+        ctypes.c_char_p, ctypes.POINTER(SolveArgs)]
+    port.chi_port_snap_width.argtypes = [
+        ctypes.c_char_p, ctypes.POINTER(SolveArgs)]
+    port.chi_port_solve2.argtypes = [
+        ctypes.c_char_p, ctypes.POINTER(SolveArgs), ctypes.c_int,
+        ctypes.c_int]
+    assert port.chi_port_sizeof_args() == ctypes.sizeof(SolveArgs), (
+        port.chi_port_sizeof_args(), ctypes.sizeof(SolveArgs))
+    return port
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -63,19 +78,14 @@ def lib():
         if not os.path.exists(path):
             from oracle.csolver import build
             build.build()
-        _lib = ctypes.CDLL(path)
-        _lib.chi_port_solve.argtypes = [
-            ctypes.c_char_p, ctypes.POINTER(SolveArgs), ctypes.c_int]
-        _lib.chi_port_fill_integrated.argtypes = [
-            ctypes.c_char_p, ctypes.POINTER(SolveArgs)]
-        _lib.chi_port_snap_width.argtypes = [
-            ctypes.c_char_p, ctypes.POINTER(SolveArgs)]
-        _lib.chi_port_solve2.argtypes = [
-            ctypes.c_char_p, ctypes.POINTER(SolveArgs), ctypes.c_int,
-            ctypes.c_int]
-        assert _lib.chi_port_sizeof_args() == ctypes.sizeof(SolveArgs), (
-            _lib.chi_port_sizeof_args(), ctypes.sizeof(SolveArgs))
+        _lib = _configure(ctypes.CDLL(path))
     return _lib
+
+
+def open_port(path):
+    """A port library built by oracle.csolver.build.build_models (models that
+    are not built in); pass it to Population(..., port=...)."""
+    return _configure(ctypes.CDLL(path))
 
 
 def max_threads():
@@ -110,10 +120,13 @@ class Population(object):
     """Static data of a population in the layout the solve expects."""
 
     def __init__(self, key, outputs, error_kinds, times, observations,
-                 out_index, regimens):
+                 out_index, regimens, info=None, port=None):
         """times/observations/out_index: per-individual arrays of records
-        (sorted by time); regimens: per-individual list of events."""
-        info = model_index()[key]
+        (sorted by time); regimens: per-individual list of events.  `info`
+        (states, constants, outputs) and `port` (open_port) for a model that
+        is not built in."""
+        info = info if info is not None else model_index()[key]
+        self._port = port
         self.key = key
         self.info = info
         self.P = len(info['states']) + len(info['constants'])
@@ -178,7 +191,7 @@ class Population(object):
         for k in range(self.P):
             a.col_param[k] = k
             a.param_col[k] = k
-        lib().chi_port_fill_integrated(self.key.encode(), ctypes.byref(a))
+        (self._port or lib()).chi_port_fill_integrated(self.key.encode(), ctypes.byref(a))
         return a
 
     def loglik(self, x, ids=None, with_grad=True, rtol=1e-8, atol=1e-10,
@@ -216,14 +229,14 @@ class Population(object):
             deferred = stream_cb != 0
         snap = None
         if deferred and stream_cb != 0:
-            width = lib().chi_port_snap_width(
+            width = (self._port or lib()).chi_port_snap_width(
                 self.key.encode(), ctypes.byref(a))
             rows = int(np.max(np.diff(self.rec_off))) if self.n_ids else 0
             snap = np.full(B * max(rows, 1) * width, np.nan)
             a.snap = _ptr(snap)
             a.snap_rows = rows
             a.snap_width = width
-        rc = lib().chi_port_solve2(self.key.encode(), ctypes.byref(a),
+        rc = (self._port or lib()).chi_port_solve2(self.key.encode(), ctypes.byref(a),
                                    n_threads, stream_cb)
         assert rc == 0, rc
         return ll, grad, status, nst, nrj
@@ -258,7 +271,7 @@ class Population(object):
         a.status = _ptr(status)
         a.n_steps = _ptr(nst)
         a.n_rej = _ptr(nrj)
-        rc = lib().chi_port_solve2(self.key.encode(), ctypes.byref(a),
+        rc = (self._port or lib()).chi_port_solve2(self.key.encode(), ctypes.byref(a),
                                    n_threads, stream_cb)
         assert rc == 0, rc
         return y, s, status, nst, nrj

@@ -49,5 +49,32 @@ def build(force=False):
     return LIB
 
 
+def build_models(headers, out_dir):
+    """Host port of the solve for models that are not built in: `headers`
+    maps model key -> generated header (chi_b200._build.write_model_sources);
+    returns the path of the shared object written to `out_dir`."""
+    lines = ['#include "%s"' % os.path.abspath(h)
+             for _, h in sorted(headers.items())]
+    lines.append('#define CHI_PORT_MODELS \\')
+    for key in sorted(headers):
+        lines.append('  CHI_PORT_MODEL("%s", Model_%s) \\' % (key, key))
+    lines.append('')
+    inc = os.path.join(out_dir, 'port_models_custom.inc')
+    with open(inc, 'w') as f:
+        f.write('\n'.join(lines) + '\n')
+    lib = os.path.join(out_dir, 'libchi_port_custom.so')
+    cmd = ['g++', '-O3', '-std=c++17', '-fPIC', '-shared', '-fopenmp',
+           '-ffp-contract=fast', '-march=x86-64-v3',
+           '-I/usr/local/cuda/include',
+           '-I' + os.path.join(ROOT, 'chi_b200', 'csrc'),
+           '-DCHI_PORT_MODELS_FILE="%s"' % inc,
+           os.path.join(HERE, 'port.cpp'), '-o', lib]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE,
+                          stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError('g++ failed:\n' + proc.stdout)
+    return lib
+
+
 if __name__ == '__main__':
     print(build(force=True))

@@ -20,7 +20,11 @@
 #endif
 
 #include "../../chi_b200/csrc/integrator.cuh"
+#ifdef CHI_PORT_MODELS_FILE
+#include CHI_PORT_MODELS_FILE   // a test's own model list (build.build_models)
+#else
 #include "port_models.inc"   // generated: includes + dispatch table
+#endif
 
 using namespace chi_b200;
 

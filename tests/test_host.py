@@ -428,3 +428,102 @@ def test_flop_model_of_the_bench_counts_the_k_stage_form():
     dense = info.copy()
     dense[3] = 1                                  # linear, dense column terms
     assert bench.flops_per_step(2, 5, dense, stages=8, n_init=2) == 1188
+
+
+TRANSIT_SBML = """<?xml version="1.0" encoding="UTF-8"?>
+<sbml xmlns="http://www.sbml.org/sbml/level3/version2/core" level="3" version="2">
+  <model id="transit_pk" timeUnits="day">
+    <listOfCompartments>
+      <compartment id="central" name="central" size="1"/>
+      <compartment id="gut" name="gut" size="1"/>
+      <compartment id="transit" name="transit" size="1"/>
+    </listOfCompartments>
+    <listOfSpecies>
+      <species id="drug" name="drug" compartment="central" initialAmount="0" hasOnlySubstanceUnits="true"/>
+      <species id="a1" name="a1" compartment="gut" initialAmount="0" hasOnlySubstanceUnits="true"/>
+      <species id="a2" name="a2" compartment="transit" initialAmount="0" hasOnlySubstanceUnits="true"/>
+    </listOfSpecies>
+    <listOfParameters>
+      <parameter id="k_tr" value="1" constant="true"/>
+      <parameter id="k_e" value="1" constant="true"/>
+    </listOfParameters>
+    <listOfReactions>
+      <reaction id="r1" reversible="false">
+        <listOfReactants><speciesReference species="a1"/></listOfReactants>
+        <listOfProducts><speciesReference species="a2"/></listOfProducts>
+        <kineticLaw><math xmlns="http://www.w3.org/1998/Math/MathML">
+          <apply><times/><ci> k_tr </ci><ci> a1 </ci></apply></math></kineticLaw>
+      </reaction>
+      <reaction id="r2" reversible="false">
+        <listOfReactants><speciesReference species="a2"/></listOfReactants>
+        <listOfProducts><speciesReference species="drug"/></listOfProducts>
+        <kineticLaw><math xmlns="http://www.w3.org/1998/Math/MathML">
+          <apply><times/><ci> k_tr </ci><ci> a2 </ci></apply></math></kineticLaw>
+      </reaction>
+      <reaction id="r3" reversible="false">
+        <listOfReactants><speciesReference species="drug"/></listOfReactants>
+        <kineticLaw><math xmlns="http://www.w3.org/1998/Math/MathML">
+          <apply><times/><ci> k_e </ci><ci> drug </ci></apply></math></kineticLaw>
+      </reaction>
+    </listOfReactions>
+  </model>
+</sbml>
+"""
+
+
+def test_cpu_port_linear_model_with_dense_column_terms(tmp_path):
+    """A linear model in which one constant multiplies two states (transit
+    compartments sharing a rate constant): its column term D_k has two
+    non-zero columns, so it takes the k-stage form with the dense
+    (W^-1 D_k) V product -- none of the built-in models does.  SBML -> code
+    generator -> host build of the kernel's routine -> exact solution."""
+    from chi_b200 import _build
+    from oracle.csolver import build as port_build
+    path = tmp_path / 'transit.xml'
+    path.write_text(TRANSIT_SBML)
+    model = chi_b200.PKPDModel(str(path))
+    model.set_administration('gut', amount_var='a1_amount', direct=True)
+    assert model.parameters() == [
+        'central.drug_amount', 'gut.a1_amount', 'transit.a2_amount',
+        'central.size', 'global.k_e', 'global.k_tr', 'gut.size',
+        'transit.size']
+    code = model.model_code()
+    assert code.linear
+    header = code.header()
+    assert 'COL_RANK1 = false' in header
+    gen = tmp_path / 'gen'
+    gen.mkdir()
+    paths = _build.write_model_sources(code, str(gen))
+    hdr = [p for p in paths if p.endswith('.cuh')][0]
+    port = cport.open_port(port_build.build_models({code.key: hdr},
+                                                   str(tmp_path)))
+    info = {'states': code.state_names, 'constants': code.const_names,
+            'outputs': code.output_names}
+    times = np.array([0.2, 0.5, 1.0, 1.7, 2.5, 4.0, 6.5, 9.0])
+    reg = [(6.0, 0.0, 0.5, 3.0, 3)]
+    psi = np.array([0.3, 0.1, 0.2, 2.0, 0.7, 1.9, 1.0, 1.0])
+    pop = cport.Population(code.key, ['central.drug_amount'], None, [times],
+                           None, None, [reg], info=info, port=port)
+    omodel = ode_exact.OdeModel(
+        ['central.drug_amount', 'gut.a1_amount', 'transit.a2_amount'],
+        ['central.size', 'global.k_e', 'global.k_tr', 'gut.size',
+         'transit.size'],
+        {'central.drug_amount':
+            'global__k_tr * transit__a2_amount'
+            ' - global__k_e * central__drug_amount',
+         'gut.a1_amount': '-global__k_tr * gut__a1_amount',
+         'transit.a2_amount':
+            'global__k_tr * gut__a1_amount'
+            ' - global__k_tr * transit__a2_amount'},
+        {'central.drug_amount': 'central__drug_amount'}, 'gut.a1_amount')
+    omodel.set_outputs(['central.drug_amount'])
+    assert omodel.parameter_names == model.parameters()
+    y_ref, s_ref = ode_exact.simulate(omodel, psi, times, reg)
+    scale = np.max(np.abs(s_ref[:, 0, :]), 0)
+    scale[scale == 0] = 1.0
+    for method in (5, 1):
+        y, s, status, nst, _ = pop.simulate(
+            psi, rtol=1e-10, atol=1e-12, stream_cb=method)
+        assert status[0] == 0
+        assert np.max(np.abs(y - y_ref[0])) / np.max(np.abs(y_ref[0])) < 1e-9
+        assert np.max(np.abs(s - s_ref[:, 0, :]) / scale) < 1e-8
