@@ -564,6 +564,42 @@ def test_user_defined_model_is_compiled_on_first_use(tmp_path):
     assert _scaled_err(s[:, 0, :], s_ref[:, 0, :]) < 2e-9
 
 
+def test_user_defined_linear_model_with_dense_column_terms(tmp_path):
+    """Transit compartments sharing a rate constant: a linear model whose
+    column term D_k has two non-zero columns (the k-stage form with the dense
+    (W^-1 D_k) V product; every built-in linear model takes the rank-one
+    path).  Compiled on first use, compared with the exact solution."""
+    from tests.test_host import TRANSIT_SBML
+    path = tmp_path / 'transit.xml'
+    path.write_text(TRANSIT_SBML)
+    model = chi_b200.PKPDModel(str(path))
+    model.set_administration('gut', amount_var='a1_amount', direct=True)
+    model.set_outputs(['central.drug_amount'])
+    model.set_dosing_regimen(dose=3, start=0, duration=0.5, period=3, num=3)
+    model.set_tolerance(**TIGHT)
+    model.enable_sensitivities(True)
+    psi = np.array([0.3, 0.1, 0.2, 2.0, 0.7, 1.9, 1.0, 1.0])
+    times = np.array([0.2, 0.5, 1.0, 1.7, 2.5, 4.0, 6.5, 9.0])
+    y, s = model.simulate(psi, times)
+    omodel = ode_exact.OdeModel(
+        ['central.drug_amount', 'gut.a1_amount', 'transit.a2_amount'],
+        ['central.size', 'global.k_e', 'global.k_tr', 'gut.size',
+         'transit.size'],
+        {'central.drug_amount':
+            'global__k_tr * transit__a2_amount'
+            ' - global__k_e * central__drug_amount',
+         'gut.a1_amount': '-global__k_tr * gut__a1_amount',
+         'transit.a2_amount':
+            'global__k_tr * gut__a1_amount'
+            ' - global__k_tr * transit__a2_amount'},
+        {'central.drug_amount': 'central__drug_amount'}, 'gut.a1_amount')
+    omodel.set_outputs(['central.drug_amount'])
+    assert omodel.parameter_names == model.parameters()
+    y_ref, s_ref = ode_exact.simulate(omodel, psi, times, _events(model))
+    assert _scaled_err(y, y_ref, axis=1) < 2e-10
+    assert _scaled_err(s[:, 0, :], s_ref[:, 0, :]) < 2e-9
+
+
 def test_dataframe_ingestion_and_batched_sampler():
     """Long-format table -> device problem (chi/_problems.py:246-376) and a
     short batched Haario-Bardenet run over it (chi/_inference.py:702-760)."""
