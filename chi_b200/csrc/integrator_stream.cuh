@@ -6,13 +6,19 @@
 // dose edges and observation times.  What differs is the mapping:
 //
 //   * ONE thread per system (no redundant state column, no shuffles), in a
-//     persistent grid whose lanes refill themselves from a global counter;
+//     persistent grid whose lanes pull work from a global counter; with at
+//     least a warp's worth of parameter vectors the lanes of a warp take the
+//     SAME individual under different vectors and refill as a whole warp, so
+//     they reach dose edges and observation times in phase
+//     (SolveArgs::order_inner, refill_wait);
 //   * per step the state column runs first; the sensitivity columns are then
 //     streamed through registers one at a time in a uniform, non-unrolled
 //     loop (every thread of the grid handles the same column at the same
 //     time: no divergence, and the hot loop stays inside the instruction
-//     cache).  Linear models take a branch-free column body that needs only
-//     V_i = Z_i + U_i of the state column (shared memory);
+//     cache).  Linear models run the method in its original k-stage form
+//     (one combination and one N x N product per stage, see the K constants)
+//     with a branch-free column body that needs only V_i = arg_i + kappa_i
+//     of the state column (shared memory);
 //   * S of the integrated columns (current and candidate), the stage values,
 //     the state, the model constants and the per-system scalars that only the
 //     event handler touches live in shared memory, slot-major (conflict
