@@ -527,3 +527,34 @@ def test_cpu_port_linear_model_with_dense_column_terms(tmp_path):
         assert status[0] == 0
         assert np.max(np.abs(y - y_ref[0])) / np.max(np.abs(y_ref[0])) < 1e-9
         assert np.max(np.abs(s - s_ref[:, 0, :]) / scale) < 1e-8
+
+
+def test_cpu_port_stiff_parameter_sweep():
+    """The k-stage form over six decades of rate constants (stiffness ratios
+    up to 1e6 with steps far outside the explicit stability range): no
+    integrator failure, and trajectories / sensitivities within the mixed
+    tolerance of the exact solution."""
+    key = cport.find_key('two_compartment_pk_model', 'central', True)
+    times = np.sort(np.random.default_rng(1).uniform(0.25, 24, 10))
+    reg = [(10.0, 0.0, 1.0, 8.0, 3)]
+    pop = cport.Population(
+        key, ['central.drug_concentration'], None, [times], None, None, [reg])
+    m = ode_exact.two_compartment(True)
+    rng = np.random.default_rng(7)
+    rtol, atol = 1e-6, 1e-8
+    for _ in range(120):
+        psi = np.array([
+            rng.uniform(0, 5), rng.uniform(0, 5), 10 ** rng.uniform(-1, 2),
+            10 ** rng.uniform(-3, 3), 10 ** rng.uniform(-3, 3),
+            10 ** rng.uniform(-3, 3), 10 ** rng.uniform(-1, 2)])
+        for method in (5, 1):
+            y, s, status, nst, nrj = pop.simulate(
+                psi, rtol=rtol, atol=atol, stream_cb=method)
+            assert status[0] == 0, (psi, method)
+            assert nst[0] + nrj[0] < 2000
+            ye, se = ode_exact.simulate(m, psi, times, reg)
+            tol_y = 20 * (atol + rtol * np.max(np.abs(ye[0])))
+            assert np.max(np.abs(y - ye[0])) < tol_y, (psi, method)
+            tol_s = 20 * (atol + rtol * np.max(np.abs(se[:, 0, :]), 0))
+            assert np.all(np.abs(s - se[:, 0, :]) < tol_s[None, :]), (
+                psi, method)
