@@ -163,13 +163,17 @@ def build_model_module(code):
     os.makedirs(MODULES, exist_ok=True)
     os.makedirs(OBJ, exist_ok=True)
     cuh, cu = write_model_sources(code, MODULES)
-    so = os.path.join(MODULES, 'libchi_b200_model_%s.so' % code.key)
+    deps = [cuh, os.path.join(CSRC, 'model_api.cuh'),
+            os.path.join(CSRC, 'integrator.cuh'),
+            os.path.join(CSRC, 'integrator_stream.cuh')]
+    # the name carries a digest of the generated code and the integrator
+    # headers: a module built against older headers is never picked up
+    tag = _digest([cu] + deps, ' '.join(NVCC_FLAGS))[:10]
+    so = os.path.join(MODULES, 'libchi_b200_model_%s_%s.so' % (code.key, tag))
     if os.path.exists(so):
         return so
-    obj = os.path.join(OBJ, 'model_%s.o' % code.key)
-    _compile(cu, obj, [cuh, os.path.join(CSRC, 'model_api.cuh'),
-                       os.path.join(CSRC, 'integrator.cuh'),
-                       os.path.join(CSRC, 'integrator_stream.cuh')])
+    obj = os.path.join(OBJ, 'model_%s_%s.o' % (code.key, tag))
+    _compile(cu, obj, deps)
     _run([nvcc(), '-shared', '-cudart', 'shared', '-o', so, obj,
           '-L' + HERE, '-lchi_b200', '-Xlinker', '-rpath=' + HERE]
          + LINK_FLAGS)
