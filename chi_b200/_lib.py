@@ -166,10 +166,9 @@ def find_model(code):
     if idx >= 0:
         return idx
     from chi_b200 import _build
-    so = os.path.join(_build.MODULES,
-                      'libchi_b200_model_%s.so' % code.key)
-    if not os.path.exists(so):
-        so = _build.build_model_module(code)
+    # returns at once when a module built from the same generated code and
+    # integrator headers exists
+    so = _build.build_model_module(code)
     load_module(so)
     idx = handle.chi_b200_model_find(code.key.encode())
     if idx < 0:
