@@ -558,3 +558,80 @@ def test_cpu_port_stiff_parameter_sweep():
             tol_s = 20 * (atol + rtol * np.max(np.abs(se[:, 0, :]), 0))
             assert np.all(np.abs(s - se[:, 0, :]) < tol_s[None, :]), (
                 psi, method)
+
+
+CLEARANCE_SBML = """<?xml version="1.0" encoding="UTF-8"?>
+<sbml xmlns="http://www.sbml.org/sbml/level3/version2/core" level="3" version="2">
+  <model id="clearance_pk" timeUnits="day">
+    <listOfCompartments>
+      <compartment id="central" name="central" size="1"/>
+    </listOfCompartments>
+    <listOfSpecies>
+      <species id="drug" name="drug" compartment="central" initialAmount="0" hasOnlySubstanceUnits="true"/>
+    </listOfSpecies>
+    <listOfParameters>
+      <parameter id="clearance" value="1" constant="true"/>
+      <parameter id="v_d" value="1" constant="true"/>
+    </listOfParameters>
+    <listOfReactions>
+      <reaction id="elimination" reversible="false">
+        <listOfReactants><speciesReference species="drug"/></listOfReactants>
+        <kineticLaw><math xmlns="http://www.w3.org/1998/Math/MathML">
+          <apply><divide/>
+            <apply><times/><ci> clearance </ci><ci> drug </ci></apply>
+            <ci> v_d </ci>
+          </apply></math></kineticLaw>
+      </reaction>
+    </listOfReactions>
+  </model>
+</sbml>
+"""
+
+
+def test_cpu_port_rank_one_terms_that_depend_on_constants(tmp_path):
+    """Clearance parametrisation dA/dt = -(CL / V_d) A + u: both column terms
+    are rank one with a coefficient that is an expression of the constants
+    (d_CL = -1/V_d, d_Vd = CL/V_d^2), not a literal as in the mass-action
+    library models."""
+    from chi_b200 import _build
+    from oracle.csolver import build as port_build
+    path = tmp_path / 'clearance.xml'
+    path.write_text(CLEARANCE_SBML)
+    model = chi_b200.PKPDModel(str(path))
+    model.set_administration('central', direct=True)
+    assert model.parameters() == [
+        'central.drug_amount', 'central.size', 'global.clearance',
+        'global.v_d']
+    code = model.model_code()
+    header = code.header()
+    assert code.linear and 'COL_RANK1 = true' in header
+    gen = tmp_path / 'gen'
+    gen.mkdir()
+    paths = _build.write_model_sources(code, str(gen))
+    hdr = [p for p in paths if p.endswith('.cuh')][0]
+    port = cport.open_port(port_build.build_models({code.key: hdr},
+                                                   str(tmp_path)))
+    info = {'states': code.state_names, 'constants': code.const_names,
+            'outputs': code.output_names}
+    times = np.array([0.1, 0.4, 1.0, 1.6, 2.5, 4.0, 7.0])
+    reg = [(5.0, 0.0, 0.25, 2.0, 3)]
+    psi = np.array([0.4, 1.0, 1.3, 2.2])
+    pop = cport.Population(code.key, ['central.drug_amount'], None, [times],
+                           None, None, [reg], info=info, port=port)
+    omodel = ode_exact.OdeModel(
+        ['central.drug_amount'],
+        ['central.size', 'global.clearance', 'global.v_d'],
+        {'central.drug_amount':
+            '-global__clearance / global__v_d * central__drug_amount'},
+        {'central.drug_amount': 'central__drug_amount'},
+        'central.drug_amount')
+    omodel.set_outputs(['central.drug_amount'])
+    assert omodel.parameter_names == model.parameters()
+    y_ref, s_ref = ode_exact.simulate(omodel, psi, times, reg)
+    scale = np.max(np.abs(s_ref[:, 0, :]), 0)
+    scale[scale == 0] = 1.0
+    y, s, status, _, _ = pop.simulate(psi, rtol=1e-10, atol=1e-12,
+                                      stream_cb=5)
+    assert status[0] == 0
+    assert np.max(np.abs(y - y_ref[0])) / np.max(np.abs(y_ref[0])) < 1e-9
+    assert np.max(np.abs(s - s_ref[:, 0, :]) / scale) < 1e-8
