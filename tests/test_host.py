@@ -635,3 +635,63 @@ def test_cpu_port_rank_one_terms_that_depend_on_constants(tmp_path):
     assert status[0] == 0
     assert np.max(np.abs(y - y_ref[0])) / np.max(np.abs(y_ref[0])) < 1e-9
     assert np.max(np.abs(s - s_ref[:, 0, :]) / scale) < 1e-8
+
+
+def test_batched_posterior_combines_prior_and_likelihood_on_the_host():
+    """HierarchicalLogPosterior.evaluate_batch / evaluateS1_batch: the host
+    prior runs on a worker thread while the likelihood call is in flight;
+    rows whose prior is -inf get score -inf and gradient +inf
+    (chi/_log_pdfs.py:463-498), with a batched prior and with a prior that
+    only offers the single-vector calls.  The GPU likelihood is replaced by a
+    stub here: this pins the host logic only."""
+    from chi_b200 import _log_pdfs
+
+    n_bottom, n_top, C = 6, 3, 5
+
+    class StubLikelihood(object):
+        def evaluate_batch(self, X, copy=True):
+            return np.sum(X, axis=1)
+
+        def evaluateS1_batch(self, X, copy=True):
+            return np.sum(X, axis=1), np.ones_like(X) * 2.0
+
+    class SinglePrior(object):
+        """log p = -0.5 |t|^2, -inf when t[0] < 0 (no batch methods)."""
+        def n_parameters(self):
+            return n_top
+
+        def __call__(self, t):
+            return -np.inf if t[0] < 0 else -0.5 * float(np.dot(t, t))
+
+        def evaluateS1(self, t):
+            if t[0] < 0:
+                return -np.inf, np.full(n_top, np.nan)
+            return -0.5 * float(np.dot(t, t)), -np.asarray(t, float)
+
+    class BatchPrior(SinglePrior):
+        def evaluateS1_batch(self, T):
+            p = np.array([self(t) for t in T])
+            s = np.array([self.evaluateS1(t)[1] for t in T])
+            return p, s
+
+    rng = np.random.default_rng(3)
+    X = rng.uniform(0.1, 1.0, size=(C, n_bottom + n_top))
+    X[2, n_bottom] = -1.0
+    for prior in (SinglePrior(), BatchPrior()):
+        post = object.__new__(_log_pdfs.HierarchicalLogPosterior)
+        post._log_likelihood = StubLikelihood()
+        post._log_prior = prior
+        post._n_bottom = n_bottom
+        post._n_parameters = n_bottom + n_top
+        score = post.evaluate_batch(X)
+        s1, grad = post.evaluateS1_batch(X)
+        expect = np.sum(X, axis=1) - 0.5 * np.sum(X[:, n_bottom:] ** 2, 1)
+        ok = np.arange(C) != 2
+        np.testing.assert_allclose(score[ok], expect[ok], rtol=1e-14)
+        np.testing.assert_allclose(s1[ok], expect[ok], rtol=1e-14)
+        assert np.isneginf(score[2]) and np.isneginf(s1[2])
+        assert np.all(np.isposinf(grad[2]))
+        np.testing.assert_allclose(grad[ok, :n_bottom], 2.0)
+        np.testing.assert_allclose(
+            grad[ok, n_bottom:], 2.0 - X[ok, n_bottom:], rtol=1e-14)
+        assert np.all(np.isfinite(grad[ok]))
