@@ -1070,7 +1070,10 @@ int launch_loglik(chi_b200_problem* p, int64_t B, const int32_t* d_ids,
     }();
     const int min_vectors = p->cfg_order >= 0 ? p->cfg_order : min_inner;
     const int wait = p->cfg_wait >= 0 ? p->cfg_wait : wait_env;
-    const bool ordered = min_vectors > 0 && order_inner >= min_vectors;
+    // (the map is a permutation of [0, B) only for a full C x n layout)
+    const bool ordered =
+        min_vectors > 0 && order_inner >= min_vectors &&
+        static_cast<int64_t>(order_inner) * order_stride == B;
     if (ordered) {
       a.order_inner = order_inner;
       a.order_stride = order_stride;
