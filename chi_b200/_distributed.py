@@ -9,13 +9,18 @@ so a population shards by individual: rank r evaluates the contiguous block
 * its own block of the bottom-level gradient (d eta_i, disjoint per rank).
 
 One all-reduce (sum) of ``[score | d theta]`` (8 B ... a few KB per parameter
-vector) completes the evaluation; the bottom blocks are disjoint and are
-all-gathered only if the caller wants the full gradient on every rank.  The
-prior acts on theta only and is added on the host after the reduction.
+vector) completes the evaluation.  On the GPU path that all-reduce happens
+INSIDE the library, on the compute stream and on the device buffers, before
+anything is copied to the host (``chi_b200_problem_comm_init``: a persistent
+NCCL communicator per problem; csrc/core.cu: run_hier): this module only sets
+the shard, hands the communicator id round and adds the (host) prior.  The
+bottom blocks are disjoint and are gathered only if the caller asks for the
+full gradient on every rank (``gather_bottom=True``).
 
-The collective goes through ``torch.distributed`` (NCCL over NVLink on the
-GPU box, gloo in the CPU tests); the per-rank evaluation is the CUDA path
-(`HierarchicalLogLikelihood.set_shard`), injectable for tests.
+``torch.distributed`` supplies the process group (rendezvous, the broadcast
+of the communicator id; NCCL on the GPU box, gloo in the CPU tests).  For the
+CPU tests the per-rank evaluation is injectable (``partial_fn``); the partial
+sums are then reduced through ``torch.distributed`` itself.
 """
 import numpy as np
 
@@ -47,11 +52,16 @@ class ShardedHierarchicalLogPosterior(object):
     :param log_posterior: the posterior (every rank holds the static data of
         all individuals; only its shard is evaluated).
     :param partial_fn: optional ``f(X, begin, end) -> (score, grad)``
-        returning the shard's partial sums (tests inject the CPU oracle).
+        returning the shard's partial sums (tests inject the CPU oracle); the
+        reduction then goes through ``torch.distributed`` on the host.
+    :param gather_bottom: also return the other ranks' blocks of the
+        bottom-level gradient (default: every rank gets the complete score
+        and top-level gradient plus its own individuals' bottom-level block,
+        the other individuals' entries are zero).
     """
 
     def __init__(self, log_posterior, group=None, partial_fn=None,
-                 gather_bottom=True):
+                 gather_bottom=False):
         import torch.distributed as dist
         self._dist = dist
         self._group = group
@@ -69,21 +79,19 @@ class ShardedHierarchicalLogPosterior(object):
         self._gather_bottom = gather_bottom
         self._partial_fn = partial_fn
         if partial_fn is None:
+            # the library's own communicator: rank 0 creates the id, the
+            # process group carries it to the others
+            box = [self._ll.new_communicator_id() if self._rank == 0
+                   else None]
+            src = 0 if group is None else dist.get_global_rank(group, 0)
+            dist.broadcast_object_list(box, src=src, group=group)
             self._ll.set_shard(self._begin, self._end)
+            self._ll.set_communicator(self._world, self._rank, box[0])
 
     def shard(self):
         return self._begin, self._end
 
-    def _partials(self, X, with_grad):
-        if self._partial_fn is not None:
-            return self._partial_fn(X, self._begin, self._end)
-        if with_grad:
-            # page-locked result buffers; entries of other shards are zero
-            return self._ll.evaluateS1_batch(X, copy=False)
-        score = self._ll.evaluate_batch(X, copy=False)
-        return score, None
-
-    def _all_reduce(self, array):
+    def _host_all_reduce(self, array):
         import torch
         t = torch.from_numpy(array)
         backend = self._dist.get_backend(self._group)
@@ -107,34 +115,55 @@ class ShardedHierarchicalLogPosterior(object):
             grad[:, self._n_bottom:] += np.where(bad[:, None], 0.0, s)
             grad[bad] = np.inf
 
-    def evaluateS1_batch(self, X, with_grad=True, copy=True):
-        """Scores and gradients of the parameter vectors ``X``.  With
-        ``gather_bottom=False`` every rank's gradient holds the reduced
-        top-level entries and its own individuals' bottom-level entries (the
-        others are zero); with ``copy=False`` the arrays are the page-locked
-        result buffers of the likelihood, valid until the next evaluation."""
-        X = np.asarray(X, dtype=float).reshape(-1, self._n_params)
-        score, grad = self._partials(X, with_grad)
-        if self._partial_fn is not None or copy:
-            score = np.array(score, dtype=float)
-            grad = None if grad is None else np.array(grad, dtype=float)
+    def _gather(self, grad):
+        """The bottom-level blocks are disjoint (zero elsewhere): a sum over
+        the ranks is their concatenation.  Works on a copy."""
+        bottom = np.ascontiguousarray(grad[:, :self._n_bottom])
+        # an invalid prior fills a rank's own columns with inf on every rank
+        # alike; take those rows out of the sum and restore them
+        bad = np.isinf(grad[:, self._n_bottom:]).all(axis=1) \
+            if grad.shape[1] > self._n_bottom else np.zeros(len(grad), bool)
+        bottom[bad] = 0.0
+        bottom = self._host_all_reduce(bottom)
+        bottom[bad] = np.inf
+        out = np.array(grad, dtype=float)
+        out[:, :self._n_bottom] = bottom
+        return out
+
+    def _evaluate_injected(self, X, with_grad):
+        score, grad = self._partial_fn(X, self._begin, self._end)
+        score = np.array(score, dtype=float)
+        grad = None if (grad is None or not with_grad) else np.array(
+            grad, dtype=float)
         if grad is None:
-            score[:] = self._all_reduce(
+            score[:] = self._host_all_reduce(
                 np.ascontiguousarray(score.reshape(-1, 1)))[:, 0]
-            grad_out = None
-        elif self._gather_bottom:
-            # bottom blocks are disjoint: a sum is a concatenation
-            buf = self._all_reduce(
-                np.ascontiguousarray(np.hstack([score[:, None], grad])))
-            score[:] = buf[:, 0]
-            grad[:] = buf[:, 1:]
-            grad_out = grad
         else:
-            buf = self._all_reduce(pack_partials(score, grad, self._n_bottom))
+            buf = self._host_all_reduce(
+                pack_partials(score, grad, self._n_bottom))
             unpack_partials(buf, score, grad, self._n_bottom)
-            grad_out = grad
-        self._add_prior(X, score, grad if grad is not None else None)
-        return score, grad_out
+            if self._gather_bottom:
+                grad = self._gather(grad)
+        self._add_prior(X, score, grad)
+        return score, grad
+
+    def evaluateS1_batch(self, X, with_grad=True, copy=True):
+        """Scores and gradients of the parameter vectors ``X`` (the same on
+        every rank, except for the other ranks' bottom-level blocks when
+        ``gather_bottom`` is off).  With ``copy=False`` the arrays are the
+        page-locked result buffers of the likelihood, valid until the next
+        evaluation."""
+        X = np.asarray(X, dtype=float).reshape(-1, self._n_params)
+        if self._partial_fn is not None:
+            return self._evaluate_injected(X, with_grad)
+        # the likelihood's evaluation ends with the all-reduce on the device;
+        # what is left is the host prior on the top-level slice
+        if not with_grad:
+            return self._post.evaluate_batch(X), None
+        score, grad = self._post.evaluateS1_batch(X, copy=copy)
+        if self._gather_bottom:
+            grad = self._gather(grad)
+        return score, grad
 
     def evaluate_batch(self, X):
         return self.evaluateS1_batch(X, with_grad=False)[0]

@@ -10,7 +10,10 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libchi_b200.so')
+# CHI_B200_LIB: an alternative build of the same library (kernel experiments)
+LIB_PATH = os.environ.get('CHI_B200_LIB') or os.path.join(
+    HERE, 'libchi_b200.so')
+COMM_ID_BYTES = 128
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)
 c_i64p = ctypes.POINTER(ctypes.c_int64)
@@ -100,6 +103,12 @@ _SIGNATURES = {
                        c_vp, c_vp, c_vp]),
     'chi_b200_problem_set_shard': (
         ctypes.c_int, [c_vp, ctypes.c_int64, ctypes.c_int64]),
+    'chi_b200_comm_unique_id': (
+        ctypes.c_int, [ctypes.POINTER(ctypes.c_uint8), ctypes.c_int32]),
+    'chi_b200_problem_comm_init': (
+        ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32,
+                       ctypes.POINTER(ctypes.c_uint8)]),
+    'chi_b200_problem_comm_destroy': (ctypes.c_int, [c_vp]),
     'chi_b200_problem_counters': (ctypes.c_int, [c_vp, c_i64p]),
     'chi_b200_problem_set_timing': (ctypes.c_int, [c_vp, ctypes.c_int32]),
     'chi_b200_problem_set_snapshot_budget': (

@@ -414,6 +414,21 @@ class LogLikelihood(_LogPDFBase):
         self._id = str(label)
 
 
+def fill_owned_columns(grad, rows, value, shard, n_ids, n_bottom):
+    """``grad[rows] = value`` restricted to the columns a shard of
+    individuals owns: its block of the bottom level and the top level.  The
+    page-locked result buffers are reused across evaluations and only the
+    owned columns are rewritten by the library, so nothing may ever be
+    written into the other individuals' columns (they have to stay zero)."""
+    begin, end = shard
+    if (begin, end) == (0, n_ids):
+        grad[rows] = value
+        return
+    n_h = n_bottom // n_ids
+    grad[rows, begin * n_h:end * n_h] = value
+    grad[rows, n_bottom:] = value
+
+
 def _same_fixed(a, b):
     if a._fixed_mask is None or b._fixed_mask is None:
         return a._fixed_mask is None and b._fixed_mask is None
@@ -643,12 +658,52 @@ class HierarchicalLogLikelihood(object):
             int(stream) if stream else None))
 
     def set_shard(self, id_begin, id_end):
-        """Restricts evaluation to individuals ``[id_begin, id_end)``; the
-        returned score and top-level gradient are then partial sums that the
-        caller all-reduces over the ranks (multi-GPU)."""
+        """Restricts evaluation to individuals ``[id_begin, id_end)``.
+        Without a communicator the returned score and top-level gradient are
+        partial sums; with one (:meth:`set_communicator`) they are the sums
+        over all ranks, reduced on the device."""
         _lib.check(_lib.lib().chi_b200_problem_set_shard(
             self._device.problem.handle, int(id_begin), int(id_end)))
+        self._shard = (int(id_begin), int(id_end))
         self._pinned = None   # result buffers are re-created zero-filled
+
+    def shard(self):
+        """Individuals ``[begin, end)`` this object evaluates."""
+        return getattr(self, '_shard', (0, self._n_ids))
+
+    @staticmethod
+    def new_communicator_id():
+        """Opaque bytes identifying a new communicator; rank 0 creates them
+        and hands them to the other ranks."""
+        import ctypes
+        buf = (ctypes.c_uint8 * _lib.COMM_ID_BYTES)()
+        _lib.check(_lib.lib().chi_b200_comm_unique_id(
+            buf, _lib.COMM_ID_BYTES))
+        return bytes(buf)
+
+    def set_communicator(self, world, rank, comm_id):
+        """Joins the all-reduce group of an evaluation whose individuals are
+        sharded over ``world`` GPUs (collective: every rank calls it with the
+        same ``comm_id``).  From then on every evaluation ends with one
+        all-reduce of ``[score | d theta]`` on the device, inside the library
+        (``chi_b200_problem_comm_init``)."""
+        import ctypes
+        comm_id = bytes(comm_id)
+        if len(comm_id) != _lib.COMM_ID_BYTES:
+            raise ValueError('Invalid communicator id.')
+        buf = (ctypes.c_uint8 * _lib.COMM_ID_BYTES).from_buffer_copy(comm_id)
+        _lib.check(_lib.lib().chi_b200_problem_comm_init(
+            self._device.problem.handle, int(world), int(rank), buf))
+        self._comm = (int(world), int(rank))
+
+    def has_communicator(self):
+        return getattr(self, '_comm', None) is not None
+
+    def _fill_rows(self, grad, rows, value):
+        """Writes ``value`` into the given rows of a gradient array -- into the
+        columns this object owns only."""
+        fill_owned_columns(grad, rows, value, self.shard(), self._n_ids,
+                           self._n_bottom)
 
     def set_snapshot_budget(self, n_bytes):
         """See ``chi_b200_problem_set_snapshot_budget`` (0: observation
@@ -835,7 +890,12 @@ class HierarchicalLogPosterior(_LogPDFBase):
         grad[:, self._n_bottom:] += s
         if np.any(bad):
             score[bad] = p[bad]
-            grad[bad] = np.inf
+            fill = getattr(self._log_likelihood, '_fill_rows', None)
+            if fill is not None:
+                # a sharded likelihood owns only part of the columns
+                fill(grad, bad, np.inf)
+            else:
+                grad[bad] = np.inf
         if copy:
             return score.copy(), grad.copy()
         return score, grad

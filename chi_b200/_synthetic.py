@@ -15,6 +15,12 @@ from chi_b200._log_pdfs import _DeviceLikelihoods
 # (V_c, k_e, k_cp, k_pc, V_p) = (2, 1, 5, 1, 10)
 TWO_CMT_TYPICAL = np.array([2.0, 1.0, 5.0, 1.0, 10.0])
 
+# Integrator tolerances of bench.py.  tests/test_gpu_bench_tolerance.py checks
+# THIS setting against the exact solution under the contract (summed log-pdf
+# 1e-8 relative, gradient 1e-6 relative).
+BENCH_RTOL = 1e-6
+BENCH_ATOL = 1e-8
+
 
 def two_compartment_model(direct=True):
     model = chi_b200.library.ModelLibrary().two_compartment_pk_model()
@@ -146,3 +152,32 @@ def two_compartment_problem(n_ids, seed=0, n_obs=10, n_doses=1,
         'observations': observations, 'regimens': regimens,
         'population_model': population_model, 'covariates': X,
         'theta_mid': theta_mid, 'sigma': sig}
+
+
+def spread_parameter_vectors(prob, n_vectors, spread, seed=0):
+    """Parameter vectors spread around the data-generating vector ``x0`` of a
+    problem built by :func:`two_compartment_problem`: additive N(0, spread)
+    on the etas and the log-means, multiplicative (1 + spread N(0,1)) on the
+    (positive) log-standard deviations and error-model sigmas, |N(0, 0.1
+    spread)| initial amounts, additive 0.3 spread N(0,1) on covariate
+    effects."""
+    rng = np.random.default_rng(seed)
+    x0 = np.asarray(prob['x0'], dtype=float)
+    n_ids = len(prob['times'])
+    n_bottom = 5 * n_ids
+    n_sig = len(prob['sigma'])
+    n_params = len(x0)
+    X = np.tile(x0, (n_vectors, 1))
+    X[:, :n_bottom] += spread * rng.normal(size=(n_vectors, n_bottom))
+    top = n_bottom
+    X[:, top:top + 2] = np.abs(0.1 * spread * rng.normal(size=(n_vectors, 2)))
+    X[:, top + 2:top + 7] += spread * rng.normal(size=(n_vectors, 5))
+    X[:, top + 7:top + 12] *= np.abs(
+        1.0 + spread * rng.normal(size=(n_vectors, 5)))
+    n_beta = n_params - n_sig - (top + 12)
+    if n_beta > 0:
+        X[:, top + 12:top + 12 + n_beta] += 0.3 * spread * rng.normal(
+            size=(n_vectors, n_beta))
+    X[:, n_params - n_sig:] *= np.abs(
+        1.0 + spread * rng.normal(size=(n_vectors, n_sig)))
+    return X

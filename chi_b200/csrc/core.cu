@@ -12,6 +12,9 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include "../../include/chi_b200.h"
 #include "model_api.cuh"
 
@@ -32,6 +35,63 @@ int fail(int code, const std::string& msg) {
     if (err__ != cudaSuccess)                                                 \
       return fail(-2, std::string(#expr) + ": " +                             \
                           cudaGetErrorString(err__));                         \
+  } while (0)
+
+// NCCL is bound at run time (dlopen) the first time a communicator is asked
+// for: the library has no link-time dependency on it, and inside a process
+// that has torch loaded the call resolves to the libnccl torch already mapped
+// (same soname), so both see one NCCL.
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t,
+                            ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string error;
+  bool ok = false;
+};
+
+NcclApi& nccl_api() {
+  static NcclApi api = [] {
+    NcclApi a;
+    const char* env = std::getenv("CHI_B200_NCCL_LIB");
+    const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+    for (const char* name : names) {
+      if (!name || !*name) continue;
+      a.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (a.handle) break;
+    }
+    if (!a.handle) {
+      a.error = std::string("libnccl.so.2 not found: ") + dlerror();
+      return a;
+    }
+    auto sym = [&](const char* n) { return dlsym(a.handle, n); };
+    a.GetUniqueId =
+        reinterpret_cast<decltype(a.GetUniqueId)>(sym("ncclGetUniqueId"));
+    a.CommInitRank =
+        reinterpret_cast<decltype(a.CommInitRank)>(sym("ncclCommInitRank"));
+    a.CommDestroy =
+        reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
+    a.AllReduce =
+        reinterpret_cast<decltype(a.AllReduce)>(sym("ncclAllReduce"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(
+        sym("ncclGetErrorString"));
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce &&
+           a.GetErrorString;
+    if (!a.ok) a.error = "libnccl.so.2 lacks an expected symbol";
+    return a;
+  }();
+  return api;
+}
+
+#define NCCL_TRY(expr)                                                       \
+  do {                                                                        \
+    ncclResult_t res__ = (expr);                                              \
+    if (res__ != ncclSuccess)                                                 \
+      return fail(-4, std::string(#expr) + ": " +                             \
+                          nccl_api().GetErrorString(res__));                  \
   } while (0)
 
 std::vector<const ModelVTable*>& registry() {
@@ -154,7 +214,14 @@ struct chi_b200_problem {
   DevBuf snap;
   int64_t max_rec = 0;          // largest number of records of an individual
   int64_t snap_budget = -1;     // bytes; -1: not determined yet
+  bool snap_budget_auto = false;  // determined by the default policy
   DevBuf hx, hscore, hgrad, hstatus, partial, popflag, r2t;
+  DevBuf step_sums;             // chi_b200_problem_counters
+  // individuals sharded over the GPUs of a node: communicator for the
+  // all-reduce of [score | d theta] and the packed partials it works on
+  ncclComm_t comm = nullptr;
+  int32_t comm_world = 1, comm_rank = 0;
+  DevBuf pack;
   int64_t counters[4] = {0, 0, 0, 0};
   bool counters_stale = false;
 
@@ -403,28 +470,68 @@ pop_backward_kernel(PopDesc P, int64_t n_ids, int64_t id_begin,
 // the top-level gradient; applies the NaN -> -inf rule of the population
 // likelihoods (chi/_population_models.py:1469-1470, 2300-2301) and the
 // invalid-population flag.
+// With `pack` set (individuals sharded over several GPUs) the sums are this
+// rank's partials: they are written as [c][n_slots + 2] = [score | d theta
+// (reduced slots) | invalid flag | failed systems] for the all-reduce, and
+// pop_unpack_kernel finishes the job afterwards.
 __global__ void pop_final_kernel(int32_t n_red, int64_t n_blocks,
                                  int64_t n_params, int64_t n_bottom,
                                  int32_t with_grad,
                                  const int32_t* __restrict__ red_to_top,
                                  const double* __restrict__ partial,
                                  const int32_t* __restrict__ popflag,
+                                 const int32_t* __restrict__ status,
                                  double* __restrict__ score,
-                                 double* __restrict__ grad) {
+                                 double* __restrict__ grad,
+                                 double* __restrict__ pack) {
   const int64_t c = blockIdx.x;
   const int n_slots = 1 + n_red;
   const bool bad = popflag && popflag[c];
   for (int s = threadIdx.x; s < n_slots; s += blockDim.x) {
     double v = 0.0;
-    for (int64_t b = 0; b < n_blocks; ++b)
-      v += partial[(c * n_blocks + b) * n_slots + s];
-    if (s == 0) {
+    if (s == 0 || with_grad)
+      for (int64_t b = 0; b < n_blocks; ++b)
+        v += partial[(c * n_blocks + b) * n_slots + s];
+    if (pack) {
+      pack[c * (n_slots + 2) + s] = v;
+    } else if (s == 0) {
       if (bad || v != v) v = -INFINITY;
       score[c] = v;
     } else if (with_grad) {
       grad[c * n_params + n_bottom + red_to_top[s - 1]] = v;
     }
   }
+  if (pack && threadIdx.x == 0) {
+    pack[c * (n_slots + 2) + n_slots] = bad ? 1.0 : 0.0;
+    pack[c * (n_slots + 2) + n_slots + 1] =
+        (status && status[c] != 0) ? 1.0 : 0.0;
+  }
+}
+
+// After the all-reduce of the packed partials: the rules of K3c on the global
+// sums.  A vector whose own systems all succeeded but that failed on another
+// rank gets status CHI_B200_ST_REMOTE_FAILURE.
+__global__ void pop_unpack_kernel(int32_t n_red, int64_t n_params,
+                                  int64_t n_bottom, int32_t with_grad,
+                                  const int32_t* __restrict__ red_to_top,
+                                  const double* __restrict__ pack,
+                                  double* __restrict__ score,
+                                  double* __restrict__ grad,
+                                  int32_t* __restrict__ status) {
+  const int64_t c = blockIdx.x;
+  const int n_slots = 1 + n_red;
+  const double* pc = pack + c * (n_slots + 2);
+  for (int s = threadIdx.x; s < n_slots; s += blockDim.x) {
+    double v = pc[s];
+    if (s == 0) {
+      if (pc[n_slots] > 0.0 || v != v) v = -INFINITY;
+      score[c] = v;
+    } else if (with_grad) {
+      grad[c * n_params + n_bottom + red_to_top[s - 1]] = v;
+    }
+  }
+  if (status && threadIdx.x == 0 && status[c] == 0 && pc[n_slots + 1] > 0.0)
+    status[c] = CHI_B200_ST_REMOTE_FAILURE;
 }
 
 __global__ void fill_kernel(double* p, int64_t n, double v) {
@@ -696,6 +803,9 @@ void chi_b200_problem_destroy(chi_b200_problem* p) {
         &p->traj_y, &p->traj_s, &p->hx, &p->hscore, &p->hgrad, &p->hstatus,
         &p->partial, &p->popflag, &p->r2t})
     b->release();
+  if (p->comm) nccl_api().CommDestroy(p->comm);
+  p->pack.release();
+  p->step_sums.release();
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   if (p->stream) cudaStreamDestroy(p->stream);
@@ -800,6 +910,47 @@ int chi_b200_problem_set_shard(chi_b200_problem* p, int64_t id_begin,
   return 0;
 }
 
+int chi_b200_comm_unique_id(uint8_t* id, int32_t capacity) {
+  NcclApi& api = nccl_api();
+  if (!api.ok) return fail(-4, api.error);
+  if (capacity < static_cast<int32_t>(sizeof(ncclUniqueId)))
+    return fail(-1, "unique id buffer too small");
+  ncclUniqueId uid;
+  NCCL_TRY(api.GetUniqueId(&uid));
+  std::memcpy(id, &uid, sizeof(uid));
+  return 0;
+}
+
+int chi_b200_problem_comm_init(chi_b200_problem* p, int32_t world,
+                               int32_t rank, const uint8_t* id) {
+  NcclApi& api = nccl_api();
+  if (!api.ok) return fail(-4, api.error);
+  if (world < 1 || rank < 0 || rank >= world)
+    return fail(-1, "invalid rank / world size");
+  CUDA_TRY(cudaSetDevice(p->device));
+  if (p->comm) {
+    NCCL_TRY(api.CommDestroy(p->comm));
+    p->comm = nullptr;
+  }
+  ncclUniqueId uid;
+  std::memcpy(&uid, id, sizeof(uid));
+  NCCL_TRY(api.CommInitRank(&p->comm, world, uid, rank));
+  p->comm_world = world;
+  p->comm_rank = rank;
+  return 0;
+}
+
+int chi_b200_problem_comm_destroy(chi_b200_problem* p) {
+  if (p->comm) {
+    CUDA_TRY(cudaSetDevice(p->device));
+    NCCL_TRY(nccl_api().CommDestroy(p->comm));
+    p->comm = nullptr;
+  }
+  p->comm_world = 1;
+  p->comm_rank = 0;
+  return 0;
+}
+
 int chi_b200_problem_set_timing(chi_b200_problem* p, int32_t enabled) {
   CUDA_TRY(cudaSetDevice(p->device));
   if (enabled && !p->ev0) {
@@ -814,6 +965,7 @@ int chi_b200_problem_set_timing(chi_b200_problem* p, int32_t enabled) {
 
 int chi_b200_problem_set_snapshot_budget(chi_b200_problem* p, int64_t bytes) {
   p->snap_budget = bytes;
+  p->snap_budget_auto = false;
   if (bytes == 0) p->snap.release();
   return 0;
 }
@@ -839,15 +991,15 @@ int chi_b200_problem_counters(chi_b200_problem* p, int64_t out[4]) {
     // over its systems (for the flop model of the bench)
     CUDA_TRY(cudaSetDevice(p->device));
     cudaStream_t s = p->stream;
-    unsigned long long* d_cnt = nullptr;
-    CUDA_TRY(cudaMalloc(&d_cnt, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(p->step_sums.reserve(2 * sizeof(unsigned long long)));
+    unsigned long long* d_cnt = p->step_sums.as<unsigned long long>();
     CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), s));
     count_kernel<<<148, 256, 0, s>>>(p->counters[0], p->nst.as<int32_t>(),
                                      p->nrj.as<int32_t>(), d_cnt);
     unsigned long long h_cnt[2] = {0, 0};
-    cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, s);
-    cudaStreamSynchronize(s);
-    cudaFree(d_cnt);
+    CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt),
+                             cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
     p->counters[1] = static_cast<int64_t>(h_cnt[0]);
     p->counters[2] = static_cast<int64_t>(h_cnt[1]);
     p->counters_stale = false;
@@ -1047,7 +1199,14 @@ int launch_loglik(chi_b200_problem* p, int64_t B, const int32_t* d_ids,
   a.snap = nullptr;
   a.snap_rows = 0;
   a.snap_width = 0;
-  a.work_counter = work_counter;
+  // the persistent kernel's work counter belongs to the problem (slot 8: the
+  // un-chunked launches; slots 0-7: the chunks of chi_b200_hier_logpdf, which
+  // may be in flight together)
+  CUDA_TRY(p->work_counters.reserve(9 * sizeof(unsigned long long)));
+  a.work_counter = work_counter
+                       ? work_counter
+                       : p->work_counters.as<unsigned long long>() + 8;
+  bool ordered = false;
   {
     // Work order of the persistent kernel (SolveArgs::order_inner): with at
     // least a warp's worth of parameter vectors the lanes of a warp take the
@@ -1071,9 +1230,8 @@ int launch_loglik(chi_b200_problem* p, int64_t B, const int32_t* d_ids,
     const int min_vectors = p->cfg_order >= 0 ? p->cfg_order : min_inner;
     const int wait = p->cfg_wait >= 0 ? p->cfg_wait : wait_env;
     // (the map is a permutation of [0, B) only for a full C x n layout)
-    const bool ordered =
-        min_vectors > 0 && order_inner >= min_vectors &&
-        static_cast<int64_t>(order_inner) * order_stride == B;
+    ordered = min_vectors > 0 && order_inner >= min_vectors &&
+              static_cast<int64_t>(order_inner) * order_stride == B;
     if (ordered) {
       a.order_inner = order_inner;
       a.order_stride = order_stride;
@@ -1081,25 +1239,38 @@ int launch_loglik(chi_b200_problem* p, int64_t B, const int32_t* d_ids,
     a.refill_wait = wait >= 0 ? wait : (ordered ? INT32_MAX : 0);
   }
   {
-    // deferred observation for the streamed kernels when the snapshots fit
+    // Observation (output map, error model, gradient) fused in the solve
+    // kernel or deferred to observe_kernel via snapshots.  Default policy:
+    // fused when the lanes of a warp share the individual (they reach the
+    // records together, the handler runs with about half a warp: on par with
+    // the deferred form, without 0.98 GB of snapshots per 1.02 M systems and
+    // the second kernel); deferred otherwise (the handler would run with one
+    // or two active lanes), when the snapshots fit half of the free memory.
+    // An explicit budget (chi_b200_problem_set_snapshot_budget /
+    // CHI_B200_SNAP_MB) overrides the policy: 0 = always fused, > 0 = deferred
+    // whenever the snapshots fit.
     const bool streamed =
         p->variant < 0 || (p->variant < p->vt->n_variants &&
                            p->vt->variant_lanes[p->variant] == 0);
+    bool explicit_budget = p->snap_budget >= 0 && !p->snap_budget_auto;
     if (p->snap_budget < 0) {
       const char* env = std::getenv("CHI_B200_SNAP_MB");
       if (env) {
         p->snap_budget = static_cast<int64_t>(std::atof(env) * 1048576.0);
+        explicit_budget = true;
       } else {
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         p->snap_budget = static_cast<int64_t>(free_b / 2);
+        p->snap_budget_auto = true;
       }
     }
+    const bool want_snap = explicit_budget || !ordered;
     const int N = p->vt->n_states;
     const int integrated = with_grad ? a.n_int : 0;
     const int64_t width = static_cast<int64_t>(N) * (1 + integrated);
     const int64_t bytes = B_res * p->max_rec * width * 8;
-    if (streamed && p->max_rec > 0 && p->max_rec <= INT32_MAX &&
+    if (streamed && want_snap && p->max_rec > 0 && p->max_rec <= INT32_MAX &&
         bytes <= p->snap_budget) {
       CUDA_TRY(p->snap.reserve(static_cast<size_t>(bytes)));
       a.snap = p->snap.as<double>() + b0 * p->max_rec * width;
@@ -1127,16 +1298,25 @@ int launch_loglik(chi_b200_problem* p, int64_t B, const int32_t* d_ids,
   return 0;
 }
 
-// DFMA micro-benchmark: 8 independent FMA chains per thread.
-__global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
-  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3,
-         x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+// DFMA micro-benchmark: 16 independent FMA chains per thread, fully unrolled
+// (8 resident warps per scheduler x 16 chains cover the 8-cycle latency of
+// the pipe many times over: the loop is bound by DFMA issue alone).
+__global__ void __launch_bounds__(256)
+fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) x[k] = threadIdx.x + k;
+#pragma unroll 1
   for (int i = 0; i < iters; ++i) {
-    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b);
-    x3 = fma(x3, a, b); x4 = fma(x4, a, b); x5 = fma(x5, a, b);
-    x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) x[k] = fma(x[k], a, b);
+    }
   }
-  const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += x[k];
   if (s == 123.456) out[0] = s;
 }
 
@@ -1199,6 +1379,7 @@ int chi_b200_loglik(chi_b200_problem* p, int64_t B, const int32_t* ids,
                              cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   p->counters[0] = B;
+  p->counters_stale = true;
   return 0;
 }
 
@@ -1247,7 +1428,22 @@ int chi_b200_simulate(chi_b200_problem* p, int64_t B, const int32_t* ids,
   a.traj_y = p->traj_y.as<double>();
   a.traj_s = p->traj_s.as<double>();
   a.status = p->status.as<int32_t>();
+  CUDA_TRY(p->nst.reserve(B * sizeof(int32_t)));
+  CUDA_TRY(p->nrj.reserve(B * sizeof(int32_t)));
+  a.n_steps = p->nst.as<int32_t>();
+  a.n_rej = p->nrj.as<int32_t>();
+  CUDA_TRY(p->work_counters.reserve(9 * sizeof(unsigned long long)));
+  a.work_counter = p->work_counters.as<unsigned long long>() + 8;
+  if (p->timing) CUDA_TRY(cudaEventRecord(p->ev0, s));
   CUDA_TRY(p->vt->launch(a, p->variant, s));
+  if (p->timing) {
+    CUDA_TRY(cudaEventRecord(p->ev1, s));
+    CUDA_TRY(cudaEventSynchronize(p->ev1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+    p->solve_ms_sum += ms;
+    p->solve_launches += 1;
+  }
   if (rows > 0) {
     CUDA_TRY(cudaMemcpyAsync(y_out, p->traj_y.ptr, rows * sizeof(double),
                              cudaMemcpyDeviceToHost, s));
@@ -1262,6 +1458,7 @@ int chi_b200_simulate(chi_b200_problem* p, int64_t B, const int32_t* ids,
   CUDA_TRY(cudaStreamSynchronize(s));
   p->counters[0] = B;
   p->counters[3] = 1;
+  p->counters_stale = true;
   return 0;
 }
 
@@ -1278,11 +1475,17 @@ int chi_b200_error_model(int32_t device, int32_t kind, const double* sigma,
   CUDA_TRY(cudaSetDevice(device));
   const int n_sig = kind == ERR_CAM ? 2 : 1;
   const int n_out = 1 + (with_grad ? n_par + n_sig : 0);
-  DevBuf d_y, d_s, d_o, d_out, d_pw;
-  auto cleanup = [&]() {
-    d_y.release(); d_s.release(); d_o.release(); d_out.release();
-    d_pw.release();
+  // scratch kept per device across calls (grown on demand, never shrunk)
+  struct Scratch {
+    DevBuf y, s, o, out, pw;
   };
+  static std::mutex mtx;
+  static Scratch cache[16];
+  if (device < 0 || device >= 16) return fail(-1, "device out of range");
+  std::lock_guard<std::mutex> lock(mtx);
+  Scratch& sc = cache[device];
+  DevBuf &d_y = sc.y, &d_s = sc.s, &d_o = sc.o, &d_out = sc.out, &d_pw = sc.pw;
+  auto cleanup = [&]() {};
   const size_t nb = std::max<int64_t>(n_obs, 1) * sizeof(double);
   cudaError_t err = d_y.reserve(nb);
   if (err == cudaSuccess) err = d_o.reserve(nb);
@@ -1546,10 +1749,31 @@ int run_hier(chi_b200_problem* p, int32_t C, const double* d_x,
       D, p->n_ids, p->id_begin, p->id_end, n_params, n_bottom, with_grad,
       d_x, p->covariates.as<double>(), d_ll, d_dlp, d_grad, d_partial);
   CUDA_TRY(cudaGetLastError());
+  // individuals sharded over several GPUs: one all-reduce (sum) of
+  // [score | d theta | flags] per evaluation, on the compute stream, before
+  // anything travels to the host (chi/_log_pdfs.py:289-292 partitions over
+  // individuals; the bottom-level blocks are disjoint and stay where they are)
+  const bool reduce = p->comm != nullptr && !skip_solve;
+  double* d_pack = nullptr;
+  if (reduce) {
+    CUDA_TRY(p->pack.reserve(static_cast<size_t>(C_res) * (n_slots + 2) *
+                             sizeof(double)));
+    d_pack = p->pack.as<double>() + static_cast<int64_t>(c0) * (n_slots + 2);
+  }
   pop_final_kernel<<<C, 64, 0, s>>>(D.n_red, n_blk, n_params, n_bottom,
                                     with_grad, d_r2t, d_partial, d_popflag,
-                                    d_score, d_grad);
+                                    d_status, d_score, d_grad, d_pack);
   CUDA_TRY(cudaGetLastError());
+  if (reduce) {
+    NCCL_TRY(nccl_api().AllReduce(
+        d_pack, d_pack, static_cast<size_t>(C) * (n_slots + 2), ncclDouble,
+        ncclSum, p->comm, s));
+    pop_unpack_kernel<<<C, 64, 0, s>>>(D.n_red, n_params, n_bottom, with_grad,
+                                       d_r2t, d_pack, d_score, d_grad,
+                                       d_status);
+    CUDA_TRY(cudaGetLastError());
+    p->counters[3] += 1;
+  }
   p->counters[3] += 2;
   p->counters[0] = b0 + B;
   return 0;
@@ -1618,8 +1842,8 @@ int chi_b200_hier_logpdf(chi_b200_problem* p, int32_t C, const double* x,
   if (n_chunks > 1) {
     if (!p->stream2)
       CUDA_TRY(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
-    CUDA_TRY(p->work_counters.reserve(8 * sizeof(unsigned long long)));
   }
+  CUDA_TRY(p->work_counters.reserve(9 * sizeof(unsigned long long)));
   p->counters[3] = 0;
   for (int k = 0; k < n_chunks; ++k) {
     const int32_t c0 = static_cast<int32_t>(static_cast<int64_t>(C) * k /
@@ -1765,17 +1989,21 @@ int chi_b200_fp64_peak(int32_t device, double* tflops, double* sm_clock_mhz) {
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0));
   CUDA_TRY(cudaEventCreate(&e1));
+  // 8 blocks of 256 threads per SM = 16 warps per scheduler; about 10 ms per
+  // launch and 24 launches, so that a clock sampler running beside it sees
+  // the SM clock under this load
   const int blocks = prop.multiProcessorCount * 8, threads = 256;
-  const int iters = 1 << 15;
+  const int iters = 1 << 12;
   double best = 0.0;
-  for (int rep = 0; rep < 6; ++rep) {
+  for (int rep = 0; rep < 24; ++rep) {
     CUDA_TRY(cudaEventRecord(e0));
     fp64_peak_kernel<<<blocks, threads>>>(d_out, iters, 0.999999, 1e-7);
     CUDA_TRY(cudaEventRecord(e1));
     CUDA_TRY(cudaEventSynchronize(e1));
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-    const double flops = 2.0 * 8.0 * iters * static_cast<double>(blocks) * threads;
+    const double flops =
+        2.0 * 64.0 * iters * static_cast<double>(blocks) * threads;
     if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
   }
   cudaEventDestroy(e0);

@@ -654,13 +654,13 @@ struct Registrar {
     constexpr size_t smem =
         sizeof(double) * stream_slots<M>() * STREAM_BLOCK;
     constexpr int MAX_DEV = 16;
-    static unsigned long long* counters[MAX_DEV] = {};
     static int resident[MAX_DEV] = {};
     int dev = 0;
     cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess) return err;
     if (dev < 0 || dev >= MAX_DEV) return cudaErrorInvalidDevice;
-    if (!counters[dev]) {
+    if (!args.work_counter) return cudaErrorInvalidValue;
+    if (!resident[dev]) {
       if (smem > 48 * 1024) {
         err = cudaFuncSetAttribute(
             solve_stream_kernel<M, CB, STREAM_BLOCK>,
@@ -676,12 +676,9 @@ struct Registrar {
       err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       if (err != cudaSuccess) return err;
       resident[dev] = bpsm * sms;
-      err = cudaMalloc(&counters[dev], sizeof(unsigned long long));
-      if (err != cudaSuccess) return err;
     }
     if (args.B == 0) return cudaSuccess;
-    unsigned long long* counter =
-        args.work_counter ? args.work_counter : counters[dev];
+    unsigned long long* counter = args.work_counter;
     err = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return err;
     int64_t blocks = (args.B + STREAM_BLOCK - 1) / STREAM_BLOCK;

@@ -60,6 +60,9 @@ extern "C" {
 #define CHI_B200_ST_MAX_STEPS 1
 #define CHI_B200_ST_STEP_UNDERFLOW 2
 #define CHI_B200_ST_NON_FINITE 3
+/* hierarchical evaluation with individuals sharded over several GPUs: all of
+ * this rank's systems succeeded, a system of another rank failed */
+#define CHI_B200_ST_REMOTE_FAILURE 4
 
 typedef struct chi_b200_problem chi_b200_problem;
 
@@ -192,7 +195,9 @@ int chi_b200_population_eval(chi_b200_problem* p, const double* top,
  * the shard of individuals evaluated by this call (multi-GPU).  With a shard
  * set, only the shard's block of bottom-level entries and the top-level
  * entries of x are read, and only those two column blocks of grad are
- * written (partial sums for the top level); the rest of grad is untouched.
+ * written (partial sums for the top level, or -- with a communicator set,
+ * chi_b200_problem_comm_init -- the sums over all ranks); the rest of grad is
+ * untouched.
  * The host-buffer entry point evaluates large batches in chunks on two
  * streams so that the copies overlap the solves (environment
  * CHI_B200_CHUNKS forces the number of chunks, 1 = one pass); page-locked
@@ -210,9 +215,29 @@ int chi_b200_hier_logpdf_dev(chi_b200_problem* p, int32_t C,
                              double* d_score, double* d_grad,
                              int32_t* d_status, void* stream);
 /* shard of individuals this problem evaluates inside hier_logpdf
- * (default: all); partial sums are left for the caller to all-reduce */
+ * (default: all); without a communicator the partial sums are left for the
+ * caller to reduce */
 int chi_b200_problem_set_shard(chi_b200_problem* p, int64_t id_begin,
                                int64_t id_end);
+/* Individuals sharded over the GPUs of one node (one process per GPU).  The
+ * reference sums the individuals' contributions in a Python loop
+ * (chi/_log_pdfs.py:289-292); with a communicator set, chi_b200_hier_logpdf
+ * and chi_b200_hier_logpdf_dev finish every evaluation with ONE all-reduce
+ * (sum, FP64, NCCL over NVLink) of [score | reduced top-level gradient |
+ * invalid-population flag | failure flag] on the compute stream, before any
+ * copy to the host: every rank returns the complete score and top-level
+ * gradient plus its own individuals' block of the bottom-level gradient.
+ *   chi_b200_comm_unique_id     rank 0 calls it and hands the
+ *                               CHI_B200_COMM_ID_BYTES bytes to the other ranks
+ *   chi_b200_problem_comm_init  collective over all ranks; the communicator is
+ *                               kept for the life of the problem
+ * All ranks must then evaluate the same number of vectors per call.  NCCL is
+ * bound at run time (libnccl.so.2; CHI_B200_NCCL_LIB overrides the name). */
+#define CHI_B200_COMM_ID_BYTES 128
+int chi_b200_comm_unique_id(uint8_t* id, int32_t capacity);
+int chi_b200_problem_comm_init(chi_b200_problem* p, int32_t world,
+                               int32_t rank, const uint8_t* id);
+int chi_b200_problem_comm_destroy(chi_b200_problem* p);
 /* work counters of the last hot-path call: systems, accepted steps,
  * rejected steps, kernel launches */
 int chi_b200_problem_counters(chi_b200_problem* p, int64_t out[4]);

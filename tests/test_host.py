@@ -349,6 +349,8 @@ def test_bench_host_design_matches_synthetic():
         np.testing.assert_array_equal(np.array(a), b.as_array())
     np.testing.assert_array_equal(
         bench.TWO_CMT_TYPICAL, _synthetic.TWO_CMT_TYPICAL)
+    assert (bench.BENCH_RTOL, bench.BENCH_ATOL) == (
+        _synthetic.BENCH_RTOL, _synthetic.BENCH_ATOL)
 
 
 def test_k_stage_tables_follow_from_the_transformed_tables():
@@ -695,3 +697,58 @@ def test_batched_posterior_combines_prior_and_likelihood_on_the_host():
         np.testing.assert_allclose(
             grad[ok, n_bottom:], 2.0 - X[ok, n_bottom:], rtol=1e-14)
         assert np.all(np.isfinite(grad[ok]))
+
+
+def test_invalid_prior_never_touches_other_shards_columns():
+    """Individuals sharded over ranks: the likelihood's page-locked gradient
+    buffer is reused across evaluations and only the rank's own columns are
+    rewritten.  A -inf prior fills the gradient row with +inf -- in the owned
+    columns only; the next evaluation must find the other individuals'
+    columns still zero (stale inf entries were all-reduced)."""
+    from chi_b200 import _log_pdfs
+
+    n_ids, n_h, n_top, C = 6, 2, 3, 4
+    n_bottom = n_ids * n_h
+    shard = (2, 4)
+
+    class ShardedStub(object):
+        """Mimics chi_b200_hier_logpdf with a shard: one cached buffer, only
+        the shard's bottom block and the top level are written."""
+        def __init__(self):
+            self.grad = np.zeros((C, n_bottom + n_top))
+            self.score = np.zeros(C)
+
+        def evaluateS1_batch(self, X, copy=True):
+            self.score[:] = np.sum(X, axis=1)
+            self.grad[:, shard[0] * n_h:shard[1] * n_h] = 2.0
+            self.grad[:, n_bottom:] = 3.0
+            return self.score, self.grad
+
+        def _fill_rows(self, grad, rows, value):
+            _log_pdfs.fill_owned_columns(
+                grad, rows, value, shard, n_ids, n_bottom)
+
+    class Prior(object):
+        def n_parameters(self):
+            return n_top
+
+        def evaluateS1_batch(self, T):
+            p = np.where(T[:, 0] < 0, -np.inf, -0.5 * np.sum(T * T, axis=1))
+            return p, -T
+
+    post = object.__new__(_log_pdfs.HierarchicalLogPosterior)
+    post._log_likelihood = ShardedStub()
+    post._log_prior = Prior()
+    post._n_bottom = n_bottom
+    post._n_parameters = n_bottom + n_top
+    X = np.random.default_rng(0).uniform(0.1, 1.0, (C, n_bottom + n_top))
+    X[1, n_bottom] = -1.0
+    s, g = post.evaluateS1_batch(X, copy=False)
+    assert np.isneginf(s[1])
+    assert np.all(np.isposinf(g[1, 4:8])) and np.all(np.isposinf(g[1, 12:]))
+    assert np.all(g[1, :4] == 0.0) and np.all(g[1, 8:12] == 0.0)
+    X[1, n_bottom] = 0.5
+    s, g = post.evaluateS1_batch(X, copy=False)
+    assert np.all(np.isfinite(s)) and np.all(np.isfinite(g))
+    assert np.all(g[:, :4] == 0.0) and np.all(g[:, 8:12] == 0.0)
+    np.testing.assert_allclose(g[:, 4:8], 2.0)
