@@ -424,8 +424,10 @@ class ModelCode(object):
         n, P = self.n, self.n + self.nc
         mc_max = {1: 8, 2: 4, 3: 3}.get(n, 2)
         # lanes == 0: streamed-columns kernel; `cols` is then the method
-        # code: 1 = RODAS4, 5 = RODAS5
-        out = [(0, 5), (0, 1)]
+        # code: 1 = RODAS4, 5 = RODAS5, 9 / 11 = ROSL(9) / ROSL(11), the
+        # Rosenbrock methods for linear models (integrator_stream.cuh)
+        out = [(0, 11), (0, 9), (0, 5), (0, 1)] if self.linear \
+            else [(0, 5), (0, 1)]
         for mc in range(min(mc_max, P), 0, -1):
             g = -(-P // mc)
             if g > 32 or any(g == v[0] for v in out):

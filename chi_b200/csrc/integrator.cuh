@@ -652,7 +652,7 @@ struct Registrar {
   static cudaError_t launch_stream(const SolveArgs& args,
                                    cudaStream_t stream) {
     constexpr size_t smem =
-        sizeof(double) * stream_slots<M>() * STREAM_BLOCK;
+        sizeof(double) * stream_slots<M, CB>() * STREAM_BLOCK;
     constexpr int MAX_DEV = 16;
     static int resident[MAX_DEV] = {};
     int dev = 0;
@@ -772,7 +772,7 @@ struct Registrar {
     cudaFuncAttributes at;
     if constexpr (G == 0) {
       constexpr size_t smem =
-          sizeof(double) * stream_slots<M>() * STREAM_BLOCK;
+          sizeof(double) * stream_slots<M, MC>() * STREAM_BLOCK;
       cudaError_t err = cudaFuncGetAttributes(
           &at, solve_stream_kernel<M, MC, STREAM_BLOCK>);
       if (err != cudaSuccess) return err;

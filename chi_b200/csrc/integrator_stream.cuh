@@ -48,10 +48,22 @@ constexpr int stream_integrated() {
   for (int k = 0; k < M::NC; ++k) n -= (M::INERT_MASK >> k) & 1u;
   return n;
 }
+// METHOD: 1 / 5 = RODAS4 / RODAS5, 9 / 11 = ROSL(9) / ROSL(11).  The ROSL
+// step keeps everything of a step in registers: no candidate copy of S and
+// no stage values in shared memory.
+constexpr bool stream_is_rosl(const int method) {
+  return method == 9 || method == 11;
+}
+template <class M, int METHOD>
+constexpr int stream_slots() {
+  const int pi = stream_integrated<M>();
+  return (stream_is_rosl(METHOD) ? pi * M::N : 2 * pi * M::N + 7 * M::N) +
+         M::P + 8 + M::NCS + M::N;
+}
+// largest of the methods (host buffers of the CPU port)
 template <class M>
 constexpr int stream_slots() {
-  return 2 * stream_integrated<M>() * M::N + M::P + 7 * M::N + 8 + M::NCS +
-         M::N;
+  return stream_slots<M, 5>();
 }
 
 namespace rodas5 {
@@ -137,6 +149,47 @@ constexpr double K8D6 = 0.10408618829845701;   // K86 - K76
 constexpr double K87 = -0.10408618829845708;
 }  // namespace rodas5
 
+
+namespace rosl {
+// ROSL(s): s-stage Rosenbrock methods for LINEAR systems z' = J z + g (g
+// constant over a step; all PK models of the library, and their augmented
+// sensitivity systems, are of this form between two dose-rate edges).  For a
+// linear system every Rosenbrock method with a single gamma reduces to
+//     z_1 = R(hJ) z_0 + h Q(hJ) g,  R(x) = 1 + x Q(x) = P(x) / (1 - gamma x)^s,
+// and only the linear order conditions R(x) = exp(x) + O(x^(p+1)) remain: with
+// P the degree s-1 section of exp(x) (1 - gamma x)^s the method has order
+// p = s - 1 (restricted Pade approximant, Norsett) and R(inf) = 0.  Written
+// in powers of E = T - I = gamma h J T, T = (I - gamma h J)^-1 (the kernel's
+// E = W^-1 J):
+//     z_1 = z_0 + sum_k c_k w_k,   w_0 = T (h f(z_0)),   w_k = E w_{k-1},
+// ONE N x N product and one accumulation per stage, nothing of the previous
+// stages kept.  E^k = O(h^k): the terms decay, the c_k are O(1), and the last
+// two terms are the difference to the embedded method of order s - 2:
+//     err = c_{s-2} w_{s-2} + c_{s-1} w_{s-1}.
+// Tables and checks (order, A-stability: max |R(iy)| = 1): tools/derive_rosl.py.
+// Against RODAS5 on the bench workload: 72 instead of 150 step attempts per
+// system at a 40 times smaller global error (tests/test_host.py).
+template <int S>
+struct Table;
+template <>
+struct Table<9> {   // order 8(7), A-stable for gamma in [0.171, 0.261]
+  static constexpr double GAMMA = 0.2;
+  static constexpr double C[9] = {
+      1.0, 1.5, 0.16666666666666666667, -0.79166666666666666667, 0.375,
+      0.21527777777777777778, -0.48313492063492063492,
+      0.38206845238095238095, 0.44714781746031746032};
+};
+template <>
+struct Table<11> {  // order 10(9), A-stable for gamma in [0.147, 0.165]
+  static constexpr double GAMMA = 0.16;
+  static constexpr double C[11] = {
+      1.0, 2.125, 1.2604166666666666667, -0.98372395833333333333,
+      -0.41194661458333333333, 0.91328260633680555556,
+      -0.45594884478856646825, -0.24326151136368040055,
+      0.6181601832573165759, -0.53172900623640265625,
+      -0.57111326014869427555};
+};
+}  // namespace rosl
 
 // Device copies of the coefficients in constant memory: the FP64 instructions
 // then take them as constant-bank operands instead of materialising 64-bit
@@ -255,6 +308,28 @@ static __constant__ double K8D6 = rodas5::K8D6;
 static __constant__ double K87 = rodas5::K87;
 }  // namespace rodas5d
 #endif
+#ifdef __CUDACC__
+namespace rosld {
+static __constant__ double C9[9] = {
+    1.0, 1.5, 0.16666666666666666667, -0.79166666666666666667, 0.375,
+    0.21527777777777777778, -0.48313492063492063492, 0.38206845238095238095,
+    0.44714781746031746032};
+static __constant__ double C11[11] = {
+    1.0, 2.125, 1.2604166666666666667, -0.98372395833333333333,
+    -0.41194661458333333333, 0.91328260633680555556, -0.45594884478856646825,
+    -0.24326151136368040055, 0.6181601832573165759, -0.53172900623640265625,
+    -0.57111326014869427555};
+}  // namespace rosld
+#endif
+// coefficient k of ROSL(S): a constant-bank operand on the device
+template <int S>
+CHI_HD double rosl_c(const int k) {
+#ifdef __CUDA_ARCH__
+  return S == 9 ? rosld::C9[k] : rosld::C11[k];
+#else
+  return rosl::Table<S>::C[k];
+#endif
+}
 #ifdef __CUDA_ARCH__
 #define CHI_R4(x) rodas4d::x
 #define CHI_R5(x) rodas5d::x
@@ -443,10 +518,15 @@ CHI_HD ErrTerms error_terms(const int kind, const double* sg, const double yb,
 template <class M, int METHOD_CODE>
 struct StreamSolver {
   static constexpr bool R5 = METHOD_CODE == 5;
-  static constexpr int NS = R5 ? 8 : 6;          // stages
-  static constexpr double GAMMA = R5 ? rodas5::GAMMA : rodas4::GAMMA;
+  // ROSL(9), ROSL(11): the linear-model methods (namespace rosl)
+  static constexpr bool ROSL = METHOD_CODE == 9 || METHOD_CODE == 11;
+  static constexpr int NS = ROSL ? METHOD_CODE : (R5 ? 8 : 6);   // stages
+  static constexpr double GAMMA =
+      ROSL ? rosl::Table<ROSL ? METHOD_CODE : 9>::GAMMA
+           : (R5 ? rodas5::GAMMA : rodas4::GAMMA);
   // step-size exponent on err^2: -1/(2 (q+1)), q = order of the estimate
-  static constexpr float EXPO = R5 ? -0.1f : -0.125f;
+  static constexpr float EXPO =
+      ROSL ? -0.5f / (METHOD_CODE - 1) : (R5 ? -0.1f : -0.125f);
   static constexpr int N = M::N;
   static constexpr int NC = M::NC;
   static constexpr int NCS = M::NCS;
@@ -460,7 +540,8 @@ struct StreamSolver {
   double u, t, h, t_stop;
   double J0[N * N];
   int cur, n_att;
-  int flags;        // bits 0-7 status, 8-27 rejected steps, 28-29 edge kind
+  int flags;        // bits 0-7 status, 8-27 rejected steps, 28-29 edge kind,
+                    // 30 all columns integrated (ROSL)
   bool invalid, after_reject;
 
   CHI_HD StreamSolver(const SolveArgs& args, double* smem, int smem_stride)
@@ -469,9 +550,15 @@ struct StreamSolver {
   static constexpr int PI = stream_integrated<M>();
 // S is stored for the integrated columns only; `m` is the column's rank
 // among them (the loops over the columns carry it along)
+  static constexpr int OFF_G = (ROSL ? 1 : 2) * PI * N;
+  static constexpr int OFF_ZY = OFF_G + P;
+  static constexpr int OFF_COLD = OFF_ZY + (ROSL ? 0 : 7 * N);
+  static constexpr int OFF_C = OFF_COLD + 8;
+  static constexpr int OFF_Y = OFF_C + NCS;
+  static_assert(OFF_Y + N == stream_slots<M, METHOD_CODE>(), "slot layout");
 #define CHI_S(buf, m, n) sm[(((buf) * PI + (m)) * N + (n)) * stride]
-#define CHI_G(k) sm[(2 * PI * N + (k)) * stride]
-#define CHI_ZY(i, n) sm[(2 * PI * N + P + ((i) - 1) * N + (n)) * stride]
+#define CHI_G(k) sm[(OFF_G + (k)) * stride]
+#define CHI_ZY(i, n) sm[(OFF_ZY + ((i) - 1) * N + (n)) * stride]
 // Cold per-system scalars, kept out of the register file because they are
 // only touched when an event is pending:
 //   0 system index     1 next dose-rate edge     2 time of the next record
@@ -482,13 +569,13 @@ struct StreamSolver {
 //     increase / decrease.  Dosing is usually periodic: the next edge of the
 //     same kind restarts from that size instead of a guess (halves the
 //     rejected steps, -2.6 % step attempts on the bench workload)
-#define CHI_COLD(k) sm[(2 * PI * N + P + 7 * N + (k)) * stride]
+#define CHI_COLD(k) sm[(OFF_COLD + (k)) * stride]
 // the model constants: needed by the state column and the event handlers,
 // not by the sensitivity columns of a linear model -- kept here and loaded
 // where used so that they do not occupy registers across the column loop
-#define CHI_C(j) sm[(2 * PI * N + P + 7 * N + 8 + (j)) * stride]
+#define CHI_C(j) sm[(OFF_C + (j)) * stride]
 // ... and the state itself
-#define CHI_Y(n) sm[(2 * PI * N + P + 7 * N + 8 + NCS + (n)) * stride]
+#define CHI_Y(n) sm[(OFF_Y + (n)) * stride]
 
   CHI_HD static bool inert(const int pk) {
     return pk >= N && ((M::INERT_MASK >> (pk - N)) & 1u);
@@ -551,7 +638,8 @@ struct StreamSolver {
   }
 
   CHI_HD void init(const int64_t b) {
-    static_assert(METHOD_CODE == 1 || METHOD_CODE == 5, "unknown method");
+    static_assert(METHOD_CODE == 1 || METHOD_CODE == 5 || ROSL,
+                  "unknown method");
     static_assert(P <= MAX_COLS, "too many mechanistic parameters");
     const int id = individual(b);
     const double* xb = a.x + b * a.x_stride;
@@ -576,7 +664,7 @@ struct StreamSolver {
 #pragma unroll
       for (int n = 0; n < N; ++n) {
         CHI_S(0, m, n) = (pk == n) ? 1.0 : 0.0;
-        CHI_S(1, m, n) = 0.0;
+        if (!ROSL) CHI_S(1, m, n) = 0.0;
       }
     }
     invalid = false;
@@ -619,6 +707,15 @@ struct StreamSolver {
     after_reject = false;
     n_att = 0;
     flags = ST_OK;
+    if (ROSL) {
+      // bit 30: the integrated columns are ALL columns of the model, in
+      // their natural order (step_rosl<1>)
+      bool full = ni == PI;
+#pragma unroll
+      for (int m = 0; m < PI; ++m)
+        if (full && a.int_param[m] != full_param(m)) full = false;
+      if (full) flags |= 1 << 30;
+    }
     if (M::LINEAR) M::jac(y, c, J0);
   }
 
@@ -905,6 +1002,312 @@ struct StreamSolver {
 
   // One step attempt towards the next stop.  Returns true on failure.
   CHI_HD bool step() {
+    if constexpr (ROSL) {
+      if constexpr (M::LINEAR) {
+        if (n_int() == 0) return step_rosl<0>();
+        if (flags & (1 << 30)) return step_rosl<1>();
+        return step_rosl<2>();
+      } else {
+        flags |= ST_NON_FINITE;   // ROSL is for linear models only
+        return true;
+      }
+    } else {
+      return step_rodas();
+    }
+  }
+
+  // parameter index of the m-th integrated column when ALL columns of the
+  // model are asked for (the usual case): known at compile time
+  static constexpr int full_param(const int m) {
+    int seen = 0;
+    for (int pk = 0; pk < P; ++pk) {
+      const bool inert_pk =
+          pk >= N && ((M::INERT_MASK >> (pk - N)) & 1u);
+      if (inert_pk) continue;
+      if (seen == m) return pk;
+      ++seen;
+    }
+    return 0;
+  }
+
+  // What step_rodas and step_rosl do with the error norm of an attempt:
+  // accept or reject, next step size, failure bookkeeping.  Returns true on
+  // failure.
+  CHI_HD bool control(const float errsq, const double hs, const bool clipped,
+                      bool& accept) {
+    accept = errsq <= 1.0f;
+    float fac;
+    if (!(errsq == errsq) || isinf(errsq)) {
+      fac = 0.2f;
+    } else {
+      fac = CHI_SAFETY * fast_powf(fmaxf(errsq, 1e-30f), EXPO);
+      fac = fminf(fmaxf(fac, 0.2f), CHI_FACMAX);
+    }
+    if (accept) {
+      t = clipped ? t_stop : t + hs;
+      if (edge_kind() != 0) {
+        set_cold_float(7, edge_kind() - 1, static_cast<float>(hs));
+        flags &= ~(3 << 28);
+      }
+      if (after_reject) fac = fminf(fac, 1.0f);
+      const double hn = hs * static_cast<double>(fac);
+      h = (hs < h) ? fmax(hn, h) : hn;
+      after_reject = false;
+    } else {
+      h = hs * static_cast<double>(fminf(fac, 0.9f));
+      after_reject = true;
+      flags += 0x100;
+      if (h <= 1e-14 * fmax(fabs(t), 1.0)) {
+        flags |= (errsq == errsq) ? ST_STEP_UNDERFLOW : ST_NON_FINITE;
+        return true;
+      }
+    }
+    if (++n_att >= a.max_steps) {
+      flags |= ST_MAX_STEPS;
+      return true;
+    }
+    return false;
+  }
+
+  // One ROSL(s) step attempt of a linear model: the state column and all
+  // integrated sensitivity columns advance TOGETHER, stage by stage, in
+  // registers -- (1 + columns) N independent FMA chains per thread, nothing
+  // of the earlier stages kept, no stage values in shared memory.
+  //   w_0^y = T h f(y),                       w_k^y = E w_{k-1}^y
+  //   w_0^S = T h (J S + D_k y + e_k) + W^-1 D_k w_0^y,
+  //   w_k^S = E w_{k-1}^S + W^-1 D_k (w_{k-1}^y + w_k^y)
+  // (the augmented Jacobian [[J, 0], [D_k, J]] is block triangular, so
+  // T_aug - I = [[E, 0], [gamma h T D_k T, E]] and T w = w + E w).
+  // MODE 0: no columns (forward only); 1: all columns of the model (their
+  // parameters are compile-time constants: the column terms fold); 2: a
+  // subset chosen at run time (fix_parameters), unused slots carry zeros.
+  template <int MODE>
+  CHI_HD bool step_rosl() {
+    constexpr int S = NS;
+    constexpr int NCOL = MODE == 0 ? 0 : PI;
+    constexpr int NCA = NCOL > 0 ? NCOL : 1;
+    constexpr bool R1 = M::COL_RANK1;
+    constexpr int WDN = R1 ? N : N * N;
+    double y[N], c[NCS];
+    load_state(y);
+    load_constants(c);
+    if (h == 0.0) {
+      h = CHI_H0_FRACTION * (t_stop - t);
+      after_reject = false;
+    }
+    const double rem = t_stop - t;
+    double hs = h;
+    bool clipped = false;
+    if (rem <= CHI_CLIP_STRETCH * h) {
+      hs = rem;
+      clipped = true;
+    } else if (rem < 2.0 * h) {
+      hs = 0.5 * rem;
+    }
+    const double hinv = rcp_newton(hs);
+    double Wi[N * N], E[N * N];
+    {
+      double W[N * N];
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+          W[i * N + j] = (i == j ? hinv * (1.0 / GAMMA) : 0.0) - J0[i * N + j];
+      invert<N>(W, Wi);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double acc = Wi[i * N] * J0[j];
+#pragma unroll
+        for (int q = 1; q < N; ++q)
+          acc = fma(Wi[i * N + q], J0[q * N + j], acc);
+        E[i * N + j] = acc;
+      }
+    // ---- stage 0 ----------------------------------------------------------
+    double ay[N], zy[N], ty[N];
+    {
+      double f0[N];
+      M::rhs(y, c, u, f0);
+#pragma unroll
+      for (int n = 0; n < N; ++n) f0[n] *= hs;
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        double acc = f0[n];
+#pragma unroll
+        for (int q = 0; q < N; ++q) acc = fma(E[n * N + q], f0[q], acc);
+        ay[n] = acc;
+        zy[n] = fma(rosl_c<S>(0), acc, y[n]);
+        ty[n] = 0.0;
+      }
+    }
+    double w[NCA][N], zs[NCA][N], ts[NCA][N], WD[NCA][WDN];
+    int qs[NCA];
+    bool terms[NCA];
+    const int ni = MODE == 2 ? n_int() : NCOL;
+#pragma unroll
+    for (int m = 0; m < NCOL; ++m) {
+      const bool live = MODE == 1 || m < ni;
+      const int pk = MODE == 1 ? full_param(m) : (live ? a.int_param[m] : 0);
+      const int kc = pk >= N ? pk - N : -1;
+      terms[m] = live && kc >= 0;
+      qs[m] = 0;
+      double S0[N], v[N];
+#pragma unroll
+      for (int n = 0; n < N; ++n) S0[n] = live ? CHI_S(cur, m, n) : 0.0;
+      matvec<N>(J0, S0, v);
+#pragma unroll
+      for (int j = 0; j < WDN; ++j) WD[m][j] = 0.0;
+      double cpl[N];
+#pragma unroll
+      for (int n = 0; n < N; ++n) cpl[n] = 0.0;
+      if (terms[m]) {
+        if constexpr (R1) {
+          double dk[N], ek[N];
+          const int q1 = M::col_rank1(kc, c, u, dk, ek);
+          qs[m] = q1;
+          double yq = y[0], aq = ay[0];
+#pragma unroll
+          for (int j = 1; j < N; ++j) {
+            yq = (q1 == j) ? y[j] : yq;
+            aq = (q1 == j) ? ay[j] : aq;
+          }
+#pragma unroll
+          for (int n = 0; n < N; ++n) v[n] += fma(dk[n], yq, ek[n]);
+          matvec<N>(Wi, dk, WD[m]);
+#pragma unroll
+          for (int n = 0; n < N; ++n) cpl[n] = WD[m][n] * aq;
+        } else {
+          double DK[N * N], ek[N];
+          M::col_linear(kc, c, u, DK, ek);
+#pragma unroll
+          for (int n = 0; n < N; ++n) {
+            double acc = ek[n];
+#pragma unroll
+            for (int q = 0; q < N; ++q) acc = fma(DK[n * N + q], y[q], acc);
+            v[n] += acc;
+          }
+#pragma unroll
+          for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+              double acc = Wi[i * N] * DK[j];
+#pragma unroll
+              for (int q = 1; q < N; ++q)
+                acc = fma(Wi[i * N + q], DK[q * N + j], acc);
+              WD[m][i * N + j] = acc;
+            }
+          matvec<N>(WD[m], ay, cpl);
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < N; ++n) v[n] *= hs;
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        double acc = v[n] + cpl[n];
+#pragma unroll
+        for (int q = 0; q < N; ++q) acc = fma(E[n * N + q], v[q], acc);
+        w[m][n] = acc;
+        zs[m][n] = fma(rosl_c<S>(0), acc, S0[n]);
+        ts[m][n] = 0.0;
+      }
+    }
+    // ---- stages 1 .. S-1 ----------------------------------------------------
+#pragma unroll
+    for (int k = 1; k < S; ++k) {
+      const double ck = rosl_c<S>(k);
+      double an[N], sig[N];
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        double acc = E[n * N] * ay[0];
+#pragma unroll
+        for (int q = 1; q < N; ++q) acc = fma(E[n * N + q], ay[q], acc);
+        an[n] = acc;
+      }
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        sig[n] = ay[n] + an[n];
+        ay[n] = an[n];
+        if (k >= S - 2) ty[n] = fma(ck, an[n], ty[n]);
+        else zy[n] = fma(ck, an[n], zy[n]);
+      }
+#pragma unroll
+      for (int m = 0; m < NCOL; ++m) {
+        double wn[N];
+        if (terms[m]) {
+          if constexpr (R1) {
+            double sq = sig[0];
+#pragma unroll
+            for (int j = 1; j < N; ++j) sq = (qs[m] == j) ? sig[j] : sq;
+#pragma unroll
+            for (int n = 0; n < N; ++n) wn[n] = WD[m][n] * sq;
+          } else {
+            matvec<N>(WD[m], sig, wn);
+          }
+#pragma unroll
+          for (int n = 0; n < N; ++n)
+#pragma unroll
+            for (int q = 0; q < N; ++q)
+              wn[n] = fma(E[n * N + q], w[m][q], wn[n]);
+        } else {
+#pragma unroll
+          for (int n = 0; n < N; ++n) {
+            double acc = E[n * N] * w[m][0];
+#pragma unroll
+            for (int q = 1; q < N; ++q) acc = fma(E[n * N + q], w[m][q], acc);
+            wn[n] = acc;
+          }
+        }
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+          w[m][n] = wn[n];
+          if (k >= S - 2) ts[m][n] = fma(ck, wn[n], ts[m][n]);
+          else zs[m][n] = fma(ck, wn[n], zs[m][n]);
+        }
+      }
+    }
+    // ---- error norm: max over the columns of the scaled RMS -----------------
+    const float atol_f = static_cast<float>(a.atol);
+    const float rtol_f = static_cast<float>(a.rtol);
+    float errsq;
+    {
+      float s2 = 0.0f;
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        zy[n] += ty[n];
+        s2 += err_term(ty[n], y[n], zy[n], atol_f, rtol_f);
+      }
+      errsq = s2 * (1.0f / N);
+    }
+#pragma unroll
+    for (int m = 0; m < NCOL; ++m) {
+      float s2 = 0.0f;
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        const double S0n = (MODE == 1 || m < ni) ? CHI_S(cur, m, n) : 0.0;
+        zs[m][n] += ts[m][n];
+        s2 += err_term(ts[m][n], S0n, zs[m][n], atol_f, rtol_f);
+      }
+      errsq = fmaxf(errsq, s2 * (1.0f / N));
+    }
+    bool accept;
+    const bool failed = control(errsq, hs, clipped, accept);
+    if (accept) {
+#pragma unroll
+      for (int n = 0; n < N; ++n) CHI_Y(n) = zy[n];
+#pragma unroll
+      for (int m = 0; m < NCOL; ++m) {
+        if (MODE == 1 || m < ni) {
+#pragma unroll
+          for (int n = 0; n < N; ++n) CHI_S(cur, m, n) = zs[m][n];
+        }
+      }
+    }
+    return failed;
+  }
+
+  CHI_HD bool step_rodas() {
     double y[N], c[NCS];
     load_state(y);
     load_constants(c);
@@ -1064,42 +1467,15 @@ struct StreamSolver {
                                  atol_f, rtol_f));
     }
 
-    const bool accept = errsq <= 1.0f;
-    float fac;
-    if (!(errsq == errsq) || isinf(errsq)) {
-      fac = 0.2f;
-    } else {
-      fac = CHI_SAFETY * fast_powf(fmaxf(errsq, 1e-30f), EXPO);
-      fac = fminf(fmaxf(fac, 0.2f), CHI_FACMAX);
-    }
+    bool accept;
+    const bool failed = control(errsq, hs, clipped, accept);
     if (accept) {
-      t = clipped ? t_stop : t + hs;
 #pragma unroll
       for (int n = 0; n < N; ++n)
         CHI_Y(n) = M::LINEAR ? CHI_ZY(NS - 1, n) : Zlast[n];
       cur = nxt;
-      if (edge_kind() != 0) {
-        set_cold_float(7, edge_kind() - 1, static_cast<float>(hs));
-        flags &= ~(3 << 28);
-      }
-      if (after_reject) fac = fminf(fac, 1.0f);
-      const double hn = hs * static_cast<double>(fac);
-      h = (hs < h) ? fmax(hn, h) : hn;
-      after_reject = false;
-    } else {
-      h = hs * static_cast<double>(fminf(fac, 0.9f));
-      after_reject = true;
-      flags += 0x100;
-      if (h <= 1e-14 * fmax(fabs(t), 1.0)) {
-        flags |= (errsq == errsq) ? ST_STEP_UNDERFLOW : ST_NON_FINITE;
-        return true;
-      }
     }
-    if (++n_att >= a.max_steps) {
-      flags |= ST_MAX_STEPS;
-      return true;
-    }
-    return false;
+    return failed;
   }
 
   CHI_HD void finish() {

@@ -120,12 +120,14 @@ class Population(object):
     """Static data of a population in the layout the solve expects."""
 
     def __init__(self, key, outputs, error_kinds, times, observations,
-                 out_index, regimens, info=None, port=None):
+                 out_index, regimens, info=None, port=None, columns=None):
         """times/observations/out_index: per-individual arrays of records
         (sorted by time); regimens: per-individual list of events.  `info`
         (states, constants, outputs) and `port` (open_port) for a model that
-        is not built in."""
+        is not built in.  `columns`: mechanistic parameters whose
+        sensitivities are computed (default: all, in order)."""
         info = info if info is not None else model_index()[key]
+        self.columns = None if columns is None else [int(c) for c in columns]
         self._port = port
         self.key = key
         self.info = info
@@ -185,12 +187,13 @@ class Population(object):
                 a.err_off[o] = off
                 off += N_SIGMA[self.err_kind[o]]
         a.n_sigma = off
-        a.n_cols = self.P
+        cols = self.columns if self.columns is not None else range(self.P)
+        a.n_cols = len(cols)
         for k in range(MAX_COLS):
             a.param_col[k] = -1
-        for k in range(self.P):
-            a.col_param[k] = k
-            a.param_col[k] = k
+        for k, pk in enumerate(cols):
+            a.col_param[k] = pk
+            a.param_col[pk] = k
         (self._port or lib()).chi_port_fill_integrated(self.key.encode(), ctypes.byref(a))
         return a
 
@@ -254,7 +257,7 @@ class Population(object):
         toff = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
         rows = int(toff[-1])
         y = np.zeros(rows)
-        s = np.zeros((rows, self.P))
+        s = np.zeros((rows, a.n_cols))
         status = np.zeros(B, np.int32)
         nst = np.zeros(B, np.int32)
         nrj = np.zeros(B, np.int32)

@@ -463,8 +463,8 @@ def test_gpu_kernel_matches_cpu_port():
     pop = cport.Population(
         key, ['central.drug_concentration'], None, [times], None, None,
         [_events(model)])
-    # same routine as the default kernel variant: streamed RODAS5
-    yc, sc, st, _, _ = pop.simulate(psi, rtol=1e-8, atol=1e-10, stream_cb=5)
+    # same routine as the default kernel variant of a linear model: ROSL(11)
+    yc, sc, st, _, _ = pop.simulate(psi, rtol=1e-8, atol=1e-10, stream_cb=11)
     assert st[0] == 0
     np.testing.assert_allclose(y[0], yc, rtol=1e-9)
     np.testing.assert_allclose(
@@ -472,14 +472,15 @@ def test_gpu_kernel_matches_cpu_port():
 
 
 def test_all_kernel_variants_agree_with_exact_solution():
-    """Every compiled sensitivity-kernel variant (streamed RODAS5 / RODAS4,
-    lane-parallel RODAS4) integrates to the same exact solution."""
+    """Every compiled sensitivity-kernel variant (streamed ROSL(11) / ROSL(9)
+    for linear models, streamed RODAS5 / RODAS4, lane-parallel RODAS4)
+    integrates to the same exact solution."""
     model, omodel, psi, times = _build('two_cmt_direct_infusion')
     y_ref, s_ref = ode_exact.simulate(omodel, psi, times, _events(model))
     model.set_tolerance(**TIGHT)
     model.enable_sensitivities(True)
     variants = model.model_code().variants()
-    assert variants[0] == (0, 5) and (0, 1) in variants
+    assert variants[0] == (0, 11) and (0, 5) in variants and (0, 1) in variants
     for v in range(len(variants)):
         model.set_kernel_variant(v)
         y, s = model.simulate(psi, times)

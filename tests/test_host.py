@@ -426,6 +426,12 @@ def test_flop_model_of_the_bench_counts_the_k_stage_form():
     import bench
     info = np.array([2, 5, 4, 3, 6, 3, 10, 0])   # linear, rank-one terms
     assert bench.flops_per_step(2, 5, info, stages=8, n_init=2) == 1048
+    # ROSL(11), the default method of linear models: 24 (W^-1, E) + 142
+    # (state) + 2 x 122 (initial-value columns) + 3 x 174 (constants)
+    assert bench.flops_per_step(
+        2, 5, info, stages=11, n_init=2, method='ROSL11') == 932
+    assert bench.flops_per_step(
+        2, 0, info, stages=11, n_init=0, method='ROSL11') == 146
     assert bench.flops_per_step(2, 0, info, stages=8, n_init=2) == 206
     dense = info.copy()
     dense[3] = 1                                  # linear, dense column terms
@@ -523,7 +529,7 @@ def test_cpu_port_linear_model_with_dense_column_terms(tmp_path):
     y_ref, s_ref = ode_exact.simulate(omodel, psi, times, reg)
     scale = np.max(np.abs(s_ref[:, 0, :]), 0)
     scale[scale == 0] = 1.0
-    for method in (5, 1):
+    for method in (11, 9, 5, 1):
         y, s, status, nst, _ = pop.simulate(
             psi, rtol=1e-10, atol=1e-12, stream_cb=method)
         assert status[0] == 0
@@ -549,7 +555,7 @@ def test_cpu_port_stiff_parameter_sweep():
             rng.uniform(0, 5), rng.uniform(0, 5), 10 ** rng.uniform(-1, 2),
             10 ** rng.uniform(-3, 3), 10 ** rng.uniform(-3, 3),
             10 ** rng.uniform(-3, 3), 10 ** rng.uniform(-1, 2)])
-        for method in (5, 1):
+        for method in (11, 9, 5, 1):
             y, s, status, nst, nrj = pop.simulate(
                 psi, rtol=rtol, atol=atol, stream_cb=method)
             assert status[0] == 0, (psi, method)
@@ -632,11 +638,12 @@ def test_cpu_port_rank_one_terms_that_depend_on_constants(tmp_path):
     y_ref, s_ref = ode_exact.simulate(omodel, psi, times, reg)
     scale = np.max(np.abs(s_ref[:, 0, :]), 0)
     scale[scale == 0] = 1.0
-    y, s, status, _, _ = pop.simulate(psi, rtol=1e-10, atol=1e-12,
-                                      stream_cb=5)
-    assert status[0] == 0
-    assert np.max(np.abs(y - y_ref[0])) / np.max(np.abs(y_ref[0])) < 1e-9
-    assert np.max(np.abs(s - s_ref[:, 0, :]) / scale) < 1e-8
+    for method in (11, 5):
+        y, s, status, _, _ = pop.simulate(psi, rtol=1e-10, atol=1e-12,
+                                          stream_cb=method)
+        assert status[0] == 0
+        assert np.max(np.abs(y - y_ref[0])) / np.max(np.abs(y_ref[0])) < 1e-9
+        assert np.max(np.abs(s - s_ref[:, 0, :]) / scale) < 1e-8
 
 
 def test_batched_posterior_combines_prior_and_likelihood_on_the_host():
@@ -752,3 +759,88 @@ def test_invalid_prior_never_touches_other_shards_columns():
     assert np.all(np.isfinite(s)) and np.all(np.isfinite(g))
     assert np.all(g[:, :4] == 0.0) and np.all(g[:, 8:12] == 0.0)
     np.testing.assert_allclose(g[:, 4:8], 2.0)
+
+
+def test_rosl_tables_order_and_stability():
+    """ROSL(9) / ROSL(11) (integrator_stream.cuh, namespace rosl): the tables
+    in the header are the ones tools/derive_rosl.py derives; stability
+    function of order s-1, embedded method (last two terms dropped) of order
+    s-2, |R(iy)| <= 1 on the imaginary axis, R(-inf) = 0."""
+    import re
+    sys_path = os.path.join(ROOT, 'tools')
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        'derive_rosl', os.path.join(sys_path, 'derive_rosl.py'))
+    derive = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(derive)
+    text = open(os.path.join(
+        ROOT, 'chi_b200', 'csrc', 'integrator_stream.cuh')).read()
+    for s_, gamma in ((9, '0.2'), (11, '0.16')):
+        c, order, order_hat, amax, rmax, rinf = derive.check(
+            s_, derive.mp.mpf(gamma))
+        assert abs(order - (s_ - 1)) < 0.1 and abs(order_hat - (s_ - 2)) < 0.1
+        assert amax <= 1 + 1e-12 and rmax <= 1 + 1e-12 and rinf < 1e-6
+        block = text[text.index('struct Table<%d>' % s_):]
+        block = block[block.index('C[%d] = {' % s_):block.index('};')]
+        vals = [float(v) for v in re.findall(
+            r'-?\d+\.\d+(?:[eE][-+]?\d+)?', block.split('{', 1)[1])]
+        assert len(vals) == s_
+        np.testing.assert_allclose(vals, [float(v) for v in c], rtol=1e-15)
+        # the device copy in constant memory carries the same numbers
+        dev = text[text.index('static __constant__ double C%d[%d]' % (s_, s_)):]
+        dev = dev[:dev.index('};')]
+        dvals = [float(v) for v in re.findall(
+            r'-?\d+\.\d+(?:[eE][-+]?\d+)?', dev.split('{', 1)[1])]
+        np.testing.assert_allclose(dvals, vals, rtol=0)
+
+
+def test_cpu_port_rosl_convergence_and_work():
+    """ROSL(11), the default method of linear models, in the host build:
+    converges to the exact solution (a decade of tolerance buys about a
+    decade of accuracy), needs about half the step attempts of RODAS5 at
+    rtol 1e-6 and less than a quarter at rtol 1e-8, and is MORE accurate at
+    the same tolerance."""
+    key = cport.find_key('two_compartment_pk_model', 'central', True)
+    rng = np.random.default_rng(3)
+    m = ode_exact.two_compartment(True)
+    for case in range(6):
+        times = np.sort(rng.uniform(0.25, 24, 10))
+        reg = [(float(rng.uniform(5, 15)), 0.0, 1.0, 8.0, 3)]
+        psi = np.concatenate([[0.0, 0.0], np.exp(
+            np.log([2.0, 1.0, 5.0, 1.0, 10.0]) + 0.4 * rng.normal(size=5))])
+        pop = cport.Population(
+            key, ['central.drug_concentration'], None, [times], None, None,
+            [reg])
+        ye, se = ode_exact.simulate(m, psi, times, reg)
+        scale = np.max(np.abs(se[:, 0, :]), 0)
+        scale[scale == 0] = 1.0
+        errs = {}
+        for rtol in (1e-6, 1e-8, 1e-10):
+            y5, s5, st5, n5, r5 = pop.simulate(
+                psi, rtol=rtol, atol=rtol * 0.01, stream_cb=5)
+            y, s, st, n, r = pop.simulate(
+                psi, rtol=rtol, atol=rtol * 0.01, stream_cb=11)
+            assert st[0] == 0
+            err = np.max(np.abs(y - ye[0]) / np.max(np.abs(ye[0])))
+            serr = np.max(np.abs(s - se[:, 0, :]) / scale)
+            err5 = np.max(np.abs(y5 - ye[0]) / np.max(np.abs(ye[0])))
+            assert err < 0.1 * rtol and serr < rtol, (case, rtol, err, serr)
+            assert err < 2 * err5 + 1e-13
+            ratio = (n[0] + r[0]) / float(n5[0] + r5[0])
+            assert ratio < (0.55 if rtol == 1e-6 else 0.3), (rtol, ratio)
+            errs[rtol] = err
+        assert errs[1e-10] < 1e-2 * errs[1e-6]
+    # forward only (no sensitivity columns) and a subset of the columns run
+    # the other two instantiations of the step (MODE 0 / MODE 2)
+    y0, _, st0, _, _ = pop.simulate(
+        psi, rtol=1e-9, atol=1e-11, stream_cb=11, with_sens=False)
+    assert st0[0] == 0
+    np.testing.assert_allclose(y0, ye[0], rtol=1e-8)
+    sub = cport.Population(
+        key, ['central.drug_concentration'], None, [times], None, None,
+        [reg], columns=[3, 5, 0])
+    _, ss, sts, _, _ = sub.simulate(psi, rtol=1e-9, atol=1e-11, stream_cb=11)
+    assert sts[0] == 0
+    np.testing.assert_allclose(
+        ss[:, :3], se[:, 0, [3, 5, 0]], rtol=1e-7,
+        atol=1e-9 * np.max(np.abs(se)))
