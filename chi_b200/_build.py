@@ -19,9 +19,13 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 GEN = os.path.join(CSRC, 'gen')
-OBJ = os.path.join(HERE, '_obj')
+# CHI_B200_BUILD_TAG=<tag>: a side build for kernel experiments (its own
+# object directory and library name; load it with CHI_B200_LIB=<path>)
+_TAG = os.environ.get('CHI_B200_BUILD_TAG', '')
+OBJ = os.path.join(HERE, '_obj' + ('_' + _TAG if _TAG else ''))
 MODULES = os.path.join(HERE, '_modules')
-LIB = os.path.join(HERE, 'libchi_b200.so')
+LIB = os.path.join(
+    HERE, 'libchi_b200%s.so' % ('_' + _TAG if _TAG else ''))
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',

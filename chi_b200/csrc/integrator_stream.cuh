@@ -34,6 +34,14 @@
 #pragma once
 #include "integrator.cuh"
 
+// unroll factor of the stage loop of step_rosl (stages 1 .. S-3)
+#ifndef CHI_ROSL_UNROLL
+#define CHI_ROSL_UNROLL 1
+#endif
+#define CHI_STR2(x) #x
+#define CHI_STR(x) CHI_STR2(x)
+#define CHI_UNROLL_N(n) _Pragma(CHI_STR(unroll n))
+
 namespace chi_b200 {
 
 // shared-memory doubles per thread: S of the integrated columns (current +
@@ -1214,9 +1222,12 @@ struct StreamSolver {
       }
     }
     // ---- stages 1 .. S-1 ----------------------------------------------------
-#pragma unroll
-    for (int k = 1; k < S; ++k) {
-      const double ck = rosl_c<S>(k);
+    // One stage of all columns; TAIL: the term belongs to the error estimate.
+    // The first S-3 of them run as a rolled loop (one stage body in the
+    // instruction cache: fully unrolled the step is ~2000 instructions and
+    // the four warps of a scheduler miss the cache, `no_instruction` 1.35
+    // stall cycles per issue), the last two are the error tail.
+    auto stage = [&](const double ck, const bool tail) {
       double an[N], sig[N];
 #pragma unroll
       for (int n = 0; n < N; ++n) {
@@ -1229,7 +1240,7 @@ struct StreamSolver {
       for (int n = 0; n < N; ++n) {
         sig[n] = ay[n] + an[n];
         ay[n] = an[n];
-        if (k >= S - 2) ty[n] = fma(ck, an[n], ty[n]);
+        if (tail) ty[n] = fma(ck, an[n], ty[n]);
         else zy[n] = fma(ck, an[n], zy[n]);
       }
 #pragma unroll
@@ -1262,11 +1273,17 @@ struct StreamSolver {
 #pragma unroll
         for (int n = 0; n < N; ++n) {
           w[m][n] = wn[n];
-          if (k >= S - 2) ts[m][n] = fma(ck, wn[n], ts[m][n]);
+          if (tail) ts[m][n] = fma(ck, wn[n], ts[m][n]);
           else zs[m][n] = fma(ck, wn[n], zs[m][n]);
         }
       }
-    }
+    };
+#ifdef __CUDA_ARCH__
+    CHI_UNROLL_N(CHI_ROSL_UNROLL)
+#endif
+    for (int k = 1; k < S - 2; ++k) stage(rosl_c<S>(k), false);
+    stage(rosl_c<S>(S - 2), true);
+    stage(rosl_c<S>(S - 1), true);
     // ---- error norm: max over the columns of the scaled RMS -----------------
     const float atol_f = static_cast<float>(a.atol);
     const float rtol_f = static_cast<float>(a.rtol);
@@ -1629,8 +1646,17 @@ __device__ __forceinline__ int64_t stream_system_of(const SolveArgs& a,
   return static_cast<int64_t>(r * static_cast<unsigned>(a.order_stride) + q);
 }
 
+// resident blocks per SM the kernel is compiled for (register cap)
+#ifndef CHI_ROSL_MIN_BLOCKS
+#define CHI_ROSL_MIN_BLOCKS 4
+#endif
+template <class M, int CB>
+constexpr int stream_min_blocks() {
+  return stream_is_rosl(CB) ? CHI_ROSL_MIN_BLOCKS : M::STREAM_MIN_BLOCKS;
+}
+
 template <class M, int CB, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, M::STREAM_MIN_BLOCKS)
+__global__ void __launch_bounds__(BLOCK, stream_min_blocks<M, CB>())
 solve_stream_kernel(const SolveArgs a, unsigned long long* counter) {
   extern __shared__ double chi_sm[];
   StreamSolver<M, CB> s(a, chi_sm + threadIdx.x, BLOCK);
