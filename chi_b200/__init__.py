@@ -22,8 +22,16 @@ from chi_b200._population_models import (  # noqa: F401
 from chi_b200._log_pdfs import (  # noqa: F401
     LogLikelihood, HierarchicalLogLikelihood, LogPosterior,
     HierarchicalLogPosterior)
+from chi_b200._population_filters import (  # noqa: F401
+    PopulationFilter, ComposedPopulationFilter, GaussianFilter,
+    GaussianKDEFilter, GaussianMixtureFilter, LogNormalFilter,
+    LogNormalKDEFilter)
+from chi_b200._filter_posterior import (  # noqa: F401
+    PopulationFilterLogPosterior)
 from chi_b200._predictive_models import (  # noqa: F401
     PredictiveModel, PopulationPredictiveModel)
+from chi_b200._averaged_predictive import (  # noqa: F401
+    AveragedPredictiveModel, PosteriorPredictiveModel, PriorPredictiveModel)
 from chi_b200._priors import (  # noqa: F401
     GaussianLogPrior, LogNormalLogPrior, UniformLogPrior, ComposedLogPrior)
 from chi_b200._inference import (  # noqa: F401

@@ -88,6 +88,11 @@ _SIGNATURES = {
         ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, c_f64p,
                        ctypes.c_int64, ctypes.c_int32, c_f64p, c_f64p,
                        c_f64p, ctypes.c_int32, c_f64p, c_f64p]),
+    'chi_b200_covariate_linear': (
+        ctypes.c_int, [ctypes.c_int32, ctypes.c_int64, ctypes.c_int32,
+                       ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                       c_i32p, c_i32p, c_f64p, c_f64p, c_f64p, c_f64p,
+                       c_f64p, c_f64p, c_f64p]),
     'chi_b200_population_set': (
         ctypes.c_int, [c_vp, ctypes.c_int32, c_i32p, c_i32p, c_i32p, c_i32p,
                        c_i32p, c_i32p, c_i32p, c_f64p]),

@@ -19,7 +19,7 @@ import warnings
 import numpy as np
 
 from chi_b200 import _lib
-from chi_b200._error_models import ErrorModel
+from chi_b200._error_models import ErrorModel, ReducedErrorModel
 from chi_b200._mechanistic_models import (
     MechanisticModel, SBMLModel, ReducedMechanisticModel, _events_of)
 from chi_b200._population_models import (
@@ -38,6 +38,15 @@ try:
     import chi as _chi
 except Exception:  # pragma: no cover
     _chi = None
+
+
+def _chi_base(name, fallback):
+    """chi's own class of that name when chi is importable, so that
+    ``isinstance(x, chi.<name>)`` holds for the classes below without any
+    change to chi (chi/_inference.py:423-429 checks the log-posterior that
+    way; chi's ``__init__`` is never called, every method is overridden)."""
+    base = getattr(_chi, name, None) if _chi is not None else None
+    return base if isinstance(base, type) else fallback
 
 
 def _vector(x):
@@ -62,9 +71,8 @@ class _DeviceLikelihoods(object):
                  regimens, device=None):
         """times / observations: per individual, per output arrays."""
         if isinstance(mechanistic_model, ReducedMechanisticModel):
-            raise NotImplementedError(
-                'ReducedMechanisticModel is not supported inside device '
-                'log-likelihoods yet; fix parameters on the log-likelihood.')
+            # (LogLikelihood passes the wrapped model and its fixed entries)
+            mechanistic_model = mechanistic_model.mechanistic_model()
         if not isinstance(mechanistic_model, SBMLModel):
             raise TypeError(
                 'Device log-likelihoods need a chi_b200.SBMLModel / '
@@ -122,6 +130,7 @@ class _DeviceLikelihoods(object):
             dose_off.append(dose_off[-1] + len(ev))
         cat = np.concatenate
         self._rec_off = np.array(rec_off, dtype=np.int64)
+        self._rec_out = rec_out      # per individual: output of each record
         a1, p1 = _lib.i64(self._rec_off)
         a2, p2 = _lib.f64(cat(rec_t) if rec_off[-1] else np.zeros(0))
         with np.errstate(all='ignore'):
@@ -200,7 +209,7 @@ class _DeviceLikelihoods(object):
         return ll, grad, status
 
 
-class LogLikelihood(_LogPDFBase):
+class LogLikelihood(_chi_base('LogLikelihood', _LogPDFBase)):
     """Log-likelihood of one individual, see chi/_log_pdfs.py:637-1149."""
 
     def __init__(
@@ -221,7 +230,7 @@ class LogLikelihood(_LogPDFBase):
                 'One error model has to be provided for each mechanistic '
                 'model output.')
         for em in error_model:
-            if not isinstance(em, ErrorModel):
+            if not isinstance(em, (ErrorModel, ReducedErrorModel)):
                 raise TypeError(
                     'The error models have to instances of a '
                     'chi.ErrorModel.')
@@ -266,11 +275,50 @@ class LogLikelihood(_LogPDFBase):
         self._n_obs = [len(obs) for obs in observations]
         self._set_error_model_parameter_names()
         self._set_number_and_parameter_names()
-        self._full_parameter_names = list(self._parameter_names)
-        self._fixed_mask = None
-        self._fixed_values = None
+        self._unwrap_reduced_models()
         self._id = None
         self._device = None
+
+    def _unwrap_reduced_models(self):
+        """The device works on the FULL vector [all mechanistic parameters |
+        all error parameters] of the wrapped models.  Entries that a
+        ReducedMechanisticModel (chi/_mechanistic_models.py:1160-1186) or a
+        ReducedErrorModel (chi/_error_models.py:1704-1750) holds fixed are
+        locked into the fixed set here; they are not parameters of this
+        log-likelihood and ``fix_parameters`` cannot release them."""
+        model = self._mechanistic_model
+        locked = {}
+        self._base_model = model
+        if isinstance(model, ReducedMechanisticModel):
+            self._base_model = model.mechanistic_model()
+            locked.update(model.fixed_parameters().values)
+        full_names = list(self._base_model.parameters())
+        n_mech = len(full_names)
+        self._error_kinds = []
+        for output_id, em in enumerate(self._error_models):
+            inner = em
+            if isinstance(em, ReducedErrorModel):
+                inner = em.get_error_model()
+                if em._fixed_mask is not None:
+                    for k in np.flatnonzero(em._fixed_mask):
+                        locked[len(full_names) + int(k)] = float(
+                            em._fixed_values[k])
+                names = list(em._parameter_names)
+            else:
+                names = inner.get_parameter_names()
+            self._error_kinds.append(inner._kind)
+            full_names += names
+        self._full_parameter_names = full_names
+        self._n_mechanistic_params = n_mech
+        self._locked = dict(locked)
+        self._fixed_mask = None
+        self._fixed_values = None
+        if locked:
+            self._fixed_mask = np.zeros(len(full_names), dtype=bool)
+            self._fixed_values = np.zeros(len(full_names))
+            for position, value in locked.items():
+                self._fixed_mask[position] = True
+                self._fixed_values[position] = value
 
     def fix_parameters(self, name_value_dict):
         """Fixes model parameters at the given values and removes them from
@@ -288,7 +336,7 @@ class LogLikelihood(_LogPDFBase):
             self._fixed_mask = np.zeros(n_full, dtype=bool)
             self._fixed_values = np.zeros(n_full)
         for index, name in enumerate(self._full_parameter_names):
-            if name not in name_value_dict:
+            if name not in name_value_dict or index in self._locked:
                 continue
             value = name_value_dict[name]
             if value is None:
@@ -331,8 +379,7 @@ class LogLikelihood(_LogPDFBase):
     def _get_device(self):
         if self._device is None:
             self._device = _DeviceLikelihoods(
-                self._mechanistic_model,
-                [em._kind for em in self._error_models],
+                self._base_model, self._error_kinds,
                 [self._output_times], [self._observations],
                 [self._regimen()])
             if self._fixed_mask is not None:
@@ -365,6 +412,33 @@ class LogLikelihood(_LogPDFBase):
         if self._fixed_mask is not None:
             grad = grad[~self._fixed_mask]
         return float(ll[0]), grad.copy()
+
+    def compute_pointwise_ll(self, parameters):
+        """Log-likelihood of every observation, output by output
+        (chi/_log_pdfs.py:932-971): one forward launch of the integrator for
+        the model outputs at the records, then the error model of each
+        output on the device (``chi_b200_error_model`` with its pointwise
+        result)."""
+        full = self._expand(parameters)
+        device = self._get_device()
+        n_mech = self._n_mechanistic_params
+        ybar, _, status = device.simulate(full[None, :n_mech])
+        if status[0] != 0:
+            _failure_warning(status[0])
+            return np.full(int(np.sum(self._n_obs)), -np.inf)
+        rec_out = device._rec_out[0]
+        start = n_mech
+        pointwise = []
+        for output_id, error_model in enumerate(self._error_models):
+            inner = error_model.get_error_model() if isinstance(
+                error_model, ReducedErrorModel) else error_model
+            end = start + inner.n_parameters()
+            pointwise.append(inner.compute_pointwise_ll(
+                parameters=full[start:end],
+                model_output=ybar[rec_out == output_id],
+                observations=self._observations[output_id]))
+            start = end
+        return np.hstack(pointwise)
 
     def _set_error_model_parameter_names(self):
         """chi/_log_pdfs.py:885-909."""
@@ -438,13 +512,13 @@ def _same_fixed(a, b):
 
 def _check_structure(log_likelihoods):
     first = log_likelihoods[0]
-    key = first._mechanistic_model.model_key()
-    outs = first._mechanistic_model._output_names
-    kinds = [em._kind for em in first._error_models]
+    key = first._base_model.model_key()
+    outs = first._base_model._output_names
+    kinds = first._error_kinds
     for ll in log_likelihoods[1:]:
-        if ll._mechanistic_model.model_key() != key or \
-                ll._mechanistic_model._output_names != outs or \
-                [em._kind for em in ll._error_models] != kinds or \
+        if ll._base_model.model_key() != key or \
+                ll._base_model._output_names != outs or \
+                ll._error_kinds != kinds or \
                 not _same_fixed(first, ll):
             raise ValueError(
                 'The log-likelihoods of a hierarchical model have to be '
@@ -452,7 +526,8 @@ def _check_structure(log_likelihoods):
                 'error models).')
 
 
-class HierarchicalLogLikelihood(object):
+class HierarchicalLogLikelihood(
+        _chi_base('HierarchicalLogLikelihood', object)):
     """chi/_log_pdfs.py:18-403."""
 
     def __init__(
@@ -490,8 +565,7 @@ class HierarchicalLogLikelihood(object):
         self._label_log_likelihoods()
         first = log_likelihoods[0]
         device = _DeviceLikelihoods(
-            first._mechanistic_model,
-            [em._kind for em in first._error_models],
+            first._base_model, first._error_kinds,
             [ll._output_times for ll in log_likelihoods],
             [ll._observations for ll in log_likelihoods],
             [ll._regimen() for ll in log_likelihoods])
@@ -526,14 +600,12 @@ class HierarchicalLogLikelihood(object):
         template = LogLikelihood(
             mechanistic_model, error_models, observations[0], times[0])
         device = _DeviceLikelihoods(
-            template._mechanistic_model,
-            [em._kind for em in template._error_models], times, observations,
+            template._base_model, template._error_kinds, times, observations,
             regimens)
         if fixed_parameters:
             template.fix_parameters(fixed_parameters)
-            if template._fixed_mask is not None:
-                device.set_fixed(
-                    template._fixed_mask, template._fixed_values)
+        if template._fixed_mask is not None:
+            device.set_fixed(template._fixed_mask, template._fixed_values)
         if population_model.n_covariates() > 0:
             if covariates is None:
                 raise ValueError(
@@ -635,6 +707,11 @@ class HierarchicalLogLikelihood(object):
         if copy:
             return score.copy(), grad.copy()
         return score, grad
+
+    def compute_pointwise_ll(self, parameters, per_individual=True):
+        """Not implemented by the reference either
+        (chi/_log_pdfs.py:161-198 raises ``NotImplementedError``)."""
+        raise NotImplementedError
 
     def __call__(self, parameters):
         """chi/_log_pdfs.py:104-145."""
@@ -795,7 +872,8 @@ class HierarchicalLogLikelihood(object):
         return self._n_obs
 
 
-class HierarchicalLogPosterior(_LogPDFBase):
+class HierarchicalLogPosterior(
+        _chi_base('HierarchicalLogPosterior', _LogPDFBase)):
     """chi/_log_pdfs.py:406-634."""
 
     def __init__(self, log_likelihood, log_prior):
@@ -967,7 +1045,7 @@ def _check_prior(log_prior):
             'The log-prior has to be an instance of a pints.LogPrior.')
 
 
-class LogPosterior(_LogPDFBase):
+class LogPosterior(_chi_base('LogPosterior', _LogPDFBase)):
     """chi/_log_pdfs.py:1152-1322."""
 
     def __init__(self, log_likelihood, log_prior):

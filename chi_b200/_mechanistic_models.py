@@ -411,13 +411,17 @@ class SBMLModel(MechanisticModel):
         sens = s[:n_t * n_out * n_cols].reshape(n_t, n_out, n_cols).copy()
         return output, sens
 
-    def simulate_batch(self, parameters, times):
+    def simulate_batch(self, parameters, times, sensitivities=False):
         """Simulates many parameter vectors on the same time grid in one
-        launch (not part of chi's API; used by the predictive models).
+        launch (not part of chi's API; used by the predictive models and the
+        population-filter posterior).
 
         :param parameters: array of shape ``(n_vectors, n_parameters)``.
-        :returns: outputs of shape ``(n_vectors, n_outputs, n_times)`` and
-            the per-vector integrator status.
+        :param sensitivities: also return d output / d parameter (of the
+            enabled sensitivity columns, all parameters if none were chosen).
+        :returns: outputs of shape ``(n_vectors, n_outputs, n_times)``, the
+            per-vector integrator status and, with ``sensitivities``, an
+            array of shape ``(n_vectors, n_times, n_outputs, n_columns)``.
         """
         parameters = np.ascontiguousarray(
             parameters, dtype=float).reshape(-1, self._n_parameters)
@@ -425,14 +429,25 @@ class SBMLModel(MechanisticModel):
         if len(times) == 0:
             raise IndexError('times must not be empty.')
         n_t, n_out, n_b = len(times), self._n_outputs, len(parameters)
+        if sensitivities and not self._has_sensitivities:
+            self.enable_sensitivities(True)
         problem = self._configure(times)
         lib = _lib.lib()
         a_psi, p_psi = _lib.f64(parameters)
         y, p_y = _lib.out_f64(n_b * n_t * n_out)
         status, p_st = _lib.out_i32(n_b)
+        if not sensitivities:
+            _lib.check(lib.chi_b200_simulate(
+                problem.handle, n_b, None, p_psi, 0, p_y, None, p_st))
+            return y.reshape(n_b, n_t, n_out).transpose(0, 2, 1).copy(), \
+                status
+        n_cols = len(self._sens_columns)
+        sens, p_s = _lib.out_f64(max(n_b * n_t * n_out * n_cols, 1))
         _lib.check(lib.chi_b200_simulate(
-            problem.handle, n_b, None, p_psi, 0, p_y, None, p_st))
-        return y.reshape(n_b, n_t, n_out).transpose(0, 2, 1).copy(), status
+            problem.handle, n_b, None, p_psi, 1, p_y, p_s, p_st))
+        return (y.reshape(n_b, n_t, n_out).transpose(0, 2, 1).copy(), status,
+                sens[:n_b * n_t * n_out * n_cols].reshape(
+                    n_b, n_t, n_out, n_cols))
 
     def time_unit(self):
         return self._time_unit
@@ -527,9 +542,79 @@ class PKPDModel(SBMLModel):
         return True
 
 
+class FixedParameters(object):
+    """Which entries of a named parameter vector are held at fixed values.
+
+    Shared by the Reduced* wrappers (chi fixes parameters with
+    ``fix_parameters({name: value})``, ``None`` releasing a parameter again:
+    chi/_mechanistic_models.py:949-1019, chi/_error_models.py:1753-1821,
+    chi/_log_pdfs.py:1029-1073).  ``expand`` always returns a fresh array
+    (the reference scatters into a shared scratch buffer and returns it).
+    """
+
+    def __init__(self, names):
+        self.names = list(names)
+        self.values = {}            # position -> value
+
+    def update(self, name_value_dict):
+        try:
+            name_value_dict = dict(name_value_dict)
+        except (TypeError, ValueError):
+            raise ValueError(
+                'The name-value dictionary has to be convertable to a python '
+                'dictionary.')
+        for position, name in enumerate(self.names):
+            if name not in name_value_dict:
+                continue
+            value = name_value_dict[name]
+            if value is None:
+                self.values.pop(position, None)
+            else:
+                self.values[position] = float(value)
+
+    def rename(self, names):
+        self.names = list(names)
+
+    def n_fixed(self):
+        return len(self.values)
+
+    def mask(self):
+        mask = np.zeros(len(self.names), dtype=bool)
+        mask[list(self.values)] = True
+        return mask
+
+    def free_names(self):
+        return [n for k, n in enumerate(self.names) if k not in self.values]
+
+    def free_positions(self):
+        return [k for k in range(len(self.names)) if k not in self.values]
+
+    def full_values(self):
+        full = np.zeros(len(self.names))
+        for position, value in self.values.items():
+            full[position] = value
+        return full
+
+    def expand(self, free_values):
+        free_values = np.asarray(free_values, dtype=float).reshape(-1)
+        if not self.values:
+            return free_values.copy()
+        full = self.full_values()
+        full[self.free_positions()] = free_values
+        return full
+
+
 class ReducedMechanisticModel(MechanisticModel):
-    """Fixes parameters of a mechanistic model, see
-    chi/_mechanistic_models.py:867-1206."""
+    """A mechanistic model with some parameters held at fixed values
+    (interface of chi/_mechanistic_models.py:867-1206).  Everything but the
+    parameter bookkeeping is forwarded to the wrapped model; inside a
+    log-likelihood the fixed entries go to the device once
+    (``chi_b200_problem_set_fixed_parameters``) and sensitivities are
+    integrated for the free parameters only."""
+
+    _FORWARDED = (
+        'has_sensitivities', 'n_outputs', 'outputs', 'set_output_names',
+        'supports_dosing', 'time_unit')
 
     def __init__(self, mechanistic_model):
         super(ReducedMechanisticModel, self).__init__()
@@ -538,117 +623,82 @@ class ReducedMechanisticModel(MechanisticModel):
                 'The mechanistic model has to be an instance of a '
                 'chi.MechanisticModel.')
         self._mechanistic_model = mechanistic_model
-        self._fixed_params_mask = None
-        self._fixed_params_values = None
-        self._n_parameters = mechanistic_model.n_parameters()
-        self._parameter_names = mechanistic_model.parameters()
+        self._fixed = FixedParameters(mechanistic_model.parameters())
 
-    def copy(self):
-        model = ReducedMechanisticModel(self._mechanistic_model.copy())
-        if self._fixed_params_mask is not None:
-            model._fixed_params_mask = self._fixed_params_mask.copy()
-            model._fixed_params_values = self._fixed_params_values.copy()
-        return model
+    def __getattr__(self, name):
+        # only reached for attributes that are not defined on the wrapper
+        if name in ReducedMechanisticModel._FORWARDED:
+            return getattr(self.__dict__['_mechanistic_model'], name)
+        raise AttributeError(name)
 
-    def dosing_regimen(self):
-        try:
-            return self._mechanistic_model.dosing_regimen()
-        except AttributeError:
-            return None
-
-    def enable_sensitivities(self, enabled):
-        """chi/_mechanistic_models.py:931-947: only free parameters."""
-        if not enabled:
-            self._mechanistic_model.enable_sensitivities(enabled)
-            return None
-        self._mechanistic_model.enable_sensitivities(
-            enabled, self.parameters())
-
-    def fix_parameters(self, name_value_dict):
-        """chi/_mechanistic_models.py:949-1019."""
-        try:
-            name_value_dict = dict(name_value_dict)
-        except (TypeError, ValueError):
-            raise ValueError(
-                'The name-value dictionary has to be convertable to a python '
-                'dictionary.')
-        if self._fixed_params_mask is None:
-            self._fixed_params_mask = np.zeros(
-                shape=self._n_parameters, dtype=bool)
-        if self._fixed_params_values is None:
-            self._fixed_params_values = np.empty(shape=self._n_parameters)
-        for index, name in enumerate(self._parameter_names):
-            try:
-                value = name_value_dict[name]
-            except KeyError:
-                continue
-            if value is None:
-                self._fixed_params_mask[index] = False
-                continue
-            self._fixed_params_mask[index] = True
-            self._fixed_params_values[index] = value
-        if np.alltrue(~self._fixed_params_mask) if hasattr(
-                np, 'alltrue') else np.all(~self._fixed_params_mask):
-            self._fixed_params_mask = None
-            self._fixed_params_values = None
-        self._mechanistic_model.enable_sensitivities(False)
-
-    def mechanistic_model(self):
-        return self._mechanistic_model
-
+    # (defined explicitly: the base class declares them)
     def has_sensitivities(self):
         return self._mechanistic_model.has_sensitivities()
-
-    def n_fixed_parameters(self):
-        if self._fixed_params_mask is None:
-            return 0
-        return int(np.sum(self._fixed_params_mask))
 
     def n_outputs(self):
         return self._mechanistic_model.n_outputs()
 
-    def n_parameters(self):
-        return self._n_parameters - self.n_fixed_parameters()
-
     def outputs(self):
         return self._mechanistic_model.outputs()
-
-    def parameters(self):
-        names = np.array(self._parameter_names)
-        if self._fixed_params_mask is not None:
-            names = names[~self._fixed_params_mask]
-        return list(names)
-
-    def set_dosing_regimen(
-            self, dose, start=0, duration=0.01, period=None, num=None):
-        try:
-            self._mechanistic_model.set_dosing_regimen(
-                dose, start, duration, period, num)
-        except AttributeError:
-            raise AttributeError(
-                'The mechanistic model does not support dosing regimens.')
-
-    def set_outputs(self, outputs):
-        self._mechanistic_model.set_outputs(outputs)
-
-    def set_output_names(self, names):
-        self._mechanistic_model.set_output_names(names)
-
-    def set_parameter_names(self, names):
-        self._mechanistic_model.set_parameter_names(names)
-        self._parameter_names = self._mechanistic_model.parameters()
-
-    def simulate(self, parameters, times):
-        """chi/_mechanistic_models.py:1160-1186 (copies on the boundary
-        instead of returning the shared scratch buffer)."""
-        if self._fixed_params_mask is not None:
-            full = np.array(self._fixed_params_values, dtype=float)
-            full[~self._fixed_params_mask] = parameters
-            parameters = full
-        return self._mechanistic_model.simulate(parameters, times)
 
     def supports_dosing(self):
         return self._mechanistic_model.supports_dosing()
 
-    def time_unit(self):
-        return self._mechanistic_model.time_unit()
+    def copy(self):
+        model = ReducedMechanisticModel(self._mechanistic_model.copy())
+        model._fixed.values = dict(self._fixed.values)
+        return model
+
+    def mechanistic_model(self):
+        return self._mechanistic_model
+
+    def fixed_parameters(self):
+        """The :class:`FixedParameters` table (positions in the wrapped
+        model's parameter vector)."""
+        return self._fixed
+
+    def fix_parameters(self, name_value_dict):
+        self._fixed.update(name_value_dict)
+        self._mechanistic_model.enable_sensitivities(False)
+
+    def n_fixed_parameters(self):
+        return self._fixed.n_fixed()
+
+    def n_parameters(self):
+        return len(self._fixed.names) - self._fixed.n_fixed()
+
+    def parameters(self):
+        return self._fixed.free_names()
+
+    def set_parameter_names(self, names):
+        self._mechanistic_model.set_parameter_names(names)
+        self._fixed.rename(self._mechanistic_model.parameters())
+
+    def set_outputs(self, outputs):
+        self._mechanistic_model.set_outputs(outputs)
+
+    def enable_sensitivities(self, enabled):
+        """Sensitivities with respect to the free parameters only
+        (chi/_mechanistic_models.py:931-947)."""
+        if enabled:
+            self._mechanistic_model.enable_sensitivities(
+                True, self.parameters())
+        else:
+            self._mechanistic_model.enable_sensitivities(False)
+
+    def dosing_regimen(self):
+        getter = getattr(self._mechanistic_model, 'dosing_regimen', None)
+        return getter() if getter is not None else None
+
+    def set_dosing_regimen(
+            self, dose, start=0, duration=0.01, period=None, num=None):
+        setter = getattr(self._mechanistic_model, 'set_dosing_regimen', None)
+        if setter is None:
+            raise AttributeError(
+                'The mechanistic model does not support dosing regimens.')
+        setter(dose, start, duration, period, num)
+
+    def simulate(self, parameters, times):
+        """chi/_mechanistic_models.py:1160-1186."""
+        return self._mechanistic_model.simulate(
+            self._fixed.expand(parameters), times)

@@ -124,16 +124,64 @@ def _batch_1d(prior, x):
 
 
 class ComposedLogPrior(_Base):
-    """``pints.ComposedLogPrior(*priors)``: independent product."""
+    """``pints.ComposedLogPrior(*priors)``: independent product.  When every
+    factor is one of the one-dimensional priors above the whole product is
+    evaluated with a handful of array expressions over the parameters (the
+    single-vector calls of a sampler spend tens of microseconds otherwise)."""
 
     def __init__(self, *priors):
         if not priors:
             raise ValueError('Must have at least one sub-prior.')
         self._priors = list(priors)
         self._n = sum(p.n_parameters() for p in self._priors)
+        self._table = None
+        known = (GaussianLogPrior, LogNormalLogPrior, UniformLogPrior)
+        if all(type(p) in known for p in self._priors):
+            kind = np.array([known.index(type(p)) for p in self._priors])
+            a = np.array([p._mean if k == 0 else (p._mu if k == 1 else p._a)
+                          for p, k in zip(self._priors, kind)])
+            b = np.array([p._sd if k == 0 else (p._s if k == 1 else p._b)
+                          for p, k in zip(self._priors, kind)])
+            const = np.where(
+                kind == 2, -np.log(np.where(kind == 2, b - a, 1.0)),
+                -0.5 * np.log(2 * np.pi) - np.log(np.where(kind == 2, 1.0, b)))
+            self._table = (kind == 0, kind == 1, kind == 2, a, b, const,
+                           bool(np.any(kind == 1)), bool(np.any(kind == 2)))
+
+    def _fast(self, X):
+        """(scores, gradients) of the rows of X through the table."""
+        gauss, logn, unif, a, b, const, any_logn, any_unif = self._table
+        v = X
+        bad = None
+        if any_logn:
+            pos = X > 0
+            bad = np.any(logn & ~pos, axis=-1)
+            with np.errstate(all='ignore'):
+                v = np.where(logn, np.log(np.where(logn & pos, X, 1.0)), X)
+        z = (v - a) / b
+        term = const - 0.5 * z * z
+        grad = -z / b
+        if any_logn:
+            term = np.where(logn, term - v, term)
+            with np.errstate(all='ignore'):
+                grad = np.where(logn, (grad - 1.0) / X, grad)
+        if any_unif:
+            inside = (X >= a) & (X < b)
+            out = np.any(unif & ~inside, axis=-1)
+            bad = out if bad is None else (bad | out)
+            term = np.where(unif, const, term)
+            grad = np.where(unif, 0.0, grad)
+        score = np.sum(term, axis=-1)
+        if bad is not None and np.any(bad):
+            score = np.where(bad, -np.inf, score)
+            if any_logn:
+                grad = np.where(logn & ~(X > 0), np.inf, grad)
+        return score, grad
 
     def __call__(self, x):
         x = np.asarray(x, dtype=float).reshape(-1)
+        if self._table is not None:
+            return float(self._fast(x)[0])
         out = 0.0
         lo = 0
         for p in self._priors:
@@ -144,6 +192,9 @@ class ComposedLogPrior(_Base):
 
     def evaluateS1(self, x):
         x = np.asarray(x, dtype=float).reshape(-1)
+        if self._table is not None:
+            score, grad = self._fast(x)
+            return float(score), grad
         out = 0.0
         grads = []
         lo = 0
@@ -158,6 +209,8 @@ class ComposedLogPrior(_Base):
     def evaluateS1_batch(self, X):
         """Scores (n,) and gradients (n, n_parameters) of many vectors."""
         X = np.asarray(X, dtype=float).reshape(-1, self._n)
+        if self._table is not None:
+            return self._fast(X)
         score = np.zeros(len(X))
         grad = np.empty(X.shape)
         lo = 0

@@ -577,6 +577,60 @@ __global__ void count_kernel(int64_t n, const int32_t* a, const int32_t* b,
   }
 }
 
+// Stand-alone linear covariate model (chi/_covariate_models.py:257-320).
+// forward: vartheta[i][k] = pop[k] + sum_c X[i][c] beta[sel(k)][c] for the
+// selected entries k = pidx * n_dim + didx (sel_of[k] = row of beta or -1).
+__global__ void covariate_forward_kernel(int64_t n_ids, int32_t n_flat,
+                                         int32_t n_cov,
+                                         const int32_t* __restrict__ sel_of,
+                                         const double* __restrict__ beta,
+                                         const double* __restrict__ pop,
+                                         const double* __restrict__ X,
+                                         double* __restrict__ vartheta) {
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= n_ids * n_flat) return;
+  const int64_t i = t / n_flat;
+  const int k = static_cast<int>(t - i * n_flat);
+  double v = pop[k];
+  const int s = sel_of[k];
+  if (s >= 0)
+    for (int c = 0; c < n_cov; ++c)
+      v = fma(X[i * n_cov + c], beta[s * n_cov + c], v);
+  vartheta[t] = v;
+}
+
+// adjoint: slot < n_flat: d pop[slot] = sum_i dl[i][slot]; else the beta
+// entry (s, c): sum_i dl[i][flat_of[s]] X[i][c].  One block per slot, fixed
+// summation order.
+__global__ void __launch_bounds__(256)
+covariate_backward_kernel(int64_t n_ids, int32_t n_flat, int32_t n_cov,
+                          const int32_t* __restrict__ flat_of,
+                          const double* __restrict__ X,
+                          const double* __restrict__ dl,
+                          double* __restrict__ out) {
+  __shared__ double part[8];
+  const int slot = blockIdx.x;
+  int k = slot, c = -1;
+  if (slot >= n_flat) {
+    const int e = slot - n_flat;
+    k = flat_of[e / n_cov];
+    c = e % n_cov;
+  }
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n_ids; i += blockDim.x) {
+    const double g = dl[i * n_flat + k];
+    acc += c < 0 ? g : g * X[i * n_cov + c];
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += part[w];
+    out[slot] = v;
+  }
+}
+
 // Stand-alone error model (one individual): one warp.
 __global__ void error_model_kernel(int32_t kind, double s0, double s1,
                                    int64_t n_obs, int32_t n_par,
@@ -1526,6 +1580,79 @@ int chi_b200_error_model(int32_t device, int32_t kind, const double* sigma,
   cleanup();
   if (err != cudaSuccess) return fail(-2, cudaGetErrorString(err));
   return 0;
+}
+
+int chi_b200_covariate_linear(int32_t device, int64_t n_ids, int32_t n_pop,
+                              int32_t n_dim, int32_t n_cov, int32_t n_sel,
+                              const int32_t* pidx, const int32_t* didx,
+                              const double* beta, const double* pop,
+                              const double* covariates,
+                              const double* dlogp_dvartheta,
+                              double* vartheta, double* dpop, double* dbeta) {
+  if (chi_b200_device_count() <= 0)
+    return fail(-3, "no CUDA device available: chi_b200 has no CPU fallback");
+  if (n_ids <= 0 || n_pop <= 0 || n_dim <= 0 || n_cov <= 0 || n_sel < 0)
+    return fail(-1, "invalid covariate model sizes");
+  const int n_flat = n_pop * n_dim;
+  std::vector<int32_t> sel_of(n_flat, -1), flat_of(std::max(n_sel, 1), 0);
+  for (int s = 0; s < n_sel; ++s) {
+    if (pidx[s] < 0 || pidx[s] >= n_pop || didx[s] < 0 || didx[s] >= n_dim)
+      return fail(-1, "covariate selection out of range");
+    flat_of[s] = pidx[s] * n_dim + didx[s];
+    sel_of[flat_of[s]] = s;
+  }
+  CUDA_TRY(cudaSetDevice(device));
+  DevBuf d_sel, d_flat, d_beta, d_pop, d_x, d_dl, d_out;
+  auto done = [&](int rc) {
+    for (DevBuf* b : {&d_sel, &d_flat, &d_beta, &d_pop, &d_x, &d_dl, &d_out})
+      b->release();
+    return rc;
+  };
+  auto put = [&](DevBuf& b, const void* src, size_t bytes) {
+    cudaError_t err = b.reserve(std::max<size_t>(bytes, 8));
+    if (err == cudaSuccess && bytes)
+      err = cudaMemcpy(b.ptr, src, bytes, cudaMemcpyHostToDevice);
+    return err;
+  };
+  cudaError_t err = put(d_sel, sel_of.data(), n_flat * sizeof(int32_t));
+  if (err == cudaSuccess)
+    err = put(d_flat, flat_of.data(), flat_of.size() * sizeof(int32_t));
+  if (err == cudaSuccess)
+    err = put(d_beta, beta, static_cast<size_t>(n_sel) * n_cov * 8);
+  if (err == cudaSuccess) err = put(d_pop, pop, n_flat * 8);
+  if (err == cudaSuccess)
+    err = put(d_x, covariates, static_cast<size_t>(n_ids) * n_cov * 8);
+  if (err != cudaSuccess) return done(fail(-2, cudaGetErrorString(err)));
+  if (vartheta) {
+    const int64_t n = n_ids * n_flat;
+    err = d_out.reserve(n * 8);
+    if (err != cudaSuccess) return done(fail(-2, cudaGetErrorString(err)));
+    covariate_forward_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(
+        n_ids, n_flat, n_cov, d_sel.as<int32_t>(), d_beta.as<double>(),
+        d_pop.as<double>(), d_x.as<double>(), d_out.as<double>());
+    err = cudaGetLastError();
+    if (err == cudaSuccess)
+      err = cudaMemcpy(vartheta, d_out.ptr, n * 8, cudaMemcpyDeviceToHost);
+    if (err != cudaSuccess) return done(fail(-2, cudaGetErrorString(err)));
+  }
+  if (dlogp_dvartheta && dpop && dbeta) {
+    const int n_slots = n_flat + n_sel * n_cov;
+    err = put(d_dl, dlogp_dvartheta, static_cast<size_t>(n_ids) * n_flat * 8);
+    if (err == cudaSuccess) err = d_out.reserve(n_slots * 8);
+    if (err != cudaSuccess) return done(fail(-2, cudaGetErrorString(err)));
+    covariate_backward_kernel<<<n_slots, 256>>>(
+        n_ids, n_flat, n_cov, d_flat.as<int32_t>(), d_x.as<double>(),
+        d_dl.as<double>(), d_out.as<double>());
+    err = cudaGetLastError();
+    std::vector<double> h(n_slots);
+    if (err == cudaSuccess)
+      err = cudaMemcpy(h.data(), d_out.ptr, n_slots * 8,
+                       cudaMemcpyDeviceToHost);
+    if (err != cudaSuccess) return done(fail(-2, cudaGetErrorString(err)));
+    std::copy(h.begin(), h.begin() + n_flat, dpop);
+    std::copy(h.begin() + n_flat, h.end(), dbeta);
+  }
+  return done(0);
 }
 
 // ---- population ---------------------------------------------------------------

@@ -169,6 +169,23 @@ int chi_b200_error_model(int32_t device, int32_t kind, const double* sigma,
                          const double* sens, const double* obs,
                          int32_t with_grad, double* out, double* pointwise);
 
+/* ---- stand-alone linear covariate model -----------------------------------
+ * LinearCovariateModel.compute_population_parameters / compute_sensitivities
+ * (chi/_covariate_models.py:257-320): vartheta_i = pop + X_i beta on the
+ * n_sel selected (param, dim) entries; adjoint d pop = sum_i d vartheta_i,
+ * d beta[s][c] = sum_i d vartheta_i[sel s] X_ic.
+ *   beta [n_sel][n_cov], pop [n_pop][n_dim], covariates [n_ids][n_cov]
+ *   vartheta (may be NULL) [n_ids][n_pop][n_dim]
+ *   dlogp_dvartheta (may be NULL) [n_ids][n_pop][n_dim] -> dpop
+ *   [n_pop * n_dim], dbeta [n_sel * n_cov] */
+int chi_b200_covariate_linear(int32_t device, int64_t n_ids, int32_t n_pop,
+                              int32_t n_dim, int32_t n_cov, int32_t n_sel,
+                              const int32_t* pidx, const int32_t* didx,
+                              const double* beta, const double* pop,
+                              const double* covariates,
+                              const double* dlogp_dvartheta,
+                              double* vartheta, double* dpop, double* dbeta);
+
 /* ---- population model ------------------------------------------------------
  * A composed population model is a list of blocks over consecutive
  * dimensions.  Per block: kind, n_dim, centered flag, n_cov (0 = none) and,

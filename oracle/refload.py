@@ -24,7 +24,8 @@ REFERENCE_ROOT = os.environ.get('CHI_REFERENCE_ROOT', '/root/reference')
 
 _MODULES = [
     '_covariate_models', '_error_models', '_population_models',
-    '_mechanistic_models', '_log_pdfs', '_predictive_models']
+    '_population_filters', '_mechanistic_models', '_log_pdfs',
+    '_predictive_models', '_problems']
 
 
 def available():
@@ -66,11 +67,22 @@ def _stub_myokit():
     class SimulationError(Exception):
         pass
 
+    class ProtocolEvent(object):
+        """(level, start, duration): what chi/_problems.py:360-372 builds."""
+        def __init__(self, level, start, duration, period=0, multiplier=0):
+            self.fields = (float(level), float(start), float(duration),
+                           float(period), float(multiplier))
+
     class Protocol(object):
-        pass
+        def __init__(self):
+            self.events = []
+
+        def add(self, event):
+            self.events.append(event.fields)
 
     myokit.SimulationError = SimulationError
     myokit.Protocol = Protocol
+    myokit.ProtocolEvent = ProtocolEvent
     formats = types.ModuleType('myokit.formats')
     sbml = types.ModuleType('myokit.formats.sbml')
     formats.sbml = sbml

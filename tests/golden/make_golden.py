@@ -18,6 +18,7 @@ Files written:
   hier_golden.json   LogLikelihood / HierarchicalLogPosterior (configs C1,
                      C2, C5 at small sizes), keyed by parameter name
 """
+import copy as copy_module
 import json
 import os
 import sys
@@ -235,6 +236,11 @@ class ExactModel(chi.MechanisticModel):
 
     def enable_sensitivities(self, enabled, parameter_names=None):
         self._sens = bool(enabled)
+        self._cols = None
+        if enabled and parameter_names is not None:
+            self._cols = [self._m.parameter_names.index(n)
+                          for n in self._m.parameter_names
+                          if n in parameter_names]
 
     def has_sensitivities(self):
         return self._sens
@@ -252,9 +258,12 @@ class ExactModel(chi.MechanisticModel):
         return list(self._m.parameter_names)
 
     def simulate(self, parameters, times):
-        return ode_exact.simulate(
+        out = ode_exact.simulate(
             self._m, parameters, times, self._events,
             sensitivities=self._sens)
+        if self._sens and getattr(self, '_cols', None) is not None:
+            return out[0], out[1][:, :, self._cols]
+        return out
 
 
 class IndependentPrior(pints.LogPrior):
@@ -464,6 +473,268 @@ def predictive_case(rng, name):
         'samples': tolist(samples)}
 
 
+# --------------------------------------------------------------------------
+# round 2: stand-alone covariate model, pointwise log-likelihood, reduced
+# models inside a log-likelihood, a 120-individual hierarchical case,
+# population filters and their posterior, DataFrame ingestion
+# --------------------------------------------------------------------------
+
+def linear_covariate_cases(rng):
+    out = []
+    for n_cov, n_pop, n_dim, sel, n_ids in (
+            (1, 2, 1, None, 4), (2, 2, 5, [[0, 1], [1, 3], [0, 4], [1, 1]], 7),
+            (3, 2, 3, [[1, 2], [0, 0], [0, 2], [1, 2]], 5)):
+        cm = chi.LinearCovariateModel(n_cov=n_cov)
+        if sel is not None:
+            cm.set_population_parameters(sel)
+        pidx, didx = cm.get_set_population_parameters()
+        beta = rng.normal(size=cm.n_parameters())
+        pop = rng.uniform(0.2, 2.0, (n_pop, n_dim))
+        X = rng.normal(size=(n_ids, n_cov))
+        vartheta = cm.compute_population_parameters(beta, pop, X)
+        dl = rng.normal(size=(n_ids, n_pop, n_dim))
+        dpop, dbeta = cm.compute_sensitivities(beta, pop, X, dl)
+        out.append({
+            'n_cov': n_cov, 'selection': sel, 'pidx': tolist(pidx),
+            'didx': tolist(didx), 'names': cm.get_parameter_names(),
+            'beta': tolist(beta), 'pop': tolist(pop), 'covariates': tolist(X),
+            'vartheta': tolist(vartheta), 'dlogp_dvartheta': tolist(dl),
+            'dpop': tolist(dpop), 'dbeta': tolist(dbeta)})
+    return out
+
+
+def pointwise_and_reduced_cases(rng):
+    """LogLikelihood.compute_pointwise_ll (chi/_log_pdfs.py:932-971) and a
+    log-likelihood over a ReducedMechanisticModel / ReducedErrorModel
+    (chi/_mechanistic_models.py:867-1206, chi/_error_models.py:1583-1906)."""
+    omodel = ode_exact.two_compartment(True)
+    omodel.set_outputs(
+        ['central.drug_concentration', 'peripheral.drug_concentration'])
+    events = [(8.0, 0.0, 1.0, 6.0, 3.0)]
+    t0 = np.sort(rng.uniform(0.3, 20, 9))
+    t1 = np.sort(rng.uniform(0.3, 20, 6))
+    psi = np.array([0.1, 0.05, 2.0, 1.0, 5.0, 1.0, 10.0])
+    y = ode_exact.simulate(omodel, psi, np.union1d(t0, t1), events, False)
+    grid = np.union1d(t0, t1)
+    obs0 = np.interp(t0, grid, y[0]) * rng.lognormal(0, 0.1, len(t0))
+    obs1 = np.abs(np.interp(t1, grid, y[1])
+                  + 0.05 * rng.normal(size=len(t1))) + 1e-3
+    ems = [chi.LogNormalErrorModel(),
+           chi.ConstantAndMultiplicativeGaussianErrorModel()]
+    ll = chi.LogLikelihood(
+        ExactModel(omodel, events), ems, [obs0, obs1], [t0, t1])
+    x = np.concatenate([psi * (1 + 0.03 * rng.normal(size=7)),
+                        [0.12, 0.04, 0.15]])
+    x[:2] = [0.1, 0.05]
+    pointwise = ll.compute_pointwise_ll(x)
+    score, grad = ll.evaluateS1(x)
+    case = {
+        'model': 'two_compartment_pk_model', 'direct': True,
+        'outputs': list(omodel.outputs), 'errors': ['lognormal', 'cam'],
+        'events': [list(e) for e in events],
+        'times': [tolist(t0), tolist(t1)], 'obs': [tolist(obs0), tolist(obs1)],
+        'names': ll.get_parameter_names(), 'x': tolist(x),
+        'pointwise': tolist(pointwise), 'score': float(score),
+        'grad': tolist(grad)}
+    # the same data under reduced models: two mechanistic parameters and
+    # one error parameter fixed
+    rmm = chi.ReducedMechanisticModel(ExactModel(omodel, events))
+    fixed_mech = {'central.drug_amount': 0.1, 'global.transition_rate_p2c': 1.1}
+    rmm.fix_parameters(fixed_mech)
+    rem = chi.ReducedErrorModel(
+        chi.ConstantAndMultiplicativeGaussianErrorModel())
+    rem.fix_parameters({'Sigma rel.': 0.15})
+    llr = chi.LogLikelihood(
+        rmm, [chi.LogNormalErrorModel(), rem], [obs0, obs1], [t0, t1])
+    names = llr.get_parameter_names()
+    xr = np.array([0.05, 2.1, 0.9, 5.2, 9.5, 0.11, 0.05])
+    score_r, grad_r = llr.evaluateS1(xr)
+    case['reduced'] = {
+        'fixed_mechanistic': fixed_mech, 'fixed_error': {'Sigma rel.': 0.15},
+        'names': names, 'x': tolist(xr), 'score': float(score_r),
+        'grad': tolist(grad_r), 'score_call': float(llr(xr))}
+    return case
+
+
+def filter_cases(rng):
+    obs = rng.uniform(0.5, 3.0, (7, 2, 4))
+    obs[2, 1, 3] = np.nan
+    obs[0, 0, 0] = np.nan
+    y = rng.uniform(0.5, 3.0, (12, 2, 4))
+    out = []
+    for name, kw in (('GaussianFilter', {}), ('LogNormalFilter', {}),
+                     ('GaussianKDEFilter', {}), ('LogNormalKDEFilter', {}),
+                     ('GaussianMixtureFilter', {'n_kernels': 3})):
+        f = getattr(chi, name)(obs, **kw)
+        s, g = f.compute_sensitivities(y)
+        out.append({'filter': name, 'kwargs': kw, 'score': float(s),
+                    'score_call': float(f.compute_log_likelihood(y)),
+                    'grad': tolist(g)})
+    comp = chi.ComposedPopulationFilter(
+        [chi.GaussianFilter(obs[:, :, :2]),
+         chi.LogNormalKDEFilter(obs[:, :, 2:])])
+    order = np.array([2, 0, 3, 1])
+    comp.sort_times(order)
+    s, g = comp.compute_sensitivities(y)
+    out.append({'filter': 'composed', 'order': tolist(order),
+                'score': float(s), 'grad': tolist(g)})
+    return {'observations': [[[None if np.isnan(v) else float(v) for v in r]
+                              for r in o] for o in obs],
+            'simulated': tolist(y), 'cases': out}
+
+
+class SamplingPrior(IndependentPrior):
+    def sample(self, n=1):
+        return np.ones((n, len(self.kinds)))
+
+
+def filter_posterior_case(rng, log_scale, sigma_fixed):
+    """PopulationFilterLogPosterior (chi/_log_pdfs.py:1325-2075) on the
+    exact solution of the one-compartment model."""
+    omodel = ode_exact.one_compartment(True)
+    events = [(10.0 / 0.5, 0.0, 0.5, 0.0, 0.0)]
+    times = np.array([4.0, 0.5, 1.5, 8.0])
+    n_data, n_sim = 9, 6
+    data = np.empty((n_data, 1, len(times)))
+    for i in range(n_data):
+        psi = [0.0, 2.0 * np.exp(0.2 * rng.normal()),
+               1.0 * np.exp(0.2 * rng.normal())]
+        data[i, 0] = ode_exact.simulate(
+            omodel, psi, np.sort(times), events, False)[0][
+                np.argsort(np.argsort(times))] * rng.lognormal(0, 0.05, 4)
+    data[3, 0, 1] = np.nan
+    filt = chi.GaussianKDEFilter(data) if not log_scale \
+        else chi.LogNormalFilter(data)
+    pm = chi.ComposedPopulationModel([
+        chi.PooledModel(1), chi.LogNormalModel(1, centered=False),
+        chi.GaussianModel(1, centered=True)])
+    n_top = pm.n_parameters() + (0 if sigma_fixed else 1)
+    prior = SamplingPrior([0] * n_top, [0.5] * n_top, [2.0] * n_top)
+    post = chi.PopulationFilterLogPosterior(
+        filt, times, ExactModel(omodel, events), pm, prior,
+        sigma=[0.07] if sigma_fixed else None,
+        error_on_log_scale=log_scale, n_samples=n_sim)
+    theta = [0.05, np.log(2.0), 0.2, 1.0, 0.15]
+    if not sigma_fixed:
+        theta = theta + [0.08]
+    eta = np.column_stack([rng.normal(size=n_sim),
+                           rng.normal(1.0, 0.15, size=n_sim)])
+    eps = rng.normal(size=(n_sim, 1, len(times)))
+    x = np.concatenate([theta, eta.reshape(-1), eps.reshape(-1)])
+    score, grad = post.evaluateS1(x)
+    return {
+        'model': 'one_compartment_pk_model', 'direct': True,
+        'output': 'central.drug_concentration',
+        'events': [list(e) for e in events], 'times': tolist(times),
+        'data': [[[None if np.isnan(v) else float(v) for v in r] for r in o]
+                 for o in data],
+        'filter': 'LogNormalFilter' if log_scale else 'GaussianKDEFilter',
+        'population': [['pooled', 1], ['lognormal', 1, False],
+                       ['gaussian', 1, True]],
+        'sigma': [0.07] if sigma_fixed else None, 'log_scale': log_scale,
+        'n_samples': n_sim, 'prior': [prior.kinds, prior.locs, prior.scales],
+        'names': post.get_parameter_names(include_ids=True),
+        'n_parameters': post.n_parameters(),
+        'n_top': post.n_parameters(exclude_bottom_level=True),
+        'x': tolist(x), 'score': float(score), 'grad': tolist(grad),
+        'score_call': float(post(x))}
+
+
+class DosedStub(chi.MechanisticModel):
+    """Just enough of a PKPD model for ProblemModellingController.set_data:
+    two outputs, supports dosing, remembers the protocol it is handed."""
+
+    def __init__(self):
+        super(DosedStub, self).__init__()
+        self.protocol = None
+
+    def copy(self):
+        return copy_module.deepcopy(self)
+
+    def n_outputs(self):
+        return 2
+
+    def n_parameters(self):
+        return 3
+
+    def outputs(self):
+        return ['central.drug_concentration', 'global.tumour_volume']
+
+    def parameters(self):
+        return ['a', 'b', 'c']
+
+    def supports_dosing(self):
+        return True
+
+    def has_sensitivities(self):
+        return False
+
+    def enable_sensitivities(self, enabled, parameter_names=None):
+        pass
+
+    def set_dosing_regimen(self, regimen, *args, **kwargs):
+        self.protocol = regimen
+
+    def simulate(self, parameters, times):
+        return np.ones((2, len(times)))
+
+
+def ingestion_case(rng):
+    """chi.ProblemModellingController.set_data and what it builds per
+    individual (chi/_problems.py:246-376, 623-734): measurement arrays per
+    output, dose events, covariates."""
+    import pandas as pd
+    rows = []
+    ids = [3, 'b7', 11, 4]
+    for k, i in enumerate(ids):
+        for t in np.sort(rng.uniform(0, 10, 5 + k)):
+            rows.append([i, t, 'Conc', rng.uniform(0.5, 2), np.nan, np.nan])
+        for t in np.sort(rng.uniform(0, 10, 3)):
+            rows.append([i, t, 'Volume', rng.uniform(0.5, 2), np.nan, np.nan])
+        rows.append([i, 2.5, 'Conc', np.nan, np.nan, np.nan])   # no value
+        rows.append([i, np.nan, 'Age', 30.0 + k, np.nan, np.nan])
+        rows.append([i, np.nan, 'Weight', 60.0 + 2 * k, np.nan, np.nan])
+        for d in range(k + 1):
+            rows.append([i, 1.0 * d, np.nan, np.nan, 5.0 + k,
+                         0.5 if d % 2 == 0 else np.nan])
+    data = pd.DataFrame(rows, columns=[
+        'ID', 'Time', 'Observable', 'Value', 'Dose', 'Duration'])
+    model = DosedStub()
+    ctrl = chi.ProblemModellingController(
+        model, [chi.GaussianErrorModel(), chi.LogNormalErrorModel()])
+    pm = chi.ComposedPopulationModel([
+        chi.PooledModel(2),
+        chi.CovariatePopulationModel(
+            chi.GaussianModel(1), chi.LinearCovariateModel(n_cov=2)),
+        chi.PooledModel(2)])
+    ctrl.set_population_model(pm)
+    cov_names = ctrl.get_covariate_names()
+    ctrl.set_data(
+        data,
+        output_observable_dict={'central.drug_concentration': 'Conc',
+                                'global.tumour_volume': 'Volume'},
+        covariate_dict={cov_names[0]: 'Age', cov_names[1]: 'Weight'})
+    per_id = []
+    for individual in ctrl._ids:
+        ll = ctrl._create_log_likelihood(individual)
+        per_id.append({
+            'id': str(individual),
+            'times': [tolist(ll._times[m]) for m in ll._obs_masks],
+            'observations': [tolist(o) for o in ll._observations],
+            'events': [list(e) for e in
+                       ctrl._dosing_regimens[individual].events]})
+    cov = ctrl._extract_covariates(cov_names)
+    return {'columns': list(data.columns),
+            'rows': [[None if (isinstance(v, float) and np.isnan(v)) else
+                      (v if isinstance(v, str) else float(v)) for v in r]
+                     for r in rows],
+            'row_id_is_str': [isinstance(r[0], str) for r in rows],
+            'output_observable_dict': {
+                'central.drug_concentration': 'Conc',
+                'global.tumour_volume': 'Volume'},
+            'individuals': per_id, 'covariates': tolist(cov)}
+
+
 def main():
     rng = np.random.default_rng(20240607)
     stats_golden = {
@@ -483,6 +754,18 @@ def main():
     with open(os.path.join(HERE, 'stats_golden_extra.json'), 'w') as f:
         json.dump({'truncated_gaussian': truncated_gaussian_cases(rng2),
                    'reduced_error_model': reduced_error_model_cases(rng2)}, f)
+    rng3 = np.random.default_rng(20261020)
+    round2 = {
+        'linear_covariate': linear_covariate_cases(rng3),
+        'pointwise_and_reduced': pointwise_and_reduced_cases(rng3),
+        'c2_120': hier_case(rng3, 120, 'lognormal', False),
+        'filters': filter_cases(rng3),
+        'filter_posterior': [
+            filter_posterior_case(rng3, False, True),
+            filter_posterior_case(rng3, True, False)],
+        'ingestion': ingestion_case(rng3)}
+    with open(os.path.join(HERE, 'round2_golden.json'), 'w') as f:
+        json.dump(round2, f)
     print('wrote', os.path.join(HERE, 'stats_golden.json'),
           os.path.join(HERE, 'hier_golden.json'),
           os.path.join(HERE, 'stats_golden_extra.json'))

@@ -166,9 +166,12 @@ def test_c1_log_posterior_matches_reference_golden():
         case['score_call'], rel=1e-8)
 
 
-@pytest.mark.parametrize('name', ['c2', 'c5'])
+@pytest.mark.parametrize('name', ['c2', 'c5', 'c2_120'])
 def test_hierarchical_posterior_matches_reference_golden(name):
-    case = _load('hier_golden.json')[name]
+    """C2 / C5 at 5-6 individuals and C2 at 120 individuals
+    (round2_golden.json)."""
+    case = _load('round2_golden.json')[name] if name == 'c2_120' \
+        else _load('hier_golden.json')[name]
     n_ids = case['n_ids']
     model = chi_b200.library.ModelLibrary().two_compartment_pk_model()
     model.set_administration('central', direct=True)

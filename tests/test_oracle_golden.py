@@ -153,11 +153,12 @@ def golden_layout(case):
         [('pooled', 2), mid, ('pooled', n_sig)], case['n_ids'])
 
 
-@pytest.mark.parametrize('name', ['c2', 'c5'])
+@pytest.mark.parametrize('name', ['c2', 'c5', 'c2_120'])
 def test_hierarchical_posterior_matches_reference_golden(name):
     """oracle (numpy restatement + exact ODE) == unmodified reference
     classes driving the same exact ODE."""
-    case = _load('hier_golden.json')[name]
+    case = _load('round2_golden.json')[name] if name == 'c2_120' \
+        else _load('hier_golden.json')[name]
     lay = golden_layout(case)
     omodel = ode_exact.two_compartment(True)
     omodel.set_outputs([case['output']])
