@@ -166,9 +166,15 @@ def test_population_filter_log_posterior_matches_reference(index):
         grad, case['grad'], rtol=1e-6,
         atol=1e-7 * np.max(np.abs(case['grad'])))
     assert post(x) == pytest.approx(case['score_call'], rel=1e-8)
-    init = post.sample_initial_parameters(n_samples=2, seed=3)
+    positive = chi_b200.ComposedLogPrior(*[
+        chi_b200.LogNormalLogPrior(0.0, 0.1)] * case['n_top'])
+    post2 = chi_b200.PopulationFilterLogPosterior(
+        filt, case['times'], model, pm, positive, sigma=case['sigma'],
+        error_on_log_scale=case['log_scale'], n_samples=case['n_samples'])
+    init = post2.sample_initial_parameters(n_samples=2, seed=3)
     assert init.shape == (2, case['n_parameters'])
     assert np.all(np.isfinite(init))
+    assert np.isfinite(post2(init[0]))
 
 
 def test_posterior_and_prior_predictive_models():
@@ -197,7 +203,8 @@ def test_posterior_and_prior_predictive_models():
     arr = ppm.sample(times, n_samples=40, individual='b', seed=1,
                      return_df=False)
     assert arr.shape == (1, 4, 40)
-    exact = model.simulate([0.0, 2.0, 1.0], np.sort(times))
+    exact = pred._mechanistic_model.simulate(
+        [0.0, 2.0, 1.0], np.sort(times))
     np.testing.assert_allclose(
         np.mean(arr[0], axis=1), exact[0], rtol=0.02)
     with pytest.raises(ValueError):
