@@ -273,7 +273,6 @@ class LogLikelihood(_chi_base('LogLikelihood', _LogPDFBase)):
         self._observations = observations
         self._output_times = times
         self._n_obs = [len(obs) for obs in observations]
-        self._set_error_model_parameter_names()
         self._set_number_and_parameter_names()
         self._unwrap_reduced_models()
         self._id = None
@@ -440,30 +439,16 @@ class LogLikelihood(_chi_base('LogLikelihood', _LogPDFBase)):
             start = end
         return np.hstack(pointwise)
 
-    def _set_error_model_parameter_names(self):
-        """chi/_log_pdfs.py:885-909."""
-        for error_model in self._error_models:
-            error_model.set_parameter_names(None)
-        n_outputs = self._mechanistic_model.n_outputs()
-        if n_outputs > 1:
-            outputs = self._mechanistic_model.outputs()
-            for output_id, error_model in enumerate(self._error_models):
-                names = error_model.get_parameter_names()
-                output = outputs[output_id]
-                names = [output + ' ' + name for name in names]
-                error_model.set_parameter_names(names)
-
     def _set_number_and_parameter_names(self):
-        """chi/_log_pdfs.py:911-930."""
-        parameter_names = self._mechanistic_model.parameters()
-        n_error_params = []
-        for error_model in self._error_models:
-            parameter_names += error_model.get_parameter_names()
-            n_error_params.append(error_model.n_parameters())
-        self._parameter_names = parameter_names
+        """Names of the mechanistic parameters, then of every output's error
+        parameters (chi/_log_pdfs.py:885-930)."""
+        from chi_b200._predictive_models import name_parameters
+        self._parameter_names = name_parameters(
+            self._mechanistic_model, self._error_models)
         self._n_parameters = len(self._parameter_names)
         self._n_mechanistic_params = self._mechanistic_model.n_parameters()
-        self._n_error_params = n_error_params
+        self._n_error_params = [
+            em.n_parameters() for em in self._error_models]
 
     def get_id(self, *args, **kwargs):
         return self._id

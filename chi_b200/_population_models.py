@@ -1,13 +1,18 @@
-"""Population models evaluated on the GPU.
+"""Population models evaluated on the GPU (interface of
+``chi/_population_models.py``).
 
-Host-side mirror of ``chi/_population_models.py`` for the models on the hot
-path (Pooled, Heterogeneous, Gaussian, LogNormal, Composed, Covariate;
-SURVEY.md section 8a rows a15-a19).  The classes keep chi's bookkeeping API
-(names, dimensions, special dims, ``n_hierarchical_parameters`` ...); every
-``compute_*`` method flattens the model into the block descriptor of the C
-ABI (``chi_b200_population_set``) and evaluates it with the population
-kernels.  ``sample`` draws on the host with numpy's generator in the
-reference's order (distribution- and seed-level parity).
+Every ``compute_*`` method flattens the model into the block descriptor of
+the C ABI (``chi_b200_population_set``) and evaluates it with the population
+kernels (csrc/core.cu).  ``sample`` draws on the host with numpy's generator
+in the reference's order (distribution- and seed-level parity).
+
+Bookkeeping.  A model is a list of LEAVES (``_leaves()``: a Pooled,
+Heterogeneous, Gaussian, LogNormal, TruncatedGaussian or Covariate model; a
+composed model concatenates the leaves of its parts).  A leaf knows its kind,
+its dimensions and how many top-level parameters it has for ``n_ids``
+individuals; everything the reference caches and patches up on every change
+(number of parameters, special dimensions, hierarchical dimensions, names) is
+derived from that list on request.
 """
 import copy
 
@@ -23,11 +28,32 @@ except Exception:  # pragma: no cover
     _chi = None
     _PopulationModelBase = object
 
+# kinds with a density over the individuals (bottom-level parameters exist)
+_DENSITY_KINDS = ('gaussian', 'lognormal', 'truncated_gaussian')
+
+
+def _default_dim_names(n_dim):
+    return ['Dim. %d' % (d + 1) for d in range(n_dim)]
+
+
+def _as_rows(parameters, n_dim, n_expected=None):
+    """Top-level parameters as an array of rows of length ``n_dim``."""
+    parameters = np.asarray(parameters)
+    if n_expected is not None and parameters.size != n_expected:
+        raise ValueError(
+            'The number of provided parameters does not match the expected'
+            ' number of top-level parameters.')
+    if parameters.ndim != 2:
+        parameters = parameters.reshape(-1, n_dim)
+    return parameters
+
 
 class PopulationModel(_PopulationModelBase):
-    """Base class, see chi/_population_models.py:18-326."""
+    """Base class (interface of chi/_population_models.py:18-326)."""
 
-    _kind = None
+    KIND = None            # block kind of a leaf
+    ROWS = ()              # default names of a leaf's parameter rows
+    SPECIAL = None         # True: pooled, False: heterogeneous, None: density
 
     def __init__(self, n_dim=1, dim_names=None):
         if n_dim < 1:
@@ -35,53 +61,69 @@ class PopulationModel(_PopulationModelBase):
                 'The dimension of the population model has to be greater or '
                 'equal to 1.')
         self._n_dim = int(n_dim)
-        self._n_hierarchical_dim = self._n_dim
-        self._special_dims = []
-        self._n_pooled_dims = 0
-        self._n_hetero_dims = 0
-        self._n_covariates = 0
         self._n_ids = 1
         self._device = None
         self._dev_cache = None
-        if dim_names:
-            if len(dim_names) != self._n_dim:
-                raise ValueError(
-                    'The number of dimension names has to match the number of '
-                    'dimensions of the population model.')
-            dim_names = [str(name) for name in dim_names]
-        else:
-            dim_names = [
-                'Dim. %d' % (id_dim + 1) for id_dim in range(self._n_dim)]
-        self._dim_names = dim_names
+        self._custom_names = None
+        if dim_names and len(dim_names) != self._n_dim:
+            raise ValueError(
+                'The number of dimension names has to match the number of '
+                'dimensions of the population model.')
+        self._dim_names = [str(n) for n in dim_names] if dim_names \
+            else _default_dim_names(self._n_dim)
 
     def __deepcopy__(self, memo):
-        cls = self.__class__
-        result = cls.__new__(cls)
-        memo[id(self)] = result
-        for k, v in self.__dict__.items():
-            setattr(result, k, None if k == '_dev_cache'
-                    else copy.deepcopy(v, memo))
-        return result
+        clone = self.__class__.__new__(self.__class__)
+        memo[id(self)] = clone
+        for key, value in self.__dict__.items():
+            # (the device problem is rebuilt on demand)
+            setattr(clone, key, None if key == '_dev_cache'
+                    else copy.deepcopy(value, memo))
+        return clone
+
+    # -- the leaf table --------------------------------------------------------
+    def _leaves(self):
+        return [self]
+
+    def _leaf_n_top(self, n_ids):
+        """Top-level parameters of this leaf for ``n_ids`` individuals."""
+        return len(self.ROWS) * self._n_dim
+
+    def _leaf_block(self):
+        """(kind, n_dim, centered, n_cov, pidx, didx) for the C ABI."""
+        return (self.KIND, self._n_dim, getattr(self, '_centered', True), 0,
+                None, None)
+
+    def _blocks(self):
+        return [leaf._leaf_block() for leaf in self._leaves()]
+
+    def _default_parameter_names(self):
+        return [row for row in self.ROWS for _ in range(self._n_dim)]
+
+    @property
+    def _parameter_names(self):
+        if self._custom_names is not None:
+            return self._custom_names
+        return self._default_parameter_names()
+
+    @property
+    def _n_parameters(self):
+        return self.n_parameters()
 
     # -- device plumbing -----------------------------------------------------
-    def _blocks(self):
-        """Flat list of block descriptors
-        (kind, n_dim, centered, n_cov, pidx, didx)."""
-        raise NotImplementedError
-
     def _n_top(self, n_ids):
         return self.n_hierarchical_parameters(n_ids)[1]
 
     def _device_problem(self, n_ids, covariates):
         blocks = self._blocks()
         cov_bytes = None
-        if self._n_covariates > 0:
+        if self.n_covariates() > 0:
             if covariates is None:
                 raise ValueError(
                     'The population model needs covariates, but no covariates '
                     'have been provided.')
             covariates = np.ascontiguousarray(
-                covariates, dtype=float).reshape(n_ids, self._n_covariates)
+                covariates, dtype=float).reshape(n_ids, self.n_covariates())
             cov_bytes = covariates.tobytes()
         sig = (n_ids, repr([(b[0], b[1], b[2], b[3],
                              None if b[4] is None else list(b[4]),
@@ -170,7 +212,7 @@ class PopulationModel(_PopulationModelBase):
         """Pooled / heterogeneous dims are delta distributions: -inf unless
         the observations equal the parameters
         (chi/_population_models.py:1986-1988, 2866-2868)."""
-        for info in self._special_dims:
+        for info in self.get_special_dims()[0]:
             s, e = info[0], info[1]
             if np.any(eta_dev[:, s:e] != observations[:, s:e]):
                 return False
@@ -215,41 +257,61 @@ class PopulationModel(_PopulationModelBase):
             t_full += nt
         return score, dpsi, dtheta
 
+    # -- interface of the reference ----------------------------------------------
     def get_covariate_names(self):
         return []
 
     def get_dim_names(self):
-        return copy.copy(self._dim_names)
+        return list(self._dim_names)
 
     def get_special_dims(self):
-        return self._special_dims, self._n_pooled_dims, self._n_hetero_dims
+        """``([[dim_start, dim_end, top_start, top_end, is_pooled], ...],
+        n_pooled_dims, n_heterogeneous_dims)`` over the leaves
+        (chi/_population_models.py:2784, 2187, 451-492)."""
+        entries, n_pooled, n_hetero = [], 0, 0
+        dim = top = 0
+        for leaf in self._leaves():
+            n_top = leaf._leaf_n_top(self._n_ids)
+            if leaf.SPECIAL is not None:
+                entries.append(
+                    [dim, dim + leaf._n_dim, top, top + n_top, leaf.SPECIAL])
+                if leaf.SPECIAL:
+                    n_pooled += leaf._n_dim
+                else:
+                    n_hetero += leaf._n_dim
+            dim += leaf._n_dim
+            top += n_top
+        return entries, n_pooled, n_hetero
 
     def get_parameter_names(self, exclude_dim_names=False):
+        names = list(self._parameter_names)
         if exclude_dim_names:
-            return copy.copy(self._parameter_names)
-        names = []
-        for name_id, name in enumerate(self._parameter_names):
-            current_dim = name_id % self._n_dim
-            names += [name + ' ' + self._dim_names[current_dim]]
-        return names
+            return names
+        return [name + ' ' + self._dim_names[k % self._n_dim]
+                for k, name in enumerate(names)]
 
     def n_covariates(self):
-        return self._n_covariates
+        return 0
 
     def n_dim(self):
         return self._n_dim
 
     def n_hierarchical_dim(self):
-        return self._n_hierarchical_dim
+        return sum(leaf._n_dim for leaf in self._leaves()
+                   if leaf.SPECIAL is None)
 
     def n_hierarchical_parameters(self, n_ids):
-        raise NotImplementedError
+        n_ids = int(n_ids)
+        n_bottom = sum(n_ids * leaf._n_dim for leaf in self._leaves()
+                       if leaf.SPECIAL is None)
+        return n_bottom, sum(
+            leaf._leaf_n_top(n_ids) for leaf in self._leaves())
 
     def n_ids(self):
         return self._n_ids
 
     def n_parameters(self):
-        return self._n_parameters
+        return sum(leaf._leaf_n_top(self._n_ids) for leaf in self._leaves())
 
     def sample(self, parameters, n_samples=None, seed=None, *args, **kwargs):
         raise NotImplementedError
@@ -259,13 +321,12 @@ class PopulationModel(_PopulationModelBase):
 
     def set_dim_names(self, names=None):
         if names is None:
-            self._dim_names = [
-                'Dim. %d' % (id_dim + 1) for id_dim in range(self._n_dim)]
-            return None
+            self._dim_names = _default_dim_names(self._n_dim)
+            return
         if len(names) != self._n_dim:
             raise ValueError(
                 'Length of names does not match the number of dimensions.')
-        self._dim_names = [str(label) for label in names]
+        self._dim_names = [str(n) for n in names]
 
     def set_n_ids(self, n_ids):
         n_ids = int(n_ids)
@@ -277,12 +338,12 @@ class PopulationModel(_PopulationModelBase):
 
     def set_parameter_names(self, names=None):
         if names is None:
-            self._parameter_names = list(self._default_parameter_names())
-            return None
-        if len(names) != self._n_parameters:
+            self._custom_names = None
+            return
+        if len(names) != self.n_parameters():
             raise ValueError(
                 'Length of names does not match the number of parameters.')
-        self._parameter_names = [str(label) for label in names]
+        self._custom_names = [str(n) for n in names]
 
 
 def _block_n_top(block, n_ids):
@@ -324,138 +385,101 @@ def set_population(problem, blocks, covariates):
         problem.handle, len(blocks), p1, p2, p3, p4, p5, p6, p7, p_cov))
 
 
+
 class _DensityModel(PopulationModel):
-    """Shared code of GaussianModel and LogNormalModel."""
+    """Leaves with a density over the individuals: top-level parameters are
+    a location row and a scale row."""
 
     def __init__(self, n_dim=1, dim_names=None, centered=True):
         super(_DensityModel, self).__init__(n_dim, dim_names)
-        self._n_parameters = 2 * self._n_dim
-        self._parameter_names = list(self._default_parameter_names())
         self._centered = bool(centered)
 
-    def _blocks(self):
-        return [(self._kind, self._n_dim, self._centered, 0, None, None)]
-
-    def n_hierarchical_parameters(self, n_ids):
-        n_ids = int(n_ids)
-        return (n_ids * self._n_dim, self._n_parameters)
+    def _location_and_scale(self, parameters):
+        rows = _as_rows(parameters, self._n_dim, 2 * self._n_dim)
+        return rows[0], rows[1]
 
     def _sample_parameters(self, parameters):
-        parameters = np.asarray(parameters)
-        if len(parameters.flatten()) != self._n_parameters:
-            raise ValueError(
-                'The number of provided parameters does not match the expected'
-                ' number of top-level parameters.')
-        if parameters.ndim != 2:
-            n_parameters = len(parameters) // self._n_dim
-            parameters = parameters.reshape(n_parameters, self._n_dim)
-        return parameters
+        return _as_rows(parameters, self._n_dim, 2 * self._n_dim)
 
 
 class GaussianModel(_DensityModel):
     """chi/_population_models.py:1385-1874."""
-    _kind = 'gaussian'
-
-    def _default_parameter_names(self):
-        return ['Mean'] * self._n_dim + ['Std.'] * self._n_dim
+    KIND = 'gaussian'
+    ROWS = ('Mean', 'Std.')
 
     def get_mean_and_std(self, parameters):
-        """chi/_population_models.py:1759-1777."""
-        parameters = self._sample_parameters(parameters)
-        return np.vstack([parameters[0], parameters[1]])
+        return np.vstack(self._location_and_scale(parameters))
 
     def sample(self, parameters, n_samples=None, seed=None, *args, **kwargs):
-        """chi/_population_models.py:1797-1846."""
-        parameters = self._sample_parameters(parameters)
-        if n_samples is None:
-            n_samples = 1
-        sample_shape = (int(n_samples), self._n_dim)
-        mus = parameters[0]
-        sigmas = parameters[1]
+        """Draws individuals -- or, non-centered, their standard-normal etas
+        (chi/_population_models.py:1797-1846)."""
+        mu, sigma = self._location_and_scale(parameters)
         if not self._centered:
-            mus = np.zeros(mus.shape)
-            sigmas = np.ones(sigmas.shape)
-        if np.any(sigmas < 0):
+            mu, sigma = np.zeros(self._n_dim), np.ones(self._n_dim)
+        if np.any(sigma < 0):
             raise ValueError(
                 'A Gaussian distribution only accepts strictly positive '
                 'standard deviations.')
         rng = np.random.default_rng(seed=seed)
-        return rng.normal(loc=mus, scale=sigmas, size=sample_shape)
+        return rng.normal(
+            loc=mu, scale=sigma, size=(int(n_samples or 1), self._n_dim))
 
 
 class LogNormalModel(_DensityModel):
     """chi/_population_models.py:2212-2756."""
-    _kind = 'lognormal'
-
-    def _default_parameter_names(self):
-        return ['Log mean'] * self._n_dim + ['Log std.'] * self._n_dim
+    KIND = 'lognormal'
+    ROWS = ('Log mean', 'Log std.')
 
     def get_mean_and_std(self, parameters):
-        """chi/_population_models.py:2601-2634."""
-        parameters = np.asarray(parameters)
-        if parameters.ndim != 2:
-            n_parameters = len(parameters) // self._n_dim
-            parameters = parameters.reshape(n_parameters, self._n_dim)
-        mus = parameters[0]
-        sigmas = parameters[1]
-        if np.any(sigmas < 0):
+        """Mean and standard deviation on the natural scale
+        (chi/_population_models.py:2601-2634)."""
+        mu, sigma = _as_rows(parameters, self._n_dim)[:2]
+        if np.any(sigma < 0):
             raise ValueError('The standard deviation cannot be negative.')
-        mean = np.exp(mus + sigmas**2 / 2)
-        std = np.sqrt(
-            np.exp(2 * mus + sigmas**2) * (np.exp(sigmas**2) - 1))
-        return np.vstack([mean, std])
+        var = sigma ** 2
+        return np.vstack([
+            np.exp(mu + var / 2),
+            np.sqrt(np.exp(2 * mu + var) * (np.exp(var) - 1))])
 
     def sample(self, parameters, n_samples=None, seed=None, *args, **kwargs):
         """chi/_population_models.py:2678-2732."""
-        parameters = self._sample_parameters(parameters)
-        if n_samples is None:
-            n_samples = 1
-        sample_shape = (int(n_samples), self._n_dim)
+        mu, sigma = self._location_and_scale(parameters)
+        shape = (int(n_samples or 1), self._n_dim)
         rng = np.random.default_rng(seed=seed)
-        mus = parameters[0]
-        sigmas = parameters[1]
         if not self._centered:
-            mus = np.zeros(mus.shape)
-            sigmas = np.ones(sigmas.shape)
-            return rng.normal(loc=mus, scale=sigmas, size=sample_shape)
-        if np.any(sigmas <= 0):
+            return rng.normal(loc=np.zeros(self._n_dim),
+                              scale=np.ones(self._n_dim), size=shape)
+        if np.any(sigma <= 0):
             raise ValueError(
                 'A log-normal distribution only accepts strictly positive '
                 'standard deviations.')
-        return rng.lognormal(mean=mus, sigma=sigmas, size=sample_shape)
+        return rng.lognormal(mean=mu, sigma=sigma, size=shape)
 
 
 class TruncatedGaussianModel(_DensityModel):
-    """Gaussian population truncated at zero,
-    chi/_population_models.py:3500-3939.  Always centered: the bottom-level
+    """Gaussian population truncated at zero
+    (chi/_population_models.py:3500-3939).  Always centered: the bottom-level
     parameters are the individual parameters themselves; sigma <= 0 or a
     negative individual parameter scores -inf (3557-3558, 3656-3658)."""
-    _kind = 'truncated_gaussian'
+    KIND = 'truncated_gaussian'
+    ROWS = ('Mu', 'Sigma')
 
     def __init__(self, n_dim=1, dim_names=None):
         super(TruncatedGaussianModel, self).__init__(
             n_dim, dim_names, centered=True)
 
-    def _default_parameter_names(self):
-        return ['Mu'] * self._n_dim + ['Sigma'] * self._n_dim
-
     def get_mean_and_std(self, parameters):
-        """chi/_population_models.py:3771-3821."""
+        """chi/_population_models.py:3771-3821 (the reference allocates
+        (n_parameters, n_dim) and fills two rows; the documented shape is
+        returned)."""
         from scipy.stats import norm
-        parameters = np.asarray(parameters)
-        if parameters.ndim != 2:
-            n_parameters = len(parameters) // self._n_dim
-            parameters = parameters.reshape(n_parameters, self._n_dim)
-        mus = parameters[0]
-        sigmas = parameters[1]
-        if np.any(sigmas < 0):
+        mu, sigma = _as_rows(parameters, self._n_dim)[:2]
+        if np.any(sigma < 0):
             raise ValueError('The standard deviation cannot be negative.')
-        f = norm.pdf(mus / sigmas) / (1 - norm.cdf(-mus / sigmas))
-        # (the reference allocates (n_parameters, n_dim) and leaves all but
-        # the first two rows uninitialised; the documented shape is returned)
+        hazard = norm.pdf(mu / sigma) / (1 - norm.cdf(-mu / sigma))
         return np.vstack([
-            mus + sigmas * f,
-            np.sqrt(sigmas**2 * (1 - mus / sigmas * f - f**2))])
+            mu + sigma * hazard,
+            np.sqrt(sigma ** 2 * (1 - mu / sigma * hazard - hazard ** 2))])
 
     def sample(self, parameters, n_samples=None, seed=None, *args, **kwargs):
         """chi/_population_models.py:3863-3919.  Like the reference this
@@ -464,13 +488,8 @@ class TruncatedGaussianModel(_DensityModel):
         units, so the draws are truncated at ``mu``; reproduced as is for
         seed-level parity)."""
         from scipy.stats import truncnorm
-        parameters = self._sample_parameters(parameters)
-        if n_samples is None:
-            n_samples = 1
-        sample_shape = (int(n_samples), self._n_dim)
-        mus = parameters[0]
-        sigmas = parameters[1]
-        if np.any(sigmas < 0):
+        mu, sigma = self._location_and_scale(parameters)
+        if np.any(sigma < 0):
             raise ValueError(
                 'A truncated Gaussian distribution only accepts strictly '
                 'positive standard deviations.')
@@ -478,66 +497,40 @@ class TruncatedGaussianModel(_DensityModel):
             seed = seed.integers(low=0, high=1E6)
         np.random.seed(seed)
         return truncnorm.rvs(
-            a=0, b=np.inf, loc=mus, scale=sigmas, size=sample_shape)
+            a=0, b=np.inf, loc=mu, scale=sigma,
+            size=(int(n_samples or 1), self._n_dim))
 
 
 class PooledModel(PopulationModel):
-    """chi/_population_models.py:2759-3061."""
-    _kind = 'pooled'
-
-    def __init__(self, n_dim=1, dim_names=None):
-        super(PooledModel, self).__init__(n_dim, dim_names)
-        self._n_parameters = self._n_dim
-        self._n_hierarchical_dim = 0
-        self._special_dims = [[0, self._n_dim, 0, self._n_parameters, True]]
-        self._n_pooled_dims = self._n_dim
-        self._n_hetero_dims = 0
-        self._parameter_names = ['Pooled'] * self._n_dim
-
-    def _default_parameter_names(self):
-        return ['Pooled'] * self._n_dim
-
-    def _blocks(self):
-        return [('pooled', self._n_dim, True, 0, None, None)]
-
-    def n_hierarchical_parameters(self, n_ids):
-        return (0, self._n_parameters)
+    """Every individual has the same value
+    (chi/_population_models.py:2759-3061)."""
+    KIND = 'pooled'
+    ROWS = ('Pooled',)
+    SPECIAL = True
 
     def sample(self, parameters, n_samples=None, seed=None, *args, **kwargs):
-        """chi/_population_models.py:3005-3037."""
-        parameters = np.asarray(parameters)
-        if len(parameters.flatten()) != self._n_parameters:
-            raise ValueError(
-                'The number of provided parameters does not match the expected'
-                ' number of top-level parameters.')
-        if parameters.ndim != 2:
-            n_parameters = len(parameters) // self._n_dim
-            parameters = parameters.reshape(n_parameters, self._n_dim)
+        rows = _as_rows(parameters, self._n_dim, self._n_dim)
         if n_samples is None:
-            return parameters
-        return np.broadcast_to(
-            parameters, shape=(int(n_samples), self._n_dim))
+            return rows
+        return np.broadcast_to(rows, shape=(int(n_samples), self._n_dim))
 
 
 class HeterogeneousModel(PopulationModel):
-    """chi/_population_models.py:1877-2209."""
-    _kind = 'heterogeneous'
+    """Every individual has its own value, no density
+    (chi/_population_models.py:1877-2209)."""
+    KIND = 'heterogeneous'
+    SPECIAL = False
 
     def __init__(self, n_dim=1, dim_names=None, n_ids=1):
         super(HeterogeneousModel, self).__init__(n_dim, dim_names)
-        self._n_hierarchical_dim = 0
-        self.set_n_ids(n_ids, no_shortcut=True)
-        self._n_pooled_dims = 0
-        self._n_hetero_dims = self._n_dim
+        self.set_n_ids(n_ids)
+
+    def _leaf_n_top(self, n_ids):
+        return int(n_ids) * self._n_dim
 
     def _default_parameter_names(self):
-        names = []
-        for _id in range(self._n_ids):
-            names += ['ID %d' % (_id + 1)] * self._n_dim
-        return names
-
-    def _blocks(self):
-        return [('heterogeneous', self._n_dim, True, 0, None, None)]
+        return ['ID %d' % (i + 1) for i in range(self._n_ids)
+                for _ in range(self._n_dim)]
 
     def _check_n_ids(self, n_ids):
         if n_ids != self._n_ids:
@@ -545,37 +538,32 @@ class HeterogeneousModel(PopulationModel):
                 'The number of individuals does not match n_ids of the '
                 'heterogeneous model.')
 
-    def n_hierarchical_parameters(self, n_ids):
-        return (0, int(n_ids) * self._n_dim)
-
     def sample(self, parameters, n_samples=None, seed=None, *args, **kwargs):
-        """chi/_population_models.py:2113-2152."""
-        parameters = np.asarray(parameters)
-        if parameters.ndim != 2:
-            parameters = parameters.reshape(self._n_ids, self._n_dim)
-        ids = np.arange(self._n_ids)
+        """A bootstrap sample of the individuals
+        (chi/_population_models.py:2113-2152)."""
+        rows = _as_rows(parameters, self._n_dim)
         rng = np.random.default_rng(seed=seed)
-        n_samples = n_samples if n_samples else 1
-        return parameters[rng.choice(ids, size=n_samples, replace=True)]
+        picks = rng.choice(
+            np.arange(self._n_ids), size=n_samples if n_samples else 1,
+            replace=True)
+        return rows[picks]
 
     def set_n_ids(self, n_ids, no_shortcut=False):
-        """chi/_population_models.py:2154-2187."""
         n_ids = int(n_ids)
         if n_ids < 1:
             raise ValueError(
                 'The number of modelled individuals needs to be greater or '
                 'equal to 1.')
-        if (n_ids == self._n_ids) and not no_shortcut:
-            return None
+        if n_ids != self._n_ids:
+            # the parameters are per individual: names start over
+            self._custom_names = None
+            self._dev_cache = None
         self._n_ids = n_ids
-        self._n_parameters = self._n_ids * self._n_dim
-        self._parameter_names = self._default_parameter_names()
-        self._special_dims = [[0, self._n_dim, 0, self._n_parameters, False]]
-        self._dev_cache = None
 
 
 class CovariatePopulationModel(PopulationModel):
-    """chi/_population_models.py:956-1382."""
+    """A Gaussian or LogNormal population whose parameters are shifted by
+    the individuals' covariates (chi/_population_models.py:956-1382)."""
 
     def __init__(self, population_model, covariate_model, dim_names=None):
         if not isinstance(population_model, PopulationModel):
@@ -591,8 +579,7 @@ class CovariatePopulationModel(PopulationModel):
                 'The population model cannot be an instance of a '
                 'chi.ComposedPopulationModel. Please compose multiple '
                 'covariate models instead.')
-        if not isinstance(population_model, _DensityModel) or isinstance(
-                population_model, TruncatedGaussianModel):
+        if population_model.KIND not in ('gaussian', 'lognormal'):
             raise TypeError(
                 'chi_b200 supports covariate models over GaussianModel and '
                 'LogNormalModel only.')
@@ -600,29 +587,40 @@ class CovariatePopulationModel(PopulationModel):
             population_model.n_dim())
         self._population_model = copy.deepcopy(population_model)
         self._covariate_model = copy.deepcopy(covariate_model)
-        self._n_dim = self._population_model.n_dim()
-        self._n_pop = self._population_model.n_parameters()
-        self._n_hierarchical_dim = self._population_model.n_hierarchical_dim()
-        self._n_covariates = self._covariate_model.n_covariates()
-        self._special_dims, self._n_pooled_dims, self._n_hetero_dims = \
-            self._population_model.get_special_dims()
-        n_cov = self._covariate_model.n_covariates()
         self._population_model.set_dim_names(dim_names)
-        indices = []
-        for dim_id in range(self._n_dim):
-            for param_id in range(self._n_pop // self._n_dim):
-                indices.append([param_id, dim_id])
-        self._covariate_model.set_population_parameters(indices)
-        names = []
-        for name in self._population_model.get_parameter_names():
-            names += [name] * n_cov
-        self._covariate_model.set_parameter_names(names)
+        # by default every (parameter row, dimension) pair is shifted
+        n_rows = self._population_model.n_parameters() // self._n_dim
+        self._covariate_model.set_population_parameters(
+            [[row, dim] for dim in range(self._n_dim)
+             for row in range(n_rows)])
+        self._name_the_shifts()
 
-    def _blocks(self):
+    def _name_the_shifts(self):
+        """A shift carries the name of the population parameter it acts on,
+        once per covariate."""
+        names = np.array(self._population_model.get_parameter_names())
+        names = names.reshape(-1, self._n_dim)
+        pidx, didx = self._covariate_model.get_set_population_parameters()
+        n_cov = self._covariate_model.n_covariates()
+        self._covariate_model.set_parameter_names(
+            [name for name in names[pidx, didx] for _ in range(n_cov)])
+
+    @property
+    def _n_pop(self):
+        return self._population_model.n_parameters()
+
+    @property
+    def KIND(self):
+        return self._population_model.KIND
+
+    def _leaf_n_top(self, n_ids):
+        return self._n_pop + self._covariate_model.n_parameters()
+
+    def _leaf_block(self):
         pidx, didx = self._covariate_model.get_set_population_parameters()
         inner = self._population_model
-        return [(inner._kind, inner._n_dim, inner._centered,
-                 self._n_covariates, list(pidx), list(didx))]
+        return (inner.KIND, inner._n_dim, inner._centered,
+                self._covariate_model.n_covariates(), list(pidx), list(didx))
 
     def get_covariate_names(self):
         return self._covariate_model.get_covariate_names()
@@ -631,177 +629,136 @@ class CovariatePopulationModel(PopulationModel):
         return self._population_model.get_dim_names()
 
     def get_parameter_names(self, exclude_dim_names=False):
-        names = self._population_model.get_parameter_names(exclude_dim_names)
-        names += self._covariate_model.get_parameter_names()
-        return names
+        return self._population_model.get_parameter_names(
+            exclude_dim_names) + self._covariate_model.get_parameter_names()
 
-    def n_hierarchical_parameters(self, n_ids):
-        n_ids, _ = self._population_model.n_hierarchical_parameters(n_ids)
-        return (n_ids, self.n_parameters())
-
-    def n_parameters(self):
-        return self._population_model.n_parameters() + \
-            self._covariate_model.n_parameters()
+    def n_covariates(self):
+        return self._covariate_model.n_covariates()
 
     def sample(self, parameters, covariates, n_samples=None, seed=None):
-        """chi/_population_models.py:1247-1299 (host RNG; the covariate
-        shift of the handful of sampled sub-populations is applied with the
-        same indexing the kernels use)."""
+        """One draw per individual from the population shifted by that
+        individual's covariates (chi/_population_models.py:1247-1299; host
+        RNG, the handful of shifts is applied with the indexing the kernels
+        use)."""
+        n_cov = self.n_covariates()
         covariates = np.array(covariates)
         if covariates.ndim == 1:
             covariates = covariates[np.newaxis, :]
-        if covariates.shape[1] != self._n_covariates:
+        if covariates.shape[1] != n_cov:
             raise ValueError(
                 'Provided covariates do not match the number of covariates.')
-        if n_samples is None:
-            n_samples = 1
-        n_samples = int(n_samples)
-        covariates = np.broadcast_to(
-            covariates, (n_samples, self._n_covariates))
+        n_samples = int(n_samples or 1)
+        covariates = np.broadcast_to(covariates, (n_samples, n_cov))
         parameters = np.asarray(parameters)
-        pop_params = parameters[:self._n_pop].reshape(
-            self._n_pop // self._n_dim, self._n_dim)
+        base = parameters[:self._n_pop].reshape(-1, self._n_dim)
         pidx, didx = self._covariate_model.get_set_population_parameters()
-        beta = parameters[self._n_pop:].reshape(
-            len(pidx), self._n_covariates)
-        vartheta = np.zeros((n_samples,) + pop_params.shape)
-        vartheta += pop_params[np.newaxis, ...]
-        vartheta[:, pidx, didx] += covariates @ beta.T
-        seed = np.random.default_rng(seed)
-        psi = np.empty(shape=(n_samples, self._n_dim))
-        for ids, params in enumerate(vartheta):
-            psi[ids] = self._population_model.sample(
-                params, n_samples=1, seed=seed)[0]
-        return psi
+        beta = parameters[self._n_pop:].reshape(len(pidx), n_cov)
+        shifted = np.repeat(base[np.newaxis], n_samples, axis=0)
+        shifted[:, pidx, didx] += covariates @ beta.T
+        rng = np.random.default_rng(seed)
+        return np.vstack([
+            self._population_model.sample(rows, n_samples=1, seed=rng)
+            for rows in shifted])
 
     def set_covariate_names(self, names=None):
         self._covariate_model.set_covariate_names(names)
 
     def set_dim_names(self, names=None):
         self._population_model.set_dim_names(names)
-        names = self._population_model.get_parameter_names()
-        names = np.array(names).reshape(
-            self._n_pop // self._n_dim, self._n_dim)
-        pidx, didx = self._covariate_model.get_set_population_parameters()
-        names = names[pidx, didx]
-        n = []
-        for name in names:
-            n += [name] * self._n_covariates
-        self._covariate_model.set_parameter_names(n)
+        self._name_the_shifts()
 
     def set_parameter_names(self, names=None):
         if names is None:
             self._population_model.set_parameter_names()
             self._covariate_model.set_parameter_names()
-            return None
+            return
         self._population_model.set_parameter_names(names[:self._n_pop])
         self._covariate_model.set_parameter_names(names[self._n_pop:])
 
     def set_population_parameters(self, indices):
-        """chi/_population_models.py:1354-1382."""
+        """Which (parameter row, dimension) pairs the covariates shift
+        (chi/_population_models.py:1354-1382)."""
         indices = np.array(indices)
-        upper = np.max(indices, axis=0)
-        n_pop = self._n_pop // self._n_dim
-        out_of_bounds = \
-            (upper[0] >= n_pop) or (upper[1] >= self._n_dim) or \
-            (np.min(indices) < 0)
-        if out_of_bounds:
+        n_rows = self._n_pop // self._n_dim
+        if np.min(indices) < 0 or np.max(indices[:, 0]) >= n_rows or \
+                np.max(indices[:, 1]) >= self._n_dim:
             raise IndexError('The provided indices are out of bounds.')
         self._covariate_model.set_population_parameters(indices)
+        # (named in the order the indices were given, as the reference does)
         names = np.array(self._population_model.get_parameter_names())
-        names = names.reshape(n_pop, self._n_dim)[indices[:, 0], indices[:, 1]]
-        n = []
-        for name in names:
-            n += [name] * self._n_covariates
-        self._covariate_model.set_parameter_names(n)
+        names = names.reshape(n_rows, self._n_dim)
+        n_cov = self._covariate_model.n_covariates()
+        self._covariate_model.set_parameter_names(
+            [name for name in names[indices[:, 0], indices[:, 1]]
+             for _ in range(n_cov)])
         self._dev_cache = None
 
 
 class ComposedPopulationModel(PopulationModel):
-    """chi/_population_models.py:329-953."""
+    """Population models over consecutive dimensions
+    (chi/_population_models.py:329-953)."""
 
     def __init__(self, population_models):
-        for pop_model in population_models:
-            if not isinstance(pop_model, PopulationModel):
+        for part in population_models:
+            if not isinstance(part, PopulationModel):
                 raise TypeError(
                     'The population models have to be instances of '
                     'chi.PopulationModel.')
         n_ids = 1
-        for pop_model in population_models:
-            if (n_ids > 1) and (pop_model.n_ids() > 1) and (
-                    n_ids != pop_model.n_ids()):
+        for part in population_models:
+            if n_ids > 1 and part.n_ids() > 1 and n_ids != part.n_ids():
                 raise ValueError(
                     'All population models must model the same number of '
                     'individuals.')
-            n_ids = n_ids if n_ids > 1 else pop_model.n_ids()
+            n_ids = n_ids if n_ids > 1 else part.n_ids()
         self._population_models = population_models
         self._n_ids = n_ids
         self._device = None
         self._dev_cache = None
-        self._n_bottom, self._n_top_cached = self.n_hierarchical_parameters(
-            self._n_ids)
-        self._set_population_model_properties()
+        self._custom_names = None
         names = self.get_parameter_names()
-        if len(np.unique(names)) != len(names):
-            dim_names = [
-                'Dim. %d' % (dim_id + 1) for dim_id in range(self._n_dim)]
-            self.set_dim_names(dim_names)
+        if len(set(names)) != len(names):
+            # ambiguous names: number the dimensions across the parts
+            self.set_dim_names(_default_dim_names(self._n_dim))
 
-    def _set_population_model_properties(self):
-        """chi/_population_models.py:451-492."""
-        n_dim = 0
-        n_parameters = 0
-        n_covariates = 0
-        n_hierarchical_dim = 0
-        special_dim = []
-        n_pooled = 0
-        n_hetero = 0
-        for pop_model in self._population_models:
-            s, p, h = pop_model.get_special_dims()
-            n_pooled += p
-            n_hetero += h
-            for entry in s:
-                special_dim += [[
-                    entry[0] + n_dim, entry[1] + n_dim,
-                    entry[2] + n_parameters, entry[3] + n_parameters,
-                    entry[4]]]
-            n_covariates += pop_model.n_covariates()
-            n_dim += pop_model.n_dim()
-            n_hierarchical_dim += pop_model.n_hierarchical_dim()
-            n_parameters += pop_model.n_parameters()
-        self._n_dim = n_dim
-        self._n_parameters = n_parameters
-        self._n_covariates = n_covariates
-        self._n_hierarchical_dim = n_hierarchical_dim
-        self._special_dims = special_dim
-        self._n_pooled_dims = n_pooled
-        self._n_hetero_dims = n_hetero
-        self._dev_cache = None
+    @property
+    def _n_dim(self):
+        return sum(part.n_dim() for part in self._population_models)
 
-    def _blocks(self):
-        blocks = []
-        for pop_model in self._population_models:
-            blocks += pop_model._blocks()
-        return blocks
+    def _leaves(self):
+        return [leaf for part in self._population_models
+                for leaf in part._leaves()]
+
+    def _parts(self, attribute):
+        """(part, start, end) along ``n_dim`` / ``n_parameters`` /
+        ``n_covariates``."""
+        start = 0
+        for part in self._population_models:
+            end = start + getattr(part, attribute)()
+            yield part, start, end
+            start = end
 
     def _check_n_ids(self, n_ids):
-        for pop_model in self._population_models:
-            pop_model._check_n_ids(n_ids)
+        for part in self._population_models:
+            part._check_n_ids(n_ids)
 
     def _shape_eta(self, eta):
-        """chi/_population_models.py:534-565."""
-        n_dim = len(eta) // self._n_ids
-        eta = eta.reshape(self._n_ids, n_dim)
-        if n_dim == self._n_dim:
+        """A flat eta of the hierarchical dimensions only becomes
+        ``(n_ids, n_dim)`` with zeros in the pooled / heterogeneous columns
+        (chi/_population_models.py:534-565)."""
+        eta = eta.reshape(self._n_ids, -1)
+        n_dim = self._n_dim
+        if eta.shape[1] == n_dim:
             return eta
-        if (n_dim + self._n_pooled_dims + self._n_hetero_dims) != self._n_dim:
+        columns = self._hier_columns()
+        if eta.shape[1] != len(columns):
             raise ValueError(
                 'eta is invalid. Eta cannot be reshaped into (n_ids, n_dim), '
                 'even after taking pooled and heterogenuous dimensions into '
                 'account.')
-        eta_prime = np.zeros(shape=(self._n_ids, self._n_dim))
-        eta_prime[:, self._hier_columns()] = eta
-        return eta_prime
+        full = np.zeros((self._n_ids, n_dim))
+        full[:, columns] = eta
+        return full
 
     def compute_individual_parameters(
             self, parameters, eta, covariates=None, return_eta=False):
@@ -813,121 +770,79 @@ class ComposedPopulationModel(PopulationModel):
         return o_eta if return_eta else o_psi
 
     def get_covariate_names(self):
-        names = []
-        for pop_model in self._population_models:
-            names += pop_model.get_covariate_names()
-        return names
+        return [n for part in self._population_models
+                for n in part.get_covariate_names()]
 
     def get_dim_names(self):
-        names = []
-        for pop_model in self._population_models:
-            names += pop_model.get_dim_names()
-        return names
+        return [n for part in self._population_models
+                for n in part.get_dim_names()]
 
     def get_parameter_names(self, exclude_dim_names=False):
-        names = []
-        for pop_model in self._population_models:
-            names += pop_model.get_parameter_names(exclude_dim_names)
-        return names
+        return [n for part in self._population_models
+                for n in part.get_parameter_names(exclude_dim_names)]
 
     def get_population_models(self):
         return self._population_models
 
-    def n_hierarchical_parameters(self, n_ids):
-        n_bottom, n_top = 0, 0
-        for pop_model in self._population_models:
-            n_b, n_t = pop_model.n_hierarchical_parameters(n_ids)
-            n_bottom += n_b
-            n_top += n_t
-        return n_bottom, n_top
+    def n_covariates(self):
+        return sum(part.n_covariates() for part in self._population_models)
 
     def sample(
             self, parameters, n_samples=None, seed=None, covariates=None,
             *args, **kwargs):
-        """chi/_population_models.py:793-872."""
+        """Part by part on one generator
+        (chi/_population_models.py:793-872)."""
         parameters = np.asarray(parameters)
-        if len(parameters) != self._n_parameters:
+        if len(parameters) != self.n_parameters():
             raise ValueError(
                 'The number of provided parameters does not match the expected'
                 ' number of top-level parameters.')
-        if self._n_covariates > 0:
+        n_cov = self.n_covariates()
+        if n_cov > 0:
             covariates = np.asarray(covariates)
             if covariates.ndim == 1:
                 covariates = covariates[np.newaxis, :]
-            if covariates.shape[1] != self._n_covariates:
+            if covariates.shape[1] != n_cov:
                 raise ValueError(
                     'Provided covariates do not match the number of '
                     'covariates.')
-        if n_samples is None:
-            n_samples = 1
-        samples = np.empty(shape=(int(n_samples), self._n_dim))
+        n_samples = 1 if n_samples is None else n_samples
+        samples = np.empty((int(n_samples), self._n_dim))
         rng = np.random.default_rng(seed=seed)
-        cov = None
-        current_dim = 0
-        current_param = 0
-        current_cov = 0
-        for pop_model in self._population_models:
-            end_dim = current_dim + pop_model.n_dim()
-            end_param = current_param + pop_model.n_parameters()
-            if self._n_covariates > 0:
-                end_cov = current_cov + pop_model.n_covariates()
-                cov = covariates[:, current_cov:end_cov]
-                current_cov = end_cov
-            kwargs = {}
-            if pop_model.n_covariates() > 0:
-                kwargs['covariates'] = cov
-            samples[:, current_dim:end_dim] = pop_model.sample(
-                parameters=parameters[current_param:end_param],
-                n_samples=n_samples, seed=rng, **kwargs)
-            current_dim = end_dim
-            current_param = end_param
+        dims = self._parts('n_dim')
+        tops = self._parts('n_parameters')
+        covs = self._parts('n_covariates')
+        for (part, d0, d1), (_, t0, t1), (_, c0, c1) in zip(dims, tops, covs):
+            kwargs = {'covariates': covariates[:, c0:c1]} if c1 > c0 else {}
+            samples[:, d0:d1] = part.sample(
+                parameters=parameters[t0:t1], n_samples=n_samples, seed=rng,
+                **kwargs)
         return samples
 
     def set_covariate_names(self, names=None):
-        current = 0
-        for pop_model in self._population_models:
-            n = pop_model.n_covariates()
-            pop_model.set_covariate_names(
-                None if names is None else names[current:current + n])
-            current += n
+        for part, c0, c1 in self._parts('n_covariates'):
+            part.set_covariate_names(None if names is None else names[c0:c1])
 
     def set_dim_names(self, names=None):
-        if names is None:
-            for pop_model in self._population_models:
-                pop_model.set_dim_names()
-            return None
-        if len(names) != self._n_dim:
+        if names is not None and len(names) != self._n_dim:
             raise ValueError(
                 'Length of names does not match the number of dimensions.')
-        names = [str(label) for label in names]
-        current_dim = 0
-        for pop_model in self._population_models:
-            end_dim = current_dim + pop_model.n_dim()
-            pop_model.set_dim_names(names[current_dim:end_dim])
-            current_dim = end_dim
+        for part, d0, d1 in self._parts('n_dim'):
+            part.set_dim_names(
+                None if names is None else [str(n) for n in names[d0:d1]])
 
     def set_n_ids(self, n_ids):
-        """chi/_population_models.py:902-927."""
         n_ids = int(n_ids)
         if n_ids == self._n_ids:
-            return None
-        for pop_model in self._population_models:
-            pop_model.set_n_ids(n_ids)
+            return
+        for part in self._population_models:
+            part.set_n_ids(n_ids)
         self._n_ids = n_ids
-        self._set_population_model_properties()
-        self._n_bottom, self._n_top_cached = self.n_hierarchical_parameters(
-            self._n_ids)
+        self._dev_cache = None
 
     def set_parameter_names(self, names=None):
-        if names is None:
-            for pop_model in self._population_models:
-                pop_model.set_parameter_names()
-            return None
-        if len(names) != self._n_parameters:
+        if names is not None and len(names) != self.n_parameters():
             raise ValueError(
                 'Length of names does not match the number of parameters.')
-        current = 0
-        for pop_model in self._population_models:
-            n = pop_model.n_parameters()
-            pop_model.set_parameter_names(names[current:current + n])
-            current += n
+        for part, t0, t1 in self._parts('n_parameters'):
+            part.set_parameter_names(None if names is None else names[t0:t1])

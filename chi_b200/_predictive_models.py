@@ -48,94 +48,108 @@ def _noise(error_model, sigma, outputs, rng):
     raise TypeError('Unknown error model.')
 
 
+def name_parameters(mechanistic_model, error_models):
+    """Parameter names of a model of the data-generating process:
+    mechanistic parameters, then every output's error parameters (prefixed
+    with the output name when there are several outputs;
+    chi/_log_pdfs.py:885-930, chi/_predictive_models.py:422-457)."""
+    outputs = mechanistic_model.outputs()
+    names = list(mechanistic_model.parameters())
+    for output, error_model in zip(outputs, error_models):
+        error_model.set_parameter_names(None)
+        if len(outputs) > 1:
+            error_model.set_parameter_names(
+                [output + ' ' + n for n in error_model.get_parameter_names()])
+        names += error_model.get_parameter_names()
+    return names
+
+
+def long_frame(measurements, times, output_names, ids=None):
+    """Measurements ``(n_outputs, n_times, n_series)`` as the long-format
+    table chi returns: ID | Time | Observable | Value, output-major, then
+    time, then series."""
+    import pandas as pd
+    n_outputs, n_times, n_series = measurements.shape
+    if ids is None:
+        ids = np.arange(1, n_series + 1)
+    return pd.DataFrame({
+        'ID': np.tile(ids, n_outputs * n_times),
+        'Time': np.tile(np.repeat(times, n_series), n_outputs),
+        'Observable': np.repeat(list(output_names), n_times * n_series),
+        'Value': measurements.reshape(-1)})
+
+
+def append_regimen(frame, regimen, ids):
+    """Adds the dose table once per ID."""
+    import pandas as pd
+    if regimen is None:
+        return frame
+    parts = [frame]
+    for _id in ids:
+        part = regimen.copy()
+        part['ID'] = _id
+        parts.append(part)
+    return pd.concat(parts)
+
+
 class PredictiveModel(object):
-    """chi/_predictive_models.py:347-809."""
+    """A mechanistic model plus one error model per output
+    (interface of chi/_predictive_models.py:347-809)."""
 
     def __init__(self, mechanistic_model, error_models, outputs=None):
         if not isinstance(mechanistic_model, MechanisticModel):
             raise TypeError(
                 'The mechanistic model has to be an instance of a '
                 'chi.MechanisticModel.')
-        error_models = \
-            error_models if isinstance(error_models, list) else [error_models]
-        for error_model in error_models:
-            if not isinstance(error_model, ErrorModel):
-                raise TypeError(
-                    'All error models have to be instances of a '
-                    'chi.ErrorModel.')
-        mechanistic_model = mechanistic_model.copy()
+        if not isinstance(error_models, list):
+            error_models = [error_models]
+        if not all(isinstance(em, ErrorModel) for em in error_models):
+            raise TypeError(
+                'All error models have to be instances of a '
+                'chi.ErrorModel.')
+        model = mechanistic_model.copy()
         if outputs is not None:
-            mechanistic_model.set_outputs(outputs)
-        n_outputs = mechanistic_model.n_outputs()
-        if len(error_models) != n_outputs:
+            model.set_outputs(outputs)
+        if len(error_models) != model.n_outputs():
             raise ValueError(
                 'Wrong number of error models. One error model has to be '
                 'provided for each mechanistic error model.')
-        error_models = [
-            copy.deepcopy(error_model) for error_model in error_models]
-        self._mechanistic_model = mechanistic_model
-        self._error_models = error_models
-        self._set_error_model_parameter_names()
-        self._set_number_and_parameter_names()
-
-    def _set_error_model_parameter_names(self):
-        for error_model in self._error_models:
-            error_model.set_parameter_names(None)
-        n_outputs = self._mechanistic_model.n_outputs()
-        if n_outputs > 1:
-            outputs = self._mechanistic_model.outputs()
-            for output_id, error_model in enumerate(self._error_models):
-                names = error_model.get_parameter_names()
-                output = outputs[output_id]
-                names = [output + ' ' + name for name in names]
-                error_model.set_parameter_names(names)
-
-    def _set_number_and_parameter_names(self):
-        parameter_names = self._mechanistic_model.parameters()
-        for error_model in self._error_models:
-            parameter_names += error_model.get_parameter_names()
-        self._parameter_names = parameter_names
+        self._mechanistic_model = model
+        self._error_models = [copy.deepcopy(em) for em in error_models]
+        self._parameter_names = name_parameters(model, self._error_models)
         self._n_parameters = len(self._parameter_names)
 
     def get_dosing_regimen(self, final_time=None):
-        """chi/_predictive_models.py:520-603: DataFrame with Time, Duration
-        and Dose columns, or None."""
+        """Dose table (Time | Duration | Dose) of the model's regimen up to
+        ``final_time``, or ``None`` (chi/_predictive_models.py:520-603): a
+        periodic event is listed dose by dose, an indefinite one up to
+        ``final_time`` (one dose when that is open too)."""
         import pandas as pd
-        try:
-            regimen = self._mechanistic_model.dosing_regimen()
-        except AttributeError:
-            return None
+        regimen = getattr(
+            self._mechanistic_model, 'dosing_regimen', lambda: None)()
         if regimen is None:
-            return regimen
-        if final_time is None:
-            final_time = np.inf
-        frames = []
-        for dose_event in regimen.events():
-            dose_duration = dose_event.duration()
-            dose_amount = dose_event.level() * dose_duration
-            start_time = dose_event.start()
-            period = dose_event.period()
-            n_doses = dose_event.multiplier()
-            if start_time > final_time:
-                continue
-            if period == 0:
-                frames.append(pd.DataFrame({
-                    'Time': [start_time], 'Duration': [dose_duration],
-                    'Dose': [dose_amount]}))
-                continue
-            if n_doses == 0:
-                n_doses = 1
-                if np.isfinite(final_time):
-                    n_doses = int(abs(final_time) // period)
-            dose_times = np.array(
-                [start_time + n * period for n in range(n_doses)])
-            dose_times = dose_times[dose_times <= final_time]
-            frames.append(pd.DataFrame({
-                'Time': dose_times, 'Duration': dose_duration,
-                'Dose': dose_amount}))
-        if not frames or all(f.empty for f in frames):
             return None
-        return pd.concat(frames)
+        horizon = np.inf if final_time is None else final_time
+        rows = []
+        for event in regimen.events():
+            duration = event.duration()
+            amount = event.level() * duration
+            first, every, count = \
+                event.start(), event.period(), event.multiplier()
+            if first > horizon:
+                continue
+            if every == 0:
+                starts = [first]
+            else:
+                if count == 0:
+                    count = int(abs(horizon) // every) \
+                        if np.isfinite(horizon) else 1
+                starts = [first + k * every for k in range(count)
+                          if first + k * every <= horizon]
+            rows += [(t, duration, amount) for t in starts]
+        if not rows:
+            return None
+        return pd.DataFrame(rows, columns=['Time', 'Duration', 'Dose'])
 
     def get_n_outputs(self):
         return self._mechanistic_model.n_outputs()
@@ -144,12 +158,11 @@ class PredictiveModel(object):
         return self._mechanistic_model.outputs()
 
     def get_parameter_names(self):
-        return copy.copy(self._parameter_names)
+        return list(self._parameter_names)
 
     def get_submodels(self):
-        return dict({
-            'Mechanistic model': self._mechanistic_model,
-            'Error models': list(self._error_models)})
+        return {'Mechanistic model': self._mechanistic_model,
+                'Error models': list(self._error_models)}
 
     def n_parameters(self):
         return self._n_parameters
@@ -161,61 +174,46 @@ class PredictiveModel(object):
     def sample(
             self, parameters, times, n_samples=None, seed=None,
             return_df=True, include_regimen=False, *args, **kwargs):
-        """chi/_predictive_models.py:659-762."""
+        """``n_samples`` noisy measurement series of one individual: one
+        solve, then every error model draws for its output
+        (chi/_predictive_models.py:659-762)."""
         parameters = np.asarray(parameters, dtype=float)
         if len(parameters) != self._n_parameters:
             raise ValueError(
                 'The length of parameters does not match n_parameters.')
-        mechanistic_params, error_params = self._split(parameters)
+        psi, sigma = self._split(parameters)
         times = np.sort(times)
-        outputs = self._mechanistic_model.simulate(mechanistic_params, times)
-        if isinstance(outputs, tuple):
-            outputs = outputs[0]
-        n_outputs = len(outputs)
-        n_times = len(times)
-        n_samples = n_samples if n_samples is not None else 1
-        container = np.empty(shape=(n_outputs, n_times, n_samples))
-        start_index = 0
-        for output_id, error_model in enumerate(self._error_models):
-            end_index = start_index + error_model.n_parameters()
-            container[output_id, ...] = error_model.sample(
-                parameters=error_params[start_index:end_index],
-                model_output=outputs[output_id], n_samples=n_samples,
-                seed=seed)
-            start_index = end_index
-        if return_df is False:
-            return container
-        import pandas as pd
-        output_names = self._mechanistic_model.outputs()
-        sample_ids = np.arange(start=1, stop=n_samples + 1)
-        frames = []
-        for output_id, name in enumerate(output_names):
-            for time_id, time in enumerate(times):
-                frames.append(pd.DataFrame({
-                    'ID': sample_ids, 'Time': time, 'Observable': name,
-                    'Value': container[output_id, time_id, :]}))
-        samples = pd.concat(frames)
-        final_time = np.max(times)
-        regimen = self.get_dosing_regimen(final_time)
-        if (regimen is not None) and (include_regimen is True):
-            for _id in sample_ids:
-                regimen = regimen.copy()
-                regimen['ID'] = _id
-                samples = pd.concat([samples, regimen])
-        return samples
+        ybar = self._mechanistic_model.simulate(psi, times)
+        if isinstance(ybar, tuple):
+            ybar = ybar[0]
+        n_series = 1 if n_samples is None else n_samples
+        measured = np.empty((len(ybar), len(times), n_series))
+        first = 0
+        for k, error_model in enumerate(self._error_models):
+            last = first + error_model.n_parameters()
+            measured[k] = error_model.sample(
+                parameters=sigma[first:last], model_output=ybar[k],
+                n_samples=n_series, seed=seed)
+            first = last
+        if not return_df:
+            return measured
+        ids = np.arange(1, n_series + 1)
+        frame = long_frame(measured, times, self.get_output_names(), ids)
+        if include_regimen:
+            frame = append_regimen(
+                frame, self.get_dosing_regimen(np.max(times)), ids)
+        return frame
 
     def set_dosing_regimen(
             self, dose, start=0, duration=0.01, period=None, num=None):
-        """chi/_predictive_models.py:764-809."""
-        try:
-            self._mechanistic_model.set_dosing_regimen(
-                dose, start, duration, period, num)
-        except AttributeError:
+        setter = getattr(self._mechanistic_model, 'set_dosing_regimen', None)
+        if setter is None:
             raise AttributeError(
                 'The mechanistic model does not support to set dosing '
                 'regimens. This may be because the underlying '
                 'chi.MechanisticModel is a '
                 'chi.PharmacodynamicModel.')
+        setter(dose, start, duration, period, num)
 
     # -- batched forward path ----------------------------------------------
     def _sample_patients(self, patients, times, rng):
@@ -346,38 +344,24 @@ class PopulationPredictiveModel(PredictiveModel):
         times = np.sort(times)
         measurements = self._predictive_model._sample_patients(
             patients, times, rng)
-        if return_df is False:
+        if not return_df:
             return measurements
         import pandas as pd
-        n_outputs, n_times = measurements.shape[:2]
-        names = self._predictive_model.get_output_names()
-        output_names = []
-        for name in names:
-            output_names += [name] * (n_times * n_samples)
-        t = np.broadcast_to(
-            times[np.newaxis, :, np.newaxis],
-            shape=(n_outputs, n_times, n_samples)).flatten()
-        sample_ids = np.arange(start=1, stop=n_samples + 1)
-        ids = np.broadcast_to(
-            sample_ids[np.newaxis, np.newaxis, :],
-            shape=(n_outputs, n_times, n_samples)).flatten()
-        df = pd.DataFrame({
-            'ID': ids, 'Time': t, 'Observable': output_names,
-            'Value': measurements.flatten()})
+        ids = np.arange(1, n_samples + 1)
+        frame = long_frame(
+            measurements, times, self._predictive_model.get_output_names(),
+            ids)
         if pop.n_covariates() > 0:
+            # one row per individual and covariate, without a time
             cov = np.broadcast_to(covariates, (n_samples, pop.n_covariates()))
-            for idc, covariate in enumerate(pop.get_covariate_names()):
-                df = pd.concat([df, pd.DataFrame({
-                    'ID': sample_ids, 'Time': np.nan,
-                    'Observable': covariate, 'Value': cov[..., idc]})])
+            frame = pd.concat([frame] + [
+                pd.DataFrame({'ID': ids, 'Time': np.nan, 'Observable': name,
+                              'Value': cov[:, k]})
+                for k, name in enumerate(pop.get_covariate_names())])
         if include_regimen:
-            regimen = self.get_dosing_regimen(np.max(times))
-            if regimen is not None:
-                for _id in sample_ids:
-                    regimen = regimen.copy()
-                    regimen['ID'] = _id
-                    df = pd.concat([df, regimen])
-        return df
+            frame = append_regimen(
+                frame, self.get_dosing_regimen(np.max(times)), ids)
+        return frame
 
     def set_dosing_regimen(
             self, dose, start=0, duration=0.01, period=None, num=None):
