@@ -124,6 +124,10 @@ struct DevBuf {
   }
 };
 
+// chunks of the host-buffer entry point (chi_b200_hier_logpdf): one work
+// counter per chunk, one more for the un-chunked launches
+constexpr int MAX_CHUNKS = 16;
+constexpr int MAX_CHUNKS_P1 = MAX_CHUNKS + 1;
 constexpr int MAX_POP_DIM = 32;
 constexpr int MAX_POP_COV = 8;
 constexpr int POP_BLOCK = 256;
@@ -1253,13 +1257,14 @@ int launch_loglik(chi_b200_problem* p, int64_t B, const int32_t* d_ids,
   a.snap = nullptr;
   a.snap_rows = 0;
   a.snap_width = 0;
-  // the persistent kernel's work counter belongs to the problem (slot 8: the
-  // un-chunked launches; slots 0-7: the chunks of chi_b200_hier_logpdf, which
+  // the persistent kernel's work counter belongs to the problem (the last
+  // slot: the un-chunked launches; the others: the chunks of
+  // chi_b200_hier_logpdf, which
   // may be in flight together)
-  CUDA_TRY(p->work_counters.reserve(9 * sizeof(unsigned long long)));
+  CUDA_TRY(p->work_counters.reserve(MAX_CHUNKS_P1 * sizeof(unsigned long long)));
   a.work_counter = work_counter
                        ? work_counter
-                       : p->work_counters.as<unsigned long long>() + 8;
+                       : p->work_counters.as<unsigned long long>() + MAX_CHUNKS;
   bool ordered = false;
   {
     // Work order of the persistent kernel (SolveArgs::order_inner): with at
@@ -1486,8 +1491,8 @@ int chi_b200_simulate(chi_b200_problem* p, int64_t B, const int32_t* ids,
   CUDA_TRY(p->nrj.reserve(B * sizeof(int32_t)));
   a.n_steps = p->nst.as<int32_t>();
   a.n_rej = p->nrj.as<int32_t>();
-  CUDA_TRY(p->work_counters.reserve(9 * sizeof(unsigned long long)));
-  a.work_counter = p->work_counters.as<unsigned long long>() + 8;
+  CUDA_TRY(p->work_counters.reserve(MAX_CHUNKS_P1 * sizeof(unsigned long long)));
+  a.work_counter = p->work_counters.as<unsigned long long>() + MAX_CHUNKS;
   if (p->timing) CUDA_TRY(cudaEventRecord(p->ev0, s));
   CUDA_TRY(p->vt->launch(a, p->variant, s));
   if (p->timing) {
@@ -1960,17 +1965,28 @@ int chi_b200_hier_logpdf(chi_b200_problem* p, int32_t C, const double* x,
     n_chunks = p->cfg_chunks;
   } else if (chunks_env > 0) {
     n_chunks = chunks_env;
-  } else if (!p->timing && C >= 128 &&
-             static_cast<size_t>(C) * (sharded ? w_b + w_t : pitch) >=
-                 (size_t(8) << 20)) {
-    n_chunks = 4;
+  } else if (!p->timing && C >= 128) {
+    // about 32 MB per chunk and direction (the first chunk's copy in and the
+    // last chunk's copy out are the part that nothing overlaps), at least
+    // four chunks once there are 8 MB to move, and no chunk below ~200 k
+    // systems (the persistent solve kernel wants a few rounds of work)
+    const size_t bytes =
+        static_cast<size_t>(C) * (sharded ? w_b + w_t : pitch);
+    const int64_t systems =
+        static_cast<int64_t>(C) * (p->id_end - p->id_begin);
+    if (bytes >= (size_t(8) << 20)) {
+      n_chunks = std::max<int>(4, static_cast<int>(bytes >> 25));
+      n_chunks = std::min<int>(
+          n_chunks, std::max<int>(4, static_cast<int>(systems / 200000)));
+    }
   }
-  n_chunks = std::max(1, std::min<int>(n_chunks, std::min<int32_t>(C, 8)));
+  n_chunks =
+      std::max(1, std::min<int>(n_chunks, std::min<int32_t>(C, MAX_CHUNKS)));
   if (n_chunks > 1) {
     if (!p->stream2)
       CUDA_TRY(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
   }
-  CUDA_TRY(p->work_counters.reserve(9 * sizeof(unsigned long long)));
+  CUDA_TRY(p->work_counters.reserve(MAX_CHUNKS_P1 * sizeof(unsigned long long)));
   p->counters[3] = 0;
   for (int k = 0; k < n_chunks; ++k) {
     const int32_t c0 = static_cast<int32_t>(static_cast<int64_t>(C) * k /

@@ -62,10 +62,14 @@ constexpr int stream_integrated() {
 constexpr bool stream_is_rosl(const int method) {
   return method == 9 || method == 11;
 }
+// ... and it keeps a one-record buffer of (y, S) per thread, so that the
+// lanes of a warp evaluate their observation records together (see
+// StreamSolver::events).
 template <class M, int METHOD>
 constexpr int stream_slots() {
   const int pi = stream_integrated<M>();
-  return (stream_is_rosl(METHOD) ? pi * M::N : 2 * pi * M::N + 7 * M::N) +
+  return (stream_is_rosl(METHOD) ? pi * M::N + (1 + pi) * M::N
+                                 : 2 * pi * M::N + 7 * M::N) +
          M::P + 8 + M::NCS + M::N;
 }
 // largest of the methods (host buffers of the CPU port)
@@ -550,7 +554,9 @@ struct StreamSolver {
   int cur, n_att;
   int flags;        // bits 0-7 status, 8-27 rejected steps, 28-29 edge kind,
                     // 30 all columns integrated (ROSL)
+  int pend;         // record held in the buffer, -1: none
   bool invalid, after_reject;
+  bool buffering;   // records go through the buffer (see events())
 
   CHI_HD StreamSolver(const SolveArgs& args, double* smem, int smem_stride)
       : a(args), sm(smem), stride(smem_stride) {}
@@ -563,7 +569,12 @@ struct StreamSolver {
   static constexpr int OFF_COLD = OFF_ZY + (ROSL ? 0 : 7 * N);
   static constexpr int OFF_C = OFF_COLD + 8;
   static constexpr int OFF_Y = OFF_C + NCS;
-  static_assert(OFF_Y + N == stream_slots<M, METHOD_CODE>(), "slot layout");
+  // record buffer (ROSL): y, then S of the integrated columns
+  static constexpr bool BUFFERED = ROSL;
+  static constexpr int OFF_BUF = OFF_Y + N;
+  static_assert(OFF_BUF + (BUFFERED ? (1 + PI) * N : 0) ==
+                    stream_slots<M, METHOD_CODE>(),
+                "slot layout");
 #define CHI_S(buf, m, n) sm[(((buf) * PI + (m)) * N + (n)) * stride]
 #define CHI_G(k) sm[(OFF_G + (k)) * stride]
 #define CHI_ZY(i, n) sm[(OFF_ZY + ((i) - 1) * N + (n)) * stride]
@@ -584,6 +595,8 @@ struct StreamSolver {
 #define CHI_C(j) sm[(OFF_C + (j)) * stride]
 // ... and the state itself
 #define CHI_Y(n) sm[(OFF_Y + (n)) * stride]
+#define CHI_BUF_Y(n) sm[(OFF_BUF + (n)) * stride]
+#define CHI_BUF_S(m, n) sm[(OFF_BUF + N + (m) * N + (n)) * stride]
 
   CHI_HD static bool inert(const int pk) {
     return pk >= N && ((M::INERT_MASK >> (pk - N)) & 1u);
@@ -676,6 +689,16 @@ struct StreamSolver {
       }
     }
     invalid = false;
+    pend = -1;
+    // Fused observation with the lanes of a warp on the same individual
+    // (whole-warp refill): a lane that reaches a record parks (y, S) in its
+    // buffer and goes on; the records are evaluated when every lane of the
+    // warp holds one -- ONE convergent pass of the handler per record instead
+    // of one per group of lanes that happen to arrive in the same iteration
+    // (the handler ran with ~9 active lanes in 42 % of the iterations: 29 %
+    // of the stall samples).
+    buffering = BUFFERED && a.mode == 1 && a.snap == nullptr &&
+                a.refill_wait == INT32_MAX;
     if (loglik()) {
       for (int o = 0; o < a.n_out; ++o) {
         const int off = a.err_off[o];
@@ -760,13 +783,35 @@ struct StreamSolver {
     set_cold_int(3, 1, static_cast<int>(next >> 32));
   }
 
-  // observation record r at the current time (fused handling)
+  // parks the state and the sensitivities at record r in the buffer
+  CHI_HD void park(const int r) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) CHI_BUF_Y(n) = CHI_Y(n);
+    const int ni = n_int();
+#pragma unroll
+    for (int m = 0; m < PI; ++m) {
+      if (m < ni) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) CHI_BUF_S(m, n) = CHI_S(cur, m, n);
+      }
+    }
+    pend = r;
+  }
+
+  // observation record r (fused handling): at the current time, or from the
+  // buffer
+  template <bool FROM_BUFFER = false>
   CHI_HD void observe(const int r) {
     const int o = a.rec_out[r];
     const int oid = a.out_id[o];
     const int nc = n_cols();
     double y[N], c[NCS], gy[N], gc[NCS];
-    load_state(y);
+    if (FROM_BUFFER) {
+#pragma unroll
+      for (int n = 0; n < N; ++n) y[n] = CHI_BUF_Y(n);
+    } else {
+      load_state(y);
+    }
     load_constants(c);
     const double yb = M::out_grad(oid, y, c, gy, gc);
     if (loglik()) {
@@ -789,7 +834,8 @@ struct StreamSolver {
         const int k = a.int_col[m];
         double d = 0.0;
 #pragma unroll
-        for (int n = 0; n < N; ++n) d = fma(gy[n], CHI_S(cur, m, n), d);
+        for (int n = 0; n < N; ++n)
+          d = fma(gy[n], FROM_BUFFER ? CHI_BUF_S(m, n) : CHI_S(cur, m, n), d);
         CHI_G(k) = fma(e.w, d, CHI_G(k));
       }
 #pragma unroll
@@ -820,26 +866,34 @@ struct StreamSolver {
   // Handles the events pending at the current time (observation records,
   // dose-rate edges).  Returns true when the system is finished.  The common
   // case -- the next stop has not been reached -- is one comparison.
-  CHI_HD bool events() {
-    if (t < t_stop) return false;
-    if (invalid) return true;
+  // Returns EV_GO (take a step), EV_DONE (system finished) or EV_WAIT (the
+  // lane holds a record in its buffer and cannot go on before the warp has
+  // evaluated it: it reached the next record, or the end).
+  static constexpr int EV_GO = 0, EV_DONE = 1, EV_WAIT = 2;
+  CHI_HD int events() {
+    if (t < t_stop) return EV_GO;
+    if (invalid) return EV_DONE;
     int r = cold_int(5, 0);
     const int r_end = cold_int(5, 1);
     double t_edge = CHI_COLD(1);
     double t_rec = CHI_COLD(2);
     for (;;) {
-      if (r >= r_end) return true;
+      if (r >= r_end) {
+        if (pend < 0) return EV_DONE;
+        break;
+      }
       if (t_rec <= t) {
-        // fetch the next record's time while this one is processed
-        const double t_next = (r + 1 < r_end) ? a.rec_t[r + 1] : INFINITY;
-        if (deferred()) {
+        if (buffering) {
+          if (pend >= 0) break;        // the buffer is taken: wait here
+          park(r);
+        } else if (deferred()) {
           snapshot();
         } else {
           observe(r);
-          if (invalid) return true;
+          if (invalid) return EV_DONE;
         }
         ++r;
-        t_rec = t_next;
+        t_rec = (r < r_end) ? a.rec_t[r] : INFINITY;
         continue;
       }
       if (t_edge <= t) {
@@ -865,8 +919,19 @@ struct StreamSolver {
       CHI_COLD(1) = t_edge;
       CHI_COLD(2) = t_rec;
       t_stop = fmin(t_rec, t_edge);
-      return false;
+      return EV_GO;
     }
+    // waiting (t >= t_stop still holds: the next call comes back here)
+    set_cold_int(5, 0, r);
+    CHI_COLD(1) = t_edge;
+    CHI_COLD(2) = t_rec;
+    return EV_WAIT;
+  }
+
+  // evaluates the record held in the buffer (all lanes of a warp together)
+  CHI_HD void observe_parked() {
+    observe<true>(pend);
+    pend = -1;
   }
 
   // All stages of sensitivity column k (constant index kc, -1 for an
@@ -1013,8 +1078,12 @@ struct StreamSolver {
     if constexpr (ROSL) {
       if constexpr (M::LINEAR) {
         if (n_int() == 0) return step_rosl<0>();
+#ifdef CHI_ROSL_NO_SUBSET
+        return step_rosl<1>();   // (register-pressure experiment only)
+#else
         if (flags & (1 << 30)) return step_rosl<1>();
         return step_rosl<2>();
+#endif
       } else {
         flags |= ST_NON_FINITE;   // ROSL is for linear models only
         return true;
@@ -1526,6 +1595,8 @@ struct StreamSolver {
 #undef CHI_COLD
 #undef CHI_C
 #undef CHI_Y
+#undef CHI_BUF_Y
+#undef CHI_BUF_S
 };
 
 template <class M, int CB>
@@ -1533,9 +1604,15 @@ CHI_HD void solve_system_stream(const SolveArgs& a, const int64_t b,
                                 double* sm, const int stride) {
   StreamSolver<M, CB> s(a, sm, stride);
   s.init(b);
-  while (!s.events()) {
-    if (s.step()) break;
+  for (;;) {
+    int ev = s.events();
+    while (ev == s.EV_WAIT) {   // (one "lane": evaluate at once)
+      s.observe_parked();
+      ev = s.events();
+    }
+    if (ev == s.EV_DONE || s.step()) break;
   }
+  if (s.pend >= 0 && !s.invalid && s.status() == ST_OK) s.observe_parked();
   s.finish();
 }
 
@@ -1694,12 +1771,25 @@ solve_stream_kernel(const SolveArgs a, unsigned long long* counter) {
       }
       waited = 0;
     }
-    bool done = active ? s.events() : true;
+    int ev = active ? s.events() : s.EV_DONE;
+    if (StreamSolver<M, CB>::BUFFERED) {
+      // records parked in the lanes' buffers are evaluated when every active
+      // lane holds one: the handler runs once, with all lanes
+      const bool holds = active && s.pend >= 0 && ev != s.EV_DONE;
+      if (__any_sync(0xffffffffu, holds) &&
+          __all_sync(0xffffffffu, holds || !active || ev == s.EV_DONE)) {
+        if (holds) {
+          s.observe_parked();
+          if (ev == s.EV_WAIT) ev = s.events();
+        }
+      }
+    }
+    bool done = ev == s.EV_DONE;
     // the vote is the convergence point: lanes that refilled or handled an
     // event re-join the others here, so the (expensive) step below is
     // executed once per iteration by all lanes that need it
     __syncwarp(0xffffffffu);
-    if (active && !done) done = s.step();
+    if (active && ev == s.EV_GO) done = s.step();
     if (active && done) {
       s.finish();
       active = false;

@@ -198,10 +198,12 @@ class Population(object):
         return a
 
     def loglik(self, x, ids=None, with_grad=True, rtol=1e-8, atol=1e-10,
-               max_steps=100000, n_threads=1, stream_cb=0, deferred=None):
+               max_steps=100000, n_threads=1, stream_cb=0, deferred=None,
+               buffered=False):
         """``deferred``: evaluate the observations from snapshots after the
-        solve (SolveArgs::snap), the streamed routines' default on the GPU;
-        False keeps them fused in the solve."""
+        solve (SolveArgs::snap); False keeps them fused in the solve.
+        ``buffered`` (fused only): records go through the one-record buffer,
+        as in a GPU launch whose warps share an individual."""
         x = np.ascontiguousarray(x, float)
         if x.ndim == 1:
             x = x[None, :]
@@ -229,7 +231,9 @@ class Population(object):
         a.n_steps = _ptr(nst)
         a.n_rej = _ptr(nrj)
         if deferred is None:
-            deferred = stream_cb != 0
+            deferred = stream_cb != 0 and not buffered
+        if buffered:
+            a.refill_wait = 2 ** 31 - 1
         snap = None
         if deferred and stream_cb != 0:
             width = (self._port or lib()).chi_port_snap_width(

@@ -844,3 +844,45 @@ def test_cpu_port_rosl_convergence_and_work():
     np.testing.assert_allclose(
         ss[:, :3], se[:, 0, [3, 5, 0]], rtol=1e-7,
         atol=1e-9 * np.max(np.abs(se)))
+
+
+def test_cpu_port_buffered_observation_equals_immediate_observation():
+    """The ROSL kernels park (y, S) at an observation record in a one-record
+    buffer and evaluate the record later (on the GPU: when every lane of the
+    warp holds one).  The arithmetic is the same as observing on arrival:
+    identical log-likelihoods and gradients, also with two outputs whose
+    records coincide in time, and agreement with the deferred (snapshot)
+    form."""
+    key = cport.find_key('two_compartment_pk_model', 'central', True)
+    rng = np.random.default_rng(11)
+    n_ids = 6
+    times, obs, out_idx, regs = [], [], [], []
+    for i in range(n_ids):
+        t = np.sort(np.concatenate([rng.uniform(0.25, 24, 7), [3.0, 3.0]]))
+        times.append(t)
+        obs.append(rng.uniform(0.2, 2.0, len(t)))
+        o = rng.integers(0, 2, len(t)).astype(np.int32)
+        out_idx.append(o)
+        regs.append([(float(rng.uniform(5, 15)), 0.0, 1.0, 8.0, 3)])
+    pop = cport.Population(
+        key, ['central.drug_concentration', 'peripheral.drug_concentration'],
+        ['lognormal', 'cam'], times, obs, out_idx, regs)
+    X = np.column_stack([
+        np.zeros((n_ids, 2)),
+        np.exp(np.log([2.0, 1.0, 5.0, 1.0, 10.0])
+               + 0.3 * rng.normal(size=(n_ids, 5))),
+        np.full(n_ids, 0.1), np.full(n_ids, 0.05), np.full(n_ids, 0.12)])
+    ids = np.arange(n_ids, dtype=np.int32)
+    for with_grad in (True, False):
+        a = pop.loglik(X, ids=ids, with_grad=with_grad, stream_cb=11,
+                       deferred=False)
+        b = pop.loglik(X, ids=ids, with_grad=with_grad, stream_cb=11,
+                       buffered=True)
+        c = pop.loglik(X, ids=ids, with_grad=with_grad, stream_cb=11,
+                       deferred=True)
+        assert not np.any(a[2]) and not np.any(b[2])
+        np.testing.assert_array_equal(a[0], b[0])
+        np.testing.assert_array_equal(a[1], b[1])
+        np.testing.assert_array_equal(a[3], b[3])
+        np.testing.assert_allclose(a[0], c[0], rtol=1e-13)
+        np.testing.assert_allclose(a[1], c[1], rtol=1e-11, atol=1e-13)
