@@ -802,8 +802,10 @@ def _ncu_traffic(cfg, args):
     mine = {'n_ids': cfg['n_ids'], 'chains': cfg['chains'],
             'n_obs': args.n_obs, 'n_doses': args.n_doses,
             'rtol': args.rtol, 'atol': args.atol}
-    same = all(rec.get(k) == v for k, v in mine.items())
-    return rec.get('dram_bytes_per_launch') if same else None
+    for entry in rec.get('records', []) if isinstance(rec, dict) else []:
+        if all(entry.get(k) == v for k, v in mine.items()):
+            return entry.get('dram_bytes_per_launch')
+    return None
 
 
 def measure_hier(ctx, cfg, steps, warmup, keep=False):

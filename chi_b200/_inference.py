@@ -42,7 +42,10 @@ class HaarioBardenetACMC(object):
             full_covariance = self._n <= 256
         self._full = bool(full_covariance)
         if sigma0 is None:
-            sigma0 = np.abs(x0) * 0.01 + 1e-4
+            # pints' default: 1 % of the starting point per dimension (a zero
+            # entry gets 1 % of one)
+            sigma0 = np.abs(x0) * 0.01
+            sigma0 = np.where(sigma0 == 0, 0.01, sigma0)
         sigma0 = np.broadcast_to(
             np.asarray(sigma0, dtype=float), x0.shape)
         if self._full:
@@ -225,6 +228,7 @@ class BatchedSamplingController(object):
         self._sampler = HaarioBardenetACMC   # chi/_inference.py:630
         self._initial_params = None
         self._initial_phase = 200  # pints.MCMCController default
+        self._n_warmup = None      # HMC: end of the step-size adaptation
 
     def set_n_runs(self, n_runs):
         n_runs = int(n_runs)
@@ -250,6 +254,15 @@ class BatchedSamplingController(object):
     def set_initial_phase_iterations(self, n):
         self._initial_phase = int(n)
 
+    def set_warmup_iterations(self, n):
+        """Iteration at which a gradient-based sampler stops adapting its
+        step size and freezes it at the dual-averaging mean (default: half of
+        the run).  Samples before it belong to the warm-up."""
+        n = int(n)
+        if n < 0:
+            raise ValueError('The number of warm-up iterations is negative.')
+        self._n_warmup = n
+
     def _x0(self):
         if self._initial_params is not None:
             return self._initial_params
@@ -271,9 +284,16 @@ class BatchedSamplingController(object):
         samples = np.empty((n, n_iterations, d))
         log_pdf = np.empty((n, n_iterations))
         evaluations = 0
+        n_warmup = self._n_warmup if self._n_warmup is not None \
+            else max(self._initial_phase, n_iterations // 2)
         for it in range(n_iterations):
             if it == self._initial_phase:
                 sampler.set_adaptive(True)
+            if sampler.needs_sensitivities and it == n_warmup and \
+                    it > self._initial_phase:
+                # freeze the step size at its averaged value: the chain is
+                # a valid Markov chain from here on
+                sampler.set_adaptive(False)
             if sampler.needs_sensitivities:
                 def f(X):
                     return post.evaluateS1_batch(X)
@@ -296,4 +316,6 @@ class BatchedSamplingController(object):
         return {
             'samples': samples, 'log_pdf': log_pdf,
             'acceptance_rate': sampler.acceptance.copy(),
-            'evaluations': evaluations, 'parameter_names': names}
+            'evaluations': evaluations, 'parameter_names': names,
+            'warmup_iterations': n_warmup if sampler.needs_sensitivities
+            else self._initial_phase}

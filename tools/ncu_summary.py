@@ -2,12 +2,14 @@
 from an `ncu --set full` report and an `ncu --metrics gpu__time_duration.sum`
 launch list of `bench.py --steps 2 --warmup 1 --no-cpu-baseline` (dev helper).
 
-usage: python tools/ncu_summary.py <report.ncu-rep> <launches.csv> <name> "<title>"
+usage: python tools/ncu_summary.py <report.ncu-rep> <launches.csv> <name> "<title>" "<bench args>" <plain.json>
 """
 import collections, csv, io, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, launches, name, title = sys.argv[1:5]
+bench_args = sys.argv[5] if len(sys.argv) > 5 else ''
+plain = json.load(open(sys.argv[6])) if len(sys.argv) > 6 else None
 txt = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'],
                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
@@ -51,7 +53,7 @@ for v in rows[2:]:
               + float(d['smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed'])) * cyc
         notes.append('* `solve_stream_kernel`: executed FP64 flops (2 DFMA + DADD + DMUL, predicated-on thread '
                      'instructions) %.3e -> %.2f TFLOP/s issued at %.2f ms; FP64 pipe active %s %%; DRAM %.0f MB '
-                     'read + %.0f MB written (the snapshots) = %.0f GB/s.' % (
+                     'read + %.0f MB written = %.0f GB/s.' % (
                          fl, fl / ms / 1e9, ms,
                          d['sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active'][:5],
                          rd / 1e6, wr / 1e6, (rd + wr) / ms / 1e6))
@@ -76,10 +78,12 @@ tab += ['| `%s` | %d | %.3f | %.1f %% |' % (k[:90], a[0], a[1], 100 * a[1] / tot
 dst_csv = os.path.join(ROOT, 'profiles', name + '_launches_ncu.csv')
 if os.path.abspath(launches) != dst_csv:
     open(dst_csv, 'w').write(open(launches).read())
+cfg = plain['config'] if plain else {}
+roof = plain['roofline'] if plain else {}
 md = '''# %s
 
-Command: `python bench.py --steps 2 --warmup 1 --no-cpu-baseline` (one B200, C2 workload, 1024 parameter
-vectors x 1000 individuals = 1 024 000 systems per launch); the plain run exited 0 first.
+Command: `python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras %s` (one B200; %s);
+the plain run exited 0 first (bench line of that run: value %s evals/s, `roofline.frac` %s, `kernel_share_of_step` %s).
 
 ## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, profiles/%s_launches_ncu.csv)
 
@@ -87,26 +91,32 @@ vectors x 1000 individuals = 1 024 000 systems per launch); the plain run exited
 
 `fp64_peak_kernel` is the DFMA micro-benchmark that measures the roofline denominator (outside the timed region);
 the `at::` kernels are bench.py's own L2 flush and result checks.  Inside a step `solve_stream_kernel`
-(integration + snapshots at the observation records) and `observe_kernel` (error model + gradient from the
-snapshots) are what `bench.py` times as "the solve" (`roofline.kernel_ms`, CUDA events around both); the
-population kernels are < 1 %% of a step.
+(integration with the observation fused) is what `bench.py` times as "the solve" (`roofline.kernel_ms`, CUDA
+events); the population kernels are about 1 %% of a step.  Launch times under ncu are cold-cache and
+serialised: compare SHARES.
 
-## `ncu --set full --clock-control none --import-source on -k regex:"solve_stream|observe_kernel" -s 2 -c 2`
+## `ncu --set full --clock-control none --import-source on -k regex:"solve_stream|observe_kernel" -s 2 -c 1`
 
 %s
 Reading:
 %s
-* No register spills (0 local loads/stores) at 128 registers / 4 blocks per SM.  Inside the sensitivity-column
-  loop the dominant stalls are `math_pipe_throttle` / `not_selected`, i.e. the FP64 pipe itself; what is left
-  outside it is the per-step serial code (step-size control, W inversion) and the event handler that runs with
-  1-3 active lanes (`python tools/ncu_blocks.py <report>` prints the per-basic-block breakdown).
-* Lane efficiency below 32: lanes leave the step while they handle dose edges / store snapshots, and the tail
-  of the persistent grid runs with partially filled warps.
-''' % (title, name, '\n'.join(tab), '\n'.join(out), '\n'.join(notes))
-open(os.path.join(ROOT, 'profiles', name + '_kernels_ncu_summary.md'), 'w').write(md)
-json.dump({'n_ids': 1000, 'chains': 1024, 'n_obs': 10, 'n_doses': 3, 'rtol': 1e-6, 'atol': 1e-8,
+''' % (title, bench_args, cfg.get('workload', '')[:160], 
+       ('%.0f' % plain['value']) if plain else '-', ('%.3f' % roof.get('frac', 0)) if plain else '-',
+       ('%.3f' % roof.get('kernel_share_of_step', 0)) if plain else '-',
+       name, '\n'.join(tab), '\n'.join(out), '\n'.join(notes))
+open(os.path.join(ROOT, 'profiles', name + '_ncu_summary.md'), 'w').write(md)
+path = os.path.join(ROOT, 'profiles', 'solve_kernel_traffic.json')
+try:
+    records = json.load(open(path)).get('records', [])
+except (OSError, ValueError, AttributeError):
+    records = []
+if plain and traffic is not None:
+    rec = {'n_ids': cfg['n_ids'], 'chains': cfg['chains_per_step'], 'n_obs': cfg['n_obs'],
+           'n_doses': cfg['n_doses'], 'rtol': cfg['rtol'], 'atol': cfg['atol'],
            'dram_bytes_per_launch': traffic,
-           'source': 'ncu --set full capture of solve_stream_kernel, profiles/%s_kernels_ncu_summary.md '
-                     '(dram__bytes_read.sum + dram__bytes_write.sum)' % name},
-          open(os.path.join(ROOT, 'profiles', 'solve_kernel_traffic.json'), 'w'), indent=1)
+           'source': 'ncu --set full capture of solve_stream_kernel, profiles/%s_ncu_summary.md '
+                     '(dram__bytes_read.sum + dram__bytes_write.sum)' % name}
+    records = [r for r in records if not all(r.get(k) == rec[k] for k in (
+        'n_ids', 'chains', 'n_obs', 'n_doses', 'rtol', 'atol'))] + [rec]
+    json.dump({'records': records}, open(path, 'w'), indent=1)
 print('\n'.join(notes))
