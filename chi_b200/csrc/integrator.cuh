@@ -27,6 +27,8 @@
 #pragma once
 #include <math.h>
 #include <initializer_list>
+#include <cstdlib>
+#include <cstdint>
 #include "model_api.cuh"
 
 namespace chi_b200 {
@@ -648,44 +650,97 @@ struct Registrar {
 
   // Variant<0, CB>: streamed-columns persistent kernel
   // (integrator_stream.cuh)
-  template <int CB>
-  static cudaError_t launch_stream(const SolveArgs& args,
-                                   cudaStream_t stream) {
-    constexpr size_t smem =
-        sizeof(double) * stream_slots<M, CB>() * STREAM_BLOCK;
+  // resident blocks of a persistent kernel on the current device (cached)
+  template <class K>
+  static cudaError_t resident_blocks(K kernel, const int block,
+                                     const size_t smem, int* cache,
+                                     int* out) {
     constexpr int MAX_DEV = 16;
-    static int resident[MAX_DEV] = {};
     int dev = 0;
     cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess) return err;
     if (dev < 0 || dev >= MAX_DEV) return cudaErrorInvalidDevice;
-    if (!args.work_counter) return cudaErrorInvalidValue;
-    if (!resident[dev]) {
+    if (!cache[dev]) {
       if (smem > 48 * 1024) {
         err = cudaFuncSetAttribute(
-            solve_stream_kernel<M, CB, STREAM_BLOCK>,
-            cudaFuncAttributeMaxDynamicSharedMemorySize,
+            kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
             static_cast<int>(smem));
         if (err != cudaSuccess) return err;
       }
       int bpsm = 0, sms = 0;
       err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &bpsm, solve_stream_kernel<M, CB, STREAM_BLOCK>, STREAM_BLOCK,
-          smem);
+          &bpsm, kernel, block, smem);
       if (err != cudaSuccess) return err;
       err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       if (err != cudaSuccess) return err;
-      resident[dev] = bpsm * sms;
+      cache[dev] = bpsm * sms;
     }
+    *out = cache[dev];
+    return cudaSuccess;
+  }
+
+  // the lanes of every warp of this launch integrate ONE individual under 32
+  // parameter vectors: the warp-synchronous kernel applies
+  // (CHI_B200_WARP_SYNC=0 keeps the general kernel, for comparisons)
+  template <int CB>
+  static bool warp_uniform(const SolveArgs& args) {
+    static const bool enabled = [] {
+      const char* e = std::getenv("CHI_B200_WARP_SYNC");
+      return !(e && std::atoi(e) == 0);
+    }();
+    return enabled && stream_is_rosl(CB) && M::LINEAR && args.mode == 1 &&
+           !args.snap && args.refill_wait == INT32_MAX &&
+           args.order_inner >= 32 && args.order_inner % 32 == 0 &&
+           static_cast<int64_t>(args.order_inner) * args.order_stride ==
+               args.B;
+  }
+
+  // Variant<0, CB>: streamed-columns persistent kernel
+  // (integrator_stream.cuh)
+  template <int CB>
+  static cudaError_t launch_stream(const SolveArgs& args,
+                                   cudaStream_t stream) {
+    constexpr size_t smem =
+        sizeof(double) * stream_slots<M, CB>() * STREAM_BLOCK;
+    static int resident[16] = {};
+    static int resident_warp[16] = {};
+    if (!args.work_counter) return cudaErrorInvalidValue;
+    bool uniform = false;
+    if constexpr (stream_is_rosl(CB) && M::LINEAR)
+      uniform = warp_uniform<CB>(args);
+    int res = 0;
+    cudaError_t err;
+    constexpr size_t smem_warp =
+        sizeof(double) * stream_slots<M, CB, false>() * WARP_BLOCK;
+    if constexpr (stream_is_rosl(CB) && M::LINEAR) {
+      if (uniform)
+        err = resident_blocks(solve_warp_kernel<M, CB>, WARP_BLOCK, smem_warp,
+                              resident_warp, &res);
+    }
+    if (!uniform)
+      err = resident_blocks(solve_stream_kernel<M, CB, STREAM_BLOCK>,
+                            STREAM_BLOCK, smem, resident, &res);
+    if (err != cudaSuccess) return err;
     if (args.B == 0) return cudaSuccess;
     unsigned long long* counter = args.work_counter;
     err = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return err;
-    int64_t blocks = (args.B + STREAM_BLOCK - 1) / STREAM_BLOCK;
-    if (blocks > resident[dev]) blocks = resident[dev];
-    solve_stream_kernel<M, CB, STREAM_BLOCK>
-        <<<static_cast<unsigned>(blocks), STREAM_BLOCK, smem, stream>>>(
-            args, counter);
+    if constexpr (stream_is_rosl(CB) && M::LINEAR) {
+      if (uniform) {
+        int64_t blocks = (args.B + WARP_BLOCK - 1) / WARP_BLOCK;
+        if (blocks > res) blocks = res;
+        solve_warp_kernel<M, CB>
+            <<<static_cast<unsigned>(blocks), WARP_BLOCK, smem_warp,
+               stream>>>(args, counter);
+      }
+    }
+    if (!uniform) {
+      int64_t blocks = (args.B + STREAM_BLOCK - 1) / STREAM_BLOCK;
+      if (blocks > res) blocks = res;
+      solve_stream_kernel<M, CB, STREAM_BLOCK>
+          <<<static_cast<unsigned>(blocks), STREAM_BLOCK, smem, stream>>>(
+              args, counter);
+    }
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     if (args.mode == 1 && args.snap) {
@@ -770,7 +825,26 @@ struct Registrar {
   static cudaError_t describe_one(int* regs, int* block, int* bpsm,
                                   int* local_bytes) {
     cudaFuncAttributes at;
-    if constexpr (G == 0) {
+    if constexpr (G == 0 && stream_is_rosl(MC) && M::LINEAR) {
+      // the kernel of the batched launches (warp-synchronous form)
+      constexpr size_t smem =
+          sizeof(double) * stream_slots<M, MC, false>() * WARP_BLOCK;
+      cudaError_t err =
+          cudaFuncGetAttributes(&at, solve_warp_kernel<M, MC>);
+      if (err != cudaSuccess) return err;
+      *regs = at.numRegs;
+      *block = WARP_BLOCK;
+      *local_bytes = static_cast<int>(at.localSizeBytes);
+      if (smem > 48 * 1024) {
+        err = cudaFuncSetAttribute(
+            solve_warp_kernel<M, MC>,
+            cudaFuncAttributeMaxDynamicSharedMemorySize,
+            static_cast<int>(smem));
+        if (err != cudaSuccess) return err;
+      }
+      return cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          bpsm, solve_warp_kernel<M, MC>, WARP_BLOCK, smem);
+    } else if constexpr (G == 0) {
       constexpr size_t smem =
           sizeof(double) * stream_slots<M, MC>() * STREAM_BLOCK;
       cudaError_t err = cudaFuncGetAttributes(

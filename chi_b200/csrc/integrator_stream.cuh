@@ -33,6 +33,7 @@
 // Compiles for the host as well (stride = 1, tid = 0) for the CPU port.
 #pragma once
 #include "integrator.cuh"
+#include <type_traits>
 
 // unroll factor of the stage loop of step_rosl (stages 1 .. S-3)
 #ifndef CHI_ROSL_UNROLL
@@ -41,6 +42,13 @@
 #define CHI_STR2(x) #x
 #define CHI_STR(x) CHI_STR2(x)
 #define CHI_UNROLL_N(n) _Pragma(CHI_STR(unroll n))
+
+// vote over the lanes of a warp (the host build has one "lane")
+#ifdef __CUDA_ARCH__
+#define CHI_WARP_ANY(p) __any_sync(0xffffffffu, (p))
+#else
+#define CHI_WARP_ANY(p) (p)
+#endif
 
 namespace chi_b200 {
 
@@ -64,12 +72,16 @@ constexpr bool stream_is_rosl(const int method) {
 }
 // ... and it keeps a one-record buffer of (y, S) per thread, so that the
 // lanes of a warp evaluate their observation records together (see
-// StreamSolver::events).
-template <class M, int METHOD>
+// StreamSolver::events), and the weights of its error norm (floats).
+// (WITH_BUF = false: the warp-synchronous kernel, which has no use for the
+// record buffer)
+template <class M, int METHOD, bool WITH_BUF = stream_is_rosl(METHOD)>
 constexpr int stream_slots() {
   const int pi = stream_integrated<M>();
-  return (stream_is_rosl(METHOD) ? pi * M::N + (1 + pi) * M::N
-                                 : 2 * pi * M::N + 7 * M::N) +
+  return (stream_is_rosl(METHOD)
+              ? pi * M::N + (WITH_BUF ? (1 + pi) * M::N : 0) +
+                    ((1 + pi) * M::N + 1) / 2
+              : 2 * pi * M::N + 7 * M::N) +
          M::P + 8 + M::NCS + M::N;
 }
 // largest of the methods (host buffers of the CPU port)
@@ -527,7 +539,8 @@ CHI_HD ErrTerms error_terms(const int kind, const double* sg, const double yb,
 // handling and the (expensive) step (solve_stream_kernel below).
 // METHOD_CODE: 1 = RODAS4 (6 stages, order 4(3)), 5 = RODAS5 (8 stages,
 // order 5(4)).
-template <class M, int METHOD_CODE>
+template <class M, int METHOD_CODE,
+          bool WITH_BUF = stream_is_rosl(METHOD_CODE)>
 struct StreamSolver {
   static constexpr bool R5 = METHOD_CODE == 5;
   // ROSL(9), ROSL(11): the linear-model methods (namespace rosl)
@@ -570,10 +583,12 @@ struct StreamSolver {
   static constexpr int OFF_C = OFF_COLD + 8;
   static constexpr int OFF_Y = OFF_C + NCS;
   // record buffer (ROSL): y, then S of the integrated columns
-  static constexpr bool BUFFERED = ROSL;
+  static constexpr bool BUFFERED = ROSL && WITH_BUF;
   static constexpr int OFF_BUF = OFF_Y + N;
-  static_assert(OFF_BUF + (BUFFERED ? (1 + PI) * N : 0) ==
-                    stream_slots<M, METHOD_CODE>(),
+  // error weights (ROSL): floats, two per slot
+  static constexpr int OFF_WT = OFF_BUF + (BUFFERED ? (1 + PI) * N : 0);
+  static_assert(OFF_WT + (ROSL ? ((1 + PI) * N + 1) / 2 : 0) ==
+                    stream_slots<M, METHOD_CODE, WITH_BUF>(),
                 "slot layout");
 #define CHI_S(buf, m, n) sm[(((buf) * PI + (m)) * N + (n)) * stride]
 #define CHI_G(k) sm[(OFF_G + (k)) * stride]
@@ -608,6 +623,26 @@ struct StreamSolver {
   CHI_HD void load_state(double (&y)[N]) const {
 #pragma unroll
     for (int n = 0; n < N; ++n) y[n] = CHI_Y(n);
+  }
+
+  CHI_HD float slot_float(const int slot, const int half) const {
+#ifdef __CUDA_ARCH__
+    return reinterpret_cast<const float*>(&sm[slot * stride])[half];
+#else
+    float v[2];
+    __builtin_memcpy(v, &sm[slot * stride], 8);
+    return v[half];
+#endif
+  }
+  CHI_HD void set_slot_float(const int slot, const int half, const float x) {
+#ifdef __CUDA_ARCH__
+    reinterpret_cast<float*>(&sm[slot * stride])[half] = x;
+#else
+    float v[2];
+    __builtin_memcpy(v, &sm[slot * stride], 8);
+    v[half] = x;
+    __builtin_memcpy(&sm[slot * stride], v, 8);
+#endif
   }
 
   CHI_HD int cold_int(const int k, const int half) const {
@@ -748,6 +783,19 @@ struct StreamSolver {
       if (full) flags |= 1 << 30;
     }
     if (M::LINEAR) M::jac(y, c, J0);
+    if (ROSL) {
+      const float atol_f = static_cast<float>(a.atol);
+      const float rtol_f = static_cast<float>(a.rtol);
+#pragma unroll
+      for (int n = 0; n < N; ++n) set_weight(n, y[n], atol_f, rtol_f);
+#pragma unroll
+      for (int m = 0; m < PI; ++m) {
+        const int pk = m < ni ? a.int_param[m] : -1;
+#pragma unroll
+        for (int n = 0; n < N; ++n)
+          set_weight(N + m * N + n, (pk == n) ? 1.0 : 0.0, atol_f, rtol_f);
+      }
+    }
   }
 
   // ll -= log(scale), deferred: the scales are multiplied up and the
@@ -863,6 +911,18 @@ struct StreamSolver {
     }
   }
 
+  // dose-rate edge: the input switches to u_new
+  CHI_HD void switch_rate(const double u_new) {
+    // restart from the first accepted step after the previous edge of this
+    // kind, if there was one; else shrink the current proposal
+    const int kind = (fabs(u_new) > fabs(u)) ? 1 : 2;
+    u = u_new;
+    const float hm = cold_float(7, kind - 1);
+    h = (hm > 0.0f) ? fmin(static_cast<double>(hm), h)
+                    : (CHI_EDGE_KEEP_H ? h * CHI_EDGE_SHRINK : 0.0);
+    flags = (flags & ~(3 << 28)) | (kind << 28);
+  }
+
   // Handles the events pending at the current time (observation records,
   // dose-rate edges).  Returns true when the system is finished.  The common
   // case -- the next stop has not been reached -- is one comparison.
@@ -901,18 +961,8 @@ struct StreamSolver {
         // the edge is kept (shrunk), the controller takes it from there
         const int seg = cold_int(6, 0) + 1;
         set_cold_int(6, 0, seg);
-        const double u_old = u;
-        u = a.seg_rate[seg];
+        switch_rate(a.seg_rate[seg]);
         t_edge = (seg + 1 < cold_int(6, 1)) ? a.seg_t[seg + 1] : INFINITY;
-        {
-          // restart from the first accepted step after the previous edge of
-          // this kind, if there was one; else shrink the current proposal
-          const int kind = (fabs(u) > fabs(u_old)) ? 1 : 2;
-          const float hm = cold_float(7, kind - 1);
-          h = (hm > 0.0f) ? fmin(static_cast<double>(hm), h)
-                          : (CHI_EDGE_KEEP_H ? h * CHI_EDGE_SHRINK : 0.0);
-          flags = (flags & ~(3 << 28)) | (kind << 28);
-        }
         continue;
       }
       set_cold_int(5, 0, r);
@@ -1149,12 +1199,21 @@ struct StreamSolver {
   // One ROSL(s) step attempt of a linear model: the state column and all
   // integrated sensitivity columns advance TOGETHER, stage by stage, in
   // registers -- (1 + columns) N independent FMA chains per thread, nothing
-  // of the earlier stages kept, no stage values in shared memory.
+  // of the earlier stages kept, no stage values in shared memory.  With
+  // g = gamma h, T = (I - g J)^-1 (ONE reciprocal per attempt), E = T g J:
   //   w_0^y = T h f(y),                       w_k^y = E w_{k-1}^y
-  //   w_0^S = T h (J S + D_k y + e_k) + W^-1 D_k w_0^y,
-  //   w_k^S = E w_{k-1}^S + W^-1 D_k (w_{k-1}^y + w_k^y)
+  //   w_0^S = (E S + G_k y) / gamma + h T e_k + G_k w_0^y,   G_k = g T D_k
+  //   w_k^S = E w_{k-1}^S + G_k (w_{k-1}^y + w_k^y)
   // (the augmented Jacobian [[J, 0], [D_k, J]] is block triangular, so
-  // T_aug - I = [[E, 0], [gamma h T D_k T, E]] and T w = w + E w).
+  // T_aug - I = [[E, 0], [G_k T, E]], T w = w + E w and T h J S = E S / gamma).
+  // The terms of the last two stages are the error estimate: stage S-2 only
+  // advances w, the last stage forms e = c_{S-2} w_{S-2} + c_{S-1} w_{S-1}
+  // component by component, adds it to the solution and to the error norm --
+  // no second set of accumulators is ever live.  The norm is weighted by
+  // 1 / (atol + rtol |z_n|) at the START of the step (as CVODES weighs its
+  // error test), kept as floats in shared memory and refreshed when a step is
+  // accepted: an attempt converts the twelve error terms, not three values per
+  // component.
   // MODE 0: no columns (forward only); 1: all columns of the model (their
   // parameters are compile-time constants: the column terms fold); 2: a
   // subset chosen at run time (fix_parameters), unused slots carry zeros.
@@ -1165,6 +1224,7 @@ struct StreamSolver {
     constexpr int NCA = NCOL > 0 ? NCOL : 1;
     constexpr bool R1 = M::COL_RANK1;
     constexpr int WDN = R1 ? N : N * N;
+    constexpr double RG = 1.0 / GAMMA;
     double y[N], c[NCS];
     load_state(y);
     load_constants(c);
@@ -1181,29 +1241,32 @@ struct StreamSolver {
     } else if (rem < 2.0 * h) {
       hs = 0.5 * rem;
     }
-    const double hinv = rcp_newton(hs);
-    double Wi[N * N], E[N * N];
+    const double g = GAMMA * hs;
+    double T[N * N], E[N * N];
     {
-      double W[N * N];
+      double GJ[N * N], A[N * N];
 #pragma unroll
       for (int i = 0; i < N; ++i)
 #pragma unroll
-        for (int j = 0; j < N; ++j)
-          W[i * N + j] = (i == j ? hinv * (1.0 / GAMMA) : 0.0) - J0[i * N + j];
-      invert<N>(W, Wi);
+        for (int j = 0; j < N; ++j) {
+          GJ[i * N + j] = g * J0[i * N + j];
+          A[i * N + j] = (i == j ? 1.0 : 0.0) - GJ[i * N + j];
+        }
+      invert<N>(A, T);
+      // E = T g J (= T - I, without the cancellation)
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          double acc = T[i * N] * GJ[j];
+#pragma unroll
+          for (int q = 1; q < N; ++q)
+            acc = fma(T[i * N + q], GJ[q * N + j], acc);
+          E[i * N + j] = acc;
+        }
     }
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        double acc = Wi[i * N] * J0[j];
-#pragma unroll
-        for (int q = 1; q < N; ++q)
-          acc = fma(Wi[i * N + q], J0[q * N + j], acc);
-        E[i * N + j] = acc;
-      }
     // ---- stage 0 ----------------------------------------------------------
-    double ay[N], zy[N], ty[N];
+    double ay[N], zy[N];
     {
       double f0[N];
       M::rhs(y, c, u, f0);
@@ -1216,10 +1279,9 @@ struct StreamSolver {
         for (int q = 0; q < N; ++q) acc = fma(E[n * N + q], f0[q], acc);
         ay[n] = acc;
         zy[n] = fma(rosl_c<S>(0), acc, y[n]);
-        ty[n] = 0.0;
       }
     }
-    double w[NCA][N], zs[NCA][N], ts[NCA][N], WD[NCA][WDN];
+    double w[NCA][N], zs[NCA][N], WD[NCA][WDN];
     int qs[NCA];
     bool terms[NCA];
     const int ni = MODE == 2 ? n_int() : NCOL;
@@ -1230,18 +1292,19 @@ struct StreamSolver {
       const int kc = pk >= N ? pk - N : -1;
       terms[m] = live && kc >= 0;
       qs[m] = 0;
-      double S0[N], v[N];
+      double S0[N], v[N], add[N];
 #pragma unroll
       for (int n = 0; n < N; ++n) S0[n] = live ? CHI_S(cur, m, n) : 0.0;
-      matvec<N>(J0, S0, v);
+      // v = E S + G_k y (times 1 / gamma below), add = G_k w_0^y + h T e_k
+      matvec<N>(E, S0, v);
 #pragma unroll
       for (int j = 0; j < WDN; ++j) WD[m][j] = 0.0;
-      double cpl[N];
 #pragma unroll
-      for (int n = 0; n < N; ++n) cpl[n] = 0.0;
+      for (int n = 0; n < N; ++n) add[n] = 0.0;
       if (terms[m]) {
+        double ek[N];
         if constexpr (R1) {
-          double dk[N], ek[N];
+          double dk[N];
           const int q1 = M::col_rank1(kc, c, u, dk, ek);
           qs[m] = q1;
           double yq = y[0], aq = ay[0];
@@ -1250,53 +1313,67 @@ struct StreamSolver {
             yq = (q1 == j) ? y[j] : yq;
             aq = (q1 == j) ? ay[j] : aq;
           }
-#pragma unroll
-          for (int n = 0; n < N; ++n) v[n] += fma(dk[n], yq, ek[n]);
-          matvec<N>(Wi, dk, WD[m]);
-#pragma unroll
-          for (int n = 0; n < N; ++n) cpl[n] = WD[m][n] * aq;
-        } else {
-          double DK[N * N], ek[N];
-          M::col_linear(kc, c, u, DK, ek);
+          // G_k = g T d_k (entries of d_k that are zero at compile time drop
+          // out)
 #pragma unroll
           for (int n = 0; n < N; ++n) {
-            double acc = ek[n];
+            double acc = 0.0;
 #pragma unroll
-            for (int q = 0; q < N; ++q) acc = fma(DK[n * N + q], y[q], acc);
-            v[n] += acc;
+            for (int q = 0; q < N; ++q)
+              if (dk[q] != 0.0) acc = fma(T[n * N + q], dk[q], acc);
+            WD[m][n] = g * acc;
           }
+#pragma unroll
+          for (int n = 0; n < N; ++n) {
+            v[n] = fma(WD[m][n], yq, v[n]);
+            add[n] = WD[m][n] * aq;
+          }
+        } else {
+          double DK[N * N];
+          M::col_linear(kc, c, u, DK, ek);
 #pragma unroll
           for (int i = 0; i < N; ++i)
 #pragma unroll
             for (int j = 0; j < N; ++j) {
-              double acc = Wi[i * N] * DK[j];
+              double acc = 0.0;
 #pragma unroll
-              for (int q = 1; q < N; ++q)
-                acc = fma(Wi[i * N + q], DK[q * N + j], acc);
-              WD[m][i * N + j] = acc;
+              for (int q = 0; q < N; ++q)
+                if (DK[q * N + j] != 0.0)
+                  acc = fma(T[i * N + q], DK[q * N + j], acc);
+              WD[m][i * N + j] = g * acc;
             }
-          matvec<N>(WD[m], ay, cpl);
-        }
-      }
 #pragma unroll
-      for (int n = 0; n < N; ++n) v[n] *= hs;
+          for (int n = 0; n < N; ++n) {
+#pragma unroll
+            for (int q = 0; q < N; ++q) {
+              v[n] = fma(WD[m][n * N + q], y[q], v[n]);
+              add[n] = fma(WD[m][n * N + q], ay[q], add[n]);
+            }
+          }
+        }
+        // h T e_k (a constant that enters the rhs additively; zero for the
+        // rate constants of the PK models)
+#pragma unroll
+        for (int n = 0; n < N; ++n)
+#pragma unroll
+          for (int q = 0; q < N; ++q)
+            if (ek[q] != 0.0) add[n] = fma(T[n * N + q], hs * ek[q], add[n]);
+      }
 #pragma unroll
       for (int n = 0; n < N; ++n) {
-        double acc = v[n] + cpl[n];
-#pragma unroll
-        for (int q = 0; q < N; ++q) acc = fma(E[n * N + q], v[q], acc);
+        const double acc = fma(RG, v[n], add[n]);
         w[m][n] = acc;
         zs[m][n] = fma(rosl_c<S>(0), acc, S0[n]);
-        ts[m][n] = 0.0;
       }
     }
-    // ---- stages 1 .. S-1 ----------------------------------------------------
-    // One stage of all columns; TAIL: the term belongs to the error estimate.
-    // The first S-3 of them run as a rolled loop (one stage body in the
-    // instruction cache: fully unrolled the step is ~2000 instructions and
+    // ---- stages 1 .. S-2 ----------------------------------------------------
+    // One stage of all columns: w <- next power; ACC: its term is added to
+    // the solution (stages 1 .. S-3: a rolled loop, one stage body in the
+    // instruction cache -- fully unrolled the step is ~2000 instructions and
     // the four warps of a scheduler miss the cache, `no_instruction` 1.35
-    // stall cycles per issue), the last two are the error tail.
-    auto stage = [&](const double ck, const bool tail) {
+    // stall cycles per issue).
+    auto stage = [&](const double ck, auto acc_tag) {
+      constexpr bool ACC = decltype(acc_tag)::value;
       double an[N], sig[N];
 #pragma unroll
       for (int n = 0; n < N; ++n) {
@@ -1309,88 +1386,141 @@ struct StreamSolver {
       for (int n = 0; n < N; ++n) {
         sig[n] = ay[n] + an[n];
         ay[n] = an[n];
-        if (tail) ty[n] = fma(ck, an[n], ty[n]);
-        else zy[n] = fma(ck, an[n], zy[n]);
+        if (ACC) zy[n] = fma(ck, an[n], zy[n]);
       }
 #pragma unroll
       for (int m = 0; m < NCOL; ++m) {
         double wn[N];
-        if (terms[m]) {
-          if constexpr (R1) {
-            double sq = sig[0];
-#pragma unroll
-            for (int j = 1; j < N; ++j) sq = (qs[m] == j) ? sig[j] : sq;
-#pragma unroll
-            for (int n = 0; n < N; ++n) wn[n] = WD[m][n] * sq;
-          } else {
-            matvec<N>(WD[m], sig, wn);
-          }
-#pragma unroll
-          for (int n = 0; n < N; ++n)
-#pragma unroll
-            for (int q = 0; q < N; ++q)
-              wn[n] = fma(E[n * N + q], w[m][q], wn[n]);
-        } else {
-#pragma unroll
-          for (int n = 0; n < N; ++n) {
-            double acc = E[n * N] * w[m][0];
-#pragma unroll
-            for (int q = 1; q < N; ++q) acc = fma(E[n * N + q], w[m][q], acc);
-            wn[n] = acc;
-          }
-        }
+        next_power<R1>(terms[m], qs[m], WD[m], E, sig, w[m], wn);
 #pragma unroll
         for (int n = 0; n < N; ++n) {
           w[m][n] = wn[n];
-          if (tail) ts[m][n] = fma(ck, wn[n], ts[m][n]);
-          else zs[m][n] = fma(ck, wn[n], zs[m][n]);
+          if (ACC) zs[m][n] = fma(ck, wn[n], zs[m][n]);
         }
       }
     };
 #ifdef __CUDA_ARCH__
     CHI_UNROLL_N(CHI_ROSL_UNROLL)
 #endif
-    for (int k = 1; k < S - 2; ++k) stage(rosl_c<S>(k), false);
-    stage(rosl_c<S>(S - 2), true);
-    stage(rosl_c<S>(S - 1), true);
-    // ---- error norm: max over the columns of the scaled RMS -----------------
-    const float atol_f = static_cast<float>(a.atol);
-    const float rtol_f = static_cast<float>(a.rtol);
+    for (int k = 1; k < S - 2; ++k)
+      stage(rosl_c<S>(k), std::integral_constant<bool, true>());
+    stage(0.0, std::integral_constant<bool, false>());
+    // ---- last stage: error estimate, new solution, error norm ---------------
+    // (max over the columns of the weighted RMS)
+    const double ca = rosl_c<S>(S - 2), cb = rosl_c<S>(S - 1);
     float errsq;
     {
+      double an[N], sig[N];
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        double acc = E[n * N] * ay[0];
+#pragma unroll
+        for (int q = 1; q < N; ++q) acc = fma(E[n * N + q], ay[q], acc);
+        an[n] = acc;
+      }
       float s2 = 0.0f;
 #pragma unroll
       for (int n = 0; n < N; ++n) {
-        zy[n] += ty[n];
-        s2 += err_term(ty[n], y[n], zy[n], atol_f, rtol_f);
+        sig[n] = ay[n] + an[n];
+        const double e = fma(cb, an[n], ca * ay[n]);
+        zy[n] += e;
+        const float q = static_cast<float>(e) * weight(n);
+        s2 = fmaf(q, q, s2);
       }
       errsq = s2 * (1.0f / N);
-    }
 #pragma unroll
-    for (int m = 0; m < NCOL; ++m) {
-      float s2 = 0.0f;
+      for (int m = 0; m < NCOL; ++m) {
+        double wn[N];
+        next_power<R1>(terms[m], qs[m], WD[m], E, sig, w[m], wn);
+        float s2m = 0.0f;
 #pragma unroll
-      for (int n = 0; n < N; ++n) {
-        const double S0n = (MODE == 1 || m < ni) ? CHI_S(cur, m, n) : 0.0;
-        zs[m][n] += ts[m][n];
-        s2 += err_term(ts[m][n], S0n, zs[m][n], atol_f, rtol_f);
+        for (int n = 0; n < N; ++n) {
+          const double e = fma(cb, wn[n], ca * w[m][n]);
+          zs[m][n] += e;
+          const float q = static_cast<float>(e) * weight(N + m * N + n);
+          s2m = fmaf(q, q, s2m);
+        }
+        errsq = fmaxf(errsq, s2m * (1.0f / N));
       }
-      errsq = fmaxf(errsq, s2 * (1.0f / N));
     }
     bool accept;
     const bool failed = control(errsq, hs, clipped, accept);
     if (accept) {
+      const float atol_f = static_cast<float>(a.atol);
+      const float rtol_f = static_cast<float>(a.rtol);
 #pragma unroll
-      for (int n = 0; n < N; ++n) CHI_Y(n) = zy[n];
+      for (int n = 0; n < N; ++n) {
+        CHI_Y(n) = zy[n];
+        set_weight(n, zy[n], atol_f, rtol_f);
+      }
 #pragma unroll
       for (int m = 0; m < NCOL; ++m) {
         if (MODE == 1 || m < ni) {
 #pragma unroll
-          for (int n = 0; n < N; ++n) CHI_S(cur, m, n) = zs[m][n];
+          for (int n = 0; n < N; ++n) {
+            CHI_S(cur, m, n) = zs[m][n];
+            set_weight(N + m * N + n, zs[m][n], atol_f, rtol_f);
+          }
         }
       }
     }
     return failed;
+  }
+
+  // w_k^S of one column from w_{k-1}^S (see step_rosl): E w + G (sig[q])
+  template <bool R1>
+  CHI_HD static void next_power(const bool has_terms, const int q1,
+                                const double* G, const double (&E)[N * N],
+                                const double (&sig)[N], const double (&w)[N],
+                                double (&wn)[N]) {
+    if (has_terms) {
+      if constexpr (R1) {
+        double sq = sig[0];
+#pragma unroll
+        for (int j = 1; j < N; ++j) sq = (q1 == j) ? sig[j] : sq;
+#pragma unroll
+        for (int n = 0; n < N; ++n) wn[n] = G[n] * sq;
+      } else {
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+          double acc = G[n * N] * sig[0];
+#pragma unroll
+          for (int q = 1; q < N; ++q) acc = fma(G[n * N + q], sig[q], acc);
+          wn[n] = acc;
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < N; ++n)
+#pragma unroll
+        for (int q = 0; q < N; ++q) wn[n] = fma(E[n * N + q], w[q], wn[n]);
+    } else {
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        double acc = E[n * N] * w[0];
+#pragma unroll
+        for (int q = 1; q < N; ++q) acc = fma(E[n * N + q], w[q], acc);
+        wn[n] = acc;
+      }
+    }
+  }
+
+  // error weights of the ROSL step: 1 / (atol + rtol |z|) of component j
+  // (0 .. N-1: the state, then the integrated columns), two floats per slot
+  CHI_HD float weight(const int j) const {
+    return slot_float(OFF_WT + j / 2, j & 1);
+  }
+  CHI_HD void set_weight(const int j, const double z, const float atol_f,
+                         const float rtol_f) {
+    const float sc = fmaf(rtol_f, fabsf(static_cast<float>(z)), atol_f);
+#ifdef __CUDA_ARCH__
+    // (approximate reciprocal: one MUFU, no slow path -- the twelve weights
+    // of a step are computed side by side)
+    float wt;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(wt) : "f"(fmaxf(sc, 1e-30f)));
+#else
+    const float wt = 1.0f / fmaxf(sc, 1e-30f);
+#endif
+    set_slot_float(OFF_WT + j / 2, j & 1, wt);
   }
 
   CHI_HD bool step_rodas() {
@@ -1564,6 +1694,59 @@ struct StreamSolver {
     return failed;
   }
 
+  // Whole solve of one system by a warp whose lanes ALL integrate the same
+  // individual under different parameter vectors (solve_warp_kernel): the
+  // stops -- observation records and dose-rate edges -- are the same for
+  // every lane, so the warp walks through them together.  Between two stops
+  // the lanes step until the last one has arrived (a lane that is there
+  // early idles: +2.7 % iterations at a parameter spread of 10 %, +8 % at
+  // 30 %, tools/exp/sync_cost.py), then every lane handles the stop in ONE
+  // convergent pass.  The loop around the step is a vote and a branch; the
+  // per-lane event cursor, the record buffer and their predicates are gone
+  // (they were 15 % of the issued instructions and 37 % of the stall samples
+  // of solve_stream_kernel on the bench workload).  Per lane the arithmetic
+  // and its order are those of solve_system_stream: bit-identical results.
+  CHI_HD void solve_uniform(const int64_t b) {
+    init(b);
+    const int id = individual(b);
+    int r = static_cast<int>(a.rec_off[id]);
+    const int r_end = static_cast<int>(a.rec_off[id + 1]);
+    int seg = static_cast<int>(a.seg_off[id]);
+    const int seg_end = static_cast<int>(a.seg_off[id + 1]);
+    bool go = !invalid;
+    double ts = 0.0;   // the current stop: every live lane has t == ts
+    for (;;) {
+      while (r < r_end && a.rec_t[r] <= ts) {
+        if (go) {
+          observe<false>(r);
+          if (invalid) go = false;
+        }
+        ++r;
+      }
+      if (r >= r_end) break;
+      while (seg + 1 < seg_end && a.seg_t[seg + 1] <= ts) {
+        ++seg;
+        if (go) switch_rate(a.seg_rate[seg]);
+      }
+      ts = fmin(a.rec_t[r],
+                (seg + 1 < seg_end) ? a.seg_t[seg + 1] : INFINITY);
+      t_stop = ts;
+      bool stepping = go;
+      while (CHI_WARP_ANY(stepping)) {
+        if (stepping) {
+          if (step()) {
+            go = false;
+            stepping = false;
+          } else {
+            stepping = t < t_stop;
+          }
+        }
+      }
+      if (!CHI_WARP_ANY(go)) break;
+    }
+    finish();
+  }
+
   CHI_HD void finish() {
     const int64_t b = system();
     const int n_rej = (flags >> 8) & 0xfffff;
@@ -1598,6 +1781,14 @@ struct StreamSolver {
 #undef CHI_BUF_Y
 #undef CHI_BUF_S
 };
+
+// the warp-synchronous form with one lane (host port: CPU tests)
+template <class M, int CB>
+CHI_HD void solve_system_uniform(const SolveArgs& a, const int64_t b,
+                                 double* sm, const int stride) {
+  StreamSolver<M, CB> s(a, sm, stride);
+  s.solve_uniform(b);
+}
 
 template <class M, int CB>
 CHI_HD void solve_system_stream(const SolveArgs& a, const int64_t b,
@@ -1794,6 +1985,45 @@ solve_stream_kernel(const SolveArgs a, unsigned long long* counter) {
       s.finish();
       active = false;
     }
+  }
+}
+
+// Warp-synchronous form (StreamSolver::solve_uniform) for launches in which
+// the 32 work items of a warp are one individual under 32 parameter vectors:
+// order_inner a multiple of 32 and B = order_inner x order_stride (the host
+// checks, Registrar::launch_stream).  The warps of this kernel never talk to
+// each other, so the block is as small as the register file's allocation
+// granularity asks for: WARP_BLOCK threads, WARP_MIN_BLOCKS resident blocks
+// per SM (the register cap is 65536 / (WARP_BLOCK x WARP_MIN_BLOCKS), rounded
+// down to a multiple of 8).
+#ifndef CHI_WARP_BLOCK
+#define CHI_WARP_BLOCK 128
+#endif
+#ifndef CHI_WARP_MIN_BLOCKS
+#define CHI_WARP_MIN_BLOCKS 4
+#endif
+constexpr int WARP_BLOCK = CHI_WARP_BLOCK;
+constexpr int WARP_MIN_BLOCKS = CHI_WARP_MIN_BLOCKS;
+
+// (CHI_WARP_MAXNREG: the register cap given directly instead)
+#ifdef CHI_WARP_MAXNREG
+#define CHI_WARP_BOUNDS __maxnreg__(CHI_WARP_MAXNREG)
+#else
+#define CHI_WARP_BOUNDS __launch_bounds__(WARP_BLOCK, WARP_MIN_BLOCKS)
+#endif
+
+template <class M, int CB>
+__global__ void CHI_WARP_BOUNDS
+solve_warp_kernel(const SolveArgs a, unsigned long long* counter) {
+  extern __shared__ double chi_sm[];
+  StreamSolver<M, CB, false> s(a, chi_sm + threadIdx.x, WARP_BLOCK);
+  const unsigned long long total = static_cast<unsigned long long>(a.B);
+  for (;;) {
+    unsigned long long base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(counter, 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= total) break;
+    s.solve_uniform(stream_system_of(a, base + (threadIdx.x & 31)));
   }
 }
 

@@ -30,7 +30,8 @@ using namespace chi_b200;
 
 // stream_cb: 0 = lanes routine (one lane, all columns in "registers"),
 // 1 = streamed-columns routine with RODAS4, 5 = with RODAS5, 9 / 11 = with
-// ROSL(9) / ROSL(11) (linear models).
+// ROSL(9) / ROSL(11) (linear models), 109 / 111 = the same through
+// StreamSolver::solve_uniform.
 template <class M>
 static void run_all(const SolveArgs& a, int n_threads, int stream_cb) {
   (void)n_threads;
@@ -46,6 +47,15 @@ static void run_all(const SolveArgs& a, int n_threads, int stream_cb) {
     } else if (stream_cb == 5) {
       double sm[stream_slots<M>()];
       solve_system_stream<M, 5>(a, b, sm, 1);
+    } else if (stream_cb == 109 || stream_cb == 111) {
+      // the warp-synchronous form of the ROSL kernels, one lane
+      double sm[stream_slots<M>()];
+      if constexpr (M::LINEAR) {
+        if (stream_cb == 109) solve_system_uniform<M, 9>(a, b, sm, 1);
+        else solve_system_uniform<M, 11>(a, b, sm, 1);
+      } else {
+        solve_system_stream<M, 5>(a, b, sm, 1);
+      }
     } else if (stream_cb == 9 || stream_cb == 11) {
       // ROSL(9) / ROSL(11): linear models only (RODAS5 otherwise)
       double sm[stream_slots<M>()];

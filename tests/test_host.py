@@ -886,3 +886,42 @@ def test_cpu_port_buffered_observation_equals_immediate_observation():
         np.testing.assert_array_equal(a[3], b[3])
         np.testing.assert_allclose(a[0], c[0], rtol=1e-13)
         np.testing.assert_allclose(a[1], c[1], rtol=1e-11, atol=1e-13)
+
+
+def test_cpu_port_warp_synchronous_form_equals_the_general_form():
+    """StreamSolver::solve_uniform (the form solve_warp_kernel runs when the
+    lanes of a warp share an individual: the warp walks through the stops --
+    records and dose-rate edges -- together) performs, per system, the same
+    arithmetic in the same order as the general event loop: identical
+    log-likelihoods, gradients and step counts, including two outputs with
+    coinciding records, an invalid sigma and the forward-only solve."""
+    key = cport.find_key('two_compartment_pk_model', 'central', True)
+    rng = np.random.default_rng(12)
+    n_ids = 8
+    times, obs, out_idx, regs = [], [], [], []
+    for i in range(n_ids):
+        t = np.sort(np.concatenate([rng.uniform(0.25, 24, 7), [8.0, 8.0]]))
+        times.append(t)
+        obs.append(rng.uniform(0.2, 2.0, len(t)))
+        out_idx.append(rng.integers(0, 2, len(t)).astype(np.int32))
+        regs.append([(float(rng.uniform(5, 15)), 0.0, 1.0, 8.0, 3)])
+    pop = cport.Population(
+        key, ['central.drug_concentration', 'peripheral.drug_concentration'],
+        ['lognormal', 'cam'], times, obs, out_idx, regs)
+    n = 3 * n_ids
+    X = np.column_stack([
+        np.abs(0.01 * rng.normal(size=(n, 2))),
+        np.exp(np.log([2.0, 1.0, 5.0, 1.0, 10.0])
+               + 0.3 * rng.normal(size=(n, 5))),
+        np.full(n, 0.1), np.full(n, 0.05), np.full(n, 0.12)])
+    X[5, 7] = -1.0      # invalid sigma: -inf, nothing integrated
+    ids = (np.arange(n) % n_ids).astype(np.int32)
+    for method in (9, 11):
+        for with_grad in (True, False):
+            a = pop.loglik(X, ids=ids, with_grad=with_grad, stream_cb=method,
+                           deferred=False)
+            b = pop.loglik(X, ids=ids, with_grad=with_grad,
+                           stream_cb=100 + method, deferred=False)
+            assert a[0][5] == -np.inf and b[0][5] == -np.inf
+            for u, v in zip(a, b):
+                np.testing.assert_array_equal(u, v)

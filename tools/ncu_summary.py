@@ -45,16 +45,17 @@ for v in rows[2:]:
     rd = float(d['dram__bytes_read.sum']) * SCALE[un['dram__bytes_read.sum']]
     wr = float(d['dram__bytes_write.sum']) * SCALE[un['dram__bytes_write.sum']]
     ms = float(d['gpu__time_duration.sum'])
-    if 'solve_stream' in d['Kernel Name']:
+    if 'solve_stream' in d['Kernel Name'] or 'solve_warp' in d['Kernel Name']:
+        kname = 'solve_warp_kernel' if 'solve_warp' in d['Kernel Name'] else 'solve_stream_kernel'
         traffic = rd + wr
         cyc = float(d['sm__cycles_elapsed.max'])
         fl = (2 * float(d['smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed'])
               + float(d['smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed'])
               + float(d['smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed'])) * cyc
-        notes.append('* `solve_stream_kernel`: executed FP64 flops (2 DFMA + DADD + DMUL, predicated-on thread '
+        notes.append('* `%s`: executed FP64 flops (2 DFMA + DADD + DMUL, predicated-on thread '
                      'instructions) %.3e -> %.2f TFLOP/s issued at %.2f ms; FP64 pipe active %s %%; DRAM %.0f MB '
                      'read + %.0f MB written = %.0f GB/s.' % (
-                         fl, fl / ms / 1e9, ms,
+                         kname, fl, fl / ms / 1e9, ms,
                          d['sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active'][:5],
                          rd / 1e6, wr / 1e6, (rd + wr) / ms / 1e6))
     else:
@@ -90,8 +91,8 @@ the plain run exited 0 first (bench line of that run: value %s evals/s, `rooflin
 %s
 
 `fp64_peak_kernel` is the DFMA micro-benchmark that measures the roofline denominator (outside the timed region);
-the `at::` kernels are bench.py's own L2 flush and result checks.  Inside a step `solve_stream_kernel`
-(integration with the observation fused) is what `bench.py` times as "the solve" (`roofline.kernel_ms`, CUDA
+the `at::` kernels are bench.py's own L2 flush and result checks.  Inside a step the solve kernel
+(`solve_warp_kernel` / `solve_stream_kernel`: integration with the observation fused) is what `bench.py` times as "the solve" (`roofline.kernel_ms`, CUDA
 events); the population kernels are about 1 %% of a step.  Launch times under ncu are cold-cache and
 serialised: compare SHARES.
 
@@ -114,7 +115,7 @@ if plain and traffic is not None:
     rec = {'n_ids': cfg['n_ids'], 'chains': cfg['chains_per_step'], 'n_obs': cfg['n_obs'],
            'n_doses': cfg['n_doses'], 'rtol': cfg['rtol'], 'atol': cfg['atol'],
            'dram_bytes_per_launch': traffic,
-           'source': 'ncu --set full capture of solve_stream_kernel, profiles/%s_ncu_summary.md '
+           'source': 'ncu --set full capture of the solve kernel, profiles/%s_ncu_summary.md '
                      '(dram__bytes_read.sum + dram__bytes_write.sum)' % name}
     records = [r for r in records if not all(r.get(k) == rec[k] for k in (
         'n_ids', 'chains', 'n_obs', 'n_doses', 'rtol', 'atol'))] + [rec]
