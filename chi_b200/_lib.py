@@ -120,6 +120,8 @@ _SIGNATURES = {
         ctypes.c_int, [c_vp, ctypes.c_int64]),
     'chi_b200_problem_set_batching': (
         ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
+    'chi_b200_problem_set_small_batch': (
+        ctypes.c_int, [c_vp, ctypes.c_int64]),
     'chi_b200_problem_timings': (ctypes.c_int, [c_vp, c_f64p]),
     'chi_b200_fp64_peak': (ctypes.c_int, [ctypes.c_int32, c_f64p, c_f64p]),
 }

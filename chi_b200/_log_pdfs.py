@@ -781,6 +781,13 @@ class HierarchicalLogLikelihood(
             self._device.problem.handle, int(n_chunks),
             int(order_min_vectors), int(refill_wait)))
 
+    def set_small_batch(self, max_systems=-1):
+        """See ``chi_b200_problem_set_small_batch``: launches of at most
+        ``max_systems`` systems run one warp per system (-1: default, 0:
+        never)."""
+        _lib.check(_lib.lib().chi_b200_problem_set_small_batch(
+            self._device.problem.handle, int(max_systems)))
+
     def set_timing(self, enabled):
         _lib.check(_lib.lib().chi_b200_problem_set_timing(
             self._device.problem.handle, 1 if enabled else 0))

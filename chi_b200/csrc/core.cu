@@ -179,6 +179,7 @@ struct chi_b200_problem {
   DevBuf work_counters;
   // chi_b200_problem_set_batching: -1 = default (environment, then built-in)
   int32_t cfg_chunks = -1, cfg_order = -1, cfg_wait = -1;
+  int64_t cfg_split_max = -1;   // chi_b200_problem_set_small_batch
 
   // configuration
   int32_t n_out = 0;
@@ -1037,6 +1038,12 @@ int chi_b200_problem_set_batching(chi_b200_problem* p, int32_t n_chunks,
   return 0;
 }
 
+int chi_b200_problem_set_small_batch(chi_b200_problem* p,
+                                     int64_t max_systems) {
+  p->cfg_split_max = max_systems;
+  return 0;
+}
+
 int chi_b200_problem_timings(chi_b200_problem* p, double out[2]) {
   out[0] = p->solve_ms_sum;
   out[1] = static_cast<double>(p->solve_launches);
@@ -1297,7 +1304,44 @@ int launch_loglik(chi_b200_problem* p, int64_t B, const int32_t* d_ids,
     }
     a.refill_wait = wait >= 0 ? wait : (ordered ? INT32_MAX : 0);
   }
+  // Small launches (single parameter vectors: what pints' samplers and
+  // optimisers ask for, chi/_inference.py:729-747): one WARP per system
+  // (SolveArgs::split).  The sensitivity columns of the system advance side
+  // by side on the first lanes of the warp, each lane with the state and one
+  // column under its own step-size control, and the warp walks through the
+  // system's stops like a warp of the batched launch does -- a third of the
+  // instructions per step attempt, no lane waits for another system's events,
+  // on a GPU that is mostly idle at this size.  ROSL kernels of linear
+  // models; applies while every system finds a resident warp
+  // (chi_b200_problem_set_small_batch / CHI_B200_SPLIT_MAX: largest number of
+  // systems, 0: never).
+  bool split = false;
   {
+    static const int64_t split_env = [] {
+      const char* e = std::getenv("CHI_B200_SPLIT_MAX");
+      return e ? std::atoll(e) : -1ll;
+    }();
+    int64_t split_max = p->cfg_split_max >= 0 ? p->cfg_split_max : split_env;
+    if (split_max < 0) {
+      int sms = 0;
+      CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount,
+                                      p->device));
+      split_max = 16ll * sms;
+    }
+    const int v = p->variant >= 0 ? p->variant : 0;
+    const bool rosl = v < p->vt->n_variants &&
+                      p->vt->variant_lanes[v] == 0 &&
+                      (p->vt->variant_cols[v] == 9 ||
+                       p->vt->variant_cols[v] == 11) &&
+                      (p->vt->linear & 1);
+    split = rosl && !ordered && B <= split_max && (!with_grad || d_grad) &&
+            (!with_grad || a.n_int <= 32);
+    if (split) {
+      a.split = with_grad && a.n_int > 1 ? a.n_int : 1;
+      CUDA_TRY(cudaMemsetAsync(d_status, 0, B * sizeof(int32_t), stream));
+    }
+  }
+  if (!split) {
     // Observation (output map, error model, gradient) fused in the solve
     // kernel or deferred to observe_kernel via snapshots.  Default policy:
     // fused when the lanes of a warp share the individual (they reach the

@@ -673,6 +673,12 @@ struct Registrar {
       if (err != cudaSuccess) return err;
       err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       if (err != cudaSuccess) return err;
+      // CHI_B200_MAX_BLOCKS_PER_SM: occupancy experiments (same binary, fewer
+      // resident warps)
+      if (const char* e = std::getenv("CHI_B200_MAX_BLOCKS_PER_SM")) {
+        const int cap = std::atoi(e);
+        if (cap > 0 && cap < bpsm) bpsm = cap;
+      }
       cache[dev] = bpsm * sms;
     }
     *out = cache[dev];
@@ -688,8 +694,11 @@ struct Registrar {
       const char* e = std::getenv("CHI_B200_WARP_SYNC");
       return !(e && std::atoi(e) == 0);
     }();
-    return enabled && stream_is_rosl(CB) && M::LINEAR && args.mode == 1 &&
-           !args.snap && args.refill_wait == INT32_MAX &&
+    if (!(stream_is_rosl(CB) && M::LINEAR && args.mode == 1 && !args.snap))
+      return false;
+    // warp-per-system launches (SolveArgs::split) always run on it
+    if (args.split > 0) return true;
+    return enabled && args.refill_wait == INT32_MAX &&
            args.order_inner >= 32 && args.order_inner % 32 == 0 &&
            static_cast<int64_t>(args.order_inner) * args.order_stride ==
                args.B;
@@ -727,7 +736,9 @@ struct Registrar {
     if (err != cudaSuccess) return err;
     if constexpr (stream_is_rosl(CB) && M::LINEAR) {
       if (uniform) {
-        int64_t blocks = (args.B + WARP_BLOCK - 1) / WARP_BLOCK;
+        // (warp-per-system launches: one warp per system)
+        const int64_t threads = args.split > 0 ? args.B * 32 : args.B;
+        int64_t blocks = (threads + WARP_BLOCK - 1) / WARP_BLOCK;
         if (blocks > res) blocks = res;
         solve_warp_kernel<M, CB>
             <<<static_cast<unsigned>(blocks), WARP_BLOCK, smem_warp,
@@ -735,7 +746,8 @@ struct Registrar {
       }
     }
     if (!uniform) {
-      int64_t blocks = (args.B + STREAM_BLOCK - 1) / STREAM_BLOCK;
+      const int64_t items = args.B * (args.split > 0 ? args.split : 1);
+      int64_t blocks = (items + STREAM_BLOCK - 1) / STREAM_BLOCK;
       if (blocks > res) blocks = res;
       solve_stream_kernel<M, CB, STREAM_BLOCK>
           <<<static_cast<unsigned>(blocks), STREAM_BLOCK, smem, stream>>>(

@@ -37,7 +37,7 @@
 
 // unroll factor of the stage loop of step_rosl (stages 1 .. S-3)
 #ifndef CHI_ROSL_UNROLL
-#define CHI_ROSL_UNROLL 1
+#define CHI_ROSL_UNROLL 4
 #endif
 #define CHI_STR2(x) #x
 #define CHI_STR(x) CHI_STR2(x)
@@ -567,6 +567,9 @@ struct StreamSolver {
   int cur, n_att;
   int flags;        // bits 0-7 status, 8-27 rejected steps, 28-29 edge kind,
                     // 30 all columns integrated (ROSL)
+  bool is_ghost = false;   // see solve_uniform
+  int col0;         // split launches: the one integrated column of this
+                    // work item (index into the integrated list), else -1
   int pend;         // record held in the buffer, -1: none
   bool invalid, after_reject;
   bool buffering;   // records go through the buffer (see events())
@@ -681,7 +684,23 @@ struct StreamSolver {
   CHI_HD int edge_kind() const { return (flags >> 28) & 3; }
 
   CHI_HD int n_cols() const { return a.with_sens ? a.n_cols : 0; }
-  CHI_HD int n_int() const { return a.with_sens ? a.n_int : 0; }
+  CHI_HD int n_int() const {
+    return a.with_sens ? (col0 >= 0 ? 1 : a.n_int) : 0;
+  }
+  // m-th integrated column of this work item: mechanistic parameter / column
+  CHI_HD int ip(const int m) const {
+    return a.int_param[(col0 >= 0 ? col0 : 0) + m];
+  }
+  CHI_HD int ic(const int m) const {
+    return a.int_col[(col0 >= 0 ? col0 : 0) + m];
+  }
+  // does this work item write gradient column k?  (split launches: the item
+  // of the column; item 0 also owns the columns that are not integrated)
+  CHI_HD bool owns(const int k) const {
+    if (col0 < 0) return true;
+    if (k == ic(0)) return true;
+    return col0 == 0 && inert(a.col_param[k]);
+  }
   CHI_HD bool loglik() const { return a.mode == 1; }
   CHI_HD bool deferred() const { return a.mode == 1 && a.snap != nullptr; }
   CHI_HD bool want_dsig() const {
@@ -693,9 +712,15 @@ struct StreamSolver {
     return a.ids ? a.ids[b] : static_cast<int>(b % a.n_ids);
   }
 
-  CHI_HD void init(const int64_t b) {
+  CHI_HD void init(const int64_t item) {
     static_assert(METHOD_CODE == 1 || METHOD_CODE == 5 || ROSL,
                   "unknown method");
+    int64_t b = item;
+    col0 = -1;
+    if (a.split > 0) {
+      b = item / a.split;
+      col0 = static_cast<int>(item - b * a.split);
+    }
     static_assert(P <= MAX_COLS, "too many mechanistic parameters");
     const int id = individual(b);
     const double* xb = a.x + b * a.x_stride;
@@ -716,7 +741,7 @@ struct StreamSolver {
     for (int k = 0; k < P; ++k) CHI_G(k) = 0.0;
     const int ni = n_int();
     for (int m = 0; m < ni; ++m) {
-      const int pk = a.int_param[m];
+      const int pk = ip(m);
 #pragma unroll
       for (int n = 0; n < N; ++n) {
         CHI_S(0, m, n) = (pk == n) ? 1.0 : 0.0;
@@ -740,7 +765,7 @@ struct StreamSolver {
         if (sg[off] <= 0.0) invalid = true;
         if (a.err_kind[o] == ERR_CAM && sg[off + 1] <= 0.0) invalid = true;
       }
-      if (want_dsig() && !deferred()) {
+      if (want_dsig() && !deferred() && col0 <= 0 && !is_ghost) {
         // the error-model gradients accumulate in the output row itself
         double* gb = a.grad + b * a.grad_stride + P;
         for (int k = 0; k < a.n_sigma; ++k) gb[k] = 0.0;
@@ -779,7 +804,7 @@ struct StreamSolver {
       bool full = ni == PI;
 #pragma unroll
       for (int m = 0; m < PI; ++m)
-        if (full && a.int_param[m] != full_param(m)) full = false;
+        if (full && ip(m) != full_param(m)) full = false;
       if (full) flags |= 1 << 30;
     }
     if (M::LINEAR) M::jac(y, c, J0);
@@ -790,7 +815,7 @@ struct StreamSolver {
       for (int n = 0; n < N; ++n) set_weight(n, y[n], atol_f, rtol_f);
 #pragma unroll
       for (int m = 0; m < PI; ++m) {
-        const int pk = m < ni ? a.int_param[m] : -1;
+        const int pk = m < ni ? ip(m) : -1;
 #pragma unroll
         for (int n = 0; n < N; ++n)
           set_weight(N + m * N + n, (pk == n) ? 1.0 : 0.0, atol_f, rtol_f);
@@ -816,14 +841,20 @@ struct StreamSolver {
         (static_cast<int64_t>(cold_int(3, 1)) << 32) |
         static_cast<int64_t>(static_cast<unsigned>(cold_int(3, 0)));
     double* row = a.snap + pos;
+    // (split launches: the items of a system share its rows -- item 0 stores
+    // the state, every item its own column)
+    if (col0 <= 0) {
 #pragma unroll
-    for (int n = 0; n < N; ++n) row[n] = CHI_Y(n);
+      for (int n = 0; n < N; ++n) row[n] = CHI_Y(n);
+    }
     const int ni = n_int();
+    const int m0 = col0 > 0 ? col0 : 0;
 #pragma unroll
     for (int m = 0; m < PI; ++m) {
       if (m < ni) {
 #pragma unroll
-        for (int n = 0; n < N; ++n) row[N + m * N + n] = CHI_S(cur, m, n);
+        for (int n = 0; n < N; ++n)
+          row[N + (m0 + m) * N + n] = CHI_S(cur, m, n);
       }
     }
     const int64_t next = pos + a.snap_width;
@@ -871,7 +902,7 @@ struct StreamSolver {
       if (e.invalid) invalid = true;
       CHI_COLD(3) += e.ll;
       add_log_scale(e.scale);
-      if (want_dsig()) {
+      if (want_dsig() && col0 <= 0) {
         double* dsig = a.grad + b * a.grad_stride + P + off;
         dsig[0] += e.ds0;
         if (a.err_kind[o] == ERR_CAM) dsig[1] += e.ds1;
@@ -879,7 +910,7 @@ struct StreamSolver {
       // d ybar / d psi_k = (dg/dy) S_k + dg/dc_k
       const int ni = n_int();
       for (int m = 0; m < ni; ++m) {
-        const int k = a.int_col[m];
+        const int k = ic(m);
         double d = 0.0;
 #pragma unroll
         for (int n = 0; n < N; ++n)
@@ -889,7 +920,7 @@ struct StreamSolver {
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
         const int k = a.param_col[N + j];
-        if (gc[j] != 0.0 && k >= 0 && k < nc)
+        if (gc[j] != 0.0 && k >= 0 && k < nc && owns(k))
           CHI_G(k) = fma(e.w, gc[j], CHI_G(k));
       }
     } else {
@@ -1128,6 +1159,7 @@ struct StreamSolver {
     if constexpr (ROSL) {
       if constexpr (M::LINEAR) {
         if (n_int() == 0) return step_rosl<0>();
+        if (col0 >= 0) return step_rosl<3>();
 #ifdef CHI_ROSL_NO_SUBSET
         return step_rosl<1>();   // (register-pressure experiment only)
 #else
@@ -1216,11 +1248,12 @@ struct StreamSolver {
   // component.
   // MODE 0: no columns (forward only); 1: all columns of the model (their
   // parameters are compile-time constants: the column terms fold); 2: a
-  // subset chosen at run time (fix_parameters), unused slots carry zeros.
+  // subset chosen at run time (fix_parameters), unused slots carry zeros;
+  // 3: the one column of a split work item (SolveArgs::split).
   template <int MODE>
   CHI_HD bool step_rosl() {
     constexpr int S = NS;
-    constexpr int NCOL = MODE == 0 ? 0 : PI;
+    constexpr int NCOL = MODE == 0 ? 0 : (MODE == 3 ? 1 : PI);
     constexpr int NCA = NCOL > 0 ? NCOL : 1;
     constexpr bool R1 = M::COL_RANK1;
     constexpr int WDN = R1 ? N : N * N;
@@ -1253,17 +1286,15 @@ struct StreamSolver {
           A[i * N + j] = (i == j ? 1.0 : 0.0) - GJ[i * N + j];
         }
       invert<N>(A, T);
-      // E = T g J (= T - I, without the cancellation)
+      // E = T g J = T - I.  The subtraction leaves an ABSOLUTE error of one
+      // ulp of 1 in the diagonal of E; E only ever multiplies increments w
+      // that are added to z with |w| <~ |z|, so that is an error of one ulp
+      // of z -- and N^3 - N operations less per attempt than the product.
 #pragma unroll
       for (int i = 0; i < N; ++i)
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-          double acc = T[i * N] * GJ[j];
-#pragma unroll
-          for (int q = 1; q < N; ++q)
-            acc = fma(T[i * N + q], GJ[q * N + j], acc);
-          E[i * N + j] = acc;
-        }
+        for (int j = 0; j < N; ++j)
+          E[i * N + j] = (i == j) ? T[i * N + j] - 1.0 : T[i * N + j];
     }
     // ---- stage 0 ----------------------------------------------------------
     double ay[N], zy[N];
@@ -1288,7 +1319,7 @@ struct StreamSolver {
 #pragma unroll
     for (int m = 0; m < NCOL; ++m) {
       const bool live = MODE == 1 || m < ni;
-      const int pk = MODE == 1 ? full_param(m) : (live ? a.int_param[m] : 0);
+      const int pk = MODE == 1 ? full_param(m) : (live ? ip(m) : 0);
       const int kc = pk >= N ? pk - N : -1;
       terms[m] = live && kc >= 0;
       qs[m] = 0;
@@ -1318,9 +1349,14 @@ struct StreamSolver {
 #pragma unroll
           for (int n = 0; n < N; ++n) {
             double acc = 0.0;
+            bool first = true;
 #pragma unroll
             for (int q = 0; q < N; ++q)
-              if (dk[q] != 0.0) acc = fma(T[n * N + q], dk[q], acc);
+              if (dk[q] != 0.0) {
+                acc = first ? T[n * N + q] * dk[q]
+                            : fma(T[n * N + q], dk[q], acc);
+                first = false;
+              }
             WD[m][n] = g * acc;
           }
 #pragma unroll
@@ -1336,10 +1372,14 @@ struct StreamSolver {
 #pragma unroll
             for (int j = 0; j < N; ++j) {
               double acc = 0.0;
+              bool first = true;
 #pragma unroll
               for (int q = 0; q < N; ++q)
-                if (DK[q * N + j] != 0.0)
-                  acc = fma(T[i * N + q], DK[q * N + j], acc);
+                if (DK[q * N + j] != 0.0) {
+                  acc = first ? T[i * N + q] * DK[q * N + j]
+                              : fma(T[i * N + q], DK[q * N + j], acc);
+                  first = false;
+                }
               WD[m][i * N + j] = g * acc;
             }
 #pragma unroll
@@ -1670,13 +1710,13 @@ struct StreamSolver {
     int m = 0;
     if (M::LINEAR) {
       // initial-value columns first (they lead the list): no column terms
-      for (; m < ni && a.int_param[m] < N; ++m)
+      for (; m < ni && ip(m) < N; ++m)
         errsq = fmaxf(errsq,
                       column<false>(-1, m, nxt, y, c, Uy, V0, Wi, E, hinv,
                                     atol_f, rtol_f));
     }
     for (; m < ni; ++m) {
-      const int pk = a.int_param[m];
+      const int pk = ip(m);
       const int kc = pk >= N ? pk - N : -1;
       errsq = fmaxf(errsq,
                     column<true>(kc, m, nxt, y, c, Uy, V0, Wi, E, hinv,
@@ -1706,14 +1746,19 @@ struct StreamSolver {
   // (they were 15 % of the issued instructions and 37 % of the stall samples
   // of solve_stream_kernel on the bench workload).  Per lane the arithmetic
   // and its order are those of solve_system_stream: bit-identical results.
-  CHI_HD void solve_uniform(const int64_t b) {
-    init(b);
+  // `ghost`: a lane without a work item of its own (warp-per-system
+  // launches, SolveArgs::split): it shadows a real item's control flow, takes
+  // no steps and writes nothing.
+  CHI_HD void solve_uniform(const int64_t item, const bool ghost = false) {
+    is_ghost = ghost;
+    init(item);
+    const int64_t b = system();
     const int id = individual(b);
     int r = static_cast<int>(a.rec_off[id]);
     const int r_end = static_cast<int>(a.rec_off[id + 1]);
     int seg = static_cast<int>(a.seg_off[id]);
     const int seg_end = static_cast<int>(a.seg_off[id + 1]);
-    bool go = !invalid;
+    bool go = !invalid && !ghost;
     double ts = 0.0;   // the current stop: every live lane has t == ts
     for (;;) {
       while (r < r_end && a.rec_t[r] <= ts) {
@@ -1744,25 +1789,38 @@ struct StreamSolver {
       }
       if (!CHI_WARP_ANY(go)) break;
     }
-    finish();
+    if (!ghost) finish();
   }
 
   CHI_HD void finish() {
     const int64_t b = system();
     const int n_rej = (flags >> 8) & 0xfffff;
-    a.status[b] = status();
-    if (a.n_steps) a.n_steps[b] = n_att - n_rej;
-    if (a.n_rej) a.n_rej[b] = n_rej;
+    if (col0 >= 0) {
+      // split launch: the status of a system is the maximum over its items
+      // (zeroed by the launcher)
+#ifdef __CUDA_ARCH__
+      if (status() != ST_OK) atomicMax(a.status + b, status());
+#else
+      if (status() > a.status[b]) a.status[b] = status();
+#endif
+    } else {
+      a.status[b] = status();
+    }
+    if (col0 <= 0) {
+      if (a.n_steps) a.n_steps[b] = n_att - n_rej;
+      if (a.n_rej) a.n_rej[b] = n_rej;
+    }
     if (deferred()) return;   // observe_system() writes ll and the gradient
     if (loglik()) {
       const bool fail = invalid || status() != ST_OK;
-      a.ll[b] = fail ? -INFINITY : CHI_COLD(3) - log(CHI_COLD(4));
+      if (col0 <= 0)
+        a.ll[b] = fail ? -INFINITY : CHI_COLD(3) - log(CHI_COLD(4));
       if (a.with_sens && a.grad) {
         const int nc = n_cols();
         double* gb = a.grad + b * a.grad_stride;
         for (int k = 0; k < nc; ++k)
-          gb[a.col_param[k]] = fail ? INFINITY : CHI_G(k);
-        if (fail)
+          if (owns(k)) gb[a.col_param[k]] = fail ? INFINITY : CHI_G(k);
+        if (fail && col0 <= 0)
           for (int k = 0; k < a.n_sigma; ++k) gb[P + k] = INFINITY;
       }
     } else if (status() != ST_OK) {
@@ -1931,7 +1989,9 @@ solve_stream_kernel(const SolveArgs a, unsigned long long* counter) {
   bool active = false;
   bool exhausted = false;
   int waited = 0;
-  const unsigned long long total = static_cast<unsigned long long>(a.B);
+  // work items: systems, or (system, column) pairs of a split launch
+  const unsigned long long total =
+      static_cast<unsigned long long>(a.B) * (a.split > 0 ? a.split : 1);
   for (;;) {
     // Refill.  A warp whose lanes are all done takes 32 consecutive work
     // items at once; a single idle lane waits up to `refill_wait` iterations
@@ -2018,6 +2078,25 @@ solve_warp_kernel(const SolveArgs a, unsigned long long* counter) {
   extern __shared__ double chi_sm[];
   StreamSolver<M, CB, false> s(a, chi_sm + threadIdx.x, WARP_BLOCK);
   const unsigned long long total = static_cast<unsigned long long>(a.B);
+  if (a.split > 0) {
+    // warp-per-system launch (small batches): the warp takes the `split`
+    // work items of ONE system -- its sensitivity columns side by side on
+    // the first lanes, each with the state -- and walks through the system's
+    // stops like a warp of the batched launch does; the other lanes are
+    // ghosts
+    const unsigned long long items = total * a.split;
+    const unsigned lane = threadIdx.x & 31;
+    for (;;) {
+      unsigned long long base = 0;
+      if (lane == 0)
+        base = atomicAdd(counter, static_cast<unsigned long long>(a.split));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= items) break;
+      const bool ghost = lane >= static_cast<unsigned>(a.split);
+      s.solve_uniform(static_cast<int64_t>(base + (ghost ? 0 : lane)), ghost);
+    }
+    return;
+  }
   for (;;) {
     unsigned long long base = 0;
     if ((threadIdx.x & 31) == 0) base = atomicAdd(counter, 32ull);

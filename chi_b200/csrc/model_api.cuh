@@ -109,6 +109,15 @@ struct SolveArgs {
   // work counter of the persistent kernel (one per launch that may be in
   // flight at a time); null: the launcher's own per-device counter
   unsigned long long* work_counter;
+  // > 0: small launches, one work item per (system, integrated column): item
+  // w integrates system w / split with the single sensitivity column
+  // w % split (split = n_int) under its own step-size control -- the columns
+  // of a system advance side by side on neighbouring lanes instead of one
+  // after the other in one thread (log-likelihood mode, fused observation).
+  // Every item integrates the state; item 0 writes the log-likelihood, the
+  // error-model gradients and the gradient entries that need no sensitivity
+  // column, item j the entry of its column; the status is the maximum.
+  int32_t split;
 };
 
 // What a compiled model contributes to the registry of the core library.

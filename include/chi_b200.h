@@ -286,6 +286,16 @@ int chi_b200_problem_set_snapshot_budget(chi_b200_problem* p, int64_t bytes);
 int chi_b200_problem_set_batching(chi_b200_problem* p, int32_t n_chunks,
                                   int32_t order_min_vectors,
                                   int32_t refill_wait);
+/* Small launches -- single parameter vectors, the way pints' samplers and
+ * optimisers call LogPDF.evaluateS1 (chi/_inference.py:729-747) -- run one
+ * warp per system, the sensitivity columns side by side on its lanes, while
+ * the launch has at most `max_systems` systems (-1: the default, one resident
+ * warp per system: 16 x the SM count; 0: never; CHI_B200_SPLIT_MAX overrides
+ * the default).  Each column is then integrated with the state under its own
+ * step-size control: results agree with the batched form within the
+ * integrator's tolerance, not bit for bit.  ROSL kernels of linear models. */
+int chi_b200_problem_set_small_batch(chi_b200_problem* p,
+                                     int64_t max_systems);
 /* measured FP64 FMA throughput of the device (DFMA micro-kernel) */
 int chi_b200_fp64_peak(int32_t device, double* tflops, double* sm_clock_mhz);
 

@@ -50,6 +50,7 @@ class SolveArgs(ctypes.Structure):
         ('snap_width', ctypes.c_int32),
         ('order_inner', ctypes.c_int32), ('order_stride', ctypes.c_int32),
         ('refill_wait', ctypes.c_int32), ('work_counter', _vp),
+        ('split', ctypes.c_int32),
     ]
 
 
@@ -199,11 +200,13 @@ class Population(object):
 
     def loglik(self, x, ids=None, with_grad=True, rtol=1e-8, atol=1e-10,
                max_steps=100000, n_threads=1, stream_cb=0, deferred=None,
-               buffered=False):
+               buffered=False, split=False):
         """``deferred``: evaluate the observations from snapshots after the
         solve (SolveArgs::snap); False keeps them fused in the solve.
         ``buffered`` (fused only): records go through the one-record buffer,
-        as in a GPU launch whose warps share an individual."""
+        as in a GPU launch whose warps share an individual.  ``split``: one
+        work item per (system, sensitivity column), as in a small GPU
+        launch."""
         x = np.ascontiguousarray(x, float)
         if x.ndim == 1:
             x = x[None, :]
@@ -234,6 +237,9 @@ class Population(object):
             deferred = stream_cb != 0 and not buffered
         if buffered:
             a.refill_wait = 2 ** 31 - 1
+        if split:
+            # one work item per (system, integrated column), SolveArgs::split
+            a.split = a.n_int
         snap = None
         if deferred and stream_cb != 0:
             width = (self._port or lib()).chi_port_snap_width(

@@ -35,10 +35,14 @@ using namespace chi_b200;
 template <class M>
 static void run_all(const SolveArgs& a, int n_threads, int stream_cb) {
   (void)n_threads;
+  // split launches (SolveArgs::split): one work item per (system, column)
+  const int64_t items = a.B * (a.split > 0 ? a.split : 1);
+  if (a.split > 0)
+    for (int64_t b = 0; b < a.B; ++b) a.status[b] = 0;
 #ifdef _OPENMP
-#pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads)
+#pragma omp parallel for schedule(dynamic, 16) num_threads(a.split > 0 ? 1 : n_threads)
 #endif
-  for (int64_t b = 0; b < a.B; ++b) {
+  for (int64_t b = 0; b < items; ++b) {
     if (!a.with_sens && stream_cb == 0) {
       solve_system<M, 1, 0>(a, b, 0, 0, 0, 1u);
     } else if (stream_cb == 1) {
@@ -68,7 +72,14 @@ static void run_all(const SolveArgs& a, int n_threads, int stream_cb) {
     } else {
       solve_system<M, 1, M::P>(a, b, 0, 0, 0, 1u);
     }
-    if (stream_cb != 0 && a.mode == 1 && a.snap) observe_system<M>(a, b);
+  }
+  // deferred observation (after the solve: the items of a split launch share
+  // their system's snapshot rows)
+  if (stream_cb != 0 && a.mode == 1 && a.snap) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads)
+#endif
+    for (int64_t b = 0; b < a.B; ++b) observe_system<M>(a, b);
   }
 }
 

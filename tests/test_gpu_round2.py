@@ -232,3 +232,43 @@ def test_posterior_and_prior_predictive_models():
     arr = ppp.sample(times, n_samples=25, seed=4, return_df=False)
     assert arr.shape == (1, 4, 25)
     np.testing.assert_allclose(np.mean(arr[0], axis=1), exact[0], rtol=0.05)
+
+
+@pytest.mark.gpu
+def test_small_launches_one_warp_per_system_against_the_oracle():
+    """Single parameter vectors (what pints asks for) run one warp per system
+    with the sensitivity columns side by side on its lanes
+    (chi_b200_problem_set_small_batch): log-likelihood, gradient, the -inf
+    convention and the forward-only call against the oracle (exact solution +
+    numpy error / population models) and against the thread-per-system
+    kernel, at the default tolerances and for two error models."""
+    from chi_b200 import _synthetic
+    from tests.test_gpu_bench_tolerance import oracle_scores
+    for error in ('lognormal', 'cam'):
+        prob = _synthetic.two_compartment_problem(
+            60, seed=21, n_doses=3, error=error,
+            rtol=_synthetic.BENCH_RTOL, atol=_synthetic.BENCH_ATOL)
+        post, ll = prob['log_posterior'], prob['log_likelihood']
+        rng = np.random.default_rng(3)
+        x = prob['x0'] * (1 + 0.05 * rng.normal(size=len(prob['x0'])))
+        ref, gref = oracle_scores(prob, x[None, :], error, True)
+        ll.set_small_batch(-1)
+        s, g = post.evaluateS1(x)
+        f = post(x)
+        ll.set_small_batch(0)
+        s_t, g_t = post.evaluateS1(x)
+        f_t = post(x)
+        ll.set_small_batch(-1)
+        assert abs(s - ref[0]) <= 1e-8 * abs(ref[0])
+        assert np.max(np.abs(g - gref[0])) <= 1e-6 * np.max(np.abs(gref[0]))
+        assert abs(f - ref[0]) <= 1e-8 * abs(ref[0])
+        assert s == pytest.approx(s_t, rel=3e-9)
+        assert f == pytest.approx(f_t, rel=3e-9)
+        np.testing.assert_allclose(g, g_t, rtol=1e-6,
+                                   atol=1e-7 * np.max(np.abs(g_t)))
+        # invalid sigma: -inf / inf from every lane of the warp
+        xb = x.copy()
+        xb[-1] = -0.1
+        with np.errstate(all='ignore'):
+            sb, gb = post.evaluateS1(xb)
+        assert np.isneginf(sb)

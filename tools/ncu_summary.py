@@ -44,7 +44,7 @@ for v in rows[2:]:
     out.append('')
     rd = float(d['dram__bytes_read.sum']) * SCALE[un['dram__bytes_read.sum']]
     wr = float(d['dram__bytes_write.sum']) * SCALE[un['dram__bytes_write.sum']]
-    ms = float(d['gpu__time_duration.sum'])
+    ms = float(d['gpu__time_duration.sum']) * {'ms': 1.0, 'us': 1e-3, 'ns': 1e-6, 's': 1e3}[un['gpu__time_duration.sum']]
     if 'solve_stream' in d['Kernel Name'] or 'solve_warp' in d['Kernel Name']:
         kname = 'solve_warp_kernel' if 'solve_warp' in d['Kernel Name'] else 'solve_stream_kernel'
         traffic = rd + wr
