@@ -1321,7 +1321,10 @@ struct StreamSolver {
       const bool live = MODE == 1 || m < ni;
       const int pk = MODE == 1 ? full_param(m) : (live ? ip(m) : 0);
       const int kc = pk >= N ? pk - N : -1;
-      terms[m] = live && kc >= 0;
+      // (MODE 3: the lanes of a warp hold different columns of one system;
+      // an initial-value column runs the general column body with G = 0
+      // instead of a branch of its own -- no divergence inside the stages)
+      terms[m] = live && (MODE == 3 || kc >= 0);
       qs[m] = 0;
       double S0[N], v[N], add[N];
 #pragma unroll
