@@ -162,32 +162,38 @@ def flops_per_step_rosl(n, n_cols, info, stages, n_init=0):
     (integrator_stream.cuh: step_rosl): state column + n_cols integrated
     sensitivity columns, n_init of them initial-value columns (no column
     terms).  FMA = 2, every other FP64 operation 1; error norm and step-size
-    controller are FP32 and not counted."""
+    controller are FP32 and not counted.  Follows the kernel's current form:
+    T = (I - g J)^-1 with one reciprocal, E = T - I, the error estimate formed
+    in the last stage (tests/test_host.py pins the count of the C2 model)."""
     rank1 = bool(info[3] & 2)
     f_rhs = int(info[4])
     s = stages
     inv = {1: 2, 2: 12, 3: 51}.get(n, (2 * n ** 3) // 3 + 2 * n * n)
     mv = n * (2 * n - 1)        # N x N product
     mvf = 2 * n * n             # N x N product accumulated onto a vector
-    e_mat = n * mv              # E = W^-1 J, once per step
-    # stage 0: w = h f + E (h f); z += c_0 w.  Stages 1..s-1: w = E w;
-    # z (or the error tail) += c_k w; the last addition z + tail
-    plain = mv + n + mvf + 2 * n + (s - 1) * (mv + 2 * n) + n
-    # state column: f(y) instead of J S; w_{k-1} + w_k for the columns
-    state = f_rhs + n + mvf + 2 * n + (s - 1) * (
-        mv + (n if n_cols else 0) + 2 * n) + n
-    # column of a constant, rank-one D_k = d e_q^T: + d y_q + e (N FMAs),
-    # W^-1 d once, + (W^-1 d) w^y_0[q] in stage 0, and per later stage the
-    # product accumulates onto (W^-1 d) (w^y_{k-1} + w^y_k)[q]
+    # once per attempt: g = gamma h, g J, I - g J, its inverse, E = T - I
+    common = 1 + n * n + n + inv + n
+    sig = n if n_cols else 0    # w_{k-1} + w_k of the state, for the columns
+    # accumulation z += c_k w_k in stages 1 .. s-3; the last stage forms
+    # e = c_{s-2} w_{s-2} + c_{s-1} w_{s-1} (3 N) and adds it (N)
+    acc = (s - 3) * 2 * n + 4 * n
+    # state column: w_0 = h f + E (h f), z = y + c_0 w_0, then w_k = E w_{k-1}
+    state = f_rhs + n + mvf + 2 * n + (s - 1) * (mv + sig) + acc
+    # initial-value column: w_0 = (E S) / gamma, z = S + c_0 w_0, w_k = E w
+    plain = mv + n + 2 * n + (s - 1) * mv + acc
     if rank1:
-        const = plain + 2 * n + mv + n + (s - 1) * (mvf + n - mv)
+        # column of a constant, D_k = d e_q^T: G = g T d (counted N),
+        # w_0 = (E S + G y_q) / gamma + G w_0^y[q], z; then
+        # w_k = E w_{k-1} + G (w_{k-1}^y + w_k^y)[q]
+        const = mv + n + 2 * n + n + 2 * n + 2 * n + \
+            (s - 1) * (n + mvf) + acc
     else:
-        # dense D_k: + D_k y + e, W^-1 D_k once, the coupling product in
-        # stage 0 and one more N x N product per later stage
-        const = plain + mvf + n * mv + mvf + (s - 1) * mvf
+        # dense D_k: G = g T D_k once, G y and G w_0^y in stage 0, one more
+        # N x N product per later stage
+        const = mv + (n * mv + n * n) + 2 * mvf + 4 * n + \
+            (s - 1) * (mv + mvf) + acc
     n_const = max(n_cols - n_init, 0)
-    return inv + e_mat + state + min(n_init, n_cols) * plain + \
-        n_const * const
+    return common + state + min(n_init, n_cols) * plain + n_const * const
 
 
 def flops_per_step(n, n_cols, info, stages=6, n_init=0, method=None):
@@ -711,7 +717,8 @@ class Context(object):
 
 
 def solve_roofline(ctx, prob_model, ll_timings, with_grad, n_sys, steps_acc,
-                   steps_rej, n_rec_total, dev_ms, variant, traffic=None):
+                   steps_rej, n_rec_total, dev_ms, variant, traffic=None,
+                   vectors=0):
     """FP64 roofline record of the solve kernel of one workload."""
     from chi_b200 import _lib
     import ctypes
@@ -769,9 +776,16 @@ def solve_roofline(ctx, prob_model, ll_timings, with_grad, n_sys, steps_acc,
             'figure); peak_nominal: %d SMs x 64 FMA/clk x 2 x %.0f MHz'
             % (pk['sms'], pk['sm_max_mhz'])),
         'kernel': (
-            'solve_stream_kernel<%s, %s> (persistent, thread per system, '
-            'sensitivity columns streamed, observation %s)' % (
-                prob_model.model_key(), method, 'fused')
+            ('solve_warp_kernel<%s, %s> (persistent, thread per system, the '
+             'lanes of a warp share an individual and walk through its '
+             'stops together, all sensitivity columns advance together in '
+             'registers, observation fused)' % (
+                 prob_model.model_key(), method)
+             if (method.startswith('ROSL') and vectors >= 32
+                 and vectors % 32 == 0) else
+             'solve_stream_kernel<%s, %s> (persistent, thread per system, '
+             'per-lane event handling, observation deferred to '
+             'observe_kernel)' % (prob_model.model_key(), method))
             if streamed else
             'solve_kernel<%s, G=%d, MC=%d>' % (
                 prob_model.model_key(), int(variants[0][vsel]),
@@ -945,7 +959,7 @@ def measure_hier(ctx, cfg, steps, warmup, keep=False):
         rec['roofline'] = solve_roofline(
             ctx, prob['model'], timings, with_grad, n_sys, steps_acc,
             steps_rej, n_sys * args.n_obs, dev_ms, args.variant,
-            traffic=_ncu_traffic(cfg, args))
+            traffic=_ncu_traffic(cfg, args), vectors=cfg['chains'])
     if shard == 'individuals' and rank == 0:
         # the sharded, all-reduced score of vector 0 against an unsharded
         # evaluation of the same vector on this rank alone (every rank holds
@@ -1250,7 +1264,9 @@ def run_product(args, rank, world, local_rank):
                     'c2_1000_individuals_call': lat['call'],
                     'c1_evaluateS1': configs['c1']['value'],
                     'what': 'one parameter vector per call through the '
-                            'public API (host buffers), mean of 200 calls'}
+                            'public API (host buffers), mean of 200 calls; '
+                            'launches of this size run one warp per system '
+                            '(solve_warp_kernel, SolveArgs::split)'}
             if rank == 0:
                 line['configs'] = configs
     elif args.config == 'c1':
@@ -1277,8 +1293,19 @@ def run_product(args, rank, world, local_rank):
         ctx.dist.destroy_process_group()
 
 
+def _only_json_on_stdout():
+    """Everything that libraries print on file descriptor 1 (e.g. NCCL's
+    version banner under NCCL_DEBUG) goes to stderr; `print` writes to a
+    duplicate of the real stdout: the JSON line is the only line there."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, 'w', buffering=1)
+
+
 def main():
     args = parse_args()
+    _only_json_on_stdout()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))

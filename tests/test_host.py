@@ -426,12 +426,12 @@ def test_flop_model_of_the_bench_counts_the_k_stage_form():
     import bench
     info = np.array([2, 5, 4, 3, 6, 3, 10, 0])   # linear, rank-one terms
     assert bench.flops_per_step(2, 5, info, stages=8, n_init=2) == 1048
-    # ROSL(11), the default method of linear models: 24 (W^-1, E) + 142
-    # (state) + 2 x 122 (initial-value columns) + 3 x 174 (constants)
+    # ROSL(11), the default method of linear models: 21 (T, E) + 140
+    # (state) + 2 x 112 (initial-value columns) + 3 x 162 (constants)
     assert bench.flops_per_step(
-        2, 5, info, stages=11, n_init=2, method='ROSL11') == 932
+        2, 5, info, stages=11, n_init=2, method='ROSL11') == 871
     assert bench.flops_per_step(
-        2, 0, info, stages=11, n_init=0, method='ROSL11') == 146
+        2, 0, info, stages=11, n_init=0, method='ROSL11') == 141
     assert bench.flops_per_step(2, 0, info, stages=8, n_init=2) == 206
     dense = info.copy()
     dense[3] = 1                                  # linear, dense column terms
