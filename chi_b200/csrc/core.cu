@@ -176,6 +176,9 @@ struct chi_b200_problem {
   // second stream of the chunked host entry point (chi_b200_hier_logpdf) and
   // the work counters of the solve launches that may be in flight together
   cudaStream_t stream2 = nullptr;
+  // copy streams and per-chunk events of the host-buffer entry point
+  cudaStream_t stream_in = nullptr, stream_out = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_comp;
   DevBuf work_counters;
   // chi_b200_problem_set_batching: -1 = default (environment, then built-in)
   int32_t cfg_chunks = -1, cfg_order = -1, cfg_wait = -1;
@@ -869,6 +872,10 @@ void chi_b200_problem_destroy(chi_b200_problem* p) {
   if (p->ev1) cudaEventDestroy(p->ev1);
   if (p->stream) cudaStreamDestroy(p->stream);
   if (p->stream2) cudaStreamDestroy(p->stream2);
+  if (p->stream_in) cudaStreamDestroy(p->stream_in);
+  if (p->stream_out) cudaStreamDestroy(p->stream_out);
+  for (auto& e : p->ev_in) cudaEventDestroy(e);
+  for (auto& e : p->ev_comp) cudaEventDestroy(e);
   p->work_counters.release();
   delete p;
 }
@@ -1994,12 +2001,18 @@ int chi_b200_hier_logpdf(chi_b200_problem* p, int32_t C, const double* x,
   const size_t w_b = static_cast<size_t>(p->id_end - p->id_begin) *
                      p->pop.n_hdim * sizeof(double);
   const size_t w_t = static_cast<size_t>(p->n_top) * sizeof(double);
-  // The vectors are evaluated in chunks that alternate between two streams:
-  // the copy of a chunk's parameters to the device and of its results back
-  // overlaps the solves of its neighbours, and the persistent solve kernel of
-  // one chunk fills the SMs as the one before it drains.  The chunks' scratch
-  // is disjoint (run_hier indexes it by the position in the batch).  One
-  // chunk when there is too little to move for that to pay.
+  // The vectors are evaluated in chunks.  Copies travel on their own streams
+  // -- every chunk's parameters on `stream_in`, its results on `stream_out`
+  // -- and the chunks' kernels alternate between two compute streams, tied
+  // together by one event per chunk and direction: the copy engines run ahead
+  // of / behind the SMs, the persistent solve kernel of one chunk fills the
+  // SMs as the one before it drains, and only the first chunk's copy in and
+  // the last chunk's copy out are exposed.  (Copies queued on the compute
+  // streams themselves do not overlap: the kernels of the two streams share
+  // the SMs, finish together, and both streams then copy while the SMs
+  // idle -- measured with CHI_B200_TIMELINE.)  The chunks' scratch is
+  // disjoint (run_hier indexes it by the position in the batch).  One chunk
+  // when there is too little to move for that to pay.
   static const int chunks_env = [] {
     const char* e = std::getenv("CHI_B200_CHUNKS");
     return e ? std::atoi(e) : 0;
@@ -2029,17 +2042,53 @@ int chi_b200_hier_logpdf(chi_b200_problem* p, int32_t C, const double* x,
   if (n_chunks > 1) {
     if (!p->stream2)
       CUDA_TRY(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
+    if (!p->stream_in)
+      CUDA_TRY(cudaStreamCreateWithFlags(&p->stream_in, cudaStreamNonBlocking));
+    if (!p->stream_out)
+      CUDA_TRY(
+          cudaStreamCreateWithFlags(&p->stream_out, cudaStreamNonBlocking));
+    while (static_cast<int>(p->ev_in.size()) < n_chunks) {
+      cudaEvent_t e0, e1;
+      CUDA_TRY(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+      p->ev_in.push_back(e0);
+      p->ev_comp.push_back(e1);
+    }
   }
+  const bool piped = n_chunks > 1;
+  // (work a caller may have queued on the problem's stream comes first)
+  if (piped) CUDA_TRY(cudaStreamSynchronize(s));
   CUDA_TRY(p->work_counters.reserve(MAX_CHUNKS_P1 * sizeof(unsigned long long)));
   p->counters[3] = 0;
+  // chunk boundaries at multiples of 32 vectors when the chunks are large
+  // enough: the warps of the solve kernel then hold 32 vectors of one
+  // individual without padding
+  const auto chunk_begin = [&](int k) {
+    int64_t c = static_cast<int64_t>(C) * k / n_chunks;
+    if (k < n_chunks && C >= 64 * n_chunks) c = c / 32 * 32;
+    return static_cast<int32_t>(k >= n_chunks ? C : c);
+  };
+  // CHI_B200_TIMELINE=1: per-chunk event times on stderr (development)
+  static const bool timeline = std::getenv("CHI_B200_TIMELINE") != nullptr;
+  std::vector<cudaEvent_t> tl;
+  if (timeline) {
+    tl.resize(static_cast<size_t>(n_chunks) * 4 + 1);
+    for (auto& e : tl) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaEventRecord(tl.back(), s));
+    if (piped) {
+      CUDA_TRY(cudaStreamWaitEvent(p->stream2, tl.back(), 0));
+      CUDA_TRY(cudaStreamWaitEvent(p->stream_in, tl.back(), 0));
+    }
+  }
   for (int k = 0; k < n_chunks; ++k) {
-    const int32_t c0 = static_cast<int32_t>(static_cast<int64_t>(C) * k /
-                                            n_chunks);
-    const int32_t c1 = static_cast<int32_t>(static_cast<int64_t>(C) * (k + 1) /
-                                            n_chunks);
+    const int32_t c0 = chunk_begin(k);
+    const int32_t c1 = chunk_begin(k + 1);
     const int32_t Ck = c1 - c0;
     if (Ck <= 0) continue;
     cudaStream_t sk = (k & 1) ? p->stream2 : s;
+    cudaStream_t s_in = piped ? p->stream_in : sk;
+    cudaStream_t s_out = piped ? p->stream_out : sk;
+    if (timeline) CUDA_TRY(cudaEventRecord(tl[k * 4], s_in));
     const double* xk = x + static_cast<int64_t>(c0) * n_params;
     double* d_xk = p->hx.as<double>() + static_cast<int64_t>(c0) * n_params;
     double* d_gk = with_grad ? p->hgrad.as<double>() +
@@ -2047,20 +2096,25 @@ int chi_b200_hier_logpdf(chi_b200_problem* p, int32_t C, const double* x,
                              : nullptr;
     if (!sharded) {
       CUDA_TRY(cudaMemcpyAsync(d_xk, xk, Ck * pitch, cudaMemcpyHostToDevice,
-                               sk));
+                               s_in));
     } else {
       if (w_b)
         CUDA_TRY(cudaMemcpy2DAsync(d_xk + off_b, pitch, xk + off_b, pitch,
-                                   w_b, Ck, cudaMemcpyHostToDevice, sk));
+                                   w_b, Ck, cudaMemcpyHostToDevice, s_in));
       if (w_t)
         CUDA_TRY(cudaMemcpy2DAsync(d_xk + n_bottom, pitch, xk + n_bottom,
                                    pitch, w_t, Ck, cudaMemcpyHostToDevice,
-                                   sk));
-      // top-level entries that belong to individuals of other shards
-      // (heterogeneous dimensions) read as zero
-      if (with_grad && w_t)
-        CUDA_TRY(cudaMemset2DAsync(d_gk + n_bottom, pitch, 0, w_t, Ck, sk));
+                                   s_in));
     }
+    if (timeline) CUDA_TRY(cudaEventRecord(tl[k * 4 + 1], s_in));
+    if (piped) {
+      CUDA_TRY(cudaEventRecord(p->ev_in[k], s_in));
+      CUDA_TRY(cudaStreamWaitEvent(sk, p->ev_in[k], 0));
+    }
+    // top-level entries that belong to individuals of other shards
+    // (heterogeneous dimensions) read as zero
+    if (sharded && with_grad && w_t)
+      CUDA_TRY(cudaMemset2DAsync(d_gk + n_bottom, pitch, 0, w_t, Ck, sk));
     int rc = run_hier(
         p, Ck, d_xk, with_grad, p->hscore.as<double>() + c0, d_gk,
         p->hstatus.as<int32_t>() + c0, false, nullptr, nullptr, nullptr, sk,
@@ -2068,31 +2122,54 @@ int chi_b200_hier_logpdf(chi_b200_problem* p, int32_t C, const double* x,
         n_chunks > 1 ? p->work_counters.as<unsigned long long>() + k
                      : nullptr);
     if (rc) return rc;
+    if (timeline) CUDA_TRY(cudaEventRecord(tl[k * 4 + 2], sk));
+    if (piped) {
+      CUDA_TRY(cudaEventRecord(p->ev_comp[k], sk));
+      CUDA_TRY(cudaStreamWaitEvent(s_out, p->ev_comp[k], 0));
+    }
     CUDA_TRY(cudaMemcpyAsync(score + c0, p->hscore.as<double>() + c0,
                              Ck * sizeof(double), cudaMemcpyDeviceToHost,
-                             sk));
+                             s_out));
     if (with_grad && grad) {
       double* gk = grad + static_cast<int64_t>(c0) * n_params;
       if (!sharded) {
         CUDA_TRY(cudaMemcpyAsync(gk, d_gk, Ck * pitch, cudaMemcpyDeviceToHost,
-                                 sk));
+                                 s_out));
       } else {
         if (w_b)
           CUDA_TRY(cudaMemcpy2DAsync(gk + off_b, pitch, d_gk + off_b, pitch,
-                                     w_b, Ck, cudaMemcpyDeviceToHost, sk));
+                                     w_b, Ck, cudaMemcpyDeviceToHost, s_out));
         if (w_t)
           CUDA_TRY(cudaMemcpy2DAsync(gk + n_bottom, pitch, d_gk + n_bottom,
                                      pitch, w_t, Ck, cudaMemcpyDeviceToHost,
-                                     sk));
+                                     s_out));
       }
     }
     if (status)
       CUDA_TRY(cudaMemcpyAsync(status + c0, p->hstatus.as<int32_t>() + c0,
                                Ck * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                               sk));
+                               s_out));
+    if (timeline) CUDA_TRY(cudaEventRecord(tl[k * 4 + 3], s_out));
   }
   CUDA_TRY(cudaStreamSynchronize(s));
-  if (n_chunks > 1) CUDA_TRY(cudaStreamSynchronize(p->stream2));
+  if (piped) {
+    CUDA_TRY(cudaStreamSynchronize(p->stream2));
+    CUDA_TRY(cudaStreamSynchronize(p->stream_out));
+    CUDA_TRY(cudaStreamSynchronize(p->stream_in));
+  }
+  if (timeline) {
+    for (int k = 0; k < n_chunks; ++k) {
+      float t[4] = {0, 0, 0, 0};
+      for (int j = 0; j < 4; ++j)
+        cudaEventElapsedTime(&t[j], tl.back(), tl[k * 4 + j]);
+      std::fprintf(stderr,
+                   "chunk %2d [%4d, %4d): start %7.3f  h2d done %7.3f  "
+                   "kernels done %7.3f  d2h done %7.3f ms\n",
+                   k, chunk_begin(k), chunk_begin(k + 1), t[0], t[1], t[2],
+                   t[3]);
+    }
+    for (auto& e : tl) cudaEventDestroy(e);
+  }
   // the step counters (counters[1], [2]) are aggregated on demand
   // (chi_b200_problem_counters), not on the evaluation path
   p->counters_stale = p->nst.ptr != nullptr;

@@ -698,8 +698,13 @@ struct Registrar {
       return false;
     // warp-per-system launches (SolveArgs::split) always run on it
     if (args.split > 0) return true;
+    // (at most an eighth of the lanes padding when the number of vectors is
+    // not a multiple of 32)
+    const int64_t padded = (static_cast<int64_t>(args.order_inner) + 31) /
+                           32 * 32;
     return enabled && args.refill_wait == INT32_MAX &&
-           args.order_inner >= 32 && args.order_inner % 32 == 0 &&
+           args.order_inner >= 32 &&
+           (padded - args.order_inner) * 8 <= args.order_inner &&
            static_cast<int64_t>(args.order_inner) * args.order_stride ==
                args.B;
   }
@@ -737,7 +742,11 @@ struct Registrar {
     if constexpr (stream_is_rosl(CB) && M::LINEAR) {
       if (uniform) {
         // (warp-per-system launches: one warp per system)
-        const int64_t threads = args.split > 0 ? args.B * 32 : args.B;
+        const int64_t threads =
+            args.split > 0
+                ? args.B * 32
+                : (static_cast<int64_t>(args.order_inner) + 31) / 32 * 32 *
+                      args.order_stride;
         int64_t blocks = (threads + WARP_BLOCK - 1) / WARP_BLOCK;
         if (blocks > res) blocks = res;
         solve_warp_kernel<M, CB>

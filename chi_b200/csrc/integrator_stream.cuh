@@ -2052,9 +2052,10 @@ solve_stream_kernel(const SolveArgs a, unsigned long long* counter) {
 }
 
 // Warp-synchronous form (StreamSolver::solve_uniform) for launches in which
-// the 32 work items of a warp are one individual under 32 parameter vectors:
-// order_inner a multiple of 32 and B = order_inner x order_stride (the host
-// checks, Registrar::launch_stream).  The warps of this kernel never talk to
+// a warp can be given one individual under (up to) 32 parameter vectors:
+// B = order_inner x order_stride with at least 32 vectors, of which at most
+// an eighth of the lanes end up as padding (the host checks,
+// Registrar::launch_stream).  The warps of this kernel never talk to
 // each other, so the block is as small as the register file's allocation
 // granularity asks for: WARP_BLOCK threads, WARP_MIN_BLOCKS resident blocks
 // per SM (the register cap is 65536 / (WARP_BLOCK x WARP_MIN_BLOCKS), rounded
@@ -2100,12 +2101,29 @@ solve_warp_kernel(const SolveArgs a, unsigned long long* counter) {
     }
     return;
   }
-  for (;;) {
-    unsigned long long base = 0;
-    if ((threadIdx.x & 31) == 0) base = atomicAdd(counter, 32ull);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= total) break;
-    s.solve_uniform(stream_system_of(a, base + (threadIdx.x & 31)));
+  // batched launch, systems laid out vector-major (b = vector x n + individual,
+  // order_inner vectors x order_stride individuals): a warp takes 32
+  // consecutive vectors of ONE individual; when the number of vectors is not a
+  // multiple of 32 the last warp of an individual is padded with ghosts
+  {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long wpi =
+        (static_cast<unsigned long long>(a.order_inner) + 31ull) / 32ull;
+    const unsigned long long n_warps =
+        static_cast<unsigned long long>(a.order_stride) * wpi;
+    for (;;) {
+      unsigned long long w = 0;
+      if (lane == 0) w = atomicAdd(counter, 1ull);
+      w = __shfl_sync(0xffffffffu, w, 0);
+      if (w >= n_warps) break;
+      const unsigned long long q = w / wpi;
+      const unsigned long long r0 = (w - q * wpi) * 32ull;
+      const bool ghost = r0 + lane >= static_cast<unsigned>(a.order_inner);
+      const unsigned long long r = ghost ? r0 : r0 + lane;
+      s.solve_uniform(
+          static_cast<int64_t>(r * static_cast<unsigned>(a.order_stride) + q),
+          ghost);
+    }
   }
 }
 
