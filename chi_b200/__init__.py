@@ -38,6 +38,8 @@ from chi_b200._inference import (  # noqa: F401
     BatchedSamplingController, HaarioBardenetACMC, HamiltonianMCMC)
 from chi_b200._problems import (  # noqa: F401
     hierarchical_log_likelihood_from_dataframe)
+from chi_b200._distributed import (  # noqa: F401
+    ShardedHierarchicalLogPosterior)
 from chi_b200 import library  # noqa: F401
 from chi_b200._lib import set_default_device  # noqa: F401
 

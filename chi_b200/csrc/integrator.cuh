@@ -718,6 +718,7 @@ struct Registrar {
         sizeof(double) * stream_slots<M, CB>() * STREAM_BLOCK;
     static int resident[16] = {};
     static int resident_warp[16] = {};
+    static int resident_split[16] = {};
     if (!args.work_counter) return cudaErrorInvalidValue;
     bool uniform = false;
     if constexpr (stream_is_rosl(CB) && M::LINEAR)
@@ -727,9 +728,12 @@ struct Registrar {
     constexpr size_t smem_warp =
         sizeof(double) * stream_slots<M, CB, false>() * WARP_BLOCK;
     if constexpr (stream_is_rosl(CB) && M::LINEAR) {
-      if (uniform)
-        err = resident_blocks(solve_warp_kernel<M, CB>, WARP_BLOCK, smem_warp,
-                              resident_warp, &res);
+      if (uniform && args.split > 0)
+        err = resident_blocks(solve_warp_kernel<M, CB, 2>, WARP_BLOCK,
+                              smem_warp, resident_split, &res);
+      else if (uniform)
+        err = resident_blocks(solve_warp_kernel<M, CB, 1>, WARP_BLOCK,
+                              smem_warp, resident_warp, &res);
     }
     if (!uniform)
       err = resident_blocks(solve_stream_kernel<M, CB, STREAM_BLOCK>,
@@ -749,13 +753,18 @@ struct Registrar {
                       args.order_stride;
         int64_t blocks = (threads + WARP_BLOCK - 1) / WARP_BLOCK;
         if (blocks > res) blocks = res;
-        solve_warp_kernel<M, CB>
-            <<<static_cast<unsigned>(blocks), WARP_BLOCK, smem_warp,
-               stream>>>(args, counter);
+        if (args.split > 0)
+          solve_warp_kernel<M, CB, 2>
+              <<<static_cast<unsigned>(blocks), WARP_BLOCK, smem_warp,
+                 stream>>>(args, counter);
+        else
+          solve_warp_kernel<M, CB, 1>
+              <<<static_cast<unsigned>(blocks), WARP_BLOCK, smem_warp,
+                 stream>>>(args, counter);
       }
     }
     if (!uniform) {
-      const int64_t items = args.B * (args.split > 0 ? args.split : 1);
+      const int64_t items = args.B;
       int64_t blocks = (items + STREAM_BLOCK - 1) / STREAM_BLOCK;
       if (blocks > res) blocks = res;
       solve_stream_kernel<M, CB, STREAM_BLOCK>
@@ -851,20 +860,20 @@ struct Registrar {
       constexpr size_t smem =
           sizeof(double) * stream_slots<M, MC, false>() * WARP_BLOCK;
       cudaError_t err =
-          cudaFuncGetAttributes(&at, solve_warp_kernel<M, MC>);
+          cudaFuncGetAttributes(&at, solve_warp_kernel<M, MC, 1>);
       if (err != cudaSuccess) return err;
       *regs = at.numRegs;
       *block = WARP_BLOCK;
       *local_bytes = static_cast<int>(at.localSizeBytes);
       if (smem > 48 * 1024) {
         err = cudaFuncSetAttribute(
-            solve_warp_kernel<M, MC>,
+            solve_warp_kernel<M, MC, 1>,
             cudaFuncAttributeMaxDynamicSharedMemorySize,
             static_cast<int>(smem));
         if (err != cudaSuccess) return err;
       }
       return cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          bpsm, solve_warp_kernel<M, MC>, WARP_BLOCK, smem);
+          bpsm, solve_warp_kernel<M, MC, 1>, WARP_BLOCK, smem);
     } else if constexpr (G == 0) {
       constexpr size_t smem =
           sizeof(double) * stream_slots<M, MC>() * STREAM_BLOCK;

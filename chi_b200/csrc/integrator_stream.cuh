@@ -539,9 +539,15 @@ CHI_HD ErrTerms error_terms(const int kind, const double* sg, const double yb,
 // handling and the (expensive) step (solve_stream_kernel below).
 // METHOD_CODE: 1 = RODAS4 (6 stages, order 4(3)), 5 = RODAS5 (8 stages,
 // order 5(4)).
-template <class M, int METHOD_CODE,
-          bool WITH_BUF = stream_is_rosl(METHOD_CODE)>
+// FORM: 0 = general event loop (per-lane event cursor, one-record buffer for
+// the ROSL methods), 1 = warp-synchronous batched form (solve_uniform), 2 =
+// warp-per-system form of small launches (solve_uniform over the split work
+// items of one system, SolveArgs::split).  Only FORM 2 carries the code of
+// split work items.
+template <class M, int METHOD_CODE, int FORM = 0>
 struct StreamSolver {
+  static constexpr bool WITH_BUF = FORM == 0;
+  static constexpr bool SPLIT = FORM == 2;
   static constexpr bool R5 = METHOD_CODE == 5;
   // ROSL(9), ROSL(11): the linear-model methods (namespace rosl)
   static constexpr bool ROSL = METHOD_CODE == 9 || METHOD_CODE == 11;
@@ -568,8 +574,9 @@ struct StreamSolver {
   int flags;        // bits 0-7 status, 8-27 rejected steps, 28-29 edge kind,
                     // 30 all columns integrated (ROSL)
   bool is_ghost = false;   // see solve_uniform
-  int col0;         // split launches: the one integrated column of this
+  int col0_;        // split launches: the one integrated column of this
                     // work item (index into the integrated list), else -1
+  CHI_HD int col() const { return SPLIT ? col0_ : -1; }
   int pend;         // record held in the buffer, -1: none
   bool invalid, after_reject;
   bool buffering;   // records go through the buffer (see events())
@@ -685,21 +692,21 @@ struct StreamSolver {
 
   CHI_HD int n_cols() const { return a.with_sens ? a.n_cols : 0; }
   CHI_HD int n_int() const {
-    return a.with_sens ? (col0 >= 0 ? 1 : a.n_int) : 0;
+    return a.with_sens ? (col() >= 0 ? 1 : a.n_int) : 0;
   }
   // m-th integrated column of this work item: mechanistic parameter / column
   CHI_HD int ip(const int m) const {
-    return a.int_param[(col0 >= 0 ? col0 : 0) + m];
+    return a.int_param[(col() >= 0 ? col() : 0) + m];
   }
   CHI_HD int ic(const int m) const {
-    return a.int_col[(col0 >= 0 ? col0 : 0) + m];
+    return a.int_col[(col() >= 0 ? col() : 0) + m];
   }
   // does this work item write gradient column k?  (split launches: the item
   // of the column; item 0 also owns the columns that are not integrated)
   CHI_HD bool owns(const int k) const {
-    if (col0 < 0) return true;
+    if (col() < 0) return true;
     if (k == ic(0)) return true;
-    return col0 == 0 && inert(a.col_param[k]);
+    return col() == 0 && inert(a.col_param[k]);
   }
   CHI_HD bool loglik() const { return a.mode == 1; }
   CHI_HD bool deferred() const { return a.mode == 1 && a.snap != nullptr; }
@@ -716,10 +723,10 @@ struct StreamSolver {
     static_assert(METHOD_CODE == 1 || METHOD_CODE == 5 || ROSL,
                   "unknown method");
     int64_t b = item;
-    col0 = -1;
-    if (a.split > 0) {
+    col0_ = -1;
+    if (SPLIT && a.split > 0) {
       b = item / a.split;
-      col0 = static_cast<int>(item - b * a.split);
+      col0_ = static_cast<int>(item - b * a.split);
     }
     static_assert(P <= MAX_COLS, "too many mechanistic parameters");
     const int id = individual(b);
@@ -765,7 +772,7 @@ struct StreamSolver {
         if (sg[off] <= 0.0) invalid = true;
         if (a.err_kind[o] == ERR_CAM && sg[off + 1] <= 0.0) invalid = true;
       }
-      if (want_dsig() && !deferred() && col0 <= 0 && !is_ghost) {
+      if (want_dsig() && !deferred() && col() <= 0 && !is_ghost) {
         // the error-model gradients accumulate in the output row itself
         double* gb = a.grad + b * a.grad_stride + P;
         for (int k = 0; k < a.n_sigma; ++k) gb[k] = 0.0;
@@ -843,12 +850,12 @@ struct StreamSolver {
     double* row = a.snap + pos;
     // (split launches: the items of a system share its rows -- item 0 stores
     // the state, every item its own column)
-    if (col0 <= 0) {
+    if (col() <= 0) {
 #pragma unroll
       for (int n = 0; n < N; ++n) row[n] = CHI_Y(n);
     }
     const int ni = n_int();
-    const int m0 = col0 > 0 ? col0 : 0;
+    const int m0 = col() > 0 ? col() : 0;
 #pragma unroll
     for (int m = 0; m < PI; ++m) {
       if (m < ni) {
@@ -902,7 +909,7 @@ struct StreamSolver {
       if (e.invalid) invalid = true;
       CHI_COLD(3) += e.ll;
       add_log_scale(e.scale);
-      if (want_dsig() && col0 <= 0) {
+      if (want_dsig() && col() <= 0) {
         double* dsig = a.grad + b * a.grad_stride + P + off;
         dsig[0] += e.ds0;
         if (a.err_kind[o] == ERR_CAM) dsig[1] += e.ds1;
@@ -1159,7 +1166,9 @@ struct StreamSolver {
     if constexpr (ROSL) {
       if constexpr (M::LINEAR) {
         if (n_int() == 0) return step_rosl<0>();
-        if (col0 >= 0) return step_rosl<3>();
+        if constexpr (SPLIT) {
+          if (col() >= 0) return step_rosl<3>();
+        }
 #ifdef CHI_ROSL_NO_SUBSET
         return step_rosl<1>();   // (register-pressure experiment only)
 #else
@@ -1798,7 +1807,7 @@ struct StreamSolver {
   CHI_HD void finish() {
     const int64_t b = system();
     const int n_rej = (flags >> 8) & 0xfffff;
-    if (col0 >= 0) {
+    if (col() >= 0) {
       // split launch: the status of a system is the maximum over its items
       // (zeroed by the launcher)
 #ifdef __CUDA_ARCH__
@@ -1809,21 +1818,21 @@ struct StreamSolver {
     } else {
       a.status[b] = status();
     }
-    if (col0 <= 0) {
+    if (col() <= 0) {
       if (a.n_steps) a.n_steps[b] = n_att - n_rej;
       if (a.n_rej) a.n_rej[b] = n_rej;
     }
     if (deferred()) return;   // observe_system() writes ll and the gradient
     if (loglik()) {
       const bool fail = invalid || status() != ST_OK;
-      if (col0 <= 0)
+      if (col() <= 0)
         a.ll[b] = fail ? -INFINITY : CHI_COLD(3) - log(CHI_COLD(4));
       if (a.with_sens && a.grad) {
         const int nc = n_cols();
         double* gb = a.grad + b * a.grad_stride;
         for (int k = 0; k < nc; ++k)
           if (owns(k)) gb[a.col_param[k]] = fail ? INFINITY : CHI_G(k);
-        if (fail && col0 <= 0)
+        if (fail && col() <= 0)
           for (int k = 0; k < a.n_sigma; ++k) gb[P + k] = INFINITY;
       }
     } else if (status() != ST_OK) {
@@ -1847,8 +1856,13 @@ struct StreamSolver {
 template <class M, int CB>
 CHI_HD void solve_system_uniform(const SolveArgs& a, const int64_t b,
                                  double* sm, const int stride) {
-  StreamSolver<M, CB> s(a, sm, stride);
-  s.solve_uniform(b);
+  if (a.split > 0) {
+    StreamSolver<M, CB, 2> s(a, sm, stride);
+    s.solve_uniform(b);
+  } else {
+    StreamSolver<M, CB, 1> s(a, sm, stride);
+    s.solve_uniform(b);
+  }
 }
 
 template <class M, int CB>
@@ -1992,9 +2006,7 @@ solve_stream_kernel(const SolveArgs a, unsigned long long* counter) {
   bool active = false;
   bool exhausted = false;
   int waited = 0;
-  // work items: systems, or (system, column) pairs of a split launch
-  const unsigned long long total =
-      static_cast<unsigned long long>(a.B) * (a.split > 0 ? a.split : 1);
+  const unsigned long long total = static_cast<unsigned long long>(a.B);
   for (;;) {
     // Refill.  A warp whose lanes are all done takes 32 consecutive work
     // items at once; a single idle lane waits up to `refill_wait` iterations
@@ -2076,20 +2088,20 @@ constexpr int WARP_MIN_BLOCKS = CHI_WARP_MIN_BLOCKS;
 #define CHI_WARP_BOUNDS __launch_bounds__(WARP_BLOCK, WARP_MIN_BLOCKS)
 #endif
 
-template <class M, int CB>
+// FORM 1: batched launch; FORM 2: warp-per-system launch (small batches)
+template <class M, int CB, int FORM>
 __global__ void CHI_WARP_BOUNDS
 solve_warp_kernel(const SolveArgs a, unsigned long long* counter) {
   extern __shared__ double chi_sm[];
-  StreamSolver<M, CB, false> s(a, chi_sm + threadIdx.x, WARP_BLOCK);
-  const unsigned long long total = static_cast<unsigned long long>(a.B);
-  if (a.split > 0) {
-    // warp-per-system launch (small batches): the warp takes the `split`
-    // work items of ONE system -- its sensitivity columns side by side on
-    // the first lanes, each with the state -- and walks through the system's
-    // stops like a warp of the batched launch does; the other lanes are
-    // ghosts
-    const unsigned long long items = total * a.split;
-    const unsigned lane = threadIdx.x & 31;
+  StreamSolver<M, CB, FORM> s(a, chi_sm + threadIdx.x, WARP_BLOCK);
+  const unsigned lane = threadIdx.x & 31;
+  if constexpr (FORM == 2) {
+    // the warp takes the `split` work items of ONE system -- its sensitivity
+    // columns side by side on the first lanes, each with the state -- and
+    // walks through the system's stops like a warp of the batched launch
+    // does; the other lanes are ghosts
+    const unsigned long long items =
+        static_cast<unsigned long long>(a.B) * a.split;
     for (;;) {
       unsigned long long base = 0;
       if (lane == 0)
@@ -2099,14 +2111,12 @@ solve_warp_kernel(const SolveArgs a, unsigned long long* counter) {
       const bool ghost = lane >= static_cast<unsigned>(a.split);
       s.solve_uniform(static_cast<int64_t>(base + (ghost ? 0 : lane)), ghost);
     }
-    return;
-  }
-  // batched launch, systems laid out vector-major (b = vector x n + individual,
-  // order_inner vectors x order_stride individuals): a warp takes 32
-  // consecutive vectors of ONE individual; when the number of vectors is not a
-  // multiple of 32 the last warp of an individual is padded with ghosts
-  {
-    const unsigned lane = threadIdx.x & 31;
+  } else {
+    // systems laid out vector-major (b = vector x n + individual,
+    // order_inner vectors x order_stride individuals): a warp takes 32
+    // consecutive vectors of ONE individual; when the number of vectors is
+    // not a multiple of 32 the last warp of an individual is padded with
+    // ghosts
     const unsigned long long wpi =
         (static_cast<unsigned long long>(a.order_inner) + 31ull) / 32ull;
     const unsigned long long n_warps =

@@ -1,0 +1,17 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r2w_pytest.log 2>&1
+tail -3 gpurun_out/r2w_pytest.log
+for cfg in c5 c2_1000 c4; do
+timeout 600 python bench.py --config $cfg --no-extras --no-cpu-baseline > gpurun_out/r2w_$cfg.json 2> gpurun_out/r2w_$cfg.err
+python - <<P
+import json
+try:
+    d=json.load(open('gpurun_out/r2w_$cfg.json')); r=d['roofline']
+    print('$cfg value %.0f e2e %.0f (%.2f ms) frac %.3f kernel_ms %.3f'%(d['value'],d['e2e']['value'],d['e2e']['ms_per_step'],r['frac'],r['kernel_ms']))
+except Exception as e: print('$cfg ERR', e)
+P
+done
+timeout 300 python tools/latency_breakdown.py 2>&1 | head -8
+timeout 300 python tools/c3_profile.py > gpurun_out/r2w_c3_profile.log 2>&1; head -45 gpurun_out/r2w_c3_profile.log
