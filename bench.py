@@ -670,6 +670,12 @@ class Context(object):
         self.dev = torch.device('cuda', local_rank)
         import chi_b200
         chi_b200.set_default_device(local_rank)
+        # several ranks on one host: keep each rank's page-locked buffers in
+        # the memory of its GPU's NUMA node
+        self.numa_node = None
+        if world > 1:
+            from chi_b200 import _lib
+            self.numa_node = _lib.bind_to_device_numa_node(local_rank)
         self.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32,
                                  device=self.dev)
         self.stream = torch.cuda.current_stream(self.dev)
@@ -1287,6 +1293,9 @@ def run_product(args, rank, world, local_rank):
                 'config': {'workload': rec['workload']},
                 'roofline': rec.get('roofline')}
     if rank == 0 and line is not None:
+        if world > 1 and isinstance(line.get('config'), dict):
+            # NUMA node rank 0 was bound to (None: topology not exposed)
+            line['config']['host_numa_node_rank0'] = ctx.numa_node
         print(json.dumps(line))
     if ctx.dist is not None:
         ctx.dist.barrier()

@@ -417,23 +417,17 @@ class ModelCode(object):
         return '\n'.join(lines) + '\n'
 
     def variants(self):
-        """(lanes per system, sensitivity columns per lane) kernel variants,
-        most preferred first.  Every lane keeps the state column plus its
-        sensitivity columns and their six stage increments in registers, so
-        the columns per lane are capped by the state dimension."""
-        n, P = self.n, self.n + self.nc
-        mc_max = {1: 8, 2: 4, 3: 3}.get(n, 2)
-        # lanes == 0: streamed-columns kernel; `cols` is then the method
-        # code: 1 = RODAS4, 5 = RODAS5, 9 / 11 = ROSL(9) / ROSL(11), the
-        # Rosenbrock methods for linear models (integrator_stream.cuh)
-        out = [(0, 11), (0, 9), (0, 5), (0, 1)] if self.linear \
+        """(lanes per system, method code) kernel variants, most preferred
+        first.  lanes == 0: the streamed-columns kernels
+        (integrator_stream.cuh); the second entry is then the method: 1 =
+        RODAS4, 5 = RODAS5, 9 / 11 = ROSL(9) / ROSL(11), the Rosenbrock
+        methods for linear models.  (The lane-parallel RODAS4 kernels of
+        round 1 -- several lanes per system, columns split over them -- were
+        slower than the streamed kernels at every batch size and are no longer
+        built; small batches run the warp-per-system form of the ROSL
+        kernels.)"""
+        return [(0, 11), (0, 9), (0, 5), (0, 1)] if self.linear \
             else [(0, 5), (0, 1)]
-        for mc in range(min(mc_max, P), 0, -1):
-            g = -(-P // mc)
-            if g > 32 or any(g == v[0] for v in out):
-                continue
-            out.append((g, mc))
-        return out[:5]
 
     def translation_unit(self):
         """Text of the .cu file that instantiates the kernels for this

@@ -36,6 +36,38 @@ def set_default_device(device):
     _default_device = int(device)
 
 
+def bind_to_device_numa_node(device=None):
+    """Restricts this process to the CPUs of the NUMA node the GPU hangs off
+    (one process per GPU on a multi-socket host): page-locked buffers that are
+    allocated afterwards land in that node's memory (first touch), so the
+    copies of eight ranks do not all cross the socket interconnect.  Returns
+    the node, or None when the topology is not exposed (nothing changes
+    then)."""
+    device = default_device() if device is None else int(device)
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(device)
+        bus = '%04x:%02x:%02x.0' % (
+            props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open('/sys/bus/pci/devices/%s/numa_node' % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:   # no sysfs / no such attribute: leave things alone
+        return None
+
+
 def default_device():
     if _default_device is not None:
         return _default_device

@@ -472,9 +472,8 @@ def test_gpu_kernel_matches_cpu_port():
 
 
 def test_all_kernel_variants_agree_with_exact_solution():
-    """Every compiled sensitivity-kernel variant (streamed ROSL(11) / ROSL(9)
-    for linear models, streamed RODAS5 / RODAS4, lane-parallel RODAS4)
-    integrates to the same exact solution."""
+    """Every compiled sensitivity-kernel variant (ROSL(11) / ROSL(9) for
+    linear models, RODAS5 / RODAS4) integrates to the same exact solution."""
     model, omodel, psi, times = _build('two_cmt_direct_infusion')
     y_ref, s_ref = ode_exact.simulate(omodel, psi, times, _events(model))
     model.set_tolerance(**TIGHT)

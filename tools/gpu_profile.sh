@@ -6,6 +6,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
   --log-file gpurun_out/launches_${tag}.csv python bench.py $ARGS \
   > gpurun_out/ncu_launches_${tag}.log 2>&1
 ncu --set full --clock-control none --import-source on \
-  -k regex:"solve_stream|solve_warp|observe_kernel" -s 2 -c 1 -f -o gpurun_out/prof_${tag} \
+  -k regex:"solve_stream|solve_warp|observe_kernel" -s 2 -c 2 -f -o gpurun_out/prof_${tag} \
   python bench.py $ARGS > gpurun_out/ncu_full_${tag}.log 2>&1
 ls -la gpurun_out/prof_${tag}.ncu-rep gpurun_out/launches_${tag}.csv

@@ -96,7 +96,7 @@ the `at::` kernels are bench.py's own L2 flush and result checks.  Inside a step
 events); the population kernels are about 1 %% of a step.  Launch times under ncu are cold-cache and
 serialised: compare SHARES.
 
-## `ncu --set full --clock-control none --import-source on -k regex:"solve_stream|observe_kernel" -s 2 -c 1`
+## `ncu --set full --clock-control none --import-source on -k regex:"solve_stream|observe_kernel" -s 2 -c 2`
 
 %s
 Reading:
