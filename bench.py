@@ -66,7 +66,7 @@ HIER_CONFIGS = {
                     name='C2'),
     'c4': dict(n_ids=500, chains=1024, with_grad=False, error='lognormal',
                covariates=False, shard='chains', name='C4'),
-    'c5': dict(n_ids=100000, chains=16, with_grad=True, error='cam',
+    'c5': dict(n_ids=100000, chains=32, with_grad=True, error='cam',
                covariates=True, shard='individuals', name='C5'),
 }
 

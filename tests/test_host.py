@@ -925,3 +925,41 @@ def test_cpu_port_warp_synchronous_form_equals_the_general_form():
             assert a[0][5] == -np.inf and b[0][5] == -np.inf
             for u, v in zip(a, b):
                 np.testing.assert_array_equal(u, v)
+
+
+def test_cpu_port_split_work_items_agree_within_the_tolerance():
+    """Small launches give every (system, sensitivity column) pair a work
+    item of its own (SolveArgs::split, the warp-per-system form on the GPU):
+    the column is integrated with the state under its own step-size control.
+    Log-likelihoods and gradients agree with the all-columns solve far inside
+    the integrator's tolerance; item 0 writes the log-likelihood, the
+    error-model gradient and the entries of constants that are not
+    integrated; an invalid sigma gives -inf / inf from every item."""
+    key = cport.find_key('two_compartment_pk_model', 'central', True)
+    rng = np.random.default_rng(13)
+    n_ids = 10
+    times = [np.sort(rng.uniform(0.25, 24, 9)) for _ in range(n_ids)]
+    obs = [rng.uniform(0.2, 2.0, 9) for _ in range(n_ids)]
+    regs = [[(float(rng.uniform(5, 15)), 0.0, 1.0, 8.0, 3)]
+            for _ in range(n_ids)]
+    pop = cport.Population(
+        key, ['central.drug_concentration'], ['cam'], times, obs, None, regs)
+    X = np.column_stack([
+        np.abs(0.01 * rng.normal(size=(n_ids, 2))),
+        np.exp(np.log([2.0, 1.0, 5.0, 1.0, 10.0])
+               + 0.3 * rng.normal(size=(n_ids, 5))),
+        np.full(n_ids, 0.05), np.full(n_ids, 0.12)])
+    X[3, 7] = -1.0
+    ids = np.arange(n_ids, dtype=np.int32)
+    a = pop.loglik(X, ids=ids, stream_cb=11, deferred=False)
+    b = pop.loglik(X, ids=ids, stream_cb=111, split=True, deferred=False)
+    ok = np.isfinite(a[0])
+    assert not ok[3] and b[0][3] == -np.inf and np.all(np.isinf(b[1][3]))
+    assert not np.any(a[2]) and not np.any(b[2])
+    np.testing.assert_allclose(b[0][ok], a[0][ok], rtol=2e-9)
+    np.testing.assert_allclose(
+        b[1][ok], a[1][ok], rtol=1e-6, atol=1e-7 * np.max(np.abs(a[1][ok])))
+    # column of central.size (not integrated: output map only) and the sigmas
+    assert np.all(b[1][ok][:, 2] != 0.0)
+    assert np.all(b[1][ok][:, 6] == 0.0)       # peripheral.size: no effect
+    assert np.all(b[1][ok][:, 7:] != 0.0)
