@@ -1014,7 +1014,15 @@ def parity_vs_exact(prob, X, n_ids_sample=48, n_vectors=2, seed=0):
         sys_ids.append(ids)
     xs = np.concatenate(xs)
     sys_ids = np.concatenate(sys_ids).astype(np.int32)
+    # the arithmetic of the batched launches (all columns of a system in one
+    # thread: the thread-per-system kernels, bit-identical per system to
+    # solve_warp_kernel), and the warp-per-system form that a launch of this
+    # size would take by default
+    ll.set_small_batch(0)
     g_ll, g_grad, status = ll._device.loglik(xs, ids=sys_ids, with_grad=True)
+    ll.set_small_batch(-1)
+    assert not np.any(status)
+    w_ll, w_grad, status = ll._device.loglik(xs, ids=sys_ids, with_grad=True)
     assert not np.any(status)
     o_ll = np.empty(len(xs))
     o_grad = np.empty((len(xs), 8))
@@ -1034,6 +1042,11 @@ def parity_vs_exact(prob, X, n_ids_sample=48, n_vectors=2, seed=0):
         'grad_rel_err_vs_exact': float(
             np.max(np.abs(g_grad - o_grad)) / np.max(np.abs(o_grad))),
         'per_individual_ll_max_abs_err': float(np.max(np.abs(g_ll - o_ll))),
+        'warp_per_system_form': {
+            'score_rel_err_vs_exact': float(
+                abs(np.sum(w_ll) - np.sum(o_ll)) / abs(np.sum(o_ll))),
+            'grad_rel_err_vs_exact': float(
+                np.max(np.abs(w_grad - o_grad)) / np.max(np.abs(o_grad)))},
         'sample': '%d individuals x %d parameter vectors at rtol %g / atol '
                   '%g against oracle/ode_exact.py + oracle/stats.py' % (
                       len(ids), n_vectors, prob['model'].tolerance()[1],

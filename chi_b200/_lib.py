@@ -152,6 +152,10 @@ _SIGNATURES = {
         ctypes.c_int, [c_vp, ctypes.c_int64]),
     'chi_b200_problem_set_batching': (
         ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
+    'chi_b200_hier_logpdf_begin': (
+        ctypes.c_int, [c_vp, ctypes.c_int32, c_f64p, ctypes.c_int32, c_f64p,
+                       c_f64p, c_i32p]),
+    'chi_b200_problem_synchronize': (ctypes.c_int, [c_vp]),
     'chi_b200_problem_set_small_batch': (
         ctypes.c_int, [c_vp, ctypes.c_int64]),
     'chi_b200_problem_timings': (ctypes.c_int, [c_vp, c_f64p]),

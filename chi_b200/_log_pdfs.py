@@ -658,6 +658,13 @@ class HierarchicalLogLikelihood(
                 grad[...] = 0.0
             cache = (C, score, status, grad)
             self._pinned = cache
+            # ctypes pointers of the buffers (creating them costs more than a
+            # microsecond each: the single-vector path counts those)
+            self._pinned_ptrs = (
+                score.ctypes.data_as(_lib.c_f64p),
+                status.ctypes.data_as(_lib.c_i32p),
+                grad.ctypes.data_as(_lib.c_f64p) if grad is not None
+                else None)
         _, score, status, grad = cache
         return score[:C], status[:C], (grad[:C] if grad is not None else None)
 
@@ -668,14 +675,38 @@ class HierarchicalLogLikelihood(
         lib = _lib.lib()
         a_x, p_x = _lib.f64(X)
         score, status, grad = self._host_buffers(C, with_grad)
-        p_s = score.ctypes.data_as(_lib.c_f64p)
-        p_st = status.ctypes.data_as(_lib.c_i32p)
-        p_g = grad.ctypes.data_as(_lib.c_f64p) if with_grad else None
+        p_s, p_st, p_g = self._pinned_ptrs
         _lib.check(lib.chi_b200_hier_logpdf(
             self._device.problem.handle, C, p_x, 1 if with_grad else 0, p_s,
             p_g if with_grad else None, p_st))
-        if np.any(status != 0):
+        if status.any():
             _failure_warning(status[status != 0][0])
+            score[status != 0] = -np.inf
+        return score, grad, status
+
+    def _begin(self, X, with_grad):
+        """Queues the evaluation of the rows of ``X`` and returns without
+        waiting (``chi_b200_hier_logpdf_begin``); :meth:`_end` waits and
+        returns what :meth:`_evaluate` returns.  The caller's host work in
+        between -- the log-prior -- overlaps the GPU."""
+        X = np.ascontiguousarray(X, dtype=float).reshape(
+            -1, self._n_parameters)
+        C = X.shape[0]
+        a_x, p_x = _lib.f64(X)
+        score, status, grad = self._host_buffers(C, with_grad)
+        p_s, p_st, p_g = self._pinned_ptrs
+        _lib.check(_lib.lib().chi_b200_hier_logpdf_begin(
+            self._device.problem.handle, C, p_x, 1 if with_grad else 0, p_s,
+            p_g if with_grad else None, p_st))
+        return a_x, score, status, grad
+
+    def _end(self, pending, warn=True):
+        _, score, status, grad = pending
+        _lib.check(_lib.lib().chi_b200_problem_synchronize(
+            self._device.problem.handle))
+        if status.any():
+            if warn:
+                _failure_warning(status[status != 0][0])
             score[status != 0] = -np.inf
         return score, grad, status
 
@@ -888,18 +919,54 @@ class HierarchicalLogPosterior(
     def __call__(self, parameters):
         """chi/_log_pdfs.py:463-472."""
         parameters = np.asarray(parameters)
-        score = self._log_prior(parameters[self._n_bottom:])
+        begin = getattr(self._log_likelihood, '_begin', None)
+        if begin is None:
+            score = self._log_prior(parameters[self._n_bottom:])
+            if np.isinf(score):
+                return score
+            return score + self._log_likelihood(parameters)
+        # likelihood queued first, prior on the host meanwhile (evaluateS1)
+        pending = begin(parameters, False)
+        try:
+            score = self._log_prior(parameters[self._n_bottom:])
+        finally:
+            ll_s, _, _ = self._log_likelihood._end(pending, warn=False)
         if np.isinf(score):
             return score
-        return score + self._log_likelihood(parameters)
+        if not np.isfinite(ll_s[0]) and pending[2].any():
+            _failure_warning(pending[2][pending[2] != 0][0])
+        return score + float(ll_s[0])
 
     def evaluateS1(self, parameters):
         """chi/_log_pdfs.py:474-498."""
         parameters = np.asarray(parameters)
-        score, sens = self._log_prior.evaluateS1(parameters[self._n_bottom:])
-        if np.isinf(score):
-            return score, np.full(shape=len(parameters), fill_value=np.inf)
-        ll_score, sensitivities = self._log_likelihood.evaluateS1(parameters)
+        begin = getattr(self._log_likelihood, '_begin', None)
+        if begin is None:
+            score, sens = self._log_prior.evaluateS1(
+                parameters[self._n_bottom:])
+            if np.isinf(score):
+                return score, np.full(
+                    shape=len(parameters), fill_value=np.inf)
+            ll_score, sensitivities = self._log_likelihood.evaluateS1(
+                parameters)
+        else:
+            # the likelihood is queued on the GPU first, the (host) prior is
+            # evaluated while it runs; a vector outside the prior's support
+            # returns as in the reference (which does not evaluate the
+            # likelihood then)
+            pending = begin(parameters, True)
+            try:
+                score, sens = self._log_prior.evaluateS1(
+                    parameters[self._n_bottom:])
+            finally:
+                ll_s, ll_g, _ = self._log_likelihood._end(
+                    pending, warn=False)
+            if np.isinf(score):
+                return score, np.full(
+                    shape=len(parameters), fill_value=np.inf)
+            if not np.isfinite(ll_s[0]) and pending[2].any():
+                _failure_warning(pending[2][pending[2] != 0][0])
+            ll_score, sensitivities = float(ll_s[0]), ll_g[0].copy()
         score += ll_score
         sensitivities[self._n_bottom:] += sens
         return score, sensitivities

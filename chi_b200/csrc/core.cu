@@ -1977,9 +1977,9 @@ int chi_b200_hier_logpdf_dev(chi_b200_problem* p, int32_t C,
                   static_cast<cudaStream_t>(stream));
 }
 
-int chi_b200_hier_logpdf(chi_b200_problem* p, int32_t C, const double* x,
-                         int32_t with_grad, double* score, double* grad,
-                         int32_t* status) {
+static int hier_logpdf_host(chi_b200_problem* p, int32_t C, const double* x,
+                            int32_t with_grad, double* score, double* grad,
+                            int32_t* status, const bool wait) {
   if (!p->has_pop) return fail(-1, "no population model set");
   if (!p->vt) return fail(-1, "problem has no mechanistic model");
   if (C <= 0) return 0;
@@ -2151,6 +2151,8 @@ int chi_b200_hier_logpdf(chi_b200_problem* p, int32_t C, const double* x,
                                s_out));
     if (timeline) CUDA_TRY(cudaEventRecord(tl[k * 4 + 3], s_out));
   }
+  p->counters_stale = p->nst.ptr != nullptr;
+  if (!wait && !timeline) return 0;   // chi_b200_problem_synchronize
   CUDA_TRY(cudaStreamSynchronize(s));
   if (piped) {
     CUDA_TRY(cudaStreamSynchronize(p->stream2));
@@ -2172,7 +2174,27 @@ int chi_b200_hier_logpdf(chi_b200_problem* p, int32_t C, const double* x,
   }
   // the step counters (counters[1], [2]) are aggregated on demand
   // (chi_b200_problem_counters), not on the evaluation path
-  p->counters_stale = p->nst.ptr != nullptr;
+  return 0;
+}
+
+int chi_b200_hier_logpdf(chi_b200_problem* p, int32_t C, const double* x,
+                         int32_t with_grad, double* score, double* grad,
+                         int32_t* status) {
+  return hier_logpdf_host(p, C, x, with_grad, score, grad, status, true);
+}
+
+int chi_b200_hier_logpdf_begin(chi_b200_problem* p, int32_t C, const double* x,
+                               int32_t with_grad, double* score, double* grad,
+                               int32_t* status) {
+  return hier_logpdf_host(p, C, x, with_grad, score, grad, status, false);
+}
+
+int chi_b200_problem_synchronize(chi_b200_problem* p) {
+  CUDA_TRY(cudaSetDevice(p->device));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  if (p->stream2) CUDA_TRY(cudaStreamSynchronize(p->stream2));
+  if (p->stream_out) CUDA_TRY(cudaStreamSynchronize(p->stream_out));
+  if (p->stream_in) CUDA_TRY(cudaStreamSynchronize(p->stream_in));
   return 0;
 }
 

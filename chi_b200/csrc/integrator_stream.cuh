@@ -692,7 +692,7 @@ struct StreamSolver {
 
   CHI_HD int n_cols() const { return a.with_sens ? a.n_cols : 0; }
   CHI_HD int n_int() const {
-    return a.with_sens ? (col() >= 0 ? 1 : a.n_int) : 0;
+    return a.with_sens ? (col() >= 0 ? (a.n_int > 0 ? 1 : 0) : a.n_int) : 0;
   }
   // m-th integrated column of this work item: mechanistic parameter / column
   CHI_HD int ip(const int m) const {
@@ -705,7 +705,7 @@ struct StreamSolver {
   // of the column; item 0 also owns the columns that are not integrated)
   CHI_HD bool owns(const int k) const {
     if (col() < 0) return true;
-    if (k == ic(0)) return true;
+    if (a.n_int > 0 && k == ic(0)) return true;
     return col() == 0 && inert(a.col_param[k]);
   }
   CHI_HD bool loglik() const { return a.mode == 1; }

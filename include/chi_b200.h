@@ -227,6 +227,15 @@ int chi_b200_population_eval(chi_b200_problem* p, const double* top,
 int chi_b200_hier_logpdf(chi_b200_problem* p, int32_t C, const double* x,
                          int32_t with_grad, double* score, double* grad,
                          int32_t* status);
+/* The same without the final wait: everything is queued (copies included, the
+ * buffers have to be page-locked and must stay untouched) and the call
+ * returns; chi_b200_problem_synchronize waits for the results.  Lets the
+ * caller evaluate the (host-side) log-prior of chi.HierarchicalLogPosterior
+ * (chi/_log_pdfs.py:474-498) while the GPU works. */
+int chi_b200_hier_logpdf_begin(chi_b200_problem* p, int32_t C, const double* x,
+                               int32_t with_grad, double* score, double* grad,
+                               int32_t* status);
+int chi_b200_problem_synchronize(chi_b200_problem* p);
 int chi_b200_hier_logpdf_dev(chi_b200_problem* p, int32_t C,
                              const double* d_x, int32_t with_grad,
                              double* d_score, double* d_grad,
