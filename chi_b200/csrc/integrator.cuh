@@ -719,6 +719,7 @@ struct Registrar {
     static int resident[16] = {};
     static int resident_warp[16] = {};
     static int resident_split[16] = {};
+    static int resident_fwd[16] = {};
     if (!args.work_counter) return cudaErrorInvalidValue;
     bool uniform = false;
     if constexpr (stream_is_rosl(CB) && M::LINEAR)
@@ -727,10 +728,17 @@ struct Registrar {
     cudaError_t err;
     constexpr size_t smem_warp =
         sizeof(double) * stream_slots<M, CB, false>() * WARP_BLOCK;
+    constexpr size_t smem_fwd =
+        sizeof(double) * stream_slots<M, CB, false, true>() * WARP_BLOCK;
+    // batched forward-only launches have an instantiation of their own
+    const bool fwd = uniform && args.split == 0 && !args.with_sens;
     if constexpr (stream_is_rosl(CB) && M::LINEAR) {
       if (uniform && args.split > 0)
         err = resident_blocks(solve_warp_kernel<M, CB, 2>, WARP_BLOCK,
                               smem_warp, resident_split, &res);
+      else if (fwd)
+        err = resident_blocks(solve_warp_kernel<M, CB, 3>, WARP_BLOCK,
+                              smem_fwd, resident_fwd, &res);
       else if (uniform)
         err = resident_blocks(solve_warp_kernel<M, CB, 1>, WARP_BLOCK,
                               smem_warp, resident_warp, &res);
@@ -756,6 +764,10 @@ struct Registrar {
         if (args.split > 0)
           solve_warp_kernel<M, CB, 2>
               <<<static_cast<unsigned>(blocks), WARP_BLOCK, smem_warp,
+                 stream>>>(args, counter);
+        else if (fwd)
+          solve_warp_kernel<M, CB, 3>
+              <<<static_cast<unsigned>(blocks), WARP_BLOCK, smem_fwd,
                  stream>>>(args, counter);
         else
           solve_warp_kernel<M, CB, 1>

@@ -75,9 +75,11 @@ constexpr bool stream_is_rosl(const int method) {
 // StreamSolver::events), and the weights of its error norm (floats).
 // (WITH_BUF = false: the warp-synchronous kernel, which has no use for the
 // record buffer)
-template <class M, int METHOD, bool WITH_BUF = stream_is_rosl(METHOD)>
+// (FWD = true: forward-only instantiation, no sensitivity columns at all)
+template <class M, int METHOD, bool WITH_BUF = stream_is_rosl(METHOD),
+          bool FWD = false>
 constexpr int stream_slots() {
-  const int pi = stream_integrated<M>();
+  const int pi = FWD ? 0 : stream_integrated<M>();
   return (stream_is_rosl(METHOD)
               ? pi * M::N + (WITH_BUF ? (1 + pi) * M::N : 0) +
                     ((1 + pi) * M::N + 1) / 2
@@ -542,12 +544,17 @@ CHI_HD ErrTerms error_terms(const int kind, const double* sg, const double yb,
 // FORM: 0 = general event loop (per-lane event cursor, one-record buffer for
 // the ROSL methods), 1 = warp-synchronous batched form (solve_uniform), 2 =
 // warp-per-system form of small launches (solve_uniform over the split work
-// items of one system, SolveArgs::split).  Only FORM 2 carries the code of
-// split work items.
+// items of one system, SolveArgs::split), 3 = FORM 1 without sensitivity
+// columns.  Only FORM 2 carries the code of split work items.
 template <class M, int METHOD_CODE, int FORM = 0>
 struct StreamSolver {
   static constexpr bool WITH_BUF = FORM == 0;
   static constexpr bool SPLIT = FORM == 2;
+  // FORM 3: FORM 1 compiled for forward-only solves (no sensitivity columns
+  // at compile time: +10 ... 18 % on the forward-only bench step over the
+  // general instantiation with zero columns; more resident warps at 64 or 80
+  // registers do NOT help, 4 blocks per SM without a register cap is best)
+  static constexpr bool FWD = FORM == 3;
   static constexpr bool R5 = METHOD_CODE == 5;
   // ROSL(9), ROSL(11): the linear-model methods (namespace rosl)
   static constexpr bool ROSL = METHOD_CODE == 9 || METHOD_CODE == 11;
@@ -584,7 +591,7 @@ struct StreamSolver {
   CHI_HD StreamSolver(const SolveArgs& args, double* smem, int smem_stride)
       : a(args), sm(smem), stride(smem_stride) {}
 
-  static constexpr int PI = stream_integrated<M>();
+  static constexpr int PI = FWD ? 0 : stream_integrated<M>();
 // S is stored for the integrated columns only; `m` is the column's rank
 // among them (the loops over the columns carry it along)
   static constexpr int OFF_G = (ROSL ? 1 : 2) * PI * N;
@@ -598,7 +605,7 @@ struct StreamSolver {
   // error weights (ROSL): floats, two per slot
   static constexpr int OFF_WT = OFF_BUF + (BUFFERED ? (1 + PI) * N : 0);
   static_assert(OFF_WT + (ROSL ? ((1 + PI) * N + 1) / 2 : 0) ==
-                    stream_slots<M, METHOD_CODE, WITH_BUF>(),
+                    stream_slots<M, METHOD_CODE, WITH_BUF, FWD>(),
                 "slot layout");
 #define CHI_S(buf, m, n) sm[(((buf) * PI + (m)) * N + (n)) * stride]
 #define CHI_G(k) sm[(OFF_G + (k)) * stride]
@@ -690,8 +697,9 @@ struct StreamSolver {
   // bits 28-29 of `flags` (1 rate increase, 2 rate decrease)
   CHI_HD int edge_kind() const { return (flags >> 28) & 3; }
 
-  CHI_HD int n_cols() const { return a.with_sens ? a.n_cols : 0; }
+  CHI_HD int n_cols() const { return (!FWD && a.with_sens) ? a.n_cols : 0; }
   CHI_HD int n_int() const {
+    if (FWD) return 0;
     return a.with_sens ? (col() >= 0 ? (a.n_int > 0 ? 1 : 0) : a.n_int) : 0;
   }
   // m-th integrated column of this work item: mechanistic parameter / column
@@ -711,7 +719,7 @@ struct StreamSolver {
   CHI_HD bool loglik() const { return a.mode == 1; }
   CHI_HD bool deferred() const { return a.mode == 1 && a.snap != nullptr; }
   CHI_HD bool want_dsig() const {
-    return a.mode == 1 && a.with_sens && a.grad != nullptr;
+    return !FWD && a.mode == 1 && a.with_sens && a.grad != nullptr;
   }
   CHI_HD int status() const { return flags & 0xff; }
   CHI_HD int64_t system() const { return static_cast<int64_t>(CHI_COLD(0)); }
@@ -1164,7 +1172,9 @@ struct StreamSolver {
   // One step attempt towards the next stop.  Returns true on failure.
   CHI_HD bool step() {
     if constexpr (ROSL) {
-      if constexpr (M::LINEAR) {
+      if constexpr (M::LINEAR && FWD) {
+        return step_rosl<0>();
+      } else if constexpr (M::LINEAR) {
         if (n_int() == 0) return step_rosl<0>();
         if constexpr (SPLIT) {
           if (col() >= 0) return step_rosl<3>();
@@ -2081,16 +2091,18 @@ solve_stream_kernel(const SolveArgs a, unsigned long long* counter) {
 constexpr int WARP_BLOCK = CHI_WARP_BLOCK;
 constexpr int WARP_MIN_BLOCKS = CHI_WARP_MIN_BLOCKS;
 
-// (CHI_WARP_MAXNREG: the register cap given directly instead)
-#ifdef CHI_WARP_MAXNREG
-#define CHI_WARP_BOUNDS __maxnreg__(CHI_WARP_MAXNREG)
-#else
-#define CHI_WARP_BOUNDS __launch_bounds__(WARP_BLOCK, WARP_MIN_BLOCKS)
+// resident blocks the forward-only instantiation is compiled for
+#ifndef CHI_WARP_FWD_MIN_BLOCKS
+#define CHI_WARP_FWD_MIN_BLOCKS 4
 #endif
+constexpr int warp_min_blocks(const int form) {
+  return form == 3 ? CHI_WARP_FWD_MIN_BLOCKS : WARP_MIN_BLOCKS;
+}
 
-// FORM 1: batched launch; FORM 2: warp-per-system launch (small batches)
+// FORM 1: batched launch; FORM 2: warp-per-system launch (small batches);
+// FORM 3: batched forward-only launch
 template <class M, int CB, int FORM>
-__global__ void CHI_WARP_BOUNDS
+__global__ void __launch_bounds__(WARP_BLOCK, warp_min_blocks(FORM))
 solve_warp_kernel(const SolveArgs a, unsigned long long* counter) {
   extern __shared__ double chi_sm[];
   StreamSolver<M, CB, FORM> s(a, chi_sm + threadIdx.x, WARP_BLOCK);
