@@ -720,6 +720,7 @@ struct Registrar {
     static int resident_warp[16] = {};
     static int resident_split[16] = {};
     static int resident_fwd[16] = {};
+    static int resident_sub[16] = {};
     if (!args.work_counter) return cudaErrorInvalidValue;
     bool uniform = false;
     if constexpr (stream_is_rosl(CB) && M::LINEAR)
@@ -732,6 +733,16 @@ struct Registrar {
         sizeof(double) * stream_slots<M, CB, false, true>() * WARP_BLOCK;
     // batched forward-only launches have an instantiation of their own
     const bool fwd = uniform && args.split == 0 && !args.with_sens;
+    // ... and so have launches that integrate only some of the columns
+    bool subset = false;
+    if constexpr (stream_is_rosl(CB) && M::LINEAR) {
+      using S1 = StreamSolver<M, CB, 1>;
+      if (uniform && args.split == 0 && args.with_sens) {
+        subset = args.n_int != S1::PI;
+        for (int m = 0; m < S1::PI && !subset; ++m)
+          subset = args.int_param[m] != S1::full_param(m);
+      }
+    }
     if constexpr (stream_is_rosl(CB) && M::LINEAR) {
       if (uniform && args.split > 0)
         err = resident_blocks(solve_warp_kernel<M, CB, 2>, WARP_BLOCK,
@@ -739,6 +750,9 @@ struct Registrar {
       else if (fwd)
         err = resident_blocks(solve_warp_kernel<M, CB, 3>, WARP_BLOCK,
                               smem_fwd, resident_fwd, &res);
+      else if (subset)
+        err = resident_blocks(solve_warp_kernel<M, CB, 4>, WARP_BLOCK,
+                              smem_warp, resident_sub, &res);
       else if (uniform)
         err = resident_blocks(solve_warp_kernel<M, CB, 1>, WARP_BLOCK,
                               smem_warp, resident_warp, &res);
@@ -768,6 +782,10 @@ struct Registrar {
         else if (fwd)
           solve_warp_kernel<M, CB, 3>
               <<<static_cast<unsigned>(blocks), WARP_BLOCK, smem_fwd,
+                 stream>>>(args, counter);
+        else if (subset)
+          solve_warp_kernel<M, CB, 4>
+              <<<static_cast<unsigned>(blocks), WARP_BLOCK, smem_warp,
                  stream>>>(args, counter);
         else
           solve_warp_kernel<M, CB, 1>

@@ -545,7 +545,9 @@ CHI_HD ErrTerms error_terms(const int kind, const double* sg, const double yb,
 // the ROSL methods), 1 = warp-synchronous batched form (solve_uniform), 2 =
 // warp-per-system form of small launches (solve_uniform over the split work
 // items of one system, SolveArgs::split), 3 = FORM 1 without sensitivity
-// columns.  Only FORM 2 carries the code of split work items.
+// columns, 4 = FORM 1 for a subset of the columns chosen at run time (FORM 1
+// itself: all columns of the model).  Only FORM 2 carries the code of split
+// work items.
 template <class M, int METHOD_CODE, int FORM = 0>
 struct StreamSolver {
   static constexpr bool WITH_BUF = FORM == 0;
@@ -716,8 +718,12 @@ struct StreamSolver {
     if (a.n_int > 0 && k == ic(0)) return true;
     return col() == 0 && inert(a.col_param[k]);
   }
-  CHI_HD bool loglik() const { return a.mode == 1; }
-  CHI_HD bool deferred() const { return a.mode == 1 && a.snap != nullptr; }
+  // (the warp-synchronous forms only run log-likelihood launches with the
+  // observation fused: known at compile time there)
+  CHI_HD bool loglik() const { return FORM != 0 || a.mode == 1; }
+  CHI_HD bool deferred() const {
+    return FORM == 0 && a.mode == 1 && a.snap != nullptr;
+  }
   CHI_HD bool want_dsig() const {
     return !FWD && a.mode == 1 && a.with_sens && a.grad != nullptr;
   }
@@ -1174,6 +1180,11 @@ struct StreamSolver {
     if constexpr (ROSL) {
       if constexpr (M::LINEAR && FWD) {
         return step_rosl<0>();
+      } else if constexpr (M::LINEAR && FORM == 1) {
+        // all columns of the model, natural order (the launcher checks)
+        return step_rosl<1>();
+      } else if constexpr (M::LINEAR && FORM == 4) {
+        return step_rosl<2>();
       } else if constexpr (M::LINEAR) {
         if (n_int() == 0) return step_rosl<0>();
         if constexpr (SPLIT) {
@@ -1866,11 +1877,22 @@ struct StreamSolver {
 template <class M, int CB>
 CHI_HD void solve_system_uniform(const SolveArgs& a, const int64_t b,
                                  double* sm, const int stride) {
+  // the instantiation the launcher would pick (Registrar::launch_stream)
+  using S1 = StreamSolver<M, CB, 1>;
+  bool subset = a.n_int != S1::PI;
+  for (int m = 0; m < S1::PI && !subset; ++m)
+    subset = a.int_param[m] != S1::full_param(m);
   if (a.split > 0) {
     StreamSolver<M, CB, 2> s(a, sm, stride);
     s.solve_uniform(b);
+  } else if (!a.with_sens) {
+    StreamSolver<M, CB, 3> s(a, sm, stride);
+    s.solve_uniform(b);
+  } else if (subset) {
+    StreamSolver<M, CB, 4> s(a, sm, stride);
+    s.solve_uniform(b);
   } else {
-    StreamSolver<M, CB, 1> s(a, sm, stride);
+    S1 s(a, sm, stride);
     s.solve_uniform(b);
   }
 }
@@ -2099,8 +2121,9 @@ constexpr int warp_min_blocks(const int form) {
   return form == 3 ? CHI_WARP_FWD_MIN_BLOCKS : WARP_MIN_BLOCKS;
 }
 
-// FORM 1: batched launch; FORM 2: warp-per-system launch (small batches);
-// FORM 3: batched forward-only launch
+// FORM 1: batched launch, all sensitivity columns of the model; FORM 4: a
+// subset of them; FORM 3: none (forward only); FORM 2: warp-per-system launch
+// (small batches)
 template <class M, int CB, int FORM>
 __global__ void __launch_bounds__(WARP_BLOCK, warp_min_blocks(FORM))
 solve_warp_kernel(const SolveArgs a, unsigned long long* counter) {
