@@ -988,12 +988,15 @@ class HierarchicalLogPosterior(
         """Starts the host prior on a worker thread so that it runs while the
         calling thread waits for the GPU inside the (GIL-free) library call;
         returns a future."""
-        pool = getattr(HierarchicalLogPosterior, '_pool', None)
+        pool = self.__dict__.get('_pool')
         if pool is None:
+            # one worker per posterior object (not shared between objects:
+            # two posteriors evaluated from two threads do not queue behind
+            # each other)
             import concurrent.futures
             pool = concurrent.futures.ThreadPoolExecutor(
                 1, thread_name_prefix='chi_b200-prior')
-            HierarchicalLogPosterior._pool = pool
+            self._pool = pool
         return pool.submit(self._prior_batch, X[:, self._n_bottom:], with_grad)
 
     def evaluate_batch(self, X, copy=True):
