@@ -10,7 +10,7 @@ def bench(f, n=300):
     for _ in range(n): f()
     return (time.perf_counter() - t0) / n * 1e6
 
-for n_ids in (1000,):
+for n_ids in ([int(v) for v in sys.argv[1:]] or [1000]):
     prob = _synthetic.two_compartment_problem(n_ids, seed=0, n_doses=3, rtol=1e-8, atol=1e-10)
     post, ll, prior = prob['log_posterior'], prob['log_likelihood'], prob['log_prior']
     x = prob['x0']
