@@ -2027,10 +2027,18 @@ static int hier_logpdf_host(chi_b200_problem* p, int32_t C, const double* x,
     // last chunk's copy out are the part that nothing overlaps), at least
     // four chunks once there are 8 MB to move, and no chunk below ~200 k
     // systems (the persistent solve kernel wants a few rounds of work)
+    // (with a communicator every rank has to cut the batch into the SAME
+    // chunks -- each chunk ends with an all-reduce --, so the count follows
+    // from the largest shard of a balanced split, not from this rank's own)
+    int64_t shard_ids = p->id_end - p->id_begin;
+    if (p->comm && p->comm_world > 1)
+      shard_ids = (p->n_ids + p->comm_world - 1) / p->comm_world;
     const size_t bytes =
-        static_cast<size_t>(C) * (sharded ? w_b + w_t : pitch);
-    const int64_t systems =
-        static_cast<int64_t>(C) * (p->id_end - p->id_begin);
+        static_cast<size_t>(C) *
+        (sharded ? static_cast<size_t>(shard_ids) * p->pop.n_hdim *
+                           sizeof(double) + w_t
+                 : pitch);
+    const int64_t systems = static_cast<int64_t>(C) * shard_ids;
     if (bytes >= (size_t(8) << 20)) {
       n_chunks = std::max<int>(4, static_cast<int>(bytes >> 25));
       n_chunks = std::min<int>(
