@@ -224,6 +224,7 @@ struct chi_b200_problem {
   int64_t snap_budget = -1;     // bytes; -1: not determined yet
   bool snap_budget_auto = false;  // determined by the default policy
   DevBuf hx, hscore, hgrad, hstatus, partial, popflag, r2t;
+  DevBuf order_perm, order_keys;
   DevBuf step_sums;             // chi_b200_problem_counters
   // individuals sharded over the GPUs of a node: communicator for the
   // all-reduce of [score | d theta] and the packed partials it works on
@@ -863,7 +864,7 @@ void chi_b200_problem_destroy(chi_b200_problem* p) {
         &p->seg_off, &p->seg_t, &p->seg_rate, &p->covariates, &p->x, &p->ll,
         &p->grad, &p->status, &p->nst, &p->nrj, &p->ids, &p->traj_off,
         &p->traj_y, &p->traj_s, &p->hx, &p->hscore, &p->hgrad, &p->hstatus,
-        &p->partial, &p->popflag, &p->r2t})
+        &p->partial, &p->popflag, &p->r2t, &p->order_perm, &p->order_keys})
     b->release();
   if (p->comm) nccl_api().CommDestroy(p->comm);
   p->pack.release();
@@ -1310,6 +1311,14 @@ int launch_loglik(chi_b200_problem* p, int64_t B, const int32_t* d_ids,
       a.order_stride = order_stride;
     }
     a.refill_wait = wait >= 0 ? wait : (ordered ? INT32_MAX : 0);
+    if (ordered) {
+      // scratch of the stiffness order of the warp-synchronous kernels
+      // (SolveArgs::perm)
+      CUDA_TRY(p->order_perm.reserve(B_res * sizeof(int32_t)));
+      CUDA_TRY(p->order_keys.reserve(B_res * sizeof(float)));
+      a.perm = p->order_perm.as<int32_t>() + b0;
+      a.order_keys = p->order_keys.as<float>() + b0;
+    }
   }
   // Small launches (single parameter vectors: what pints' samplers and
   // optimisers ask for, chi/_inference.py:729-747): one WARP per system
@@ -1405,6 +1414,31 @@ int launch_loglik(chi_b200_problem* p, int64_t B, const int32_t* d_ids,
     p->solve_launches += 1;
   }
   p->counters[3] += a.snap ? 2 : 1;
+  {
+    // the two kernels of the stiffness order (Registrar::launch_stream runs
+    // them under exactly these conditions)
+    static const bool sort_enabled = [] {
+      const char* e = std::getenv("CHI_B200_SORT");
+      return !(e && std::atoi(e) == 0);
+    }();
+    static const bool warp_enabled = [] {
+      const char* e = std::getenv("CHI_B200_WARP_SYNC");
+      return !(e && std::atoi(e) == 0);
+    }();
+    const int v = p->variant >= 0 ? p->variant : 0;
+    const bool rosl = v < p->vt->n_variants &&
+                      p->vt->variant_lanes[v] == 0 &&
+                      (p->vt->variant_cols[v] == 9 ||
+                       p->vt->variant_cols[v] == 11) &&
+                      (p->vt->linear & 1);
+    const int64_t padded = (static_cast<int64_t>(a.order_inner) + 31) / 32 * 32;
+    if (rosl && sort_enabled && warp_enabled && a.split == 0 && !a.snap &&
+        a.perm && a.refill_wait == INT32_MAX && a.order_inner > 32 &&
+        a.order_inner <= 4096 &&
+        (padded - a.order_inner) * 8 <= a.order_inner &&
+        static_cast<int64_t>(a.order_inner) * a.order_stride == a.B)
+      p->counters[3] += 2;
+  }
   return 0;
 }
 

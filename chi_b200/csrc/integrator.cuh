@@ -765,6 +765,34 @@ struct Registrar {
     unsigned long long* counter = args.work_counter;
     err = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return err;
+    SolveArgs sorted = args;
+    if constexpr (stream_is_rosl(CB) && M::LINEAR) {
+      // batched launch: the vectors of an individual go to the warps in the
+      // order of a stiffness key (order_keys_kernel / order_sort_kernel);
+      // CHI_B200_SORT=0 keeps the batch order (comparisons)
+      static const bool sort_enabled = [] {
+        const char* e = std::getenv("CHI_B200_SORT");
+        return !(e && std::atoi(e) == 0);
+      }();
+      sorted.perm = nullptr;
+      if (uniform && args.split == 0 && sort_enabled && args.perm &&
+          args.order_keys && args.order_inner > 32 &&
+          args.order_inner <= ORDER_MAX_VECTORS) {
+        int p2 = 64;
+        while (p2 < args.order_inner) p2 <<= 1;
+        order_keys_kernel<M>
+            <<<static_cast<unsigned>((args.B + 255) / 256), 256, 0, stream>>>(
+                args);
+        const int threads = p2 / 2 < 1024 ? p2 / 2 : 1024;
+        order_sort_kernel<0>
+            <<<static_cast<unsigned>(args.order_stride), threads,
+               static_cast<size_t>(p2) * 8, stream>>>(
+                args.order_inner, p2, args.order_keys, args.perm);
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+        sorted.perm = args.perm;
+      }
+    }
     if constexpr (stream_is_rosl(CB) && M::LINEAR) {
       if (uniform) {
         // (warp-per-system launches: one warp per system)
@@ -778,19 +806,19 @@ struct Registrar {
         if (args.split > 0)
           solve_warp_kernel<M, CB, 2>
               <<<static_cast<unsigned>(blocks), WARP_BLOCK, smem_warp,
-                 stream>>>(args, counter);
+                 stream>>>(sorted, counter);
         else if (fwd)
           solve_warp_kernel<M, CB, 3>
               <<<static_cast<unsigned>(blocks), WARP_BLOCK, smem_fwd,
-                 stream>>>(args, counter);
+                 stream>>>(sorted, counter);
         else if (subset)
           solve_warp_kernel<M, CB, 4>
               <<<static_cast<unsigned>(blocks), WARP_BLOCK, smem_warp,
-                 stream>>>(args, counter);
+                 stream>>>(sorted, counter);
         else
           solve_warp_kernel<M, CB, 1>
               <<<static_cast<unsigned>(blocks), WARP_BLOCK, smem_warp,
-                 stream>>>(args, counter);
+                 stream>>>(sorted, counter);
       }
     }
     if (!uniform) {

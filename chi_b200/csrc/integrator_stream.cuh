@@ -2121,6 +2121,76 @@ constexpr int warp_min_blocks(const int form) {
   return form == 3 ? CHI_WARP_FWD_MIN_BLOCKS : WARP_MIN_BLOCKS;
 }
 
+// Work order of the batched warp-synchronous launches.  The lanes of a warp
+// wait for each other at every stop, so a warp is as slow as its slowest lane
+// between any two stops; vectors with similar dynamics take similar step
+// sequences.  The vectors of an individual are therefore handed to the warps
+// in the order of a stiffness key, -trace J (the sum of the rate constants
+// of a mass-action model): measured on the host build (tools/exp/
+// group_cost.py) the lane efficiency of the step rises from 0.93 to 0.97 at a
+// parameter spread of 10 % and from 0.84 to 0.94 at 30 %.  Two kernels: the
+// keys (model specific), then one block per individual sorts its vectors
+// (bitonic, shared memory).  Only the assignment of systems to lanes changes:
+// results are bit-identical.
+constexpr int ORDER_MAX_VECTORS = 4096;
+
+template <class M>
+__global__ void __launch_bounds__(256)
+order_keys_kernel(const SolveArgs a) {
+  const int64_t b = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (b >= a.B) return;
+  const double* xb = a.x + b * a.x_stride;
+  double y[M::N], c[M::NCS], J[M::N * M::N];
+#pragma unroll
+  for (int n = 0; n < M::N; ++n) y[n] = xb[n];
+#pragma unroll
+  for (int j = 0; j < M::NC; ++j) c[j] = xb[M::N + j];
+  if (M::NC == 0) c[0] = 0.0;
+  M::jac(y, c, J);
+  double k = 0.0;
+#pragma unroll
+  for (int n = 0; n < M::N; ++n) k -= J[n * M::N + n];
+  const int64_t vec = b / a.order_stride;          // b = vector * n + individual
+  const int64_t ind = b - vec * a.order_stride;
+  a.order_keys[ind * a.order_inner + vec] = static_cast<float>(k);
+}
+
+// one block per individual; P2 = order_inner rounded up to a power of two
+template <int UNUSED>
+__global__ void __launch_bounds__(1024)
+order_sort_kernel(const int32_t n_vec, const int32_t p2,
+                  const float* __restrict__ keys, int32_t* __restrict__ perm) {
+  extern __shared__ double chi_sm[];
+  float* sk = reinterpret_cast<float*>(chi_sm);
+  int32_t* si = reinterpret_cast<int32_t*>(sk + p2);
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * n_vec;
+  for (int t = threadIdx.x; t < p2; t += blockDim.x) {
+    const float k = t < n_vec ? keys[base + t] : INFINITY;
+    sk[t] = (k == k) ? k : INFINITY;   // NaN keys sort last
+    si[t] = t;
+  }
+  __syncthreads();
+  for (int size = 2; size <= p2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (p2 >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const float kl = sk[lo], kh = sk[hi];
+        const int il = si[lo], ih = si[hi];
+        // (ties by index: a deterministic order)
+        const bool gt = kl > kh || (kl == kh && il > ih);
+        if (gt == up) {
+          sk[lo] = kh; sk[hi] = kl;
+          si[lo] = ih; si[hi] = il;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int t = threadIdx.x; t < n_vec; t += blockDim.x) perm[base + t] = si[t];
+}
+
 // FORM 1: batched launch, all sensitivity columns of the model; FORM 4: a
 // subset of them; FORM 3: none (forward only); FORM 2: warp-per-system launch
 // (small batches)
@@ -2164,7 +2234,9 @@ solve_warp_kernel(const SolveArgs a, unsigned long long* counter) {
       const unsigned long long q = w / wpi;
       const unsigned long long r0 = (w - q * wpi) * 32ull;
       const bool ghost = r0 + lane >= static_cast<unsigned>(a.order_inner);
-      const unsigned long long r = ghost ? r0 : r0 + lane;
+      unsigned long long r = ghost ? r0 : r0 + lane;
+      // rank r of individual q in the stiffness order -> vector
+      if (a.perm) r = static_cast<unsigned>(a.perm[q * a.order_inner + r]);
       s.solve_uniform(
           static_cast<int64_t>(r * static_cast<unsigned>(a.order_stride) + q),
           ghost);

@@ -118,6 +118,14 @@ struct SolveArgs {
   // error-model gradients and the gradient entries that need no sensitivity
   // column, item j the entry of its column; the status is the maximum.
   int32_t split;
+  // Batched launches of the warp-synchronous kernels: scratch for handing
+  // the vectors of an individual to the warps in the order of a stiffness
+  // key (-trace J) instead of their order in the batch -- vectors that need
+  // similar step sequences then share a warp, and fewer lanes wait at the
+  // stops.  perm[i * order_inner + r] = vector at rank r of individual i
+  // (written by the launcher, null: batch order), order_keys: the keys.
+  int32_t* perm;
+  float* order_keys;
 };
 
 // What a compiled model contributes to the registry of the core library.

@@ -51,6 +51,7 @@ class SolveArgs(ctypes.Structure):
         ('order_inner', ctypes.c_int32), ('order_stride', ctypes.c_int32),
         ('refill_wait', ctypes.c_int32), ('work_counter', _vp),
         ('split', ctypes.c_int32),
+        ('perm', _vp), ('order_keys', _vp),
     ]
 
 

@@ -786,7 +786,8 @@ def test_individual_shards_sum_to_the_full_evaluation():
 
 
 @pytest.mark.gpu
-def test_results_do_not_depend_on_how_the_batch_is_worked_through():
+@pytest.mark.parametrize('C', [77, 120])
+def test_results_do_not_depend_on_how_the_batch_is_worked_through(C):
     """Chunks of the host entry point on two streams, individual-major work
     order and whole-warp refill of the persistent solve kernel
     (chi_b200_problem_set_batching) only change the schedule: every system
@@ -800,7 +801,10 @@ def test_results_do_not_depend_on_how_the_batch_is_worked_through():
     ll = prob['log_likelihood']
     n_params = len(prob['x0'])
     rng = np.random.default_rng(4)
-    C = 77   # not a multiple of the warp size or of the chunk count
+    # 77: not a multiple of the warp size or of the chunk count (general
+    # kernel in individual-major order); 120: four warps per individual, the
+    # last one padded with ghost lanes, vectors handed out in the stiffness
+    # order (warp-synchronous kernel)
     X = prob['x0'][None, :] * (1 + 0.05 * rng.normal(size=(C, n_params)))
     X[5, -1] = -0.1       # invalid sigma: -inf score, inf gradient
     # (the warp-per-system form of small launches is a different
