@@ -1,34 +1,29 @@
-// chi_b200 -- "streamed columns" sensitivity solve (the default kernels).
+// chi_b200 -- the thread-per-system solve kernels (the default kernels).
 //
-// Same method family and semantics as solve_system<M, G, MC> (integrator.cuh):
-// a stiffly accurate Rosenbrock method (RODAS5 by default, RODAS4 as a
-// variant) on [y | S] with the exact block-triangular Jacobian, exact hits of
-// dose edges and observation times.  What differs is the mapping:
+// StreamSolver<M, METHOD, FORM> integrates ONE system -- an individual under
+// one parameter vector -- per thread: a stiffly accurate Rosenbrock method on
+// [y | S] with the exact block-triangular Jacobian, exact hits of dose edges
+// and observation times, per-system scratch in shared memory (slot-major,
+// conflict free: sm[slot * stride + tid]).
 //
-//   * ONE thread per system (no redundant state column, no shuffles), in a
-//     persistent grid whose lanes pull work from a global counter; with at
-//     least a warp's worth of parameter vectors the lanes of a warp take the
-//     SAME individual under different vectors and refill as a whole warp, so
-//     they reach dose edges and observation times in phase
-//     (SolveArgs::order_inner, refill_wait);
-//   * per step the state column runs first; the sensitivity columns are then
-//     streamed through registers one at a time in a uniform, non-unrolled
-//     loop (every thread of the grid handles the same column at the same
-//     time: no divergence, and the hot loop stays inside the instruction
-//     cache).  Linear models run the method in its original k-stage form
-//     (one combination and one N x N product per stage, see the K constants)
-//     with a branch-free column body that needs only V_i = arg_i + kappa_i
-//     of the state column (shared memory);
-//   * S of the integrated columns (current and candidate), the stage values,
-//     the state, the model constants and the per-system scalars that only the
-//     event handler touches live in shared memory, slot-major (conflict
-//     free): sm[slot * stride + tid], stream_slots<M>() doubles per thread --
-//     the kernel then fits 128 registers without spills at 4 blocks per SM;
-//   * at an observation record the thread only stores a snapshot of y and S
-//     (SolveArgs::snap); observe_system / observe_kernel evaluate output map,
-//     error model and gradient afterwards with all lanes busy.  Without a
-//     snapshot buffer the same arithmetic (error_terms) runs fused in the
-//     event handler.
+//   METHOD  9 / 11 = ROSL(9) / ROSL(11), the methods for LINEAR models: state
+//           and all sensitivity columns advance together in registers, one
+//           N x N product and one accumulation per stage (step_rosl);
+//           1 / 5 = RODAS4 / RODAS5 (nonlinear models): the state column
+//           first, then the sensitivity columns streamed through registers
+//           one at a time in a uniform loop (step_rodas, column).
+//   FORM    0  general event loop (solve_stream_kernel): persistent grid, the
+//              lanes pull work from a global counter and handle their own
+//              events; observation fused, or deferred to observe_kernel via
+//              snapshots of (y, S) at the records;
+//           1 / 3 / 4  warp-synchronous batched form (solve_warp_kernel,
+//              solve_uniform): the 32 lanes of a warp integrate one
+//              individual under 32 parameter vectors and walk through its
+//              stops together, observation fused (1: all columns of the
+//              model, 3: none, 4: a run-time subset);
+//           2  warp-per-system form of small launches: the columns of a
+//              system side by side on the lanes of one warp
+//              (SolveArgs::split).
 //
 // Compiles for the host as well (stride = 1, tid = 0) for the CPU port.
 #pragma once
