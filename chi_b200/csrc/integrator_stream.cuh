@@ -1467,10 +1467,11 @@ struct StreamSolver {
         }
       }
     };
-    // (the all-columns batched kernel unrolls the loop completely: +2.4 %
-    // there once the kernel holds nothing but this one step body; the other
-    // forms keep four stages per trip)
-    constexpr int UNROLL = FORM == 1 ? 8 : CHI_ROSL_UNROLL;
+    // (the warp-synchronous kernels unroll the loop completely: +2.4 % on
+    // the all-columns batched kernel once it holds nothing but this one step
+    // body, -4 % solve time for single vectors; the general kernel, which
+    // carries every step body, keeps four stages per trip)
+    constexpr int UNROLL = FORM != 0 ? 8 : CHI_ROSL_UNROLL;
 #ifdef __CUDA_ARCH__
 #pragma unroll UNROLL
 #endif
