@@ -1328,7 +1328,8 @@ int launch_loglik(chi_b200_problem* p, int64_t B, const int32_t* d_ids,
   // system's stops like a warp of the batched launch does -- a third of the
   // instructions per step attempt, no lane waits for another system's events,
   // on a GPU that is mostly idle at this size.  ROSL kernels of linear
-  // models; applies while every system finds a resident warp
+  // models; applies while every system finds a resident warp -- 12 per SM
+  // at the 165 registers this form is compiled for
   // (chi_b200_problem_set_small_batch / CHI_B200_SPLIT_MAX: largest number of
   // systems, 0: never).
   bool split = false;
@@ -1342,7 +1343,8 @@ int launch_loglik(chi_b200_problem* p, int64_t B, const int32_t* d_ids,
       int sms = 0;
       CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount,
                                       p->device));
-      split_max = 16ll * sms;
+      // (three resident blocks of four warps per SM: one wave)
+      split_max = 12ll * sms;
     }
     const int v = p->variant >= 0 ? p->variant : 0;
     const bool rosl = v < p->vt->n_variants &&

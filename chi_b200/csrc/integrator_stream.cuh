@@ -2117,8 +2117,15 @@ constexpr int WARP_MIN_BLOCKS = CHI_WARP_MIN_BLOCKS;
 #ifndef CHI_WARP_FWD_MIN_BLOCKS
 #define CHI_WARP_FWD_MIN_BLOCKS 4
 #endif
+// ... and the warp-per-system form: its launches are small by definition, a
+// single resident warp per scheduler is the normal case, so it gets the
+// registers of three blocks per SM (168) instead of four (128: 78 B spilled)
+#ifndef CHI_WARP_SPLIT_MIN_BLOCKS
+#define CHI_WARP_SPLIT_MIN_BLOCKS 3
+#endif
 constexpr int warp_min_blocks(const int form) {
-  return form == 3 ? CHI_WARP_FWD_MIN_BLOCKS : WARP_MIN_BLOCKS;
+  return form == 3 ? CHI_WARP_FWD_MIN_BLOCKS
+                   : (form == 2 ? CHI_WARP_SPLIT_MIN_BLOCKS : WARP_MIN_BLOCKS);
 }
 
 // Work order of the batched warp-synchronous launches.  The lanes of a warp

@@ -299,7 +299,7 @@ int chi_b200_problem_set_batching(chi_b200_problem* p, int32_t n_chunks,
  * optimisers call LogPDF.evaluateS1 (chi/_inference.py:729-747) -- run one
  * warp per system, the sensitivity columns side by side on its lanes, while
  * the launch has at most `max_systems` systems (-1: the default, one resident
- * warp per system: 16 x the SM count; 0: never; CHI_B200_SPLIT_MAX overrides
+ * warp per system: 12 x the SM count; 0: never; CHI_B200_SPLIT_MAX overrides
  * the default).  Each column is then integrated with the state under its own
  * step-size control: results agree with the batched form within the
  * integrator's tolerance, not bit for bit.  ROSL kernels of linear models. */
